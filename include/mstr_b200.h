@@ -1,0 +1,160 @@
+/*
+ * mstr_b200.h - C ABI of the B200 (sm_100a) word-crop recognition forward pass.
+ *
+ * The reference (JoshuaPlacidi/multimodal_scene_text_recognition) has no FFI layer: its hot path is
+ * a set of Python nn.Module classes whose arithmetic is dispatched to PyTorch ATen.  Each entry
+ * point below replaces the ATen work done by one reference call site (cited per function, paths
+ * relative to the reference root).  The Python modules in
+ * multimodal_scene_text_recognition_b200/modules/ keep the reference's class names and forward
+ * signatures and bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative mstr_status code; no exceptions, no
+ *     host synchronisation; all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - all pointers are DEVICE pointers borrowed for the duration of the call, caller-allocated;
+ *   - activations are NHWC ([B][H][W][C], C contiguous) unless stated otherwise;
+ *   - `mstr_last_error_string()` describes the most recent failure on the calling thread.
+ */
+#ifndef MSTR_B200_H_
+#define MSTR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mstr_stream_t; /* cudaStream_t */
+
+enum mstr_status {
+  MSTR_OK = 0,
+  MSTR_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, misaligned pointer */
+  MSTR_ERR_UNSUPPORTED = -2,  /* shape / mode the kernels are not written for */
+  MSTR_ERR_CUDA = -3,         /* a CUDA runtime / driver call failed (see error string) */
+  MSTR_ERR_NO_DEVICE = -4     /* no sm_100 device */
+};
+
+enum mstr_dtype { MSTR_F32 = 0, MSTR_BF16 = 1 };
+
+/* Library / ABI version (major*1000 + minor). */
+int mstr_version(void);
+const char* mstr_last_error_string(void);
+/* Number of kernels this library has launched since load (bench.py's "gpu_launches"). */
+int64_t mstr_launch_count(void);
+
+/* ---- TPS rectification ------------------------------------------------------------------
+ * Replaces GridGenerator.build_P_prime (modules/transformation.py:154-163: two repeat() copies
+ * and two torch.bmm) fused with F.grid_sample(bilinear, padding_mode='border',
+ * align_corners=True) (modules/transformation.py:33-34).
+ *   img      [B][C][H][W] f32  (NCHW, as the reference's DataLoader yields it)
+ *   c_prime  [B][F][2]    f32  fiducial points from the localisation network
+ *   basis    mode 0: P_hat^T        [F+3][H*W] f32  (reference order: T = inv_delta_C [C';0], P' = P_hat T)
+ *            mode 1: (P_hat inv_delta_C[:, :F])^T  [F][H*W] f32 (folded constant, fp64-precomputed)
+ *   inv_delta_C  [F+3][F+3] f32, used by mode 0 only (may be null in mode 1)
+ *   out      [B][C][H][W] f32 rectified image
+ *   grid_out optional [B][H*W][2] f32 sampling grid (null to skip)
+ */
+int mstr_tps_rectify(const float* img, const float* c_prime, const float* basis,
+                     const float* inv_delta_C, float* out, float* grid_out,
+                     int B, int C, int H, int W, int F, int mode, mstr_stream_t stream);
+
+/* ---- first-layer convolution (C_in = 1..4) -------------------------------------------------
+ * Replaces Conv2d(C_in, C_out, 3, 1, 1, bias=False) + BatchNorm2d(eval) + ReLU
+ * [+ MaxPool2d(2,2)] for the two layers that read the image directly
+ * (modules/feature_extraction.py:58-60,111-113 conv0_1/bn0_1; modules/transformation.py:49-51
+ * conv.0/conv.1/ReLU/MaxPool).  SIMT: K = 9*C_in is too small for tensor cores.
+ *   x [B][C_in][H][W] f32 NCHW;  w [C_out][C_in][3][3] f32;  scale/shift [C_out] f32 (folded BN)
+ *   out NHWC [B][H'][W'][C_out] of out_dtype, H' = H/2 if pool else H.
+ */
+int mstr_conv3x3_first(const float* x, const float* w, const float* scale, const float* shift,
+                       void* out, int out_dtype, int B, int C_in, int H, int W, int C_out,
+                       int pool, mstr_stream_t stream);
+
+/* ---- implicit-GEMM convolution + folded BN + residual + ReLU --------------------------------
+ * Replaces nn.Conv2d(bias=False) -> nn.BatchNorm2d(eval) [-> += residual] [-> ReLU]
+ * (modules/feature_extraction.py:32-47,109-150; modules/transformation.py:52-57) and, with
+ * R=S=1,H=W=1, nn.Linear (modules/encoders.py:15,28; modules/decoders.py:71,81).
+ *   x        NHWC [B][H][W][C_in]
+ *   w        [C_out][R][S][C_in]  (K-major, K = (r*S+s)*C_in + c)
+ *   scale/shift [C_out] f32: y = acc*scale + shift   (scale may be null => 1)
+ *   residual optional NHWC [B][P][Q][C_out], added before the ReLU
+ *   out      NHWC [B][P][Q][C_out];  P = (H+2*pad_h-R)/stride_h+1, Q likewise
+ * mstr_conv_gemm_f32 : fp32 operands, fp32 FMA (exact parity mode), x/w/residual/out f32.
+ * mstr_conv_gemm_bf16: bf16 operands on tcgen05 tensor cores (TMA im2col loads, TMEM fp32
+ *                      accumulators); residual bf16; out_bf16 and/or out_f32 may be given.
+ *                      Requires C_in % 32 == 0, C_out % 16 == 0.
+ */
+int mstr_conv_gemm_f32(const float* x, const float* w, const float* scale, const float* shift,
+                       const float* residual, float* out, int B, int H, int W, int C_in,
+                       int C_out, int R, int S, int stride_h, int stride_w, int pad_h, int pad_w,
+                       int relu, mstr_stream_t stream);
+int mstr_conv_gemm_bf16(const void* x, const void* w, const float* scale, const float* shift,
+                        const void* residual, void* out_bf16, float* out_f32, int B, int H, int W,
+                        int C_in, int C_out, int R, int S, int stride_h, int stride_w, int pad_h,
+                        int pad_w, int relu, mstr_stream_t stream);
+
+/* ---- pooling / layout helpers -------------------------------------------------------------
+ * mstr_maxpool_nhwc : nn.MaxPool2d with -inf padding (feature_extraction.py:66,72,78).
+ * mstr_mean_hw      : AdaptiveAvgPool2d(1) of the localisation net (transformation.py:57):
+ *                     NHWC [B][H][W][C] -> [B][C] f32.
+ * mstr_mean_h       : model.py:92-93 permute+AdaptiveAvgPool2d((None,1))+squeeze:
+ *                     NHWC [B][H][W][C] -> [B][W][C] (mean over H) in out_dtype (+ optional f32).
+ * mstr_cast         : f32 <-> bf16 element cast.
+ */
+int mstr_maxpool_nhwc(const void* x, void* out, int dtype, int B, int H, int W, int C, int kh,
+                      int kw, int sh, int sw, int ph, int pw, mstr_stream_t stream);
+int mstr_mean_hw(const void* x, float* out, int dtype, int B, int H, int W, int C,
+                 mstr_stream_t stream);
+int mstr_mean_h(const void* x, void* out, float* out_f32, int dtype, int B, int H, int W, int C,
+                mstr_stream_t stream);
+int mstr_cast(const void* x, void* out, int src_dtype, int dst_dtype, int64_t n,
+              mstr_stream_t stream);
+
+/* ---- semantic vectors -----------------------------------------------------------------------
+ * Replaces Linear_Embedding.forward (modules/semantic_vectors.py:33-49).
+ *   ids   [B][n] f32 object ids (cast like .long());  table [rows][D] f32
+ *   ious  [B][n] f32, mode 1 ('scene') only: out = softmax(ious, dim=1)[..., None] * table[ids]
+ *   mode 0 = 'overlap' (plain gather).   out [B][n][D] f32.
+ */
+int mstr_embed_semantics(const float* ids, const float* table, const float* ious, float* out,
+                         int B, int n, int D, int rows, int mode, mstr_stream_t stream);
+
+/* ---- BiLSTM recurrence ----------------------------------------------------------------------
+ * Replaces the recurrent part of nn.LSTM(bidirectional=True, batch_first=True)
+ * (modules/encoders.py:14,24); the input projection x W_ih^T + b_ih + b_hh is a GEMM done with
+ * mstr_conv_gemm_* beforehand.
+ *   gates_x [B][T][2][4*Hd] f32   (dir 0 = forward, 1 = reverse; gate order i,f,g,o)
+ *   w_hh    [2][4*Hd][Hd]   f32
+ *   out_f32 / out_bf16  [B][T][2*Hd]  ([fwd | bwd]); either may be null.  Hd must be 256.
+ */
+int mstr_bilstm_recurrent(const float* gates_x, const float* w_hh, float* out_f32, void* out_bf16,
+                          int B, int T, int Hd, mstr_stream_t stream);
+
+/* ---- attention decoder ---------------------------------------------------------------------
+ * Replaces Attention.forward (modules/decoders.py:26-64) with AttentionCell.forward (:79-101),
+ * the generator (:17,:59) and the argmax feedback (:61-62), all steps in one persistent launch.
+ *   enc   [B][T][Hd] f32 encoder output (batch_H);  proj [B][T][Hd] f32 = i2h(enc) (loop invariant, :81)
+ *   w_h2h [Hd][Hd], b_h2h [Hd], w_score [Hd]
+ *   w_ctx [4Hd][Hd]   = rnn.weight_ih[:, :Hd];  w_tok [C][4Hd] = rnn.weight_ih[:, Hd:]^T (one-hot == row gather)
+ *   w_hh  [4Hd][Hd],  bias [4Hd] = rnn.bias_ih + rnn.bias_hh
+ *   w_gen [C][Hd], b_gen [C]
+ *   text  optional [B][steps] int64: teacher-forced tokens (is_train=True, :41-50); null => greedy (:52-62)
+ *   h0/c0 optional [B][Hd] f32 initial state (null = zeros, :36-38); h_out/c_out optional final state
+ *   logits [B][steps][C] f32 (must be zero-initialised by the caller when early_exit != 0)
+ *   ids    [B][steps] int32 argmax per step; lengths [B] int32 = index of the first [s] (id 1) or steps
+ *   alpha_out optional [B][steps][T] f32 attention weights (the `alpha` AttentionCell returns, :87,:101)
+ *   early_exit != 0: a crop stops after it emits [s]; the reference always runs all steps
+ *                    (decoders.py:34,56) but its callers cut at the first [s]
+ *                    (training_functions.py:188-189).
+ */
+int mstr_attn_decode(const float* enc, const float* proj, const float* w_h2h, const float* b_h2h,
+                     const float* w_score, const float* w_ctx, const float* w_tok,
+                     const float* w_hh, const float* bias, const float* w_gen, const float* b_gen,
+                     const int64_t* text, const float* h0, const float* c0, float* logits,
+                     int32_t* ids, int32_t* lengths, float* alpha_out, float* h_out, float* c_out,
+                     int B, int T, int Hd, int C, int steps, int early_exit, mstr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSTR_B200_H_ */

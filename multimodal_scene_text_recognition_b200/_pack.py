@@ -1,0 +1,72 @@
+"""Weight pre-packing helpers: fold eval-mode BatchNorm, re-lay conv/LSTM weights for the kernels.
+
+Parameters stay ordinary nn.Parameters with the reference's names and shapes (so .pt files load
+unchanged, SURVEY.md 5 "checkpoint").  Packed copies are derived lazily and cached on the module;
+the cache key is (data_ptr, _version, device, dtype) of every source tensor, so
+``load_state_dict`` / ``.to()`` / in-place updates invalidate it.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable
+
+import torch
+
+BN_EPS_DEFAULT = 1e-5
+
+
+def cached(module: torch.nn.Module, key, sources: Iterable[torch.Tensor], build: Callable[[], object]):
+    store = module.__dict__.get('_mstr_pack')
+    if store is None:
+        store = {}
+        object.__setattr__(module, '_mstr_pack', store)
+    stamp = tuple((t.data_ptr(), t._version, str(t.device), t.dtype) for t in sources)
+    hit = store.get(key)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    with torch.no_grad():
+        value = build()
+    store[key] = (stamp, value)
+    return value
+
+
+def act_dtype(precision: str) -> torch.dtype:
+    if precision == 'bf16':
+        return torch.bfloat16
+    if precision == 'fp32':
+        return torch.float32
+    raise ValueError("config.PRECISION must be 'bf16' or 'fp32', got %r" % (precision,))
+
+
+def bn_sources(bn: torch.nn.BatchNorm2d):
+    return [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+
+def fold_bn(bn: torch.nn.BatchNorm2d):
+    """scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (fp32, eval-mode BN)."""
+    scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+    shift = bn.bias.float() - bn.running_mean.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def pack_conv(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, precision: str):
+    """-> (w [Cout,R,S,Cin] in the activation dtype, scale, shift)."""
+    def build():
+        w = conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(act_dtype(precision))
+        scale, shift = fold_bn(bn)
+        return w, scale, shift
+    return cached(conv, ('conv', precision), [conv.weight] + bn_sources(bn), build)
+
+
+def pack_first_conv(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d):
+    """Image-reading conv: fp32 [Cout,Cin,3,3] weights (SIMT kernel) + folded BN."""
+    def build():
+        scale, shift = fold_bn(bn)
+        return conv.weight.detach().float().contiguous(), scale, shift
+    return cached(conv, ('first',), [conv.weight] + bn_sources(bn), build)
+
+
+def require_inference(*tensors) -> None:
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise RuntimeError(
+            "the B200 kernels implement the inference forward only (SURVEY.md 8b): call under "
+            "torch.no_grad() / model.eval(); autograd through them is not supported")

@@ -1,0 +1,57 @@
+"""Run-time configuration, attribute-compatible with the reference's ``config.py`` (config.py:1-70).
+
+The modules read these attributes at call time exactly where the reference does
+(``MAX_TEXT_LENGTH`` in Attention.forward, decoders.py:34; ``SEMANTIC_VECTOR`` in
+Linear_Embedding.forward, semantic_vectors.py:35-47; ``ENCODER`` in Model.forward, model.py:99).
+Only the LSTM/LSTM recognition path is implemented; the attributes of the
+transformer / fusion experiments are kept so that code reading them does not break.
+"""
+import string
+
+# devices (reference default is [1]; one process per GPU here, see parallel.py)
+DEVICE_IDS = [0]
+PRIMARY_DEVICE = 'cuda:' + str(DEVICE_IDS[0])
+
+EXPERIMENT = 'mstr_b200'
+SAVED_MODEL = None
+
+RANDOM_SEED = 999
+BATCH_SIZE = 192
+EPOCHS = 8
+MAX_TEXT_LENGTH = 25
+CHARS = string.printable[:-6]
+MODEL_SAVE_THRESHOLD = 0
+
+ENCODER = 'LSTM'   # only 'LSTM' is on the hot path of this repo
+DECODER = 'LSTM'   # only 'LSTM' (the attention decoder)
+
+EMBED_DIM = 256
+HIDDEN_DIM = 512
+
+SEMANTIC_VECTOR = 'overlap'     # overlap | scene   ('combined' crashes in the reference as well)
+SEMANTIC_SOURCE = 'vinvl'       # coco | vg | vinvl | zero | rand
+SEMANTIC_ASSIGNMENT = 'resize'
+SEMANTIC_EMBEDDING = 'linear'   # linear   ('bert' is broken in the reference: semantic_vectors.py:63)
+
+PRINT_ATTENTION_SCORES = False
+PRE_ENCODER_MLP = False
+OSCAR_ENCODER = False
+PRE_DECODER_MLP = False
+CLS_DECODER_INIT = False
+MULTIHEAD_PRE_TARGET = False
+MULTIHEAD_PRE_MEMORY = False
+MULTIHEAD_POST_MEMORY = False
+POST_DECODER_MLP = False
+
+# ---- additions of this implementation -----------------------------------------------------------
+# 'bf16' : throughput mode - tcgen05 tensor-core GEMMs with bf16 operands, fp32 accumulation/epilogues
+# 'fp32' : parity mode - every product in fp32 FMA (stands in for the north star's "TF32 mode",
+#          which is specified by bit-identical ids; single-pass TF32 cannot deliver that here)
+PRECISION = 'bf16'
+# 'folded'    : grid = (P_hat inv_delta_C[:, :F]) C'  with the constant folded in fp64 (more accurate)
+# 'reference' : T = inv_delta_C [C';0] then P' = P_hat T in fp32, the order of transformation.py:161-162
+TPS_GRID = 'folded'
+# stop decoding a crop once it has emitted [s]; logits after [s] stay zero.  The reference always
+# runs MAX_TEXT_LENGTH+1 steps (decoders.py:34) but its callers cut at the first [s]
+# (training_functions.py:188-189).  False reproduces every logit of the reference.
+DECODER_EARLY_EXIT = True

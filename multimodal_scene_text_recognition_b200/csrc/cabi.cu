@@ -1,0 +1,38 @@
+// Library-level C ABI: version, per-thread error string, launch counter.
+#include <stdarg.h>
+#include <atomic>
+
+#include "common.cuh"
+
+namespace mstr {
+
+static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+}  // namespace mstr
+
+extern "C" __attribute__((visibility("default"))) int mstr_version(void) { return 1000; }
+extern "C" __attribute__((visibility("default"))) const char* mstr_last_error_string(void) { return mstr::g_error; }
+extern "C" __attribute__((visibility("default"))) int64_t mstr_launch_count(void) { return (int64_t)mstr::g_launches.load(); }

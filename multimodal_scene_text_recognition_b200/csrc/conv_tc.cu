@@ -1,0 +1,494 @@
+// bf16 implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// out[m][n] = act( (sum_k A[m][k] W[n][k]) * scale[n] + shift[n] + residual[m][n] )
+//   m = (b,p,q) output pixel, k = (r,s,c);  A is never materialised: the producer warp issues
+//   TMA *im2col* loads (cp.async.bulk.tensor.4d...im2col) straight from the NHWC activation
+//   tensor, one 128-pixel x BLOCK_K-channel box per filter tap, zero-filling the halo in hardware.
+//   1x1 / linear layers use a plain 2-D tiled map instead.
+// Reference call sites replaced: every nn.Conv2d(bias=False)+BatchNorm2d(eval)[+residual][+ReLU]
+// with C_in >= 32 in modules/feature_extraction.py:32-47,109-150 and
+// modules/transformation.py:52-57, and nn.Linear in modules/encoders.py:15,28 /
+// modules/decoders.py:71,81.
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer  : STAGES-deep smem ring, mbarrier full/empty
+//   warp 1      MMA issuer    : one thread issues tcgen05.mma.cta_group::1.kind::f16 (128 x BLOCK_N x 16),
+//                               accumulators in TMEM (2 x BLOCK_N fp32 columns, double buffered)
+//   warps 2..5  epilogue      : tcgen05.ld 32x32b.x32 -> folded BN, residual, ReLU -> bf16/f32 NHWC stores,
+//                               overlapped with the next tile's MMAs through the second TMEM buffer
+// Roofline: tensor pipe.  Algorithmic FLOPs = 2 * M * C_out * R*S*C_in per launch.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace mstr {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+      printf("mstr: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c,
+                                                   int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
+      "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, rows of BLOCK_K bf16 (= one swizzle span):
+//   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   bits [32,46) stride byte offset >> 4   (8 rows x row bytes: distance between 8-row core groups)
+//   bits [46,48) descriptor version = 1 (Blackwell)      bits [61,64) swizzle: 2 = 128B, 4 = 64B
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = (ROW_BYTES == 128) ? 2ull : 4ull;
+  constexpr uint64_t sbo = (8ull * ROW_BYTES) >> 4;
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// Instruction descriptor for kind::f16: D = f32 (bits [4,6) = 1), A = B = bf16 (bits [7,10) = [10,13) = 1),
+// both operands K-major (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+struct TcParams {
+  int M, Cout;
+  int num_m_tiles, num_n_tiles;
+  int taps, S, cin_chunks;  // K loop = taps x cin_chunks blocks of BLOCK_K channels
+  int P, Q, sh, sw, ph, pw;
+  int im2col;               // 1: A via im2col map; 0: A via 2-D tiled map [M][K]
+  int relu;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+};
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_THREADS = 192;
+
+template <int BLOCK_N, int BLOCK_K>
+struct TcCfg {
+  static constexpr int ROW_BYTES = BLOCK_K * 2;
+  static constexpr int A_BYTES = TC_BLOCK_M * ROW_BYTES;
+  static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 4 * BLOCK_N * 4 /*scale/shift x2*/ +
+                                    (2 * STAGES + 4) * 8 + 16;
+};
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const TcParams p) {
+  using Cfg = TcCfg<BLOCK_N, BLOCK_K>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  float* sScale = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BLOCK_N]
+  float* sShift = sScale + 2 * BLOCK_N;                                        // [2][BLOCK_N]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + 2 * BLOCK_N);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_k = p.taps * p.cin_chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+        const int m0 = (tile / p.num_n_tiles) * TC_BLOCK_M;
+        int cw = 0, chh = 0, cn = 0;
+        if (p.im2col) {
+          const int q = m0 % p.Q, pp = (m0 / p.Q) % p.P;
+          cn = m0 / (p.Q * p.P);
+          cw = q * p.sw - p.pw;
+          chh = pp * p.sh - p.ph;
+        }
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int r = tap / p.S, s = tap - r * p.S;
+          for (int cc = 0; cc < p.cin_chunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (p.im2col)
+              tma_load_im2col_4d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cc * BLOCK_K, cw, chh, cn,
+                                 (uint16_t)s, (uint16_t)r);
+            else
+              tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cc * BLOCK_K, m0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], (tap * p.cin_chunks + cc) * BLOCK_K, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t da = make_smem_desc<Cfg::ROW_BYTES>(a_addr + k * 32);
+            const uint64_t db = make_smem_desc<Cfg::ROW_BYTES>(b_addr + k * 32);
+            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                  // frees the smem slot once these MMAs retire
+          if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int ep_tid = threadIdx.x - 64;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      const int m0 = (tile / p.num_n_tiles) * TC_BLOCK_M;
+      float* sc = sScale + acc * BLOCK_N;
+      float* sf = sShift + acc * BLOCK_N;
+      for (int i = ep_tid; i < BLOCK_N; i += 128) {
+        sc[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
+        sf[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int m = m0 + row;
+      const bool valid = m < p.M;
+      const size_t row_off = (size_t)m * p.Cout + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
+        tmem_ld_wait();
+        if (valid) {
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint4 rv = __ldg(rp + u);
+              const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w4[e]);
+                y[u * 8 + e * 2] += f.x;
+                y[u * 8 + e * 2 + 1] += f.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+          }
+          if (p.out_bf16) {
+            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_off + c0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 o;
+              o.x = pack_bf16x2(y[u * 8 + 0], y[u * 8 + 1]);
+              o.y = pack_bf16x2(y[u * 8 + 2], y[u * 8 + 3]);
+              o.z = pack_bf16x2(y[u * 8 + 4], y[u * 8 + 5]);
+              o.w = pack_bf16x2(y[u * 8 + 6], y[u * 8 + 7]);
+              op[u] = o;
+            }
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + row_off + c0);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) op[u] = make_float4(y[u * 4], y[u * 4 + 1], y[u * 4 + 2], y[u * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+static PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+
+static int load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return MSTR_OK;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  MSTR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  MSTR_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  fn = nullptr;
+  MSTR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+  MSTR_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, MSTR_ERR_CUDA, "cuTensorMapEncodeIm2col not available");
+  g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+  return MSTR_OK;
+}
+
+static int encode_tiled_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                           uint32_t box_outer, CUtensorMapSwizzle swz) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return MSTR_OK;
+}
+
+template <int BLOCK_N, int BLOCK_K>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BLOCK_N, BLOCK_K>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  MSTR_LAUNCH_CHECK("conv_gemm_bf16_kernel");
+  return MSTR_OK;
+}
+
+}  // namespace mstr
+
+extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const void* x, const void* w, const float* scale, const float* shift,
+                                   const void* residual, void* out_bf16, float* out_f32, int B, int H, int W,
+                                   int C_in, int C_out, int R, int S, int stride_h, int stride_w, int pad_h,
+                                   int pad_w, int relu, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x && w && (out_bf16 || out_f32), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: null pointer");
+  MSTR_REQUIRE(B > 0 && H > 0 && W > 0 && C_in > 0 && C_out > 0 && R > 0 && S > 0 && stride_h > 0 && stride_w > 0 &&
+                   pad_h >= 0 && pad_w >= 0,
+               MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad size");
+  MSTR_REQUIRE(C_in % 32 == 0, MSTR_ERR_UNSUPPORTED, "mstr_conv_gemm_bf16: C_in=%d must be a multiple of 32", C_in);
+  MSTR_REQUIRE(C_out % 64 == 0, MSTR_ERR_UNSUPPORTED, "mstr_conv_gemm_bf16: C_out=%d must be a multiple of 64", C_out);
+  MSTR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(residual) && aligned16(out_bf16) && aligned16(out_f32),
+               MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: pointers must be 16-byte aligned");
+  MSTR_REQUIRE(R <= 16 && S <= 16 && pad_h < 16 && pad_w < 16, MSTR_ERR_UNSUPPORTED, "mstr_conv_gemm_bf16: filter too large");
+  int rc = load_driver_entry_points();
+  if (rc != MSTR_OK) return rc;
+
+  TcParams p;
+  p.P = (H + 2 * pad_h - R) / stride_h + 1;
+  p.Q = (W + 2 * pad_w - S) / stride_w + 1;
+  MSTR_REQUIRE(p.P > 0 && p.Q > 0, MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: empty output");
+  const int64_t M64 = (int64_t)B * p.P * p.Q;
+  MSTR_REQUIRE(M64 < (1ll << 31), MSTR_ERR_UNSUPPORTED, "mstr_conv_gemm_bf16: too many output pixels");
+  p.M = (int)M64;
+  p.Cout = C_out;
+  const int block_k = (C_in % 64 == 0) ? 64 : 32;
+  const int block_n = (C_out % 256 == 0) ? 256 : (C_out % 128 == 0 ? 128 : 64);
+  p.num_m_tiles = ceil_div(p.M, TC_BLOCK_M);
+  p.num_n_tiles = C_out / block_n;
+  p.taps = R * S;
+  p.S = S;
+  p.cin_chunks = C_in / block_k;
+  p.sh = stride_h; p.sw = stride_w; p.ph = pad_h; p.pw = pad_w;
+  p.im2col = !(R == 1 && S == 1 && stride_h == 1 && stride_w == 1 && pad_h == 0 && pad_w == 0);
+  p.relu = relu;
+  p.scale = scale; p.shift = shift;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.out_bf16 = (__nv_bfloat16*)out_bf16;
+  p.out_f32 = out_f32;
+
+  const CUtensorMapSwizzle swz = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  alignas(64) CUtensorMap tmA, tmB;
+  const int64_t K = (int64_t)R * S * C_in;
+  rc = encode_tiled_2d(&tmB, w, (uint64_t)K, (uint64_t)C_out, (uint32_t)block_k, (uint32_t)block_n, swz);
+  if (rc != MSTR_OK) return rc;
+  if (!p.im2col) {
+    // A is a plain [M][C_in] matrix (1x1 convolution / linear layer)
+    rc = encode_tiled_2d(&tmA, x, (uint64_t)C_in, (uint64_t)((int64_t)B * H * W), (uint32_t)block_k, TC_BLOCK_M, swz);
+    if (rc != MSTR_OK) return rc;
+  } else {
+    cuuint64_t dims[4] = {(cuuint64_t)C_in, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C_in * 2, (cuuint64_t)W * C_in * 2, (cuuint64_t)H * W * C_in * 2};
+    // bounding box of filter-tap origins: [-pad, dim + pad - (filter-1) - 1]
+    int lower[2] = {-pad_w, -pad_h};
+    int upper[2] = {pad_w - (S - 1), pad_h - (R - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
+    CUresult r = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+                                 upper, (cuuint32_t)block_k, (cuuint32_t)TC_BLOCK_M, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
+    // Drivers up to CUDA 13.1 set a descriptor flag that must be cleared for im2col tensors smaller
+    // than 128 KiB (same guard as the vendor's own GEMM library applies).
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (int64_t)B * H * W * C_in * 2 < 131072)
+      reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
+  }
+
+  cudaStream_t st = (cudaStream_t)stream;
+  if (block_k == 64) {
+    if (block_n == 256) return launch_tc<256, 64>(tmA, tmB, p, st);
+    if (block_n == 128) return launch_tc<128, 64>(tmA, tmB, p, st);
+    return launch_tc<64, 64>(tmA, tmB, p, st);
+  } else {
+    if (block_n == 256) return launch_tc<256, 32>(tmA, tmB, p, st);
+    if (block_n == 128) return launch_tc<128, 32>(tmA, tmB, p, st);
+    return launch_tc<64, 32>(tmA, tmB, p, st);
+  }
+}

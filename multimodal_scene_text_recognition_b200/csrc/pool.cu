@@ -1,0 +1,176 @@
+// NHWC pooling / reduction / cast helpers (all HBM-bound, 16-byte vectorised along C).
+//
+//   maxpool_nhwc : nn.MaxPool2d incl. the asymmetric k2 s(2,1) p(0,1) of maxpool3
+//                  (modules/feature_extraction.py:66,72,78); padding behaves as -inf.
+//   mean_hw      : AdaptiveAvgPool2d(1) of the localisation network (modules/transformation.py:57).
+//   mean_h       : permute + AdaptiveAvgPool2d((None,1)) + squeeze of model.py:92-93.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace mstr {
+
+// one thread = one output pixel x 8 (bf16) or 4 (f32) channels
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int P,
+                    int Q, int kh, int kw, int sh, int sw, int ph, int pw) {
+  const int cv = C / VEC;
+  const int64_t total = (int64_t)B * P * Q * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * VEC;
+    int64_t r = i / cv;
+    const int q = (int)(r % Q); r /= Q;
+    const int p = (int)(r % P);
+    const int b = (int)(r / P);
+    float m[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) m[v] = -FLT_MAX;
+    bool any = false;
+    for (int dy = 0; dy < kh; ++dy) {
+      const int y = p * sh - ph + dy;
+      if (y < 0 || y >= H) continue;
+      for (int dx = 0; dx < kw; ++dx) {
+        const int xx = q * sw - pw + dx;
+        if (xx < 0 || xx >= W) continue;
+        any = true;
+        const T* src = x + (((int64_t)b * H + y) * W + xx) * C + c;
+        uint4 raw = *reinterpret_cast<const uint4*>(src);
+        const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], Elem<T>::load(e + v));
+      }
+    }
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) Elem<T>::store(oe + v, any ? m[v] : -INFINITY);
+    *reinterpret_cast<uint4*>(out + (((int64_t)b * P + p) * Q + q) * C + c) = o;
+  }
+}
+
+// [B][HW][C] -> [B][C] f32 mean; one thread per (b, c), coalesced across c.
+template <typename T>
+__global__ void __launch_bounds__(256)
+mean_hw_kernel(const T* __restrict__ x, float* __restrict__ out, int B, int HW, int C) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * C) return;
+  const int c = (int)(i % C);
+  const int b = (int)(i / C);
+  const T* src = x + (int64_t)b * HW * C + c;
+  float acc = 0.f;
+  for (int j = 0; j < HW; ++j) acc += Elem<T>::load(src + (int64_t)j * C);
+  out[i] = acc / (float)HW;
+}
+
+// [B][H][W][C] -> [B][W][C] mean over H.
+template <typename T>
+__global__ void __launch_bounds__(256)
+mean_h_kernel(const T* __restrict__ x, T* __restrict__ out, float* __restrict__ out_f32, int B, int H,
+              int W, int C) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * W * C) return;
+  const int c = (int)(i % C);
+  const int w = (int)((i / C) % W);
+  const int b = (int)(i / ((int64_t)C * W));
+  float acc = 0.f;
+  for (int h = 0; h < H; ++h) acc += Elem<T>::load(x + (((int64_t)b * H + h) * W + w) * C + c);
+  acc /= (float)H;
+  if (out) Elem<T>::store(out + i, acc);
+  if (out_f32) out_f32[i] = acc;
+}
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) cast_kernel(const S* __restrict__ x, D* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    Elem<D>::store(out + i, Elem<S>::load(x + i));
+}
+
+static int grid_for(int64_t work_items, int threads) {
+  int64_t blocks = ceil_div64(work_items, threads);
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace mstr
+
+extern "C" __attribute__((visibility("default"))) int mstr_maxpool_nhwc(const void* x, void* out, int dtype, int B, int H, int W, int C,
+                                 int kh, int kw, int sh, int sw, int ph, int pw, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x && out, MSTR_ERR_BAD_ARG, "mstr_maxpool_nhwc: null pointer");
+  MSTR_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && ph >= 0 && pw >= 0,
+               MSTR_ERR_BAD_ARG, "mstr_maxpool_nhwc: bad size");
+  MSTR_REQUIRE(aligned16(x) && aligned16(out), MSTR_ERR_BAD_ARG, "mstr_maxpool_nhwc: pointers must be 16-byte aligned");
+  const int P = (H + 2 * ph - kh) / sh + 1, Q = (W + 2 * pw - kw) / sw + 1;
+  MSTR_REQUIRE(P > 0 && Q > 0, MSTR_ERR_BAD_ARG, "mstr_maxpool_nhwc: empty output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MSTR_BF16) {
+    MSTR_REQUIRE(C % 8 == 0, MSTR_ERR_UNSUPPORTED, "mstr_maxpool_nhwc: C %% 8 != 0 for bf16");
+    const int64_t items = (int64_t)B * P * Q * (C / 8);
+    maxpool_nhwc_kernel<__nv_bfloat16, 8><<<grid_for(items, 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, P, Q, kh, kw, sh, sw, ph, pw);
+  } else if (dtype == MSTR_F32) {
+    MSTR_REQUIRE(C % 4 == 0, MSTR_ERR_UNSUPPORTED, "mstr_maxpool_nhwc: C %% 4 != 0 for f32");
+    const int64_t items = (int64_t)B * P * Q * (C / 4);
+    maxpool_nhwc_kernel<float, 4><<<grid_for(items, 256), 256, 0, st>>>(
+        (const float*)x, (float*)out, B, H, W, C, P, Q, kh, kw, sh, sw, ph, pw);
+  } else {
+    MSTR_REQUIRE(false, MSTR_ERR_BAD_ARG, "mstr_maxpool_nhwc: unknown dtype %d", dtype);
+  }
+  MSTR_LAUNCH_CHECK("maxpool_nhwc_kernel");
+  return MSTR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mstr_mean_hw(const void* x, float* out, int dtype, int B, int H, int W, int C,
+                            mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x && out, MSTR_ERR_BAD_ARG, "mstr_mean_hw: null pointer");
+  MSTR_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, MSTR_ERR_BAD_ARG, "mstr_mean_hw: bad size");
+  const int64_t items = (int64_t)B * C;
+  const int blocks = (int)ceil_div64(items, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MSTR_BF16)
+    mean_hw_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, out, B, H * W, C);
+  else if (dtype == MSTR_F32)
+    mean_hw_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, out, B, H * W, C);
+  else
+    MSTR_REQUIRE(false, MSTR_ERR_BAD_ARG, "mstr_mean_hw: unknown dtype %d", dtype);
+  MSTR_LAUNCH_CHECK("mean_hw_kernel");
+  return MSTR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mstr_mean_h(const void* x, void* out, float* out_f32, int dtype, int B, int H, int W,
+                           int C, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x && (out || out_f32), MSTR_ERR_BAD_ARG, "mstr_mean_h: null pointer");
+  MSTR_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, MSTR_ERR_BAD_ARG, "mstr_mean_h: bad size");
+  const int64_t items = (int64_t)B * W * C;
+  const int blocks = (int)ceil_div64(items, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MSTR_BF16)
+    mean_h_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, out_f32, B, H, W, C);
+  else if (dtype == MSTR_F32)
+    mean_h_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)out, out_f32, B, H, W, C);
+  else
+    MSTR_REQUIRE(false, MSTR_ERR_BAD_ARG, "mstr_mean_h: unknown dtype %d", dtype);
+  MSTR_LAUNCH_CHECK("mean_h_kernel");
+  return MSTR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mstr_cast(const void* x, void* out, int src_dtype, int dst_dtype, int64_t n,
+                         mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x && out && n > 0, MSTR_ERR_BAD_ARG, "mstr_cast: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = grid_for(n, 256);
+  if (src_dtype == MSTR_F32 && dst_dtype == MSTR_BF16)
+    cast_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)out, n);
+  else if (src_dtype == MSTR_BF16 && dst_dtype == MSTR_F32)
+    cast_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)out, n);
+  else
+    MSTR_REQUIRE(false, MSTR_ERR_UNSUPPORTED, "mstr_cast: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+  MSTR_LAUNCH_CHECK("cast_kernel");
+  return MSTR_OK;
+}

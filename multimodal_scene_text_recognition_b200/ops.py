@@ -1,0 +1,214 @@
+"""Torch-tensor front ends of the C-ABI kernels.
+
+Each function validates its tensors (CUDA, contiguous, dtype), allocates the output with torch
+(memory stays torch-owned; the C side only borrows pointers) and enqueues the kernel on the
+current CUDA stream.  No function here has a PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import MSTR_BF16, MSTR_F32, check, lib, ptr, stream_ptr
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return MSTR_F32
+    if t.dtype == torch.bfloat16:
+        return MSTR_BF16
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def _req(t: Optional[torch.Tensor], name: str, dtype=None) -> None:
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _cabi.MstrError("%s must be a CUDA tensor: this path has no CPU implementation" % name)
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def tps_rectify(img: torch.Tensor, c_prime: torch.Tensor, basis: torch.Tensor,
+                inv_delta_C: Optional[torch.Tensor], mode: int, want_grid: bool = False):
+    """img [B,C,H,W] f32, c_prime [B,F,2] f32 -> rectified [B,C,H,W] f32 (and the grid [B,H*W,2])."""
+    _req(img, "img", torch.float32); _req(c_prime, "c_prime", torch.float32)
+    _req(basis, "basis", torch.float32); _req(inv_delta_C, "inv_delta_C", torch.float32)
+    B, C, H, W = img.shape
+    F = c_prime.shape[1]
+    assert c_prime.shape == (B, F, 2)
+    assert basis.shape == ((F + 3) if mode == 0 else F, H * W)
+    out = torch.empty_like(img)
+    grid = torch.empty((B, H * W, 2), device=img.device, dtype=torch.float32) if want_grid else None
+    check(lib().mstr_tps_rectify(ptr(img), ptr(c_prime), ptr(basis), ptr(inv_delta_C), ptr(out), ptr(grid),
+                                 B, C, H, W, F, mode, stream_ptr()), "mstr_tps_rectify")
+    return (out, grid) if want_grid else out
+
+
+def conv3x3_first(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                  out_dtype: torch.dtype, pool: bool) -> torch.Tensor:
+    """x [B,Cin,H,W] f32 NCHW -> NHWC [B,H',W',Cout] (conv3x3 pad1 + folded BN + ReLU [+ maxpool 2x2])."""
+    _req(x, "x", torch.float32); _req(w, "w", torch.float32)
+    _req(scale, "scale", torch.float32); _req(shift, "shift", torch.float32)
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    assert w.shape == (Cout, Cin, 3, 3)
+    P, Q = (H // 2, W // 2) if pool else (H, W)
+    out = torch.empty((B, P, Q, Cout), device=x.device, dtype=out_dtype)
+    check(lib().mstr_conv3x3_first(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(out), _dt(out), B, Cin, H, W,
+                                   Cout, int(pool), stream_ptr()), "mstr_conv3x3_first")
+    return out
+
+
+def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+              residual: Optional[torch.Tensor] = None, *, stride: Tuple[int, int] = (1, 1),
+              pad: Tuple[int, int] = (0, 0), relu: bool = False, want_f32: bool = False,
+              want_bf16: bool = True):
+    """Implicit-GEMM convolution + folded BN + residual + ReLU.
+
+    x NHWC [B,H,W,Cin]; w [Cout,R,S,Cin] of the same dtype.  f32 tensors run the exact fp32-FMA
+    kernel and return an f32 tensor; bf16 tensors run the tcgen05 kernel and return
+    (out_bf16 or None, out_f32 or None) according to want_bf16 / want_f32.
+    """
+    _req(x, "x"); _req(w, "w", x.dtype); _req(scale, "scale", torch.float32); _req(shift, "shift", torch.float32)
+    _req(residual, "residual", x.dtype)
+    B, H, W, Cin = x.shape
+    Cout, R, S, Cin2 = w.shape
+    assert Cin == Cin2, (x.shape, w.shape)
+    P = (H + 2 * pad[0] - R) // stride[0] + 1
+    Q = (W + 2 * pad[1] - S) // stride[1] + 1
+    if residual is not None:
+        assert residual.shape == (B, P, Q, Cout)
+    if x.dtype == torch.float32:
+        out = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32)
+        check(lib().mstr_conv_gemm_f32(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out), B, H, W,
+                                       Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
+                                       stream_ptr()), "mstr_conv_gemm_f32")
+        return out
+    if x.dtype != torch.bfloat16:
+        raise TypeError("conv_gemm: unsupported dtype %s" % x.dtype)
+    out_b = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    out_f = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32) if want_f32 else None
+    check(lib().mstr_conv_gemm_bf16(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out_b), ptr(out_f),
+                                    B, H, W, Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
+                                    stream_ptr()), "mstr_conv_gemm_bf16")
+    if want_f32 and want_bf16:
+        return out_b, out_f
+    return out_f if want_f32 else out_b
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
+           want_f32: bool = False, want_bf16: bool = True):
+    """nn.Linear on the last dimension through the same GEMM kernels (x [..., K], w [N, K])."""
+    lead = x.shape[:-1]
+    K = x.shape[-1]
+    M = 1
+    for d in lead:
+        M *= d
+    x4 = x.reshape(M, 1, 1, K)
+    w4 = w.reshape(w.shape[0], 1, 1, K)
+    res = conv_gemm(x4, w4, None, bias, relu=relu, want_f32=want_f32, want_bf16=want_bf16)
+    shape = tuple(lead) + (w.shape[0],)
+    if isinstance(res, tuple):
+        return tuple(r.reshape(shape) for r in res)
+    return res.reshape(shape)
+
+
+def maxpool_nhwc(x: torch.Tensor, kernel=(2, 2), stride=(2, 2), pad=(0, 0)) -> torch.Tensor:
+    _req(x, "x")
+    B, H, W, C = x.shape
+    P = (H + 2 * pad[0] - kernel[0]) // stride[0] + 1
+    Q = (W + 2 * pad[1] - kernel[1]) // stride[1] + 1
+    out = torch.empty((B, P, Q, C), device=x.device, dtype=x.dtype)
+    check(lib().mstr_maxpool_nhwc(ptr(x), ptr(out), _dt(x), B, H, W, C, kernel[0], kernel[1], stride[0], stride[1],
+                                  pad[0], pad[1], stream_ptr()), "mstr_maxpool_nhwc")
+    return out
+
+
+def mean_hw(x: torch.Tensor) -> torch.Tensor:
+    """NHWC [B,H,W,C] -> [B,C] f32 (AdaptiveAvgPool2d(1))."""
+    _req(x, "x")
+    B, H, W, C = x.shape
+    out = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    check(lib().mstr_mean_hw(ptr(x), ptr(out), _dt(x), B, H, W, C, stream_ptr()), "mstr_mean_hw")
+    return out
+
+
+def mean_h(x: torch.Tensor, want_f32: bool = False):
+    """NHWC [B,H,W,C] -> [B,W,C] mean over H, in x.dtype (and optionally an f32 copy)."""
+    _req(x, "x")
+    B, H, W, C = x.shape
+    out = torch.empty((B, W, C), device=x.device, dtype=x.dtype)
+    out_f = torch.empty((B, W, C), device=x.device, dtype=torch.float32) if want_f32 else None
+    check(lib().mstr_mean_h(ptr(x), ptr(out), ptr(out_f), _dt(x), B, H, W, C, stream_ptr()), "mstr_mean_h")
+    return (out, out_f) if want_f32 else out
+
+
+def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _req(x, "x")
+    if x.dtype == dtype:
+        return x
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    check(lib().mstr_cast(ptr(x), ptr(out), _dt(x), _dt(out), x.numel(), stream_ptr()), "mstr_cast")
+    return out
+
+
+def embed_semantics(ids: torch.Tensor, table: torch.Tensor, ious: Optional[torch.Tensor], mode: int) -> torch.Tensor:
+    _req(ids, "ids", torch.float32); _req(table, "table", torch.float32); _req(ious, "ious", torch.float32)
+    B, n = ids.shape
+    rows, D = table.shape
+    out = torch.empty((B, n, D), device=ids.device, dtype=torch.float32)
+    check(lib().mstr_embed_semantics(ptr(ids), ptr(table), ptr(ious), ptr(out), B, n, D, rows, mode, stream_ptr()),
+          "mstr_embed_semantics")
+    return out
+
+
+def bilstm_recurrent(gates_x: torch.Tensor, w_hh: torch.Tensor, want_f32: bool, want_bf16: bool):
+    """gates_x [B,T,2,4H] f32, w_hh [2,4H,H] f32 -> [B,T,2H] in f32 and/or bf16."""
+    _req(gates_x, "gates_x", torch.float32); _req(w_hh, "w_hh", torch.float32)
+    B, T = gates_x.shape[:2]
+    Hd = w_hh.shape[2]
+    assert gates_x.shape == (B, T, 2, 4 * Hd) and w_hh.shape == (2, 4 * Hd, Hd)
+    out_f = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.float32) if want_f32 else None
+    out_b = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.bfloat16) if want_bf16 else None
+    check(lib().mstr_bilstm_recurrent(ptr(gates_x), ptr(w_hh), ptr(out_f), ptr(out_b), B, T, Hd, stream_ptr()),
+          "mstr_bilstm_recurrent")
+    if want_f32 and want_bf16:
+        return out_f, out_b
+    return out_f if want_f32 else out_b
+
+
+def attn_decode(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int, text: Optional[torch.Tensor],
+                early_exit: bool, h0: Optional[torch.Tensor] = None, c0: Optional[torch.Tensor] = None,
+                want_alpha: bool = False, want_state: bool = False) -> dict:
+    """Greedy / teacher-forced attention decode.
+
+    Returns a dict with logits [B,steps,C] f32, ids [B,steps] i32, lengths [B] i32 and, on request,
+    alpha [B,steps,T] f32 and the final (h, c) [B,H] f32.
+    """
+    _req(enc, "enc", torch.float32); _req(proj, "proj", torch.float32); _req(text, "text", torch.int64)
+    _req(h0, "h0", torch.float32); _req(c0, "c0", torch.float32)
+    B, T, Hd = enc.shape
+    C = packed["w_gen"].shape[0]
+    dev = enc.device
+    logits = torch.zeros((B, steps, C), device=dev, dtype=torch.float32)
+    ids = torch.empty((B, steps), device=dev, dtype=torch.int32)
+    lengths = torch.empty((B,), device=dev, dtype=torch.int32)
+    alpha = torch.zeros((B, steps, T), device=dev, dtype=torch.float32) if want_alpha else None
+    h_out = torch.empty((B, Hd), device=dev, dtype=torch.float32) if want_state else None
+    c_out = torch.empty((B, Hd), device=dev, dtype=torch.float32) if want_state else None
+    if text is not None:
+        assert text.shape[0] == B and text.shape[1] >= steps
+        if text.shape[1] != steps:
+            text = text[:, :steps].contiguous()
+    check(lib().mstr_attn_decode(ptr(enc), ptr(proj), ptr(packed["w_h2h"]), ptr(packed["b_h2h"]),
+                                 ptr(packed["w_score"]), ptr(packed["w_ctx"]), ptr(packed["w_tok"]),
+                                 ptr(packed["w_hh"]), ptr(packed["bias"]), ptr(packed["w_gen"]),
+                                 ptr(packed["b_gen"]), ptr(text), ptr(h0), ptr(c0), ptr(logits), ptr(ids),
+                                 ptr(lengths), ptr(alpha), ptr(h_out), ptr(c_out),
+                                 B, T, Hd, C, steps, int(early_exit), stream_ptr()), "mstr_attn_decode")
+    return {"logits": logits, "ids": ids, "lengths": lengths, "alpha": alpha, "h": h_out, "c": c_out}

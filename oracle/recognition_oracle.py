@@ -126,10 +126,11 @@ def grid_sample_bilinear_border(img: np.ndarray, grid: np.ndarray) -> np.ndarray
     iy = np.clip(iy, 0, H - 1)
     x0 = np.floor(ix)
     y0 = np.floor(iy)
+    # ATen forms the corner weights from the neighbour coordinates ((x0+1) - ix, ix - x0, ...)
     wx1 = ix - x0
     wy1 = iy - y0
-    wx0 = 1 - wx1
-    wy0 = 1 - wy1
+    wx0 = (x0 + 1) - ix
+    wy0 = (y0 + 1) - iy
     x0i = x0.astype(np.int64)
     y0i = y0.astype(np.int64)
     x1i = x0i + 1

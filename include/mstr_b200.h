@@ -53,6 +53,8 @@ int64_t mstr_launch_count(void);
  *   inv_delta_C  [F+3][F+3] f32, used by mode 0 only (may be null in mode 1)
  *   out      [B][C][H][W] f32 rectified image
  *   grid_out optional [B][H*W][2] f32 sampling grid (null to skip)
+ * img and out may both be null when grid_out is given: only the grid is produced (that is
+ * GridGenerator.build_P_prime called on its own).
  */
 int mstr_tps_rectify(const float* img, const float* c_prime, const float* basis,
                      const float* inv_delta_C, float* out, float* grid_out,

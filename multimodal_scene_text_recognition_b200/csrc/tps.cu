@@ -69,6 +69,7 @@ tps_rectify_kernel(const float* __restrict__ img, const float* __restrict__ c_pr
     }
     const size_t crop = (size_t)(b0 + b);
     if (grid_out) reinterpret_cast<float2*>(grid_out)[crop * n + p] = make_float2(gx, gy);
+    if (!img) continue;  // grid-only call (GridGenerator.build_P_prime on its own)
     // grid_sample(bilinear, border, align_corners=True)
     float ix = (gx + 1.f) * 0.5f * wm1;
     float iy = (gy + 1.f) * 0.5f * hm1;
@@ -98,7 +99,9 @@ extern "C" __attribute__((visibility("default"))) int mstr_tps_rectify(const flo
                                 const float* inv_delta_C, float* out, float* grid_out, int B, int C,
                                 int H, int W, int F, int mode, mstr_stream_t stream) {
   using namespace mstr;
-  MSTR_REQUIRE(img && c_prime && basis && out, MSTR_ERR_BAD_ARG, "mstr_tps_rectify: null pointer");
+  MSTR_REQUIRE(c_prime && basis, MSTR_ERR_BAD_ARG, "mstr_tps_rectify: null pointer");
+  MSTR_REQUIRE((img && out) || (!img && !out && grid_out), MSTR_ERR_BAD_ARG,
+               "mstr_tps_rectify: give img and out, or neither together with grid_out");
   MSTR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && F > 0, MSTR_ERR_BAD_ARG,
                "mstr_tps_rectify: non-positive size");
   MSTR_REQUIRE(mode == 0 || mode == 1, MSTR_ERR_BAD_ARG, "mstr_tps_rectify: mode must be 0 or 1");

@@ -14,6 +14,45 @@ from . import _cabi
 from ._cabi import MSTR_BF16, MSTR_F32, check, lib, ptr, stream_ptr
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing (bench.py's roofline / stage breakdown).  While
+    ``ops.TIMER`` is set, every front end below brackets its launch with two events recorded on
+    the current stream; ``summary()`` (after a synchronize) aggregates time and work per kernel."""
+
+    def __init__(self):
+        self.records = []   # (name, work, start event, end event)
+
+    def summary(self):
+        out = {}
+        for name, work, s, e in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["work"] += work
+        return out
+
+
+TIMER: Optional[KernelTimer] = None
+
+
+class _timed:
+    def __init__(self, name: str, work: float = 0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if TIMER is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMER is not None and exc[0] is None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            TIMER.records.append((self.name, self.work, self.s, e))
+        return False
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return MSTR_F32
@@ -33,19 +72,31 @@ def _req(t: Optional[torch.Tensor], name: str, dtype=None) -> None:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
 
 
-def tps_rectify(img: torch.Tensor, c_prime: torch.Tensor, basis: torch.Tensor,
+def tps_rectify(img: Optional[torch.Tensor], c_prime: torch.Tensor, basis: torch.Tensor,
                 inv_delta_C: Optional[torch.Tensor], mode: int, want_grid: bool = False):
-    """img [B,C,H,W] f32, c_prime [B,F,2] f32 -> rectified [B,C,H,W] f32 (and the grid [B,H*W,2])."""
+    """img [B,C,H,W] f32, c_prime [B,F,2] f32 -> rectified [B,C,H,W] f32 (and the grid [B,H*W,2]).
+
+    ``img=None`` with ``want_grid=True`` produces only the grid (GridGenerator.build_P_prime)."""
     _req(img, "img", torch.float32); _req(c_prime, "c_prime", torch.float32)
     _req(basis, "basis", torch.float32); _req(inv_delta_C, "inv_delta_C", torch.float32)
-    B, C, H, W = img.shape
-    F = c_prime.shape[1]
+    B, F = c_prime.shape[0], c_prime.shape[1]
+    n = basis.shape[1]
     assert c_prime.shape == (B, F, 2)
-    assert basis.shape == ((F + 3) if mode == 0 else F, H * W)
-    out = torch.empty_like(img)
-    grid = torch.empty((B, H * W, 2), device=img.device, dtype=torch.float32) if want_grid else None
-    check(lib().mstr_tps_rectify(ptr(img), ptr(c_prime), ptr(basis), ptr(inv_delta_C), ptr(out), ptr(grid),
-                                 B, C, H, W, F, mode, stream_ptr()), "mstr_tps_rectify")
+    assert basis.shape[0] == ((F + 3) if mode == 0 else F)
+    if img is None:
+        if not want_grid:
+            raise ValueError("tps_rectify: nothing to compute (no image and no grid requested)")
+        C, H, W, out = 1, 1, n, None
+    else:
+        _, C, H, W = img.shape
+        assert img.shape[0] == B and H * W == n, (img.shape, basis.shape)
+        out = torch.empty_like(img)
+    grid = torch.empty((B, n, 2), device=c_prime.device, dtype=torch.float32) if want_grid else None
+    with _timed("tps_rectify", float(B) * C * n * 8):            # work = algorithmic bytes (image in + out)
+        check(lib().mstr_tps_rectify(ptr(img), ptr(c_prime), ptr(basis), ptr(inv_delta_C), ptr(out), ptr(grid),
+                                     B, C, H, W, F, mode, stream_ptr()), "mstr_tps_rectify")
+    if img is None:
+        return grid
     return (out, grid) if want_grid else out
 
 
@@ -59,8 +110,9 @@ def conv3x3_first(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: 
     assert w.shape == (Cout, Cin, 3, 3)
     P, Q = (H // 2, W // 2) if pool else (H, W)
     out = torch.empty((B, P, Q, Cout), device=x.device, dtype=out_dtype)
-    check(lib().mstr_conv3x3_first(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(out), _dt(out), B, Cin, H, W,
-                                   Cout, int(pool), stream_ptr()), "mstr_conv3x3_first")
+    with _timed("conv3x3_first", 2.0 * B * H * W * Cout * 9 * Cin):
+        check(lib().mstr_conv3x3_first(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(out), _dt(out), B, Cin, H, W,
+                                       Cout, int(pool), stream_ptr()), "mstr_conv3x3_first")
     return out
 
 
@@ -83,19 +135,22 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
     Q = (W + 2 * pad[1] - S) // stride[1] + 1
     if residual is not None:
         assert residual.shape == (B, P, Q, Cout)
+    flops = 2.0 * B * P * Q * Cout * R * S * Cin
     if x.dtype == torch.float32:
         out = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32)
-        check(lib().mstr_conv_gemm_f32(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out), B, H, W,
-                                       Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
-                                       stream_ptr()), "mstr_conv_gemm_f32")
+        with _timed("conv_gemm_f32", flops):
+            check(lib().mstr_conv_gemm_f32(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out), B, H, W,
+                                           Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
+                                           stream_ptr()), "mstr_conv_gemm_f32")
         return out
     if x.dtype != torch.bfloat16:
         raise TypeError("conv_gemm: unsupported dtype %s" % x.dtype)
     out_b = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     out_f = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32) if want_f32 else None
-    check(lib().mstr_conv_gemm_bf16(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out_b), ptr(out_f),
-                                    B, H, W, Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
-                                    stream_ptr()), "mstr_conv_gemm_bf16")
+    with _timed("conv_gemm_bf16", flops):
+        check(lib().mstr_conv_gemm_bf16(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out_b), ptr(out_f),
+                                        B, H, W, Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
+                                        stream_ptr()), "mstr_conv_gemm_bf16")
     if want_f32 and want_bf16:
         return out_b, out_f
     return out_f if want_f32 else out_b
@@ -124,8 +179,9 @@ def maxpool_nhwc(x: torch.Tensor, kernel=(2, 2), stride=(2, 2), pad=(0, 0)) -> t
     P = (H + 2 * pad[0] - kernel[0]) // stride[0] + 1
     Q = (W + 2 * pad[1] - kernel[1]) // stride[1] + 1
     out = torch.empty((B, P, Q, C), device=x.device, dtype=x.dtype)
-    check(lib().mstr_maxpool_nhwc(ptr(x), ptr(out), _dt(x), B, H, W, C, kernel[0], kernel[1], stride[0], stride[1],
-                                  pad[0], pad[1], stream_ptr()), "mstr_maxpool_nhwc")
+    with _timed("maxpool_nhwc", float(x.numel() + out.numel()) * x.element_size()):
+        check(lib().mstr_maxpool_nhwc(ptr(x), ptr(out), _dt(x), B, H, W, C, kernel[0], kernel[1], stride[0], stride[1],
+                                      pad[0], pad[1], stream_ptr()), "mstr_maxpool_nhwc")
     return out
 
 
@@ -175,8 +231,9 @@ def bilstm_recurrent(gates_x: torch.Tensor, w_hh: torch.Tensor, want_f32: bool, 
     assert gates_x.shape == (B, T, 2, 4 * Hd) and w_hh.shape == (2, 4 * Hd, Hd)
     out_f = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.float32) if want_f32 else None
     out_b = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.bfloat16) if want_bf16 else None
-    check(lib().mstr_bilstm_recurrent(ptr(gates_x), ptr(w_hh), ptr(out_f), ptr(out_b), B, T, Hd, stream_ptr()),
-          "mstr_bilstm_recurrent")
+    with _timed("bilstm_recurrent", 2.0 * B * T * 2 * 4 * Hd * Hd):
+        check(lib().mstr_bilstm_recurrent(ptr(gates_x), ptr(w_hh), ptr(out_f), ptr(out_b), B, T, Hd, stream_ptr()),
+              "mstr_bilstm_recurrent")
     if want_f32 and want_bf16:
         return out_f, out_b
     return out_f if want_f32 else out_b
@@ -205,10 +262,12 @@ def attn_decode(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int,
         assert text.shape[0] == B and text.shape[1] >= steps
         if text.shape[1] != steps:
             text = text[:, :steps].contiguous()
-    check(lib().mstr_attn_decode(ptr(enc), ptr(proj), ptr(packed["w_h2h"]), ptr(packed["b_h2h"]),
-                                 ptr(packed["w_score"]), ptr(packed["w_ctx"]), ptr(packed["w_tok"]),
-                                 ptr(packed["w_hh"]), ptr(packed["bias"]), ptr(packed["w_gen"]),
-                                 ptr(packed["b_gen"]), ptr(text), ptr(h0), ptr(c0), ptr(logits), ptr(ids),
-                                 ptr(lengths), ptr(alpha), ptr(h_out), ptr(c_out),
-                                 B, T, Hd, C, steps, int(early_exit), stream_ptr()), "mstr_attn_decode")
+    macs = Hd * Hd + 2 * T * Hd + 4 * Hd * 2 * Hd + C * Hd      # h2h, score+context, LSTMCell, generator
+    with _timed("attn_decode", 2.0 * B * steps * macs):
+        check(lib().mstr_attn_decode(ptr(enc), ptr(proj), ptr(packed["w_h2h"]), ptr(packed["b_h2h"]),
+                                     ptr(packed["w_score"]), ptr(packed["w_ctx"]), ptr(packed["w_tok"]),
+                                     ptr(packed["w_hh"]), ptr(packed["bias"]), ptr(packed["w_gen"]),
+                                     ptr(packed["b_gen"]), ptr(text), ptr(h0), ptr(c0), ptr(logits), ptr(ids),
+                                     ptr(lengths), ptr(alpha), ptr(h_out), ptr(c_out),
+                                     B, T, Hd, C, steps, int(early_exit), stream_ptr()), "mstr_attn_decode")
     return {"logits": logits, "ids": ids, "lengths": lengths, "alpha": alpha, "h": h_out, "c": c_out}

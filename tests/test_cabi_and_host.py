@@ -1,0 +1,142 @@
+"""CPU-side checks of the drop-in boundary and the host logic (no GPU compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mstr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mstr_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from multimodal_scene_text_recognition_b200 import build
+    return build.build_extension()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from multimodal_scene_text_recognition_b200 import _cabi
+    names = _declared_symbols()
+    assert len(names) >= 14
+    handle = ctypes.CDLL(built_lib)
+    for n in names:
+        assert hasattr(handle, n), "libmstr_b200.so does not export %s" % n
+    assert sorted(_cabi.SIGNATURES) == names, "ctypes signatures out of sync with include/mstr_b200.h"
+    lib = _cabi.lib()
+    assert lib.mstr_version() == 1000
+    assert isinstance(_cabi.launch_count(), int)
+
+
+def test_kernels_are_blackwell_native(built_lib):
+    """SASS evidence (B200_PROFILING.md): UTC*MMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", built_lib], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, "expected %s in the SASS of libmstr_b200.so" % mnemonic
+
+
+def test_bad_arguments_return_status_not_crash(built_lib):
+    from multimodal_scene_text_recognition_b200 import _cabi
+    lib = _cabi.lib()
+    rc = lib.mstr_tps_rectify(0, 0, 0, 0, 0, 0, 1, 1, 32, 100, 20, 0, 0)
+    assert rc == -1 and b"null pointer" in lib.mstr_last_error_string()
+    rc = lib.mstr_bilstm_recurrent(16, 16, 16, 0, 4, 26, 128, 0)   # hidden size the kernel is not written for
+    assert rc == -2 and b"hidden size" in lib.mstr_last_error_string()
+    with pytest.raises(_cabi.MstrError):
+        _cabi.check(rc, "mstr_bilstm_recurrent")
+
+
+def test_cpu_tensors_are_rejected_no_fallback():
+    from multimodal_scene_text_recognition_b200 import _cabi, config, model as M
+    config.PRECISION = "fp32"
+    m = M.Model().eval()
+    z = torch.zeros
+    with pytest.raises(_cabi.MstrError, match="no CPU implementation"):
+        with torch.no_grad():
+            m(z(1, 1, 32, 100), None, z(1, 15), z(1, 52), z(1, 52), is_train=False)
+    config.PRECISION = "bf16"
+
+
+def test_module_interface_matches_reference_contract(sd_cfg_a):
+    """Class names, ctor args, forward signatures and state-dict keys of SURVEY.md 8b."""
+    import inspect
+    from multimodal_scene_text_recognition_b200 import model as M, synth
+    from multimodal_scene_text_recognition_b200.modules import decoders, encoders, feature_extraction, semantic_vectors, transformation
+    m = M.Model()
+    assert list(m.state_dict().keys()) == [k for k, _, _ in synth.state_dict_spec()]
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == sd_cfg_a[k].shape, k
+    M.load_numpy_state_dict(m, sd_cfg_a)
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(M.Model.forward) == ["self", "input", "text", "overlap", "scene", "ious", "is_train"]
+    assert inspect.signature(M.Model.forward).parameters["is_train"].default is True
+    assert sig(M.get_model) == ["saved_model"]
+    assert sig(transformation.TPS_SpatialTransformerNetwork.__init__) == ["self", "F", "I_size", "I_r_size", "I_channel_num"]
+    assert sig(transformation.GridGenerator.build_P_prime) == ["self", "batch_C_prime"]
+    assert sig(feature_extraction.ResNet_FeatureExtractor.__init__) == ["self", "input_channel", "output_channel"]
+    assert sig(feature_extraction.BasicBlock.__init__) == ["self", "inplanes", "planes", "stride", "downsample"]
+    assert sig(encoders.BidirectionalLSTM.__init__) == ["self", "input_size", "hidden_size", "output_size"]
+    assert sig(encoders.BidirectionalLSTM.forward) == ["self", "col_feats"]
+    assert sig(decoders.Attention.forward) == ["self", "encoder_output", "text", "semantics", "is_train"]
+    assert sig(decoders.AttentionCell.forward) == ["self", "prev_hidden", "batch_H", "char_onehots", "semantics"]
+    assert sig(semantic_vectors.Linear_Embedding.forward) == ["self", "overlap", "scene", "ious"]
+    assert sig(semantic_vectors.Zero.forward) == ["self", "overlap", "scene"]
+    # TPS buffers equal the fp64 -> fp32 construction the reference performs (transformation.py:94-98)
+    assert np.array_equal(m.Transformation.GridGenerator.P_hat.numpy(), sd_cfg_a["Transformation.GridGenerator.P_hat"])
+    # zero-init fc2 weight + RARE bias on a fresh module (transformation.py:64-72)
+    fresh = transformation.LocalizationNetwork(20, 1)
+    assert not fresh.localization_fc2.weight.any()
+    assert np.allclose(fresh.localization_fc2.bias.detach().numpy(), synth.rare_fiducial_bias(20))
+    for cls in (encoders.TF_Encoder, encoders.Oscar_Bert, decoders.TF_Decoder, decoders.Linear_Decoder):
+        with pytest.raises(NotImplementedError):
+            cls()
+
+
+def test_pack_cache_invalidation():
+    from multimodal_scene_text_recognition_b200 import _pack
+    conv = torch.nn.Conv2d(32, 64, 3, bias=False)
+    bn = torch.nn.BatchNorm2d(64).eval()
+    w1, s1, b1 = _pack.pack_conv(conv, bn, "fp32")
+    assert w1.shape == (64, 3, 3, 32) and torch.equal(w1, conv.weight.detach().permute(0, 2, 3, 1))
+    assert _pack.pack_conv(conv, bn, "fp32")[0] is w1                 # cached
+    with torch.no_grad():
+        conv.weight.mul_(2.0)                                          # in-place update bumps _version
+        bn.running_var.fill_(4.0)
+    w2, s2, _ = _pack.pack_conv(conv, bn, "fp32")
+    assert w2 is not w1 and torch.allclose(w2, 2 * w1)
+    assert torch.allclose(s2, bn.weight / torch.sqrt(torch.tensor(4.0 + 1e-5)))
+    assert _pack.pack_conv(conv, bn, "bf16")[0].dtype == torch.bfloat16
+
+
+def test_label_converter_matches_reference_semantics():
+    from multimodal_scene_text_recognition_b200 import config
+    from multimodal_scene_text_recognition_b200.utils import AttnLabelConverter
+    conv = AttnLabelConverter(config.CHARS)
+    assert len(conv.character) == 97 and conv.character[:3] == ["[GO]", "[s]", "[PAD]"]
+    ids = torch.tensor([[3, 4, 1, 5], [3, 4, 5, 6]])
+    assert conv.decode_ids(ids) == ["01", "012"]      # no [s]: find() == -1 drops the last char
+    assert conv.decode(ids, [4, 4])[0] == "01[s]2"
+
+
+def test_shard_bounds_cover_batch():
+    from multimodal_scene_text_recognition_b200.parallel import shard_bounds
+    for B in (1, 7, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    with pytest.raises(ValueError):
+        shard_bounds(8, 2, 2)

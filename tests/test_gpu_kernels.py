@@ -1,0 +1,315 @@
+"""Per-kernel parity: every C-ABI entry point (called through ops.py -> ctypes -> libmstr_b200.so)
+against the numpy oracle on the same seeded inputs.  GPU only."""
+import numpy as np
+import pytest
+import torch
+
+from multimodal_scene_text_recognition_b200 import ops, synth
+from oracle import recognition_oracle as orc
+from gpu_util import DEV, assert_close, dev, err, host, nchw, nhwc
+
+pytestmark = pytest.mark.gpu
+
+
+def rng(seed):
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+# ------------------------------------------------------------------------------------------------
+# TPS
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("geom,B", [(synth.CFG_A, 19), (synth.CFG_S, 3)])
+def test_tps_rectify(geom, B):
+    r = rng(1)
+    inv_delta_C, P_hat = synth.tps_constants(geom.F, geom.H, geom.W)
+    sd = {"Transformation.GridGenerator.inv_delta_C": inv_delta_C.astype(np.float32),
+          "Transformation.GridGenerator.P_hat": P_hat.astype(np.float32)}
+    img = synth.make_crops(7, B, geom)
+    # fiducials around the RARE initialisation, perturbed enough that ~1-5 % of the grid leaves [-1,1]
+    c_prime = (synth.rare_fiducial_bias(geom.F).reshape(1, geom.F, 2) +
+               r.normal(0, 0.08, (B, geom.F, 2))).astype(np.float32)
+    grid64 = orc.build_P_prime(c_prime.astype(np.float64), {k: v.astype(np.float64) for k, v in sd.items()})
+    outside = float((np.abs(grid64) > 1).mean())
+    assert outside > 0.002, "test recipe must exercise the border clamp (got %.4f)" % outside
+    ref_img = orc.grid_sample_bilinear_border(img.astype(np.float64), grid64.reshape(B, geom.H, geom.W, 2))
+
+    basis0 = dev(np.ascontiguousarray(sd["Transformation.GridGenerator.P_hat"].T))
+    folded = (P_hat @ inv_delta_C[:, :geom.F]).T.astype(np.float32)
+    inv_d = dev(sd["Transformation.GridGenerator.inv_delta_C"])
+    for mode, basis, gtol in ((0, basis0, 3e-5), (1, dev(np.ascontiguousarray(folded)), 3e-6)):
+        out, grid = ops.tps_rectify(dev(img), dev(c_prime), basis, inv_d, mode, want_grid=True)
+        torch.cuda.synchronize()
+        assert_close(host(grid), grid64, gtol, "tps grid mode %d" % mode)
+        d, _ = err(host(out), ref_img)
+        assert d < 4e-4, "tps image mode %d: max abs err %.3e" % (mode, d)
+        only = ops.tps_rectify(None, dev(c_prime), basis, inv_d, mode, want_grid=True)
+        assert torch.equal(only, grid), "grid-only call differs from the fused call"
+    # against the fp32 oracle in the reference's own order the fused kernel is at fp32 noise level
+    g32 = orc.build_P_prime(c_prime, sd)
+    out0, grid0 = ops.tps_rectify(dev(img), dev(c_prime), basis0, inv_d, 0, want_grid=True)
+    assert_close(host(grid0), g32, 3e-5, "tps grid vs fp32 oracle")
+
+
+# ------------------------------------------------------------------------------------------------
+# first-layer conv
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,pool,dtype", [(1, 32, False, torch.bfloat16), (1, 64, True, torch.bfloat16),
+                                                 (3, 32, False, torch.float32), (3, 64, True, torch.float32)])
+def test_conv3x3_first(cin, cout, pool, dtype):
+    r = rng(2)
+    B, H, W = 5, 32, 100
+    x = r.uniform(0, 1, (B, cin, H, W)).astype(np.float32)
+    w = (r.standard_normal((cout, cin, 3, 3)) * 0.3).astype(np.float32)
+    scale = r.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = r.normal(0, 0.2, cout).astype(np.float32)
+    ref = orc.relu(orc.conv2d(x.astype(np.float64), w.astype(np.float64), (1, 1), (1, 1)) *
+                   scale[None, :, None, None] + shift[None, :, None, None])
+    if pool:
+        ref = orc.maxpool2d(ref)
+    out = ops.conv3x3_first(dev(x), dev(w), dev(scale), dev(shift), dtype, pool)
+    torch.cuda.synchronize()
+    assert_close(nchw(host(out)), ref, 1e-5 if dtype == torch.float32 else 5e-3, "conv3x3_first")
+
+
+# ------------------------------------------------------------------------------------------------
+# implicit-GEMM conv, fp32 and tcgen05 bf16
+# ------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # B, H, W, Cin, Cout, R, S, stride, pad, residual, relu
+    (3, 8, 25, 128, 256, 3, 3, (1, 1), (1, 1), False, True),     # layer2 conv, M=600 (ragged tile)
+    (2, 4, 26, 64, 64, 2, 2, (2, 1), (0, 1), False, True),       # conv4_1 geometry (k2 s(2,1) p(0,1))
+    (2, 2, 27, 64, 128, 2, 2, (1, 1), (0, 0), False, True),      # conv4_2 geometry (k2 s1 p0)
+    (5, 16, 50, 64, 128, 1, 1, (1, 1), (0, 0), False, False),    # 1x1 downsample
+    (4, 4, 26, 512, 512, 3, 3, (1, 1), (1, 1), True, True),      # dominant layer + residual, K=4608
+    (7, 32, 100, 32, 64, 3, 3, (1, 1), (1, 1), False, True),     # conv0_2: Cin=32 (64-byte swizzle), M=22400
+    (1, 1, 1, 256, 1024, 1, 1, (1, 1), (0, 0), False, False),    # a single-row linear
+]
+
+
+def _conv_ref(x, w, scale, shift, res, stride, pad, relu):
+    y = orc.conv2d(nchw(x).astype(np.float64), w.transpose(0, 3, 1, 2).astype(np.float64), stride, pad)
+    y = y * scale[None, :, None, None] + shift[None, :, None, None]
+    if res is not None:
+        y = y + nchw(res).astype(np.float64)
+    return nhwc(orc.relu(y) if relu else y)
+
+
+def _conv_inputs(case, seed, bf16):
+    B, H, W, Cin, Cout, R, S, stride, pad, residual, relu = case
+    r = rng(seed)
+    x = r.standard_normal((B, H, W, Cin)).astype(np.float32)
+    w = (r.standard_normal((Cout, R, S, Cin)) / np.sqrt(R * S * Cin)).astype(np.float32)
+    scale = r.uniform(0.5, 1.5, Cout).astype(np.float32)
+    shift = r.normal(0, 0.2, Cout).astype(np.float32)
+    P = (H + 2 * pad[0] - R) // stride[0] + 1
+    Q = (W + 2 * pad[1] - S) // stride[1] + 1
+    res = r.standard_normal((B, P, Q, Cout)).astype(np.float32) if residual else None
+    if bf16:
+        x, w = orc.round_bf16(x), orc.round_bf16(w)
+        res = None if res is None else orc.round_bf16(res)
+    return x, w, scale, shift, res
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_gemm_f32(case):
+    stride, pad, relu = case[7], case[8], case[10]
+    x, w, scale, shift, res = _conv_inputs(case, 3, False)
+    ref = _conv_ref(x, w, scale, shift, res, stride, pad, relu)
+    out = ops.conv_gemm(dev(x), dev(w), dev(scale), dev(shift), None if res is None else dev(res),
+                        stride=stride, pad=pad, relu=relu)
+    torch.cuda.synchronize()
+    assert_close(host(out), ref, 5e-6, "conv_gemm_f32 %s" % (case,))
+
+
+def test_linear_f32_small_n():
+    """nn.Linear with N=40 (localization_fc2) and a bias but no scale."""
+    r = rng(4)
+    x = r.standard_normal((9, 256)).astype(np.float32)
+    w = (r.standard_normal((40, 256)) / 16).astype(np.float32)
+    b = r.standard_normal(40).astype(np.float32)
+    out = ops.linear(dev(x), dev(w), dev(b), relu=True)
+    torch.cuda.synchronize()
+    assert_close(host(out), np.maximum(x.astype(np.float64) @ w.T + b, 0), 2e-6, "linear f32 N=40")
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_gemm_bf16_tcgen05(case):
+    stride, pad, relu = case[7], case[8], case[10]
+    x, w, scale, shift, res = _conv_inputs(case, 5, True)
+    ref = _conv_ref(x, w, scale, shift, res, stride, pad, relu)      # fp64 on the bf16-rounded operands
+    bf = torch.bfloat16
+    out_b, out_f = ops.conv_gemm(dev(x, bf), dev(w, bf), dev(scale), dev(shift),
+                                 None if res is None else dev(res, bf), stride=stride, pad=pad, relu=relu,
+                                 want_f32=True, want_bf16=True)
+    torch.cuda.synchronize()
+    # fp32 accumulation of exact bf16 products: only summation-order noise remains
+    assert_close(host(out_f), ref, 2e-5, "conv_gemm_bf16 f32 output %s" % (case,))
+    assert np.array_equal(host(out_b), orc.round_bf16(host(out_f))), "bf16 output is not the rounded f32 output"
+
+
+def test_conv_gemm_bf16_many_tiles():
+    """More M tiles than SMs: exercises the persistent tile loop, the smem ring wrap-around and both
+    TMEM accumulator buffers.  M = 64*16*50 = 51200 -> 400 M tiles x 1 N tile."""
+    case = (64, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), True, True)
+    x, w, scale, shift, res = _conv_inputs(case, 6, True)
+    ref = _conv_ref(x, w, scale, shift, res, (1, 1), (1, 1), True)
+    bf = torch.bfloat16
+    out_f = ops.conv_gemm(dev(x, bf), dev(w, bf), dev(scale), dev(shift), dev(res, bf), stride=(1, 1),
+                          pad=(1, 1), relu=True, want_f32=True, want_bf16=False)
+    torch.cuda.synchronize()
+    assert_close(host(out_f), ref, 2e-5, "conv_gemm_bf16 400 tiles")
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling / reductions / cast / embedding
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,W,k,s,p", [(32, 100, (2, 2), (2, 2), (0, 0)), (8, 25, (2, 2), (2, 1), (0, 1)),
+                                        (16, 50, (2, 2), (2, 2), (0, 0))])
+def test_maxpool_nhwc(dtype, H, W, k, s, p):
+    x = orc.round_bf16(rng(7).standard_normal((3, H, W, 64)).astype(np.float32))
+    ref = nhwc(orc.maxpool2d(nchw(x), k, s, p))
+    out = ops.maxpool_nhwc(dev(x, dtype), k, s, p)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(out), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_mean_reductions_and_cast(dtype):
+    x = orc.round_bf16(rng(8).standard_normal((5, 3, 65, 512)).astype(np.float32))
+    xd = dev(x, dtype)
+    assert_close(host(ops.mean_hw(xd)), x.astype(np.float64).mean(axis=(1, 2)), 2e-6, "mean_hw")
+    out, out_f = ops.mean_h(xd, want_f32=True)
+    assert_close(host(out_f), x.astype(np.float64).mean(axis=1), 2e-6, "mean_h f32")
+    if dtype == torch.bfloat16:
+        assert np.array_equal(host(out), orc.round_bf16(host(out_f)))
+    else:
+        assert np.array_equal(host(out), host(out_f))
+    y = rng(9).standard_normal(100003).astype(np.float32)
+    assert np.array_equal(host(ops.cast(dev(y), torch.bfloat16)), orc.round_bf16(y))
+    assert np.array_equal(host(ops.cast(dev(y, torch.bfloat16), torch.float32)), orc.round_bf16(y))
+
+
+def test_embed_semantics():
+    B = 33
+    table = rng(10).standard_normal((2000, 256)).astype(np.float32)
+    ov, sc, io = synth.make_semantics(11, B)
+    out = ops.embed_semantics(dev(ov), dev(table), None, 0)
+    assert np.array_equal(host(out), orc.linear_embedding(ov, sc, io, table, "overlap"))
+    out = ops.embed_semantics(dev(sc), dev(table), dev(io), 1)
+    assert_close(host(out), orc.linear_embedding(ov, sc, io.astype(np.float64), table, "scene", np.float64), 1e-6,
+                 "embed scene (-1000 ious)")
+    io2 = rng(12).uniform(0, 1, io.shape).astype(np.float32)
+    out = ops.embed_semantics(dev(sc), dev(table), dev(io2), 1)
+    assert_close(host(out), orc.linear_embedding(ov, sc, io2.astype(np.float64), table, "scene", np.float64), 1e-6,
+                 "embed scene (random ious)")
+
+
+# ------------------------------------------------------------------------------------------------
+# BiLSTM recurrence
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T", [(1, 26), (60, 26), (57, 7), (3, 65)])
+def test_bilstm_recurrent(B, T):
+    r = rng(13)
+    Hd = 256
+    gx = r.standard_normal((B, T, 2, 4 * Hd)).astype(np.float32)
+    w_hh = (r.uniform(-1, 1, (2, 4 * Hd, Hd)) / 16).astype(np.float32)
+    ref = np.concatenate([orc._lstm_direction(gx[:, :, d].astype(np.float64), w_hh[d].astype(np.float64), bool(d))
+                          for d in range(2)], axis=2)
+    out_f, out_b = ops.bilstm_recurrent(dev(gx), dev(w_hh), want_f32=True, want_bf16=True)
+    torch.cuda.synchronize()
+    assert_close(host(out_f), ref, 2e-5, "bilstm_recurrent")
+    assert np.array_equal(host(out_b), orc.round_bf16(host(out_f)))
+
+
+# ------------------------------------------------------------------------------------------------
+# attention decoder
+# ------------------------------------------------------------------------------------------------
+def _decoder_pack(sd, Hd=256):
+    p = "decoder.attention_cell."
+    w_ih = sd[p + "rnn.weight_ih"]
+    pk = {"w_h2h": sd[p + "h2h.weight"], "b_h2h": sd[p + "h2h.bias"], "w_score": sd[p + "score.weight"][0],
+          "w_ctx": w_ih[:, :Hd], "w_tok": w_ih[:, Hd:].T, "w_hh": sd[p + "rnn.weight_hh"],
+          "bias": sd[p + "rnn.bias_ih"] + sd[p + "rnn.bias_hh"],
+          "w_gen": sd["decoder.generator.weight"], "b_gen": sd["decoder.generator.bias"]}
+    return {k: dev(np.ascontiguousarray(v, dtype=np.float32)) for k, v in pk.items()}
+
+
+@pytest.fixture(scope="module")
+def decoder_case(sd_cfg_a):
+    B, T, Hd = 37, 26, 256
+    enc = (rng(14).standard_normal((B, T, Hd)) * 0.5).astype(np.float32)
+    proj = (enc.astype(np.float64) @ sd_cfg_a["decoder.attention_cell.i2h.weight"].astype(np.float64).T).astype(np.float32)
+    return enc, proj, _decoder_pack(sd_cfg_a)
+
+
+def test_attn_decode_greedy(sd_cfg_a, decoder_case):
+    enc, proj, pk = decoder_case
+    B, steps = enc.shape[0], 26
+    ref, ref_alpha = orc.attention_decode(enc, sd_cfg_a, steps, 97, dt=np.float64, return_alpha=True)
+    res = ops.attn_decode(dev(enc), dev(proj), pk, steps, None, early_exit=False, want_alpha=True)
+    torch.cuda.synchronize()
+    ids = host(res["ids"])
+    ref_ids = ref.argmax(2)
+    assert np.array_equal(ids, ref_ids), "greedy ids differ on %d of %d crops" % ((ids != ref_ids).any(1).sum(), B)
+    assert_close(host(res["logits"]), ref, 1e-4, "greedy logits")
+    assert_close(host(res["alpha"]), ref_alpha, 1e-4, "attention weights")
+    first = np.where((ref_ids == 1).any(1), (ref_ids == 1).argmax(1), steps)
+    assert np.array_equal(host(res["lengths"]), first)
+
+
+def test_attn_decode_early_exit(sd_cfg_a, decoder_case):
+    enc, proj, pk = decoder_case
+    steps = 26
+    full = ops.attn_decode(dev(enc), dev(proj), pk, steps, None, early_exit=False)
+    early = ops.attn_decode(dev(enc), dev(proj), pk, steps, None, early_exit=True)
+    torch.cuda.synchronize()
+    L = host(full["lengths"])
+    assert np.array_equal(host(early["lengths"]), L)
+    fl, el, fi, ei = host(full["logits"]), host(early["logits"]), host(full["ids"]), host(early["ids"])
+    for b in range(enc.shape[0]):
+        k = min(int(L[b]) + 1, steps)           # steps up to and including the one that emitted [s]
+        assert np.array_equal(el[b, :k], fl[b, :k]) and np.array_equal(ei[b, :k], fi[b, :k])
+        assert not el[b, k:].any() and not ei[b, k:].any()
+
+
+def test_attn_decode_teacher_forced_and_single_step(sd_cfg_a, decoder_case):
+    enc, proj, pk = decoder_case
+    B, steps = enc.shape[0], 26
+    text = rng(15).integers(0, 97, (B, steps)).astype(np.int64)
+    text[:, 0] = 0
+    ref = orc.attention_decode(enc, sd_cfg_a, steps, 97, text=text, dt=np.float64)
+    res = ops.attn_decode(dev(enc), dev(proj), pk, steps, dev(text), early_exit=False)
+    assert_close(host(res["logits"]), ref, 1e-4, "teacher-forced logits")
+    # two single steps chained through (h, c) equal the first two steps of the fused loop
+    s1 = ops.attn_decode(dev(enc), dev(proj), pk, 1, dev(text[:, :1]), early_exit=False, want_state=True)
+    s2 = ops.attn_decode(dev(enc), dev(proj), pk, 1, dev(np.ascontiguousarray(text[:, 1:2])), early_exit=False,
+                         h0=s1["h"], c0=s1["c"], want_state=True)
+    torch.cuda.synchronize()
+    assert_close(host(s1["logits"])[:, 0], ref[:, 0], 1e-4, "single step 0")
+    assert_close(host(s2["logits"])[:, 0], ref[:, 1], 1e-4, "single step 1")
+
+
+def test_attn_decode_long_sequence(sd_cfg_a):
+    """T=65 encoder columns, 51 steps (stress configuration)."""
+    B, T, Hd, steps = 5, 65, 256, 51
+    enc = (rng(16).standard_normal((B, T, Hd)) * 0.5).astype(np.float32)
+    proj = (enc.astype(np.float64) @ sd_cfg_a["decoder.attention_cell.i2h.weight"].astype(np.float64).T).astype(np.float32)
+    ref = orc.attention_decode(enc, sd_cfg_a, steps, 97, dt=np.float64)
+    res = ops.attn_decode(dev(enc), dev(proj), _decoder_pack(sd_cfg_a), steps, None, early_exit=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(res["ids"]), ref.argmax(2))
+    assert_close(host(res["logits"]), ref, 2e-4, "long-sequence logits")
+
+
+# ------------------------------------------------------------------------------------------------
+# error behaviour of the boundary
+# ------------------------------------------------------------------------------------------------
+def test_errors_are_loud():
+    from multimodal_scene_text_recognition_b200._cabi import MstrError
+    x = torch.zeros((1, 4, 4, 24), device=DEV)
+    w = torch.zeros((8, 3, 3, 24), device=DEV)
+    with pytest.raises(MstrError, match="multiple of 16"):
+        ops.conv_gemm(x, w, None, None, pad=(1, 1))
+    with pytest.raises(MstrError, match="CUDA tensor"):
+        ops.maxpool_nhwc(torch.zeros(1, 4, 4, 8))

@@ -129,3 +129,21 @@ def test_round_bf16():
     a = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 37.0
     ref = torch.from_numpy(a).to(torch.bfloat16).float().numpy()
     assert np.array_equal(orc.round_bf16(a), ref)
+
+
+def test_torch_port_matches_reference_golden(sd_cfg_a, golden_a):
+    """oracle/torch_port.py (the CPU baseline bench.py times) against the reference's outputs."""
+    import torch
+    from oracle import torch_port as tp
+    wseed, dseed, B = [int(v) for v in golden_a["meta"]]
+    x = synth.make_crops(dseed, B)
+    ov, sc, io = synth.make_semantics(dseed + 1, B)
+    tsd = tp.to_torch(sd_cfg_a)
+    st = tp.forward(tsd, torch.from_numpy(x), torch.from_numpy(ov), torch.from_numpy(sc), torch.from_numpy(io),
+                    stages=True)
+    assert rel_err(st["features"].numpy(), golden_a["features"]) < 1e-5
+    assert rel_err(st["enc1"].numpy(), golden_a["enc1"]) < 1e-5
+    assert np.array_equal(st["ids"].numpy(), golden_a["ids"])
+    assert rel_err(st["logits"].numpy(), golden_a["logits"]) < 1e-5
+    tf = tp.forward(tsd, torch.from_numpy(x), text=torch.from_numpy(golden_a["tf_text"]), is_train=True)
+    assert rel_err(tf.numpy(), golden_a["logits_tf"]) < 1e-5

@@ -36,7 +36,8 @@ def test_tps_rectify(geom, B):
     basis0 = dev(np.ascontiguousarray(sd["Transformation.GridGenerator.P_hat"].T))
     folded = (P_hat @ inv_delta_C[:, :geom.F]).T.astype(np.float32)
     inv_d = dev(sd["Transformation.GridGenerator.inv_delta_C"])
-    for mode, basis, gtol in ((0, basis0, 3e-5), (1, dev(np.ascontiguousarray(folded)), 3e-6)):
+    # mode 1 carries the fp32 rounding of the folded [F, n] constant (|A| <= 0.97, 20 terms): ~1e-5
+    for mode, basis, gtol in ((0, basis0, 3e-5), (1, dev(np.ascontiguousarray(folded)), 2e-5)):
         out, grid = ops.tps_rectify(dev(img), dev(c_prime), basis, inv_d, mode, want_grid=True)
         torch.cuda.synchronize()
         assert_close(host(grid), grid64, gtol, "tps grid mode %d" % mode)

@@ -236,12 +236,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, trace=None):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for k in range(steps):
+            t0 = time.perf_counter()
             fn(k)
+            if trace is not None:
+                trace.append(round(1e3 * (time.perf_counter() - t0), 2))
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
@@ -259,7 +262,12 @@ def run_ours(args):
     total_ms = timed(step_device, args.steps)
     timer, ops.TIMER = ops.TIMER, None
     launches = _cabi.launch_count() - launches0
-    e2e_ms = timed(step_e2e, args.steps)
+    for k in range(2):                     # the host-buffer path has its own allocation pattern: warm it up too
+        step_e2e(k)
+    e2e_trace = []
+    e2e_ms = timed(step_e2e, args.steps, e2e_trace)
+    if rank == 0:
+        print("e2e per-step host wall ms: %s" % e2e_trace, file=sys.stderr)
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:

@@ -131,6 +131,17 @@ int mstr_embed_semantics(const float* ids, const float* table, const float* ious
  */
 int mstr_bilstm_recurrent(const float* gates_x, const float* w_hh, float* out_f32, void* out_bf16,
                           int B, int T, int Hd, mstr_stream_t stream);
+/* Tensor-core variant for the bf16 throughput mode: h_t is kept in shared memory as bf16 (the
+ * operand of tcgen05.mma), c_t in TMEM as f32, W_hh streamed by TMA; gate non-linearities use
+ * tanh.approx.  One launch for all T steps of both directions.
+ *   w_hh_packed [2][4*Hd][Hd] bf16 with the rows of each direction re-ordered so that packed row
+ *               chunk*128 + g*32 + j  holds original row  g*Hd + chunk*32 + j  (chunk = 0..7,
+ *               g = gate i,f,g,o, j = 0..31): one 128-column accumulator chunk then carries all four
+ *               gates of the same 32 hidden units.
+ *   out_bf16    [B][T][2*Hd] bf16.   Hd must be 256.
+ */
+int mstr_bilstm_recurrent_bf16(const float* gates_x, const void* w_hh_packed, void* out_bf16, int B, int T,
+                               int Hd, mstr_stream_t stream);
 
 /* ---- attention decoder ---------------------------------------------------------------------
  * Replaces Attention.forward (modules/decoders.py:26-64) with AttentionCell.forward (:79-101),

@@ -59,3 +59,6 @@ DECODER_EARLY_EXIT = True
 # an out-of-range id).  It needs a device->host sync, so the hot path leaves it off; the kernel then
 # maps an out-of-range id to row 0.
 CHECK_INPUTS = False
+# bf16 mode only: run the recurrent GEMMs of the BiLSTM / attention decoder on the tensor cores (h_t in
+# bf16, fp32 accumulation and cell state, tanh.approx gates).  False keeps the fp32 SIMT recurrences.
+RNN_TENSOR_CORES = True

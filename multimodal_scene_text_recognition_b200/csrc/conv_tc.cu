@@ -17,129 +17,9 @@
 //   warps 2..5  epilogue      : tcgen05.ld 32x32b.x32 -> folded BN, residual, ReLU -> bf16/f32 NHWC stores,
 //                               overlapped with the next tile's MMAs through the second TMEM buffer
 // Roofline: tensor pipe.  Algorithmic FLOPs = 2 * M * C_out * R*S*C_in per launch.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mstr {
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
-      printf("mstr: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c,
-                                                   int w, int h, int n, uint16_t off_w, uint16_t off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
-      "r"(n), "h"(off_w), "h"(off_h)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, K-major operand, rows of BLOCK_K bf16 (= one swizzle span):
-//   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for swizzled K-major)
-//   bits [32,46) stride byte offset >> 4   (8 rows x row bytes: distance between 8-row core groups)
-//   bits [46,48) descriptor version = 1 (Blackwell)      bits [61,64) swizzle: 2 = 128B, 4 = 64B
-template <int ROW_BYTES>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  constexpr uint64_t layout = (ROW_BYTES == 128) ? 2ull : 4ull;
-  constexpr uint64_t sbo = (8ull * ROW_BYTES) >> 4;
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
-// Instruction descriptor for kind::f16: D = f32 (bits [4,6) = 1), A = B = bf16 (bits [7,10) = [10,13) = 1),
-// both operands K-major (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
 
 // ---------------------------------------------------------------------------------------------
 // kernel
@@ -364,35 +244,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ---------------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
-static PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
-
-static int load_driver_entry_points() {
-  if (g_encode_tiled && g_encode_im2col) return MSTR_OK;
-  cudaDriverEntryPointQueryResult qres;
-  void* fn = nullptr;
-  MSTR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  MSTR_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-  g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-  fn = nullptr;
-  MSTR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
-  MSTR_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, MSTR_ERR_CUDA, "cuTensorMapEncodeIm2col not available");
-  g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
-  return MSTR_OK;
-}
-
-static int encode_tiled_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
-                           uint32_t box_outer, CUtensorMapSwizzle swz) {
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return MSTR_OK;
-}
+static TmaEncoders g_enc;
 
 template <int BLOCK_N, int BLOCK_K>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
@@ -426,7 +278,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   MSTR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(residual) && aligned16(out_bf16) && aligned16(out_f32),
                MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: pointers must be 16-byte aligned");
   MSTR_REQUIRE(R <= 16 && S <= 16 && pad_h < 16 && pad_w < 16, MSTR_ERR_UNSUPPORTED, "mstr_conv_gemm_bf16: filter too large");
-  int rc = load_driver_entry_points();
+  int rc = load_tma_encoders(g_enc);
   if (rc != MSTR_OK) return rc;
 
   TcParams p;
@@ -455,11 +307,11 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   const CUtensorMapSwizzle swz = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   alignas(64) CUtensorMap tmA, tmB;
   const int64_t K = (int64_t)R * S * C_in;
-  rc = encode_tiled_2d(&tmB, w, (uint64_t)K, (uint64_t)C_out, (uint32_t)block_k, (uint32_t)block_n, swz);
+  rc = encode_tiled_2d_bf16(g_enc, &tmB, w, (uint64_t)K, (uint64_t)C_out, (uint32_t)block_k, (uint32_t)block_n, swz);
   if (rc != MSTR_OK) return rc;
   if (!p.im2col) {
     // A is a plain [M][C_in] matrix (1x1 convolution / linear layer)
-    rc = encode_tiled_2d(&tmA, x, (uint64_t)C_in, (uint64_t)((int64_t)B * H * W), (uint32_t)block_k, TC_BLOCK_M, swz);
+    rc = encode_tiled_2d_bf16(g_enc, &tmA, x, (uint64_t)C_in, (uint64_t)((int64_t)B * H * W), (uint32_t)block_k, TC_BLOCK_M, swz);
     if (rc != MSTR_OK) return rc;
   } else {
     cuuint64_t dims[4] = {(cuuint64_t)C_in, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -468,7 +320,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
     int lower[2] = {-pad_w, -pad_h};
     int upper[2] = {pad_w - (S - 1), pad_h - (R - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
-    CUresult r = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+    CUresult r = g_enc.im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
                                  upper, (cuuint32_t)block_k, (cuuint32_t)TC_BLOCK_M, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -6,7 +6,9 @@ reference's; neither container's own forward is ever called.  The work is three 
 
 1. input projection of both directions  x [W_ih_fwd; W_ih_bwd]^T + (b_ih + b_hh)  - GEMM
    (``mstr_conv_gemm_bf16`` on tcgen05, or ``mstr_conv_gemm_f32`` in parity mode);
-2. ``mstr_bilstm_recurrent`` - ONE persistent launch for all T steps of both directions;
+2. ``mstr_bilstm_recurrent_bf16`` (bf16 mode: h_t W_hh^T on tcgen05, c_t in TMEM) or
+   ``mstr_bilstm_recurrent`` (fp32 parity mode, SIMT) - ONE persistent launch for all T steps of both
+   directions;
 3. Linear(2H -> out) + bias - GEMM.
 
 The transformer / Oscar encoders of the reference (encoders.py:32-243) are a different model
@@ -41,6 +43,7 @@ class BidirectionalLSTM(nn.Module):
                               r.bias_ih_l0_reverse + r.bias_hh_l0_reverse], 0).detach().float()  # [2*4H]
             w_hh = torch.stack([r.weight_hh_l0, r.weight_hh_l0_reverse], 0).detach().float()     # [2, 4H, H]
             return {"w_ih": w_ih.to(dt).contiguous(), "bias": bias.contiguous(), "w_hh": w_hh.contiguous(),
+                    "w_hh_tc": ops.pack_w_hh_bf16(w_hh) if precision == 'bf16' else None,
                     "w_lin": self.linear.weight.detach().float().to(dt).contiguous(),
                     "b_lin": self.linear.bias.detach().float().contiguous()}
         return cached(self, ("bilstm", precision), src, build)
@@ -57,7 +60,10 @@ class BidirectionalLSTM(nn.Module):
         hd = self.rnn.hidden_size
         if precision == 'bf16':
             gx = ops.linear(x, pk["w_ih"], pk["bias"], want_f32=True, want_bf16=False)    # [B,T,2*4H] f32
-            rec = ops.bilstm_recurrent(gx.view(B, T, 2, 4 * hd), pk["w_hh"], want_f32=False, want_bf16=True)
+            if config.RNN_TENSOR_CORES:
+                rec = ops.bilstm_recurrent_bf16(gx.view(B, T, 2, 4 * hd), pk["w_hh_tc"])
+            else:
+                rec = ops.bilstm_recurrent(gx.view(B, T, 2, 4 * hd), pk["w_hh"], want_f32=False, want_bf16=True)
             return ops.linear(rec, pk["w_lin"], pk["b_lin"], want_f32=want_f32, want_bf16=want_act)
         gx = ops.linear(x, pk["w_ih"], pk["bias"])
         rec = ops.bilstm_recurrent(gx.view(B, T, 2, 4 * hd), pk["w_hh"], want_f32=True, want_bf16=False)

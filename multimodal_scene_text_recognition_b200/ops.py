@@ -239,6 +239,28 @@ def bilstm_recurrent(gates_x: torch.Tensor, w_hh: torch.Tensor, want_f32: bool, 
     return out_f if want_f32 else out_b
 
 
+def pack_w_hh_bf16(w_hh: torch.Tensor) -> torch.Tensor:
+    """[2, 4H, H] f32 (gate-major rows i,f,g,o) -> bf16 with rows ordered (chunk of 32 units, gate, unit),
+    the layout mstr_bilstm_recurrent_bf16 streams (see include/mstr_b200.h)."""
+    two, four_h, hd = w_hh.shape
+    assert two == 2 and four_h == 4 * hd and hd % 32 == 0
+    w = w_hh.reshape(2, 4, hd // 32, 32, hd).permute(0, 2, 1, 3, 4)      # [dir, chunk, gate, unit, k]
+    return w.reshape(2, 4 * hd, hd).to(torch.bfloat16).contiguous()
+
+
+def bilstm_recurrent_bf16(gates_x: torch.Tensor, w_hh_packed: torch.Tensor) -> torch.Tensor:
+    """gates_x [B,T,2,4H] f32, w_hh_packed [2,4H,H] bf16 (pack_w_hh_bf16) -> [B,T,2H] bf16."""
+    _req(gates_x, "gates_x", torch.float32); _req(w_hh_packed, "w_hh_packed", torch.bfloat16)
+    B, T = gates_x.shape[:2]
+    Hd = w_hh_packed.shape[2]
+    assert gates_x.shape == (B, T, 2, 4 * Hd) and w_hh_packed.shape == (2, 4 * Hd, Hd)
+    out = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.bfloat16)
+    with _timed("bilstm_recurrent_bf16", 2.0 * B * T * 2 * 4 * Hd * Hd):
+        check(lib().mstr_bilstm_recurrent_bf16(ptr(gates_x), ptr(w_hh_packed), ptr(out), B, T, Hd, stream_ptr()),
+              "mstr_bilstm_recurrent_bf16")
+    return out
+
+
 def attn_decode(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int, text: Optional[torch.Tensor],
                 early_exit: bool, h0: Optional[torch.Tensor] = None, c0: Optional[torch.Tensor] = None,
                 want_alpha: bool = False, want_state: bool = False) -> dict:

@@ -274,17 +274,19 @@ def linear_embedding(overlap, scene, ious, table, mode="overlap", dt=np.float32)
 # --------------------------------------------------------------------------------------
 # BiLSTM encoder (modules/encoders.py:10-30)
 # --------------------------------------------------------------------------------------
-def _lstm_direction(gx, w_hh, reverse):
-    """One direction of nn.LSTM given precomputed input gates gx [B,T,4H] (bias included)."""
+def _lstm_direction(gx, w_hh, reverse, quant=None):
+    """One direction of nn.LSTM given precomputed input gates gx [B,T,4H] (bias included).
+    ``quant='bf16'``: W_hh and the fed-back h_t are rounded to bf16 (the tensor-core recurrence of
+    the CUDA bf16 mode keeps h_t in bf16; the cell state and accumulation stay fp32)."""
     B, T, G = gx.shape
     Hd = G // 4
     h = np.zeros((B, Hd), gx.dtype)
     c = np.zeros((B, Hd), gx.dtype)
     out = np.empty((B, T, Hd), gx.dtype)
-    w_hh_t = w_hh.T.astype(gx.dtype)
+    w_hh_t = _q(w_hh.astype(gx.dtype), quant).T
     steps = range(T - 1, -1, -1) if reverse else range(T)
     for t in steps:
-        g = gx[:, t] + h @ w_hh_t
+        g = gx[:, t] + _q(h, quant) @ w_hh_t
         i = sigmoid(g[:, :Hd]); f = sigmoid(g[:, Hd:2 * Hd])
         gg = np.tanh(g[:, 2 * Hd:3 * Hd]); o = sigmoid(g[:, 3 * Hd:])
         c = f * c + i * gg
@@ -301,7 +303,7 @@ def bidirectional_lstm(x, sd, prefix, dt=np.float32, quant=None):
         w_ih = _q(sd[f"{prefix}.rnn.weight_ih_l0{sfx}"].astype(dt), quant)
         bias = (sd[f"{prefix}.rnn.bias_ih_l0{sfx}"].astype(dt) + sd[f"{prefix}.rnn.bias_hh_l0{sfx}"].astype(dt))
         gx = _q(x, quant) @ w_ih.T + bias
-        outs.append(_lstm_direction(gx, sd[f"{prefix}.rnn.weight_hh_l0{sfx}"], rev))
+        outs.append(_lstm_direction(gx, sd[f"{prefix}.rnn.weight_hh_l0{sfx}"], rev, quant))
     rec = _q(np.concatenate(outs, axis=2), quant)   # [fwd | bwd], stored bf16 for the Linear GEMM
     w = _q(sd[prefix + ".linear.weight"].astype(dt), quant)
     return rec @ w.T + sd[prefix + ".linear.bias"].astype(dt)

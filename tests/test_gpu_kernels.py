@@ -223,6 +223,23 @@ def test_bilstm_recurrent(B, T):
     assert np.array_equal(host(out_b), orc.round_bf16(host(out_f)))
 
 
+@pytest.mark.parametrize("B,T", [(1, 26), (130, 26), (128, 5), (3, 65)])
+def test_bilstm_recurrent_bf16_tensor_cores(B, T):
+    """tcgen05 recurrence (h_t in bf16, tanh.approx gates) vs the oracle with bf16-rounded W_hh / h_t."""
+    r = rng(17)
+    Hd = 256
+    gx = r.standard_normal((B, T, 2, 4 * Hd)).astype(np.float32)
+    w_hh = (r.uniform(-1, 1, (2, 4 * Hd, Hd)) / 16).astype(np.float32)
+    ref = np.concatenate([orc._lstm_direction(gx[:, :, d].astype(np.float64), w_hh[d].astype(np.float64), bool(d),
+                                              quant="bf16") for d in range(2)], axis=2)
+    out = ops.bilstm_recurrent_bf16(dev(gx), ops.pack_w_hh_bf16(dev(w_hh)))
+    torch.cuda.synchronize()
+    # tanh.approx (2^-11) and bf16 storage of h (2^-9): a rounding flip of h_t moves later steps by ~1 ulp
+    assert_close(host(out), ref, 2e-2, "bilstm_recurrent_bf16")
+    d = np.abs(host(out).astype(np.float64) - ref)
+    assert d.mean() < 2e-3, "mean abs error %.3e" % d.mean()
+
+
 # ------------------------------------------------------------------------------------------------
 # attention decoder
 # ------------------------------------------------------------------------------------------------

@@ -21,7 +21,7 @@ run conv_f32   300 $PT tests/test_gpu_kernels.py -k "conv_gemm_f32 or linear_f32
 run conv_tc    300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "bf16_tcgen05"
 run conv_tc2   300 $PT tests/test_gpu_kernels.py -k "many_tiles"
 run small      300 $PT tests/test_gpu_kernels.py -k "maxpool or mean or embed or errors"
-run bilstm     300 $PT tests/test_gpu_kernels.py -k "bilstm"
+run bilstm     300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "bilstm"
 run attn       300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "attn"
 run model_fp32 600 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_model.py -k "fp32 or scene"
 run model_bf16 600 python -m pytest -q -m gpu -p no:cacheprovider -s tests/test_gpu_model.py -k "bf16"

@@ -11,10 +11,10 @@ tail -1 gpurun_out/${TAG}_plain.log
 # launches per step (LAUNCHES_PER_STEP is printed by the plain run's JSON: gpu_launches / steps)
 LPS=$(python -c "import json,sys; print(json.loads(open('gpurun_out/${TAG}_plain.log').read().strip().splitlines()[-1])['gpu_launches'])")
 echo "launches per step: $LPS"
-ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * LPS)) -c $LPS --csv \
-    --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:mstr:: \
+    -s $((3 * LPS)) -c $LPS --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches exit $?"
-ncu --set full --clock-control none --import-source on -k regex:conv_gemm_bf16 -s 18 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:conv_gemm_bf16 -s $((39 * 3 + 18)) -c 2 \
     -o gpurun_out/${TAG}_conv $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la gpurun_out/

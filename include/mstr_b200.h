@@ -167,6 +167,26 @@ int mstr_attn_decode(const float* enc, const float* proj, const float* w_h2h, co
                      int32_t* ids, int32_t* lengths, float* alpha_out, float* h_out, float* c_out,
                      int B, int T, int Hd, int C, int steps, int early_exit, mstr_stream_t stream);
 
+/* Tensor-core variant for the bf16 throughput mode: ONE call enqueues the whole greedy (or
+ * teacher-forced) loop as three launches per step - a tcgen05 GEMM for [h2h | generator] with the
+ * argmax in its epilogue, the attention-context kernel, and a tcgen05 GEMM for the LSTMCell gates with
+ * the cell update in its epilogue.  bf16 operands (enc, proj, h, ctx, weights), f32 accumulation,
+ * cell state, logits.
+ *   enc_bf16, proj_bf16 [B][T][Hd] bf16
+ *   w_head [384][Hd] bf16: rows 0..255 = h2h.weight, rows 256..256+C-1 = generator.weight, rest zero
+ *   w_cat  [4*Hd][2*Hd] bf16: [rnn.weight_ih[:, :Hd] | rnn.weight_hh] with rows re-ordered like
+ *          mstr_bilstm_recurrent_bf16's w_hh_packed (chunk*128 + g*32 + j <- g*Hd + chunk*32 + j)
+ *   w_tok  [C][4*Hd] f32 = rnn.weight_ih[:, Hd:]^T (original gate-major columns); bias [4*Hd] f32
+ *   workspace: mstr_attn_decode_bf16_workspace_bytes(B, Hd) bytes of device memory (16-byte aligned)
+ *   logits must be zero-initialised by the caller; ids / lengths / alpha_out as in mstr_attn_decode.
+ */
+int64_t mstr_attn_decode_bf16_workspace_bytes(int B, int Hd);
+int mstr_attn_decode_bf16(const void* enc_bf16, const void* proj_bf16, const void* w_head, const float* b_h2h,
+                          const float* b_gen, const float* w_score, const void* w_cat, const float* w_tok,
+                          const float* bias, const int64_t* text, void* workspace, float* logits, int32_t* ids,
+                          int32_t* lengths, float* alpha_out, int B, int T, int Hd, int C, int steps,
+                          int early_exit, mstr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

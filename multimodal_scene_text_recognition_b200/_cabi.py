@@ -34,6 +34,8 @@ SIGNATURES = {
     "mstr_bilstm_recurrent": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "mstr_bilstm_recurrent_bf16": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "mstr_attn_decode": (c_int, [_P] * 20 + [_I] * 6 + [_P]),
+    "mstr_attn_decode_bf16_workspace_bytes": (c_int64, [_I, _I]),
+    "mstr_attn_decode_bf16": (c_int, [_P] * 15 + [_I] * 6 + [_P]),
 }
 
 _lib = None

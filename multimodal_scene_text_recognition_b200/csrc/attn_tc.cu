@@ -1,0 +1,434 @@
+// Attention decoder for the bf16 throughput mode: the three GEMMs of every decode step run on the
+// tensor cores, the Bahdanau attention on all SMs, and the whole greedy loop is enqueued by ONE
+// C-ABI call (mstr_attn_decode_bf16) as three launches per step:
+//
+//   head_i   [hp_i | logits_{i-1}] = h_i [W_h2h ; W_gen]^T      tcgen05 GEMM, N = 384 (3 tiles of 128)
+//            epilogue: hp_i += b_h2h (f32, for the attention kernel); logits_{i-1} += b_gen -> stored,
+//            thread-local argmax over the 97 classes (TMEM lane = crop) -> id, next token, [s] bookkeeping
+//   ctx_i    e_t = w_score . tanh(proj[b,t,:] + hp_i[b,:]), alpha = softmax_T(e), ctx = sum_t alpha_t enc[b,t,:]
+//            one warp per crop, 16-byte bf16 loads, shuffle reductions, tanh.approx; writes ctx (bf16) into
+//            the left half of the [ctx | h] operand buffer
+//   cell_i   gates = [ctx_i | h_i] [W_ctx | W_hh]^T + W_tok[token_i] + bias -> (h_{i+1}, c_{i+1})
+//            tcgen05 GEMM, N = 1024 with rows packed (chunk of 32 units, gate, unit) so that one
+//            128-column tile carries i,f,g,o of the same units and the LSTM cell is thread-local in the
+//            epilogue; c stays f32 in global memory (L2 resident), h_{i+1} is written as bf16 into the
+//            right half of the other [ctx | h] buffer
+//
+// Replaces modules/decoders.py:26-64 (Attention.forward greedy :52-62 and teacher-forced :41-50
+// branches), :79-101 (AttentionCell.forward), :17/:59 (generator), :19-24 (_char_to_onehot: a one-hot
+// times W_ih is a row gather of W_tok).  proj = i2h(enc) is loop invariant (:81) and computed once by
+// the caller.  Differences to the fp32 SIMT kernel (attn_decode.cu): proj / enc / h / ctx are bf16
+// operands (fp32 accumulation everywhere), tanh.approx in the attention scores.
+#include "tc_common.cuh"
+
+namespace mstr {
+
+constexpr int AT_H = 256;
+constexpr int AT_BLOCK = 128;      // BLOCK_M = BLOCK_N
+constexpr int AT_STAGES = 3;
+constexpr int AT_TILE_BYTES = 128 * 128;   // [128 rows][64 k] bf16, 128B swizzle
+constexpr int AT_THREADS = 192;
+constexpr int AT_SMEM_BYTES = 1024 + AT_STAGES * 2 * AT_TILE_BYTES + 256;
+
+struct DecodeState {
+  // operand / state buffers (device)
+  __nv_bfloat16* xh[2];   // [B][512]: cols 0..255 ctx_i, cols 256..511 h_i   (double buffered by step parity)
+  float* hp;              // [B][256]
+  float* cst;             // [B][256]
+  int32_t* tok;           // [B] token fed to the current step
+  int32_t* done;          // [B] crop has emitted [s]
+  int32_t* live;          // [1] number of crops still decoding (early exit)
+  // parameters
+  const float* b_h2h; const float* b_gen; const float* w_score; const float* w_tok; const float* bias;
+  const int64_t* text;    // optional teacher forcing [B][steps]
+  // outputs
+  float* logits; int32_t* ids; int32_t* lengths; float* alpha_out;
+  int B, T, C, steps, early_exit;
+};
+
+__device__ __forceinline__ float at_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float at_tanh(float x) { return fmaf(2.f, at_sigmoid(2.f * x), -1.f); }
+
+// EPI 0: head (hp + logits/argmax), EPI 1: LSTM cell.  One 128x128 output tile per CTA; K = num_k * 64.
+template <int EPI>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const DecodeState s, const int step, const int num_k) {
+  if (s.early_exit && *s.live == 0) return;   // every crop has emitted [s]
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + AT_STAGES * AT_TILE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * AT_STAGES * AT_TILE_BYTES);
+  uint64_t* empty_bar = full_bar + AT_STAGES;
+  uint64_t* tfull_bar = empty_bar + AT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m0 = blockIdx.y * AT_BLOCK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], 2 * AT_TILE_BYTES);
+        tma_load_2d(sA + stage * AT_TILE_BYTES, &tmA, &full_bar[stage], kb * 64, m0);
+        tma_load_2d(sB + stage * AT_TILE_BYTES, &tmB, &full_bar[stage], kb * 64, n_tile * AT_BLOCK);
+        if (++stage == AT_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(AT_BLOCK, AT_BLOCK);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + stage * AT_TILE_BYTES);
+        const uint32_t b_addr = smem_u32(sB + stage * AT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, make_smem_desc<128>(a_addr + k * 32), make_smem_desc<128>(b_addr + k * 32), idesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_k - 1) umma_commit(tfull_bar);
+        if (++stage == AT_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM lane = crop row =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int crop = m0 + row;
+    const bool valid = crop < s.B;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    if constexpr (EPI == 0) {
+      if (n_tile < 2) {
+        // hp_i = h_i W_h2h^T + b_h2h  (consumed by attn_context_kernel of this step)
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT_BLOCK; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(s.hp + (size_t)crop * AT_H + n_tile * AT_BLOCK + c0);
+            const float4* bb = reinterpret_cast<const float4*>(s.b_h2h + n_tile * AT_BLOCK + c0);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 b4 = __ldg(bb + u);
+              dst[u] = make_float4(__uint_as_float(v[4 * u]) + b4.x, __uint_as_float(v[4 * u + 1]) + b4.y,
+                                   __uint_as_float(v[4 * u + 2]) + b4.z, __uint_as_float(v[4 * u + 3]) + b4.w);
+            }
+          }
+        }
+      } else if (step > 0) {
+        // logits of decode step (step-1) = h_step W_gen^T + b_gen; argmax feeds the token of `step`
+        const int ls = step - 1;
+        const bool was_done = valid && s.early_exit && s.done[crop];
+        float best = -INFINITY;
+        int besti = 0;
+        float* lrow = s.logits + ((size_t)(valid ? crop : 0) * s.steps + ls) * s.C;
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT_BLOCK; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int cls = c0 + j;
+            if (cls < s.C) {
+              const float y = __uint_as_float(v[j]) + __ldg(s.b_gen + cls);
+              if (valid && !was_done) lrow[cls] = y;
+              if (y > best) { best = y; besti = cls; }      // ascending: the lowest index wins ties
+            }
+          }
+        }
+        if (valid) {
+          if (was_done) {
+            s.ids[(size_t)crop * s.steps + ls] = 0;          // argmax of the zero-initialised logits row
+          } else {
+            s.ids[(size_t)crop * s.steps + ls] = besti;
+            if (besti == 1 && !s.done[crop]) {
+              if (s.lengths && s.lengths[crop] == s.steps) s.lengths[crop] = ls;
+              if (s.early_exit) {
+                s.done[crop] = 1;
+                atomicSub(s.live, 1);
+              }
+            }
+          }
+          if (step < s.steps) s.tok[crop] = s.text ? (int)s.text[(size_t)crop * s.steps + step] : besti;
+        }
+      }
+    } else {
+      // LSTM cell: this tile = 32 hidden units x 4 gates of 128 crops
+      const int unit0 = n_tile * 32;
+      const int tok = valid ? s.tok[crop] : 0;
+      const float* wt = s.w_tok + (size_t)tok * (4 * AT_H);
+      float* crow = s.cst + (size_t)(valid ? crop : 0) * AT_H + unit0;
+      __nv_bfloat16* hrow = s.xh[(step + 1) & 1] + (size_t)(valid ? crop : 0) * (2 * AT_H) + AT_H + unit0;
+#pragma unroll 1
+      for (int sub = 0; sub < 4; ++sub) {            // 8 units at a time
+        uint32_t a[4][8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld8(taddr + (uint32_t)(g * 32 + sub * 8), a[g]);
+        tmem_ld_wait();
+        if (valid) {
+          float add[4][8];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = g * AT_H + unit0 + sub * 8;
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(wt + col));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(wt + col) + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(s.bias + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(s.bias + col) + 1);
+            add[g][0] = t0.x + b0.x; add[g][1] = t0.y + b0.y; add[g][2] = t0.z + b0.z; add[g][3] = t0.w + b0.w;
+            add[g][4] = t1.x + b1.x; add[g][5] = t1.y + b1.y; add[g][6] = t1.z + b1.z; add[g][7] = t1.w + b1.w;
+          }
+          float4 c0v = reinterpret_cast<const float4*>(crow + sub * 8)[0];
+          float4 c1v = reinterpret_cast<const float4*>(crow + sub * 8)[1];
+          float cp[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+          float hv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float gi = __uint_as_float(a[0][j]) + add[0][j];
+            const float gf = __uint_as_float(a[1][j]) + add[1][j];
+            const float gg = __uint_as_float(a[2][j]) + add[2][j];
+            const float go = __uint_as_float(a[3][j]) + add[3][j];
+            const float cn = fmaf(at_sigmoid(gf), cp[j], at_sigmoid(gi) * at_tanh(gg));
+            cp[j] = cn;
+            hv[j] = at_sigmoid(go) * at_tanh(cn);
+          }
+          reinterpret_cast<float4*>(crow + sub * 8)[0] = make_float4(cp[0], cp[1], cp[2], cp[3]);
+          reinterpret_cast<float4*>(crow + sub * 8)[1] = make_float4(cp[4], cp[5], cp[6], cp[7]);
+          *reinterpret_cast<uint4*>(hrow + sub * 8) =
+              make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]),
+                         pack_bf16x2(hv[6], hv[7]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// Bahdanau attention of one decode step: one warp per crop, lane = 8 channels.
+__global__ void __launch_bounds__(256)
+attn_context_kernel(const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ proj,
+                    const DecodeState s, const int step) {
+  if (s.early_exit && *s.live == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int crop = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (crop >= s.B) return;
+  const int T = s.T;
+  float hp[8], ws[8];
+  {
+    const float4* hp4 = reinterpret_cast<const float4*>(s.hp + (size_t)crop * AT_H + lane * 8);
+    const float4* ws4 = reinterpret_cast<const float4*>(s.w_score + lane * 8);
+    const float4 a = hp4[0], b = hp4[1], c = __ldg(ws4), d = __ldg(ws4 + 1);
+    hp[0] = a.x; hp[1] = a.y; hp[2] = a.z; hp[3] = a.w; hp[4] = b.x; hp[5] = b.y; hp[6] = b.z; hp[7] = b.w;
+    ws[0] = c.x; ws[1] = c.y; ws[2] = c.z; ws[3] = c.w; ws[4] = d.x; ws[5] = d.y; ws[6] = d.z; ws[7] = d.w;
+  }
+  const uint4* pj = reinterpret_cast<const uint4*>(proj + (size_t)crop * T * AT_H) + lane;   // 32 uint4 per time step
+  const uint4* en = reinterpret_cast<const uint4*>(enc + (size_t)crop * T * AT_H) + lane;
+  constexpr int MAX_SLOTS = 3;   // T <= 96
+  float e_slot[MAX_SLOTS];
+#pragma unroll
+  for (int k = 0; k < MAX_SLOTS; ++k) e_slot[k] = -INFINITY;
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (t0 + u < T) ? __ldg(pj + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      float part = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack_bf16x2(w4[q]);
+        part = fmaf(ws[2 * q], tanh_approx(f.x + hp[2 * q]), part);
+        part = fmaf(ws[2 * q + 1], tanh_approx(f.y + hp[2 * q + 1]), part);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const int t = t0 + u;
+      if (t < T && (t & 31) == lane) {
+#pragma unroll
+        for (int k = 0; k < MAX_SLOTS; ++k)
+          if ((t >> 5) == k) e_slot[k] = part;
+      }
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < MAX_SLOTS; ++k) mx = fmaxf(mx, e_slot[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAX_SLOTS; ++k) {
+    e_slot[k] = (e_slot[k] == -INFINITY) ? 0.f : __expf(e_slot[k] - mx);
+    den += e_slot[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  const float inv = 1.f / den;
+  if (s.alpha_out) {
+#pragma unroll
+    for (int k = 0; k < MAX_SLOTS; ++k) {
+      const int t = k * 32 + lane;
+      if (t < T) s.alpha_out[((size_t)crop * s.steps + step) * T + t] = e_slot[k] * inv;
+    }
+  }
+  float cx[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) cx[q] = 0.f;
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (t0 + u < T) ? __ldg(en + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u;
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAX_SLOTS; ++k) {
+        const float cand = __shfl_sync(0xffffffffu, e_slot[k], t & 31);
+        if ((t >> 5) == k) a = cand;
+      }
+      a = (t < T) ? a * inv : 0.f;
+      const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack_bf16x2(w4[q]);
+        cx[2 * q] = fmaf(a, f.x, cx[2 * q]);
+        cx[2 * q + 1] = fmaf(a, f.y, cx[2 * q + 1]);
+      }
+    }
+  }
+  __nv_bfloat16* dst = s.xh[step & 1] + (size_t)crop * (2 * AT_H) + lane * 8;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(cx[0], cx[1]), pack_bf16x2(cx[2], cx[3]),
+                                              pack_bf16x2(cx[4], cx[5]), pack_bf16x2(cx[6], cx[7]));
+}
+
+// token_0 = [GO] (0) or text[:, 0]; lengths = steps; done = 0; live = B; ids zero-filled.
+__global__ void decode_init_kernel(const DecodeState s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *s.live = s.B;
+  if (i < s.B) {
+    s.tok[i] = s.text ? (int)s.text[(size_t)i * s.steps] : 0;
+    s.done[i] = 0;
+    if (s.lengths) s.lengths[i] = s.steps;
+  }
+  for (int j = i; j < s.B * s.steps; j += gridDim.x * blockDim.x) s.ids[j] = 0;
+}
+
+static TmaEncoders g_attn_enc;
+
+}  // namespace mstr
+
+extern "C" __attribute__((visibility("default"))) int64_t mstr_attn_decode_bf16_workspace_bytes(int B, int Hd) {
+  // xh[2][B][2H] bf16 | hp [B][H] f32 | c [B][H] f32 | tok [B] | done [B] | live (16 bytes)
+  return (int64_t)B * Hd * (2 * 2 * 2 + 4 + 4) + (int64_t)B * 8 + 16;
+}
+
+extern "C" __attribute__((visibility("default"))) int mstr_attn_decode_bf16(
+    const void* enc_bf16, const void* proj_bf16, const void* w_head, const float* b_h2h, const float* b_gen,
+    const float* w_score, const void* w_cat, const float* w_tok, const float* bias, const int64_t* text,
+    void* workspace, float* logits, int32_t* ids, int32_t* lengths, float* alpha_out, int B, int T, int Hd, int C,
+    int steps, int early_exit, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(enc_bf16 && proj_bf16 && w_head && b_h2h && b_gen && w_score && w_cat && w_tok && bias && workspace &&
+                   logits && ids,
+               MSTR_ERR_BAD_ARG, "mstr_attn_decode_bf16: null pointer");
+  MSTR_REQUIRE(B > 0 && T > 0 && steps > 0 && C > 0, MSTR_ERR_BAD_ARG, "mstr_attn_decode_bf16: bad size");
+  MSTR_REQUIRE(Hd == AT_H, MSTR_ERR_UNSUPPORTED, "mstr_attn_decode_bf16: hidden size %d != %d", Hd, AT_H);
+  MSTR_REQUIRE(C <= AT_BLOCK, MSTR_ERR_UNSUPPORTED, "mstr_attn_decode_bf16: num_classes %d > %d", C, AT_BLOCK);
+  MSTR_REQUIRE(T <= 96, MSTR_ERR_UNSUPPORTED, "mstr_attn_decode_bf16: T=%d > 96", T);
+  MSTR_REQUIRE(aligned16(enc_bf16) && aligned16(proj_bf16) && aligned16(w_head) && aligned16(w_cat) &&
+                   aligned16(w_tok) && aligned16(bias) && aligned16(workspace) && aligned16(w_score) && aligned16(b_h2h),
+               MSTR_ERR_BAD_ARG, "mstr_attn_decode_bf16: pointers must be 16-byte aligned");
+  if (text) early_exit = 0;   // the teacher-forced branch always runs every step (decoders.py:41-50)
+  int rc = load_tma_encoders(g_attn_enc);
+  if (rc != MSTR_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  DecodeState s;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t xh_bytes = (size_t)B * 2 * AT_H * 2;
+  s.xh[0] = reinterpret_cast<__nv_bfloat16*>(ws);
+  s.xh[1] = reinterpret_cast<__nv_bfloat16*>(ws + xh_bytes);
+  s.hp = reinterpret_cast<float*>(ws + 2 * xh_bytes);
+  s.cst = s.hp + (size_t)B * AT_H;
+  s.tok = reinterpret_cast<int32_t*>(s.cst + (size_t)B * AT_H);
+  s.done = s.tok + B;
+  s.live = s.done + B;
+  s.b_h2h = b_h2h; s.b_gen = b_gen; s.w_score = w_score; s.w_tok = w_tok; s.bias = bias; s.text = text;
+  s.logits = logits; s.ids = ids; s.lengths = lengths; s.alpha_out = alpha_out;
+  s.B = B; s.T = T; s.C = C; s.steps = steps; s.early_exit = early_exit;
+  // h_0 = c_0 = 0 (decoders.py:36-38); ctx halves are overwritten before use
+  MSTR_CUDA(cudaMemsetAsync(ws, 0, 2 * xh_bytes + (size_t)B * AT_H * 8, st));
+  decode_init_kernel<<<ceil_div(B, 256), 256, 0, st>>>(s);
+  MSTR_LAUNCH_CHECK("decode_init_kernel");
+
+  // tensor maps: h view [B][256] with row stride 512 elements; [ctx|h] view [B][512]; weights
+  alignas(64) CUtensorMap tmH[2], tmXH[2], tmHead, tmCat;
+  for (int p = 0; p < 2; ++p) {
+    cuuint64_t dims[2] = {(cuuint64_t)AT_H, (cuuint64_t)B};
+    cuuint64_t strides[1] = {(cuuint64_t)(2 * AT_H * 2)};
+    cuuint32_t box[2] = {64, AT_BLOCK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_attn_enc.tiled(&tmH[p], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, s.xh[p] + AT_H, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled(h) failed with CUresult %d", (int)r);
+    rc = encode_tiled_2d_bf16(g_attn_enc, &tmXH[p], s.xh[p], 2 * AT_H, B, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != MSTR_OK) return rc;
+  }
+  rc = encode_tiled_2d_bf16(g_attn_enc, &tmHead, w_head, AT_H, 3 * AT_BLOCK, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != MSTR_OK) return rc;
+  rc = encode_tiled_2d_bf16(g_attn_enc, &tmCat, w_cat, 2 * AT_H, 4 * AT_H, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != MSTR_OK) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSTR_CUDA(cudaFuncSetAttribute(rnn_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    MSTR_CUDA(cudaFuncSetAttribute(rnn_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = ceil_div(B, AT_BLOCK);
+  const __nv_bfloat16* enc = static_cast<const __nv_bfloat16*>(enc_bf16);
+  const __nv_bfloat16* proj = static_cast<const __nv_bfloat16*>(proj_bf16);
+  for (int i = 0; i <= steps; ++i) {
+    // head_i: hp_i (tiles 0,1) and logits_{i-1} (tile 2); the last iteration only needs the logits tile
+    rnn_gemm_kernel<0><<<dim3(3, m_tiles), AT_THREADS, AT_SMEM_BYTES, st>>>(tmH[i & 1], tmHead, s, i, AT_H / 64);
+    MSTR_LAUNCH_CHECK("rnn_gemm_kernel<head>");
+    if (i == steps) break;
+    attn_context_kernel<<<ceil_div(B, 8), 256, 0, st>>>(enc, proj, s, i);
+    MSTR_LAUNCH_CHECK("attn_context_kernel");
+    rnn_gemm_kernel<1><<<dim3(4 * AT_H / AT_BLOCK, m_tiles), AT_THREADS, AT_SMEM_BYTES, st>>>(tmXH[i & 1], tmCat, s, i,
+                                                                                           2 * AT_H / 64);
+    MSTR_LAUNCH_CHECK("rnn_gemm_kernel<cell>");
+  }
+  return MSTR_OK;
+}

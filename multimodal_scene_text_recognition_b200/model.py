@@ -96,10 +96,16 @@ class Model(nn.Module):
         # Encode (model.py:100)
         bf16 = config.PRECISION == 'bf16'
         enc0 = self.encoder[0].forward_features(visual, want_f32=not bf16, want_act=bf16)
-        enc1 = self.encoder[1].forward_features(enc0, want_f32=True, want_act=bf16)
-        enc1_act, enc1_f32 = (enc1 if bf16 else (None, enc1))     # ops.linear returns (bf16, f32)
+        # the tensor-core decoder consumes the bf16 encoder output only; the f32 copy is produced for the
+        # fp32 SIMT decoder and for stage dumps
+        need_f32 = (not bf16) or (not config.RNN_TENSOR_CORES) or stages is not None
+        enc1 = self.encoder[1].forward_features(enc0, want_f32=need_f32, want_act=bf16)
+        if bf16:
+            enc1_act, enc1_f32 = enc1 if need_f32 else (enc1, None)     # ops.linear returns (bf16, f32)
+        else:
+            enc1_act, enc1_f32 = None, enc1
         # Decode (model.py:105)
-        out = self.decoder.decode(enc1_f32, text, is_train, enc_act=enc1_act)
+        out = self.decoder.decode(enc1_f32 if enc1_f32 is not None else enc1_act, text, is_train, enc_act=enc1_act)
         if stages is not None:
             stages.update(rectified=rect, features=feat, visual=visual, semantics=semantics,
                           enc0=enc0, enc1=enc1_f32)

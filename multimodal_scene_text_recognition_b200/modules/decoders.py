@@ -30,7 +30,7 @@ def _cell_pack(cell: "AttentionCell", generator: nn.Linear, precision: str):
     def build():
         f = lambda t: t.detach().float().contiguous()
         w_ih = cell.rnn.weight_ih.detach().float()
-        return {
+        pk = {
             "w_i2h": f(cell.i2h.weight).to(act_dtype(precision)).contiguous(),
             "w_h2h": f(cell.h2h.weight), "b_h2h": f(cell.h2h.bias),
             "w_score": f(cell.score.weight).view(-1).contiguous(),
@@ -40,6 +40,13 @@ def _cell_pack(cell: "AttentionCell", generator: nn.Linear, precision: str):
             "bias": (cell.rnn.bias_ih.detach().float() + cell.rnn.bias_hh.detach().float()).contiguous(),
             "w_gen": f(generator.weight), "b_gen": f(generator.bias),
         }
+        if precision == 'bf16':   # operands of the tensor-core decode (mstr_attn_decode_bf16)
+            head = torch.zeros((384, hd), device=w_ih.device, dtype=torch.float32)
+            head[:hd] = cell.h2h.weight.detach().float()
+            head[hd:hd + generator.weight.shape[0]] = generator.weight.detach().float()
+            pk["w_head"] = head.to(torch.bfloat16).contiguous()
+            pk["w_cat"] = ops.pack_gate_rows_bf16(torch.cat([w_ih[:, :hd], cell.rnn.weight_hh.detach().float()], 1))
+        return pk
     return cached(cell, ("attn", precision, id(generator)), src, build)
 
 
@@ -71,16 +78,25 @@ class Attention(nn.Module):
         require_inference(encoder_output)
         precision = config.PRECISION
         num_steps = config.MAX_TEXT_LENGTH + 1          # decoders.py:34, read at call time
-        enc = ops.cast(encoder_output.contiguous(), torch.float32)
         pk = _cell_pack(self.attention_cell, self.generator, precision)
+        tokens = None
+        if is_train:
+            if text is None:
+                raise ValueError("is_train=True needs the teacher-forcing text (decoders.py:41-50)")
+            tokens = text.to(device=encoder_output.device, dtype=torch.int64).contiguous()
+        if (precision == 'bf16' and config.RNN_TENSOR_CORES and self.hidden_size == 256
+                and encoder_output.shape[1] <= 96 and self.num_classes <= 128):
+            enc_b = enc_act if enc_act is not None else ops.cast(encoder_output.contiguous(), torch.bfloat16)
+            proj_b = ops.linear(enc_b, pk["w_i2h"], None, want_f32=False, want_bf16=True)
+            return ops.attn_decode_bf16(enc_b, proj_b, pk, num_steps, tokens,
+                                        early_exit=(not is_train) and bool(config.DECODER_EARLY_EXIT),
+                                        want_alpha=want_alpha)
+        enc = ops.cast(encoder_output.contiguous(), torch.float32)
         if precision == 'bf16' and enc_act is not None:
             proj = ops.linear(enc_act, pk["w_i2h"], None, want_f32=True, want_bf16=False)
         else:
             proj = _project(enc, pk, precision)
         if is_train:
-            if text is None:
-                raise ValueError("is_train=True needs the teacher-forcing text (decoders.py:41-50)")
-            tokens = text.to(device=enc.device, dtype=torch.int64).contiguous()
             return ops.attn_decode(enc, proj, pk, num_steps, tokens, early_exit=False, want_alpha=want_alpha)
         return ops.attn_decode(enc, proj, pk, num_steps, None, early_exit=bool(config.DECODER_EARLY_EXIT),
                                want_alpha=want_alpha)

@@ -293,3 +293,38 @@ def attn_decode(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int,
                                      ptr(lengths), ptr(alpha), ptr(h_out), ptr(c_out),
                                      B, T, Hd, C, steps, int(early_exit), stream_ptr()), "mstr_attn_decode")
     return {"logits": logits, "ids": ids, "lengths": lengths, "alpha": alpha, "h": h_out, "c": c_out}
+
+
+def pack_gate_rows_bf16(w: torch.Tensor) -> torch.Tensor:
+    """[4H, K] f32 (gate-major rows i,f,g,o) -> bf16 with rows ordered (chunk of 32 units, gate, unit)."""
+    four_h, k = w.shape
+    hd = four_h // 4
+    assert four_h == 4 * hd and hd % 32 == 0
+    return w.reshape(4, hd // 32, 32, k).permute(1, 0, 2, 3).reshape(four_h, k).to(torch.bfloat16).contiguous()
+
+
+def attn_decode_bf16(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int, text: Optional[torch.Tensor],
+                     early_exit: bool, want_alpha: bool = False) -> dict:
+    """Tensor-core greedy / teacher-forced attention decode (bf16 mode).  enc, proj [B,T,H] bf16;
+    ``packed`` holds w_head, w_cat (bf16) and b_h2h, b_gen, w_score, w_tok, bias (f32)."""
+    _req(enc, "enc", torch.bfloat16); _req(proj, "proj", torch.bfloat16); _req(text, "text", torch.int64)
+    B, T, Hd = enc.shape
+    C = packed["w_tok"].shape[0]
+    dev = enc.device
+    logits = torch.zeros((B, steps, C), device=dev, dtype=torch.float32)
+    ids = torch.empty((B, steps), device=dev, dtype=torch.int32)
+    lengths = torch.empty((B,), device=dev, dtype=torch.int32)
+    alpha = torch.zeros((B, steps, T), device=dev, dtype=torch.float32) if want_alpha else None
+    ws = torch.empty((int(lib().mstr_attn_decode_bf16_workspace_bytes(B, Hd)),), device=dev, dtype=torch.uint8)
+    if text is not None:
+        assert text.shape[0] == B and text.shape[1] >= steps
+        if text.shape[1] != steps:
+            text = text[:, :steps].contiguous()
+    macs = Hd * Hd + 2 * T * Hd + 4 * Hd * 2 * Hd + C * Hd
+    with _timed("attn_decode_bf16", 2.0 * B * steps * macs):
+        check(lib().mstr_attn_decode_bf16(ptr(enc), ptr(proj), ptr(packed["w_head"]), ptr(packed["b_h2h"]),
+                                          ptr(packed["b_gen"]), ptr(packed["w_score"]), ptr(packed["w_cat"]),
+                                          ptr(packed["w_tok"]), ptr(packed["bias"]), ptr(text), ptr(ws), ptr(logits),
+                                          ptr(ids), ptr(lengths), ptr(alpha), B, T, Hd, C, steps, int(early_exit),
+                                          stream_ptr()), "mstr_attn_decode_bf16")
+    return {"logits": logits, "ids": ids, "lengths": lengths, "alpha": alpha, "h": None, "c": None}

@@ -201,6 +201,10 @@ def rare_fiducial_bias(F: int) -> np.ndarray:
     return np.concatenate([top, bot], 0).reshape(-1)
 
 
+# Gains over PyTorch's default U(-1/sqrt(fan), 1/sqrt(fan)) for the sequence model (see _sequence_gain).
+SEQUENCE_GAINS = {"enc_w_ih": 3.0, "enc_linear": 8.0, "dec_w_ih": 3.0, "dec_i2h": 8.0, "dec_score": 8.0}
+
+
 def _sequence_gain(name: str) -> float:
     """Gains over PyTorch's default U(-1/sqrt(fan), 1/sqrt(fan)) for the sequence model.
 
@@ -209,14 +213,17 @@ def _sequence_gain(name: str) -> float:
     modules (B=128, seed 999/123): 59/128 distinct strings, 29 distinct characters, [s] emitted
     by 23 % of the crops, median top-1/top-2 margin 0.36 x logit std.
     """
+    g = SEQUENCE_GAINS
     if name.startswith("encoder.") and "weight_ih" in name:
-        return 3.0
+        return g["enc_w_ih"]
     if name.startswith("encoder.") and name.endswith("linear.weight"):
-        return 8.0
+        return g["enc_linear"]
     if name == "decoder.attention_cell.rnn.weight_ih":
-        return 3.0
-    if name in ("decoder.attention_cell.i2h.weight", "decoder.attention_cell.score.weight"):
-        return 8.0
+        return g["dec_w_ih"]
+    if name == "decoder.attention_cell.i2h.weight":
+        return g["dec_i2h"]
+    if name == "decoder.attention_cell.score.weight":
+        return g["dec_score"]
     return 1.0
 
 

@@ -327,12 +327,16 @@ def attention_decode(enc, sd, steps, num_classes, text=None, dt=np.float32, quan
     enc = enc.astype(dt)
     B, T, Hd = enc.shape
     w_i2h = _q(sd[p + "i2h.weight"].astype(dt), quant)
-    proj = _q(enc, quant) @ w_i2h.T                               # :81 (loop invariant)
-    w_h2h = sd[p + "h2h.weight"].astype(dt); b_h2h = sd[p + "h2h.bias"].astype(dt)
+    # quant='bf16' restates the tensor-core decode of the CUDA bf16 mode: enc, proj, h and ctx are bf16
+    # operands of the GEMMs (weights bf16 as well), accumulation / cell state / logits stay fp32
+    enc = _q(enc, quant)
+    proj = _q(enc @ w_i2h.T, quant)                               # :81 (loop invariant)
+    w_h2h = _q(sd[p + "h2h.weight"].astype(dt), quant); b_h2h = sd[p + "h2h.bias"].astype(dt)
     w_score = sd[p + "score.weight"].astype(dt)[0]
-    w_ih = sd[p + "rnn.weight_ih"].astype(dt); w_hh = sd[p + "rnn.weight_hh"].astype(dt)
+    w_ih = sd[p + "rnn.weight_ih"].astype(dt); w_hh = _q(sd[p + "rnn.weight_hh"].astype(dt), quant)
+    w_ctx = _q(w_ih[:, :Hd], quant)
     bias = sd[p + "rnn.bias_ih"].astype(dt) + sd[p + "rnn.bias_hh"].astype(dt)
-    w_gen = sd["decoder.generator.weight"].astype(dt); b_gen = sd["decoder.generator.bias"].astype(dt)
+    w_gen = _q(sd["decoder.generator.weight"].astype(dt), quant); b_gen = sd["decoder.generator.bias"].astype(dt)
     h = np.zeros((B, Hd), dt); c = np.zeros((B, Hd), dt)
     tok = np.zeros(B, np.int64)                                   # [GO]
     logits = np.zeros((B, steps, num_classes), dt)
@@ -340,16 +344,17 @@ def attention_decode(enc, sd, steps, num_classes, text=None, dt=np.float32, quan
     for i in range(steps):
         if text is not None:
             tok = text[:, i].astype(np.int64)
-        hp = h @ w_h2h.T + b_h2h                                  # :82
+        hq = _q(h, quant)
+        hp = hq @ w_h2h.T + b_h2h                                 # :82
         e = np.tanh(proj + hp[:, None, :]) @ w_score              # :85  [B,T]
         alpha = softmax(e, axis=1)                                # :87
         ctx = np.einsum("bt,btc->bc", alpha, enc)                 # :88
-        g = ctx @ w_ih[:, :Hd].T + w_ih[:, Hd + tok].T + h @ w_hh.T + bias   # :90,:99 (one-hot = column gather)
+        g = _q(ctx, quant) @ w_ctx.T + w_ih[:, Hd + tok].T + hq @ w_hh.T + bias   # :90,:99 (one-hot = column gather)
         ii = sigmoid(g[:, :Hd]); f = sigmoid(g[:, Hd:2 * Hd])
         gg = np.tanh(g[:, 2 * Hd:3 * Hd]); o = sigmoid(g[:, 3 * Hd:])
         c = f * c + ii * gg
         h = o * np.tanh(c)
-        step_logits = h @ w_gen.T + b_gen                         # :59 / :50
+        step_logits = _q(h, quant) @ w_gen.T + b_gen              # :59 / :50
         logits[:, i] = step_logits
         alphas[:, i] = alpha
         if text is None:

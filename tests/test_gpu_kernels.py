@@ -320,6 +320,68 @@ def test_attn_decode_long_sequence(sd_cfg_a):
     assert_close(host(res["logits"]), ref, 2e-4, "long-sequence logits")
 
 
+def _decoder_pack_bf16(sd, Hd=256):
+    p = "decoder.attention_cell."
+    t = lambda k: torch.from_numpy(np.ascontiguousarray(sd[k])).to(DEV)
+    w_ih = t(p + "rnn.weight_ih")
+    C = sd["decoder.generator.weight"].shape[0]
+    head = torch.zeros((384, Hd), device=DEV)
+    head[:Hd] = t(p + "h2h.weight")
+    head[Hd:Hd + C] = t("decoder.generator.weight")
+    return {"w_head": head.to(torch.bfloat16).contiguous(),
+            "w_cat": ops.pack_gate_rows_bf16(torch.cat([w_ih[:, :Hd], t(p + "rnn.weight_hh")], 1)),
+            "w_tok": w_ih[:, Hd:].t().contiguous(), "bias": (t(p + "rnn.bias_ih") + t(p + "rnn.bias_hh")).contiguous(),
+            "b_h2h": t(p + "h2h.bias"), "b_gen": t("decoder.generator.bias"),
+            "w_score": t(p + "score.weight").view(-1).contiguous()}
+
+
+@pytest.mark.parametrize("B,T,steps", [(37, 26, 26), (130, 26, 26), (5, 65, 51)])
+def test_attn_decode_bf16_tensor_cores(sd_cfg_a, B, T, steps):
+    """Tensor-core decode vs the oracle with bf16 rounding at the same operands.  Teacher-forced logits
+    are compared tightly (no feedback); greedy ids must agree wherever the oracle's top-2 margin is
+    larger than the bf16-level logit error."""
+    Hd = 256
+    enc = orc.round_bf16((rng(18).standard_normal((B, T, Hd)) * 0.5).astype(np.float32))
+    w_i2h = orc.round_bf16(sd_cfg_a["decoder.attention_cell.i2h.weight"])
+    proj = orc.round_bf16((enc.astype(np.float64) @ w_i2h.astype(np.float64).T).astype(np.float32))
+    pk = _decoder_pack_bf16(sd_cfg_a)
+    bf = torch.bfloat16
+    text = rng(19).integers(0, 97, (B, steps)).astype(np.int64)
+    text[:, 0] = 0
+    ref_tf, ref_alpha = orc.attention_decode(enc, sd_cfg_a, steps, 97, text=text, dt=np.float64, quant="bf16",
+                                             return_alpha=True)
+    res = ops.attn_decode_bf16(dev(enc, bf), dev(proj, bf), pk, steps, dev(text), early_exit=False, want_alpha=True)
+    torch.cuda.synchronize()
+    # bf16 rounding of h / ctx flips (1 ulp = 0.4 %) decorrelate the two sides: ~1e-2 of the logit range
+    assert_close(host(res["logits"]), ref_tf, 3e-2, "teacher-forced logits (tensor cores)")
+    assert_close(host(res["alpha"]), ref_alpha, 3e-2, "attention weights (tensor cores)")
+    d = np.abs(host(res["logits"]).astype(np.float64) - ref_tf)
+    assert d.mean() < 3e-3 * np.abs(ref_tf).max(), "mean logit error %.3e" % d.mean()
+    # greedy, with and without early exit
+    ref = orc.attention_decode(enc, sd_cfg_a, steps, 97, dt=np.float64, quant="bf16")
+    full = ops.attn_decode_bf16(dev(enc, bf), dev(proj, bf), pk, steps, None, early_exit=False)
+    early = ops.attn_decode_bf16(dev(enc, bf), dev(proj, bf), pk, steps, None, early_exit=True)
+    torch.cuda.synchronize()
+    ids, ref_ids = host(full["ids"]), ref.argmax(2)
+    srt = np.sort(ref, axis=2)
+    margin = srt[:, :, -1] - srt[:, :, -2]
+    # compare step by step until the first disagreement; a disagreement is only legitimate at a thin margin
+    for b in range(B):
+        neq = np.nonzero(ids[b] != ref_ids[b])[0]
+        if len(neq):
+            k = neq[0]
+            assert margin[b, k] < 5e-2 * np.abs(ref).max(), "crop %d step %d differs at margin %.3e" % (b, k, margin[b, k])
+    assert (ids == ref_ids).all(axis=1).mean() > 0.7
+    L = host(full["lengths"])
+    first = np.where((ids == 1).any(1), (ids == 1).argmax(1), steps)
+    assert np.array_equal(L, first) and np.array_equal(host(early["lengths"]), L)
+    fl, el, ei = host(full["logits"]), host(early["logits"]), host(early["ids"])
+    for b in range(B):
+        k = min(int(L[b]) + 1, steps)
+        assert np.array_equal(el[b, :k], fl[b, :k]) and np.array_equal(ei[b, :k], ids[b, :k])
+        assert not el[b, k:].any() and not ei[b, k:].any()
+
+
 # ------------------------------------------------------------------------------------------------
 # error behaviour of the boundary
 # ------------------------------------------------------------------------------------------------

@@ -22,7 +22,8 @@ run conv_tc    300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu
 run conv_tc2   300 $PT tests/test_gpu_kernels.py -k "many_tiles"
 run small      300 $PT tests/test_gpu_kernels.py -k "maxpool or mean or embed or errors"
 run bilstm     300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "bilstm"
-run attn       300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "attn"
+run attn       300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "attn and not bf16"
+run attn_tc    300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "attn_decode_bf16"
 run model_fp32 600 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_model.py -k "fp32 or scene"
 run model_bf16 600 python -m pytest -q -m gpu -p no:cacheprovider -s tests/test_gpu_model.py -k "bf16"
 run smoke      300 python -c "import __graft_entry__ as g; g.smoke()"

@@ -193,7 +193,7 @@ def run_ours(args):
 
     config.PRECISION = args.precision
     config.DECODER_EARLY_EXIT = False      # every step and logit the reference computes
-    config.TPS_GRID = "folded"
+    config.TPS_GRID = "reference"
     config.SEMANTIC_VECTOR = "overlap"
     B = args.batch
     sd = synth.make_state_dict(WEIGHT_SEED)

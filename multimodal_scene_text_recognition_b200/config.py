@@ -50,7 +50,7 @@ POST_DECODER_MLP = False
 PRECISION = 'bf16'
 # 'folded'    : grid = (P_hat inv_delta_C[:, :F]) C'  with the constant folded in fp64 (more accurate)
 # 'reference' : T = inv_delta_C [C';0] then P' = P_hat T in fp32, the order of transformation.py:161-162
-TPS_GRID = 'folded'
+TPS_GRID = 'reference'
 # stop decoding a crop once it has emitted [s]; logits after [s] stay zero.  The reference always
 # runs MAX_TEXT_LENGTH+1 steps (decoders.py:34) but its callers cut at the first [s]
 # (training_functions.py:188-189).  False reproduces every logit of the reference.

@@ -17,6 +17,8 @@
 //   warps 2..5  epilogue      : tcgen05.ld 32x32b.x32 -> folded BN, residual, ReLU -> bf16/f32 NHWC stores,
 //                               overlapped with the next tile's MMAs through the second TMEM buffer
 // Roofline: tensor pipe.  Algorithmic FLOPs = 2 * M * C_out * R*S*C_in per launch.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace mstr {
@@ -31,6 +33,7 @@ struct TcParams {
   int P, Q, sh, sw, ph, pw;
   int im2col;               // 1: A via im2col map; 0: A via 2-D tiled map [M][K]
   int relu;
+  int prefetch;             // L2-prefetch the next tile's A rows (MSTR_CONV_PREFETCH=0 disables it)
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
@@ -110,9 +113,26 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           cw = q * p.sw - p.pw;
           chh = pp * p.sh - p.ph;
         }
+        // While this tile streams, pull the A rows of this CTA's NEXT tile from HBM into L2 (the taps of
+        // a tile re-read almost the same pixels, so one tap's worth of prefetch covers the tile): the
+        // first k-blocks of a tile otherwise expose DRAM latency that the 4-stage ring cannot hide.
+        const int next_tile = tile + gridDim.x;
+        const bool do_prefetch = p.prefetch && next_tile < num_tiles && (next_tile % p.num_n_tiles) == 0;
+        int kb_index = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int r = tap / p.S, s = tap - r * p.S;
-          for (int cc = 0; cc < p.cin_chunks; ++cc) {
+          for (int cc = 0; cc < p.cin_chunks; ++cc, ++kb_index) {
+            if (do_prefetch && kb_index == 2) {
+              const int nm0 = (next_tile / p.num_n_tiles) * TC_BLOCK_M;
+              if (p.im2col) {
+                const int nq = nm0 % p.Q, npp = (nm0 / p.Q) % p.P, nn = nm0 / (p.Q * p.P);
+                for (int c2 = 0; c2 < p.cin_chunks; ++c2)
+                  tma_prefetch_im2col_4d(&tmA, c2 * BLOCK_K, nq * p.sw - p.pw, npp * p.sh - p.ph, nn,
+                                         (uint16_t)((p.S - 1) / 2), (uint16_t)((p.taps / p.S - 1) / 2));
+              } else {
+                for (int c2 = 0; c2 < p.cin_chunks; ++c2) tma_prefetch_2d(&tmA, c2 * BLOCK_K, nm0);
+              }
+            }
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             if (p.im2col)
@@ -299,6 +319,8 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   p.sh = stride_h; p.sw = stride_w; p.ph = pad_h; p.pw = pad_w;
   p.im2col = !(R == 1 && S == 1 && stride_h == 1 && stride_w == 1 && pad_h == 0 && pad_w == 0);
   p.relu = relu;
+  static const int prefetch_on = [] { const char* e = getenv("MSTR_CONV_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.prefetch = prefetch_on;
   p.scale = scale; p.shift = shift;
   p.residual = (const __nv_bfloat16*)residual;
   p.out_bf16 = (__nv_bfloat16*)out_bf16;

@@ -33,7 +33,7 @@ struct TcParams {
   int P, Q, sh, sw, ph, pw;
   int im2col;               // 1: A via im2col map; 0: A via 2-D tiled map [M][K]
   int relu;
-  int prefetch;             // L2-prefetch the next tile's A rows (MSTR_CONV_PREFETCH=0 disables it)
+  int prefetch;             // L2-prefetch the next tile's A rows (off: measured -3 %; MSTR_CONV_PREFETCH=1 enables)
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
@@ -282,6 +282,11 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
   return MSTR_OK;
 }
 
+// conv_tc2.cu: CTA-pair (cta_group::2) variant
+int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
+                        void* out_bf16, float* out_f32, int B, int H, int W, int C_in, int C_out, int R, int S,
+                        int stride_h, int stride_w, int pad_h, int pad_w, int relu, cudaStream_t st);
+
 }  // namespace mstr
 
 extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const void* x, const void* w, const float* scale, const float* shift,
@@ -298,6 +303,14 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   MSTR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(residual) && aligned16(out_bf16) && aligned16(out_f32),
                MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: pointers must be 16-byte aligned");
   MSTR_REQUIRE(R <= 16 && S <= 16 && pad_h < 16 && pad_w < 16, MSTR_ERR_UNSUPPORTED, "mstr_conv_gemm_bf16: filter too large");
+  // CTA-pair kernel for the layers it supports (MSTR_CONV_2CTA=0 forces the single-CTA kernel)
+  static const int use_2cta = [] { const char* e = getenv("MSTR_CONV_2CTA"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (use_2cta && C_in % 64 == 0 && C_out % 128 == 0 && (int64_t)B * H * W < (1ll << 31) && sm_count() >= 2) {
+    const int64_t M2 = (int64_t)B * ((H + 2 * pad_h - R) / stride_h + 1) * ((W + 2 * pad_w - S) / stride_w + 1);
+    MSTR_REQUIRE(M2 > 0 && M2 < (1ll << 31), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad output size");
+    return conv_gemm_bf16_2cta(x, w, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,
+                               stride_w, pad_h, pad_w, relu, (cudaStream_t)stream);
+  }
   int rc = load_tma_encoders(g_enc);
   if (rc != MSTR_OK) return rc;
 
@@ -319,7 +332,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   p.sh = stride_h; p.sw = stride_w; p.ph = pad_h; p.pw = pad_w;
   p.im2col = !(R == 1 && S == 1 && stride_h == 1 && stride_w == 1 && pad_h == 0 && pad_w == 0);
   p.relu = relu;
-  static const int prefetch_on = [] { const char* e = getenv("MSTR_CONV_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
+  static const int prefetch_on = [] { const char* e = getenv("MSTR_CONV_PREFETCH"); return (e && e[0] == '1') ? 1 : 0; }();
   p.prefetch = prefetch_on;
   p.scale = scale; p.shift = shift;
   p.residual = (const __nv_bfloat16*)residual;

@@ -70,3 +70,31 @@ def require_inference(*tensors) -> None:
         raise RuntimeError(
             "the B200 kernels implement the inference forward only (SURVEY.md 8b): call under "
             "torch.no_grad() / model.eval(); autograd through them is not supported")
+
+
+def pack_conv_pixel_pairs(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, precision: str):
+    """3x3 / stride 1 / pad 1 convolution with few channels, re-expressed over horizontal PIXEL PAIRS.
+
+    NHWC [B,H,W,C] with even W is bit-for-bit the same memory as [B,H,W/2,2C]; a conv C_in -> C_out
+    becomes a conv 2*C_in -> 2*C_out over super-pixels whose 3x3 weights are the original taps placed
+    at (input sub-pixel, output sub-pixel) offsets, the other half structurally zero.  It doubles the
+    MMA work but turns a K-block of 32 channels / N = 64 tile (64-byte TMA rows, 64-column MMAs) into
+    64 channels / N = 128, which is what the tcgen05 pipeline is efficient at: conv0_2 (32 -> 64 at
+    32x100) went from 2.5 ms to the figure in profiles/.  Results are identical: every output is the
+    same sum of the same products (zeros add exactly).
+    -> (w [2*Cout, 3, 3, 2*Cin], scale [2*Cout], shift [2*Cout])
+    """
+    def build():
+        w = conv.weight.detach().float()                      # [Cout, Cin, 3, 3]
+        cout, cin = w.shape[:2]
+        wp = torch.zeros((2, cout, 3, 3, 2, cin), device=w.device, dtype=torch.float32)   # [po, co, r, s', pi, ci]
+        for po in range(2):
+            for sp in range(3):
+                for pi in range(2):
+                    s_tap = 2 * (sp - 1) + pi - po + 1          # original horizontal tap
+                    if 0 <= s_tap <= 2:
+                        wp[po, :, :, sp, pi, :] = w[:, :, :, s_tap].permute(0, 2, 1)
+        wp = wp.reshape(2 * cout, 3, 3, 2 * cin).to(act_dtype(precision)).contiguous()
+        scale, shift = fold_bn(bn)
+        return wp, scale.repeat(2).contiguous(), shift.repeat(2).contiguous()
+    return cached(conv, ('pairs', precision), [conv.weight] + bn_sources(bn), build)

@@ -62,3 +62,6 @@ CHECK_INPUTS = False
 # bf16 mode only: run the recurrent GEMMs of the BiLSTM / attention decoder on the tensor cores (h_t in
 # bf16, fp32 accumulation and cell state, tanh.approx gates).  False keeps the fp32 SIMT recurrences.
 RNN_TENSOR_CORES = True
+# bf16 mode only: run the 32-channel 3x3 convolution (conv0_2) over horizontal pixel pairs
+# (_pack.pack_conv_pixel_pairs): identical results, better tensor-core tile shapes.
+CONV_PIXEL_PAIRS = True

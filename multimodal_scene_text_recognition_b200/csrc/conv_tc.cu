@@ -303,9 +303,10 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   MSTR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(residual) && aligned16(out_bf16) && aligned16(out_f32),
                MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: pointers must be 16-byte aligned");
   MSTR_REQUIRE(R <= 16 && S <= 16 && pad_h < 16 && pad_w < 16, MSTR_ERR_UNSUPPORTED, "mstr_conv_gemm_bf16: filter too large");
-  // CTA-pair kernel for the layers it supports (MSTR_CONV_2CTA=0 forces the single-CTA kernel)
+  // CTA-pair kernel for C_out % 256 == 0 (measured: +9 % on the 512->512 layers, -8 % on C_out = 128 layers,
+  // which therefore stay on the single-CTA kernel); MSTR_CONV_2CTA=0 forces the single-CTA kernel
   static const int use_2cta = [] { const char* e = getenv("MSTR_CONV_2CTA"); return (e && e[0] == '0') ? 0 : 1; }();
-  if (use_2cta && C_in % 64 == 0 && C_out % 128 == 0 && (int64_t)B * H * W < (1ll << 31) && sm_count() >= 2) {
+  if (use_2cta && C_in % 64 == 0 && C_out % 256 == 0 && (int64_t)B * H * W < (1ll << 31) && sm_count() >= 2) {
     const int64_t M2 = (int64_t)B * ((H + 2 * pad_h - R) / stride_h + 1) * ((W + 2 * pad_w - S) / stride_w + 1);
     MSTR_REQUIRE(M2 > 0 && M2 < (1ll << 31), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad output size");
     return conv_gemm_bf16_2cta(x, w, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,

@@ -89,7 +89,8 @@ class Model(nn.Module):
         # Feature extraction (model.py:91-93): NHWC result; permute + AdaptiveAvgPool2d((None,1)) +
         # squeeze is the mean over H of the NHWC tensor
         feat = self.FeatureExtraction.forward_nhwc(rect)
-        visual = ops.mean_h(feat)                                   # [B, W', C] activation dtype
+        # [B, W', C] activation dtype; with H' == 1 (the reference geometry) the mean is the tensor itself
+        visual = feat.view(feat.shape[0], feat.shape[2], feat.shape[3]) if feat.shape[1] == 1 else ops.mean_h(feat)
         # Semantic vectors (model.py:96); computed because the reference computes them - the LSTM
         # encoder / attention decoder never read them (decoders.py:79-101)
         semantics = self.get_semantic_vectors(overlap, scene, ious)

@@ -20,10 +20,17 @@ import torch
 import torch.nn as nn
 
 from .. import config, ops
-from .._pack import act_dtype, pack_conv, pack_first_conv, require_inference
+from .._pack import act_dtype, pack_conv, pack_conv_pixel_pairs, pack_first_conv, require_inference
 
 
 def _conv_bn(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, precision: str, relu: bool, residual=None, **kw):
+    B, H, W, C = x.shape
+    if (precision == 'bf16' and config.CONV_PIXEL_PAIRS and C == 32 and W % 2 == 0 and residual is None
+            and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (1, 1)):
+        # 32-channel input (conv0_2): run it over horizontal pixel pairs (see _pack.pack_conv_pixel_pairs)
+        w, scale, shift = pack_conv_pixel_pairs(conv, bn, precision)
+        out = ops.conv_gemm(x.view(B, H, W // 2, 2 * C), w, scale, shift, None, stride=(1, 1), pad=(1, 1), relu=relu, **kw)
+        return out.view(B, H, W, conv.out_channels)
     w, scale, shift = pack_conv(conv, bn, precision)
     return ops.conv_gemm(x, w, scale, shift, residual, stride=tuple(conv.stride), pad=tuple(conv.padding),
                          relu=relu, **kw)

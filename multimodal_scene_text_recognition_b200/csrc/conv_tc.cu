@@ -287,6 +287,11 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
                         void* out_bf16, float* out_f32, int B, int H, int W, int C_in, int C_out, int R, int S,
                         int stride_h, int stride_w, int pad_h, int pad_w, int relu, cudaStream_t st);
 
+// conv_tc_swap.cu: operand-swapped variant for C_out = 128 layers
+int conv_gemm_bf16_swap(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
+                        void* out_bf16, int B, int H, int W, int C_in, int C_out, int R, int S, int stride_h,
+                        int stride_w, int pad_h, int pad_w, int relu, cudaStream_t st);
+
 }  // namespace mstr
 
 extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const void* x, const void* w, const float* scale, const float* shift,
@@ -311,6 +316,14 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
     MSTR_REQUIRE(M2 > 0 && M2 < (1ll << 31), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad output size");
     return conv_gemm_bf16_2cta(x, w, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,
                                stride_w, pad_h, pad_w, relu, (cudaStream_t)stream);
+  }
+  // operand-swapped kernel for C_out = 128-type layers with bf16 output (MSTR_CONV_SWAP=0 disables it)
+  static const int use_swap = [] { const char* e = getenv("MSTR_CONV_SWAP"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (use_swap && C_in % 64 == 0 && C_out % 128 == 0 && C_out % 256 != 0 && out_bf16 && !out_f32) {
+    const int64_t M2 = (int64_t)B * ((H + 2 * pad_h - R) / stride_h + 1) * ((W + 2 * pad_w - S) / stride_w + 1);
+    MSTR_REQUIRE(M2 > 0 && M2 < (1ll << 31), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad output size");
+    return conv_gemm_bf16_swap(x, w, scale, shift, residual, out_bf16, B, H, W, C_in, C_out, R, S, stride_h, stride_w,
+                               pad_h, pad_w, relu, (cudaStream_t)stream);
   }
   int rc = load_tma_encoders(g_enc);
   if (rc != MSTR_OK) return rc;

@@ -148,6 +148,33 @@ def test_conv_gemm_bf16_tcgen05(case):
     assert np.array_equal(host(out_b), orc.round_bf16(host(out_f))), "bf16 output is not the rounded f32 output"
 
 
+SWAP_CASES = [
+    (5, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), False, True),     # layer1 conv1 geometry, M = 4000 (ragged 256-tile)
+    (3, 16, 50, 128, 128, 3, 3, (1, 1), (1, 1), True, True),     # 128 -> 128 with residual
+    (5, 16, 50, 64, 128, 1, 1, (1, 1), (0, 0), False, False),    # 1x1 downsample
+    (2, 8, 25, 64, 384, 3, 3, (1, 1), (1, 1), True, False),      # three 128-channel tiles
+    (40, 32, 50, 64, 128, 3, 3, (1, 1), (1, 1), False, True),    # conv0_2 over pixel pairs: M = 64000 (250 tiles)
+]
+
+
+@pytest.mark.parametrize("case", SWAP_CASES)
+def test_conv_gemm_bf16_swapped_operands(case):
+    """C_out = 128-type layers with bf16-only output take the operand-swapped kernel (conv_tc_swap.cu)."""
+    stride, pad, relu = case[7], case[8], case[10]
+    x, w, scale, shift, res = _conv_inputs(case, 21, True)
+    ref = _conv_ref(x, w, scale, shift, res, stride, pad, relu)
+    bf = torch.bfloat16
+    out_b = ops.conv_gemm(dev(x, bf), dev(w, bf), dev(scale), dev(shift), None if res is None else dev(res, bf),
+                          stride=stride, pad=pad, relu=relu, want_f32=False, want_bf16=True)
+    torch.cuda.synchronize()
+    got = host(out_b).astype(np.float64)
+    # the bf16 result is the rounding of an fp32 value within ~1e-5 of ref: allow one bf16 ulp
+    tol = np.maximum(np.abs(ref), 1e-3) * 2.0 ** -7
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), "%d of %d outputs off by more than a bf16 ulp (max err %.3e)" % (
+        bad.sum(), bad.size, np.abs(got - ref).max())
+
+
 def test_conv_gemm_bf16_many_tiles():
     """More M tiles than SMs: exercises the persistent tile loop, the smem ring wrap-around and both
     TMEM accumulator buffers.  M = 64*16*50 = 51200 -> 400 M tiles x 1 N tile."""

@@ -15,7 +15,8 @@
 //   gates [128 x 128] fp32 accumulators are double buffered in TMEM columns 256..511, so the MMAs
 //         of chunk c+1 overlap the gate math of chunk c.
 // Per step: 8 chunks x 4 k-blocks x 4 tcgen05.mma (128x128x16).  Warp roles: warp 0 = TMA producer,
-// warp 1 = MMA issuer, warps 2..9 = epilogue (two warps per TMEM lane quarter, 16 units each).
+// warp 1 = MMA issuer, warps 2..17 = epilogue (four warps per TMEM lane quarter, 8 units each: 16 warps
+// hide the latency of the gates_x loads and TMEM round trips better than 8 did, 0.65 -> see profiles/).
 // The gate non-linearities use tanh.approx (1 MUFU each; sigmoid(x) = 0.5 tanh(x/2) + 0.5), which is
 // what bounds the kernel: 5 MUFU per hidden unit per crop per step at 16 MUFU/clk/SM.
 #include "tc_common.cuh"
@@ -31,8 +32,8 @@ constexpr int LT_STAGES = 4;
 constexpr int LT_W_TILE_BYTES = 128 * 128;         // [128 gate rows][64 k] bf16
 constexpr int LT_H_KB_BYTES = LT_M * 128;          // one k-block of h: 128 rows x 128 bytes
 constexpr int LT_H_BUF_BYTES = LT_KB * LT_H_KB_BYTES;  // 64 KB
-constexpr int LT_THREADS = 320;
-constexpr int LT_EPI_WARPS = 8;
+constexpr int LT_THREADS = 576;
+constexpr int LT_EPI_WARPS = 16;
 constexpr int LT_SMEM_BYTES = 1024 + 2 * LT_H_BUF_BYTES + LT_STAGES * LT_W_TILE_BYTES + 256;
 constexpr uint32_t LT_ACC_COL0 = 256;  // TMEM: [0,256) cell state, [256,384) / [384,512) accumulators
 
@@ -68,7 +69,7 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
     prefetch_tensormap(&tmW);
     for (int i = 0; i < LT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], LT_EPI_WARPS); }
-    for (int i = 0; i < LT_KB; ++i) mbar_init(&hready_bar[i], 2 * LT_EPI_WARPS);  // 2 chunks x 8 warps per k-block
+    for (int i = 0; i < LT_KB; ++i) mbar_init(&hready_bar[i], 2 * LT_EPI_WARPS);  // 2 chunks x 16 warps per k-block
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -126,9 +127,9 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
     }
   } else {
     // ===================== epilogue: gate math, c in TMEM, h -> smem (next A operand) + global ===========
-    const int ew = warp - 2;                 // 0..7
+    const int ew = warp - 2;                 // 0..15
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int hf = ew >> 2;                  // which 16 of the chunk's 32 units
+    const int uq = ew >> 2;                  // which 8 of the chunk's 32 units
     const int row = quarter * 32 + lane;     // crop row within the tile
     const int crop = crop0 + row;
     const bool valid = crop < p.B;
@@ -141,64 +142,52 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
       __nv_bfloat16* out_row = p.out + ((size_t)(valid ? crop : 0) * T + t) * (2 * LT_H) + dir * LT_H;
       for (int chunk = 0; chunk < LT_CHUNKS; ++chunk, ++n) {
         const int buf = n & 1;
-        const int unit0 = chunk * LT_CHUNK_UNITS + hf * 16;      // first of this thread's 16 hidden units
+        const int unit0 = chunk * LT_CHUNK_UNITS + uq * 8;       // first of this thread's 8 hidden units
         // input-projection gates for these units: issued before waiting for the MMA
-        float4 gx[4][4];
+        float4 gx[4][2];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
+          for (int v = 0; v < 2; ++v)
             gx[g][v] = valid ? __ldg(reinterpret_cast<const float4*>(gx_row + g * LT_H + unit0) + v)
                              : make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_wait(&tfull_bar[buf], (n >> 1) & 1);
         tc_fence_after();
-        const uint32_t acc_addr = lane_addr + LT_ACC_COL0 + (uint32_t)(buf * 128 + hf * 16);
-        uint32_t hpk[8];                                       // 16 bf16 h values
+        const uint32_t acc_addr = lane_addr + LT_ACC_COL0 + (uint32_t)(buf * 128 + uq * 8);
+        uint32_t a[4][8], cst[8];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {                 // 8 units at a time
-          uint32_t a[4][8], cst[8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld8(acc_addr + (uint32_t)(g * 32 + half * 8), a[g]);
-          if (step > 0) tmem_ld8(lane_addr + (uint32_t)(unit0 + half * 8), cst);
-          tmem_ld_wait();
-          float hv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int v = half * 2 + (j >> 2);
-            const float gi = reinterpret_cast<const float*>(&gx[0][v])[j & 3] + __uint_as_float(a[0][j]);
-            const float gf = reinterpret_cast<const float*>(&gx[1][v])[j & 3] + __uint_as_float(a[1][j]);
-            const float gg = reinterpret_cast<const float*>(&gx[2][v])[j & 3] + __uint_as_float(a[2][j]);
-            const float go = reinterpret_cast<const float*>(&gx[3][v])[j & 3] + __uint_as_float(a[3][j]);
-            const float c_prev = step > 0 ? __uint_as_float(cst[j]) : 0.f;
-            const float c_new = fmaf(sigmoid_approx(gf), c_prev, sigmoid_approx(gi) * tanh_approx(gg));
-            cst[j] = __float_as_uint(c_new);
-            hv[j] = sigmoid_approx(go) * tanh_approx(c_new);
-          }
-          tmem_st8(lane_addr + (uint32_t)(unit0 + half * 8), cst);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) hpk[half * 4 + j] = pack_bf16x2(hv[2 * j], hv[2 * j + 1]);
-        }
-        // accumulator buffer drained: hand it back to the MMA warp
+        for (int g = 0; g < 4; ++g) tmem_ld8(acc_addr + (uint32_t)(g * 32), a[g]);
+        if (step > 0) tmem_ld8(lane_addr + (uint32_t)unit0, cst);
+        tmem_ld_wait();
+        // accumulator values are in registers: hand the buffer back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-        // h_{t+1}: two 16-byte chunks of row `row` in k-block unit0/64 (128B swizzle: chunk ^= row & 7)
-        {
-          const int kb = unit0 >> 6;
-          const int c0 = (unit0 & 63) >> 3;                    // 16-byte chunk index within the 128-byte row
-          uint8_t* base = h_next + kb * LT_H_KB_BYTES + row * 128;
-          *reinterpret_cast<uint4*>(base + (((c0) ^ (row & 7)) << 4)) = make_uint4(hpk[0], hpk[1], hpk[2], hpk[3]);
-          *reinterpret_cast<uint4*>(base + (((c0 + 1) ^ (row & 7)) << 4)) = make_uint4(hpk[4], hpk[5], hpk[6], hpk[7]);
-          if (valid) {
-            uint4* o = reinterpret_cast<uint4*>(out_row + unit0);
-            o[0] = make_uint4(hpk[0], hpk[1], hpk[2], hpk[3]);
-            o[1] = make_uint4(hpk[4], hpk[5], hpk[6], hpk[7]);
-          }
-          tmem_st_wait();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&hready_bar[kb]);
+        float hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int v = j >> 2;
+          const float gi = reinterpret_cast<const float*>(&gx[0][v])[j & 3] + __uint_as_float(a[0][j]);
+          const float gf = reinterpret_cast<const float*>(&gx[1][v])[j & 3] + __uint_as_float(a[1][j]);
+          const float gg = reinterpret_cast<const float*>(&gx[2][v])[j & 3] + __uint_as_float(a[2][j]);
+          const float go = reinterpret_cast<const float*>(&gx[3][v])[j & 3] + __uint_as_float(a[3][j]);
+          const float c_prev = step > 0 ? __uint_as_float(cst[j]) : 0.f;
+          const float c_new = fmaf(sigmoid_approx(gf), c_prev, sigmoid_approx(gi) * tanh_approx(gg));
+          cst[j] = __float_as_uint(c_new);
+          hv[j] = sigmoid_approx(go) * tanh_approx(c_new);
         }
+        tmem_st8(lane_addr + (uint32_t)unit0, cst);
+        const uint4 hpk = make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]),
+                                     pack_bf16x2(hv[6], hv[7]));
+        // h_{t+1}: one 16-byte chunk of row `row` in k-block unit0/64 (128B swizzle: chunk ^= row & 7)
+        const int kb = unit0 >> 6;
+        const int c0 = (unit0 & 63) >> 3;
+        *reinterpret_cast<uint4*>(h_next + kb * LT_H_KB_BYTES + row * 128 + ((c0 ^ (row & 7)) << 4)) = hpk;
+        if (valid) *reinterpret_cast<uint4*>(out_row + unit0) = hpk;
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hready_bar[kb]);
       }
     }
   }

@@ -317,8 +317,9 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
     return conv_gemm_bf16_2cta(x, w, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,
                                stride_w, pad_h, pad_w, relu, (cudaStream_t)stream);
   }
-  // operand-swapped kernel for C_out = 128-type layers with bf16 output (MSTR_CONV_SWAP=0 disables it)
-  static const int use_swap = [] { const char* e = getenv("MSTR_CONV_SWAP"); return (e && e[0] == '0') ? 0 : 1; }();
+  // operand-swapped kernel for C_out = 128-type layers with bf16 output.  Correct (tests) but measured SLOWER
+  // than the 128x128 kernel (epilogue-bound: 2-byte stores), so it is opt-in: MSTR_CONV_SWAP=1
+  static const int use_swap = [] { const char* e = getenv("MSTR_CONV_SWAP"); return (e && e[0] == '1') ? 1 : 0; }();
   if (use_swap && C_in % 64 == 0 && C_out % 128 == 0 && C_out % 256 != 0 && out_bf16 && !out_f32) {
     const int64_t M2 = (int64_t)B * ((H + 2 * pad_h - R) / stride_h + 1) * ((W + 2 * pad_w - S) / stride_w + 1);
     MSTR_REQUIRE(M2 > 0 && M2 < (1ll << 31), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad output size");

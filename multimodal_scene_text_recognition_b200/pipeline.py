@@ -1,0 +1,52 @@
+"""Host-side input pipeline: overlap the host->device copy of the next batch with the recognition of
+the current one.
+
+The reference feeds its model from a ``DataLoader`` and calls ``.to(device)`` on every tensor right
+before the forward (training_functions.py:166-176), so the copy sits on the critical path.  Here the
+copy of batch k+1 is enqueued on a dedicated CUDA stream while batch k runs; device buffers are double
+buffered and handed over with an event.  Used by ``bench.py``'s end-to-end measurement and usable by any
+caller of ``Model.recognize``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+
+class HostBatchPrefetcher:
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.depth = depth
+        self._slots: List[List[torch.Tensor]] = []
+        self._free: List[Optional[torch.cuda.Event]] = []
+        self._next = 0
+
+    def stage(self, host_tensors: Sequence[torch.Tensor]) -> Tuple[List[torch.Tensor], torch.cuda.Event, int]:
+        """Enqueue the H2D copies of one batch (pinned host tensors) on the copy stream.  Returns the
+        device tensors, the event the consumer stream must wait for before reading them, and the slot id
+        to hand to ``release`` once the consumer's work on them has been enqueued."""
+        for t in host_tensors:
+            if not t.is_pinned():
+                raise ValueError("HostBatchPrefetcher needs pinned host tensors (torch.Tensor.pin_memory())")
+        sid = self._next % self.depth
+        self._next += 1
+        if sid >= len(self._slots):
+            self._slots.append([torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_tensors])
+            self._free.append(None)
+        slot = self._slots[sid]
+        with torch.cuda.stream(self.stream):
+            if self._free[sid] is not None:          # do not overwrite a slot its last consumer may still read
+                self.stream.wait_event(self._free[sid])
+            for d, h in zip(slot, host_tensors):
+                d.copy_(h, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        return slot, ready, sid
+
+    def release(self, sid: int) -> None:
+        """Call after enqueuing the consumer's work on slot ``sid`` (on the current stream)."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._free[sid] = ev

@@ -159,7 +159,8 @@ SWAP_CASES = [
 
 @pytest.mark.parametrize("case", SWAP_CASES)
 def test_conv_gemm_bf16_swapped_operands(case):
-    """C_out = 128-type layers with bf16-only output take the operand-swapped kernel (conv_tc_swap.cu)."""
+    """C_out = 128-type layers with bf16-only output: the 128x128 kernel by default, the operand-swapped
+    kernel (conv_tc_swap.cu) when MSTR_CONV_SWAP=1 is set before the library is first used."""
     stride, pad, relu = case[7], case[8], case[10]
     x, w, scale, shift, res = _conv_inputs(case, 21, True)
     ref = _conv_ref(x, w, scale, shift, res, stride, pad, relu)

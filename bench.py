@@ -232,18 +232,26 @@ def run_ours(args):
         # one step ahead so that it overlaps the previous step's compute) and reads the decoded ids back
         if k not in staged:
             stage(k)
+        t0 = time.perf_counter()
         tensors, ready, sid = staged.pop(k)
         torch.cuda.current_stream().wait_event(ready)
         with torch.no_grad():
             out = model.recognize(tensors[0], *tensors[1:])
         prefetcher.release(sid)
+        t1 = time.perf_counter()
         stage(k + 1)                                    # H2D of the next step's inputs, overlapped
+        t2 = time.perf_counter()
         ids, lengths = out["ids"], out["lengths"]
         if world > 1:
             ids, lengths = parallel.allgather_ids(ids, lengths, B * world)
         ids_host.copy_(ids, non_blocking=True)
         len_host.copy_(lengths, non_blocking=True)
+        t3 = time.perf_counter()
         torch.cuda.current_stream().synchronize()      # the caller needs the decoded ids of this step
+        if os.environ.get("MSTR_BENCH_TRACE"):
+            print("rank %d e2e step %d: launch %.1f stage %.1f gather+d2h %.1f sync %.1f ms" % (
+                rank, k, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (time.perf_counter() - t3)),
+                file=sys.stderr)
 
     def barrier():
         if world > 1:

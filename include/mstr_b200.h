@@ -42,6 +42,12 @@ const char* mstr_last_error_string(void);
 /* Number of kernels this library has launched since load (bench.py's "gpu_launches"). */
 int64_t mstr_launch_count(void);
 
+/* Asynchronous host<->device copies on `stream` (one cudaMemcpyAsync; the host buffer should be pinned).
+ * Plumbing for the input pipeline that stands in for the reference's per-batch `.to(device)` calls
+ * (training_functions.py:166-176). */
+int mstr_copy_h2d_async(void* dst_device, const void* src_host, int64_t bytes, mstr_stream_t stream);
+int mstr_copy_d2h_async(void* dst_host, const void* src_device, int64_t bytes, mstr_stream_t stream);
+
 /* ---- TPS rectification ------------------------------------------------------------------
  * Replaces GridGenerator.build_P_prime (modules/transformation.py:154-163: two repeat() copies
  * and two torch.bmm) fused with F.grid_sample(bilinear, padding_mode='border',

@@ -22,6 +22,8 @@ SIGNATURES = {
     "mstr_version": (c_int, []),
     "mstr_last_error_string": (c_char_p, []),
     "mstr_launch_count": (c_int64, []),
+    "mstr_copy_h2d_async": (c_int, [_P, _P, c_int64, _P]),
+    "mstr_copy_d2h_async": (c_int, [_P, _P, c_int64, _P]),
     "mstr_tps_rectify": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mstr_conv3x3_first": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "mstr_conv_gemm_f32": (c_int, [_P, _P, _P, _P, _P, _P] + [_I] * 12 + [_P]),

@@ -36,3 +36,18 @@ int sm_count() {
 extern "C" __attribute__((visibility("default"))) int mstr_version(void) { return 1000; }
 extern "C" __attribute__((visibility("default"))) const char* mstr_last_error_string(void) { return mstr::g_error; }
 extern "C" __attribute__((visibility("default"))) int64_t mstr_launch_count(void) { return (int64_t)mstr::g_launches.load(); }
+
+// Plain asynchronous host<->device copies on a caller-supplied stream (pinned host memory expected), used by
+// pipeline.HostBatchPrefetcher so that the input copies are exactly one cudaMemcpyAsync each.
+extern "C" __attribute__((visibility("default"))) int mstr_copy_h2d_async(void* dst_device, const void* src_host,
+                                                                          int64_t bytes, mstr_stream_t stream) {
+  MSTR_REQUIRE(dst_device && src_host && bytes > 0, MSTR_ERR_BAD_ARG, "mstr_copy_h2d_async: bad argument");
+  MSTR_CUDA(cudaMemcpyAsync(dst_device, src_host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return MSTR_OK;
+}
+extern "C" __attribute__((visibility("default"))) int mstr_copy_d2h_async(void* dst_host, const void* src_device,
+                                                                          int64_t bytes, mstr_stream_t stream) {
+  MSTR_REQUIRE(dst_host && src_device && bytes > 0, MSTR_ERR_BAD_ARG, "mstr_copy_d2h_async: bad argument");
+  MSTR_CUDA(cudaMemcpyAsync(dst_host, src_device, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return MSTR_OK;
+}

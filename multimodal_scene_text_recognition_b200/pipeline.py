@@ -13,6 +13,8 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
+from . import _cabi
+
 
 class HostBatchPrefetcher:
     def __init__(self, device, depth: int = 2):
@@ -36,13 +38,26 @@ class HostBatchPrefetcher:
             self._slots.append([torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_tensors])
             self._free.append(None)
         slot = self._slots[sid]
+        import os, sys, time
+        trace = os.environ.get("MSTR_BENCH_TRACE")
+        ts = [time.perf_counter()]
         with torch.cuda.stream(self.stream):
             if self._free[sid] is not None:          # do not overwrite a slot its last consumer may still read
                 self.stream.wait_event(self._free[sid])
+            ts.append(time.perf_counter())
             for d, h in zip(slot, host_tensors):
-                d.copy_(h, non_blocking=True)
+                # one cudaMemcpyAsync per tensor through the C ABI (torch's copy_ was measured to block the host
+                # for the duration of a CPU-side pass over the 52 MB batch in this configuration)
+                if not h.is_contiguous():
+                    raise ValueError("HostBatchPrefetcher needs contiguous host tensors")
+                _cabi.check(_cabi.lib().mstr_copy_h2d_async(d.data_ptr(), h.data_ptr(), h.numel() * h.element_size(),
+                                                            self.stream.cuda_stream), "mstr_copy_h2d_async")
+                ts.append(time.perf_counter())
             ready = torch.cuda.Event()
             ready.record(self.stream)
+        ts.append(time.perf_counter())
+        if trace:
+            print("stage: " + " ".join("%.2f" % (1e3 * (b - a)) for a, b in zip(ts, ts[1:])), file=sys.stderr)
         return slot, ready, sid
 
     def release(self, sid: int) -> None:

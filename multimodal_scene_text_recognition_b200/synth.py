@@ -314,7 +314,7 @@ def make_crops(seed: int, batch: int, geom: Geometry = CFG_A, stroke: float = 0.
     low = _upsample_bilinear(rng.uniform(0.0, 1.0, shape + (4, 13)), geom.H, geom.W)
     mid = _upsample_bilinear(rng.uniform(0.0, 1.0, shape + (geom.H // 4, geom.W // 4)), geom.H, geom.W)
     img = low * (1.0 - stroke - noise) + mid * stroke + noise * rng.uniform(0.0, 1.0, low.shape)
-    return np.clip(img, 0.0, 1.0).astype(np.float32)
+    return np.ascontiguousarray(np.clip(img, 0.0, 1.0), dtype=np.float32)   # C order (fancy indexing above is not)
 
 
 def make_semantics(seed: int, batch: int, n_overlap: int = 15, n_scene: int = 52,

@@ -2,104 +2,135 @@
 // conv0_1/bn0_1/ReLU of the ResNet (modules/feature_extraction.py:58-60,111-113) and
 // conv.0/BN/ReLU/MaxPool2d(2,2) of the localisation network (modules/transformation.py:49-52).
 //
-// K = 9*C_in (9 or 27) is far below a tensor-core tile, and the layer is HBM-bound on its
-// NHWC output (~9 FLOP/B), so it is SIMT (see the kernel comment for the thread mapping).
+// K = 9*C_in (9 or 27) is far below a tensor-core tile and the layer is bound by its NHWC output
+// write, so it is SIMT.  Register blocking: one thread computes a strip of 4 horizontally adjacent
+// conv pixels (x 2 rows in the pooled variant) for 8 output channels.  Per filter tap the 8 weights
+// come from shared memory with two broadcast 16-byte loads and feed 32 (64) FMAs - the first version
+// (1 pixel x 32 channels per thread) issued one shared load per 4 FMAs and ran at 25 % of the FMA
+// pipe.  The input strip (3 or 4 rows x 6 columns per channel) is read once into registers with
+// coalesced loads.  Lanes of a warp cover consecutive channel groups first, so the 16-byte bf16
+// stores of 4 (8) neighbouring lanes form one contiguous 64-byte (128-byte) run of the NHWC output.
 #include "common.cuh"
 
 namespace mstr {
 
 constexpr int kFirstMaxCin = 4;
 constexpr int kFirstMaxCout = 64;
-template <bool POOL> struct FirstCg { static constexpr int value = 32; };   // output channels per thread
 
-// One thread = one (pooled) output pixel x 32 output channels.  grid = (pixel tiles of 256, crop,
-// channel group).  The 3x3 input patch is loaded into registers with coalesced loads along W; the folded weights sit in shared memory as [tap][32] and are read with broadcast
-// 16-byte loads (all lanes of a warp use the same tap at the same time), so the inner loop is
-// 32 FMAs per 8 LDS.128.  The 32 results go out as one contiguous 64-byte (bf16) / 128-byte (f32) run.
 template <typename T, bool POOL, int CIN>
 __global__ void __launch_bounds__(256)
 conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      T* __restrict__ out, int H, int W, int Cout) {
-  constexpr int kFirstCg = FirstCg<POOL>::value;
-  __shared__ __align__(16) float sW[CIN * 9][kFirstCg];
-  __shared__ float sScale[kFirstCg], sShift[kFirstCg];
+  __shared__ __align__(16) float sW[CIN * 9][kFirstMaxCout];
+  __shared__ __align__(16) float sScale[kFirstMaxCout], sShift[kFirstMaxCout];
   constexpr int K = CIN * 9;
-  const int cg0 = blockIdx.z * kFirstCg;
-  for (int i = threadIdx.x; i < K * kFirstCg; i += blockDim.x) {
-    const int o = i % kFirstCg, k = i / kFirstCg;   // w is [Cout][Cin][3][3] => [o][k]
-    sW[k][o] = w[(cg0 + o) * K + k];
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int o = i % Cout, k = i / Cout;   // w is [Cout][Cin][3][3] => [o][k]
+    sW[k][o] = w[o * K + k];
   }
-  if (threadIdx.x < kFirstCg) {
-    sScale[threadIdx.x] = scale[cg0 + threadIdx.x];
-    sShift[threadIdx.x] = shift[cg0 + threadIdx.x];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
+    sScale[i] = scale[i];
+    sShift[i] = shift[i];
   }
   __syncthreads();
 
-  const int P = POOL ? H / 2 : H, Q = POOL ? W / 2 : W;
-  const int pix = blockIdx.x * 256 + threadIdx.x;
-  if (pix >= P * Q) return;
-  const int p = pix / Q, q = pix - p * Q;
+  constexpr int PH = POOL ? 2 : 1;             // conv rows per thread
+  const int groups = Cout >> 3;                // channel groups of 8
+  const int strips = W >> 2;                   // 4-pixel strips per row
+  const int rows = H / PH;
+  const int item = blockIdx.x * 256 + threadIdx.x;
+  if (item >= rows * strips * groups) return;
+  const int g = item % groups;
+  const int rest = item / groups;
+  const int sx = rest % strips, ry = rest / strips;
   const int b = blockIdx.y;
-  float best[kFirstCg];
+  const int y0 = ry * PH - 1, x0 = sx * 4 - 1;
+
+  float in[CIN][PH + 2][6];
 #pragma unroll
-  for (int j = 0; j < kFirstCg; ++j) best[j] = 0.f;   // ReLU output is >= 0, so 0 is the identity of the max
-  // pooled variant: the four conv pixels of the 2x2 window one after the other (not unrolled: keeping
-  // 4 x 32 accumulators live would spill); their patches overlap and hit L1
-#pragma unroll 1
-  for (int sub = 0; sub < (POOL ? 4 : 1); ++sub) {
-    const int y0 = (POOL ? 2 * p + (sub >> 1) : p) - 1, x0 = (POOL ? 2 * q + (sub & 1) : q) - 1;
-    float in[CIN][3][3];
+  for (int c = 0; c < CIN; ++c) {
+    const float* plane = x + ((size_t)b * CIN + c) * H * W;
 #pragma unroll
-    for (int c = 0; c < CIN; ++c) {
-      const float* plane = x + ((size_t)b * CIN + c) * H * W;
+    for (int dy = 0; dy < PH + 2; ++dy) {
+      const int yy = y0 + dy;
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const int yy = y0 + dy;
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int xs = x0 + dx;
-          in[c][dy][dx] = (yy >= 0 && yy < H && xs >= 0 && xs < W) ? __ldg(plane + yy * W + xs) : 0.f;
-        }
+      for (int dx = 0; dx < 6; ++dx) {
+        const int xs = x0 + dx;
+        in[c][dy][dx] = (yy >= 0 && yy < H && xs >= 0 && xs < W) ? __ldg(plane + yy * W + xs) : 0.f;
       }
     }
-    float acc[kFirstCg];
-#pragma unroll
-    for (int j = 0; j < kFirstCg; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int c = 0; c < CIN; ++c)
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const float v = in[c][dy][dx];
-          const float4* wr = reinterpret_cast<const float4*>(&sW[c * 9 + dy * 3 + dx][0]);
-#pragma unroll
-          for (int u = 0; u < kFirstCg / 4; ++u) {
-            const float4 wv = wr[u];
-            acc[4 * u + 0] = fmaf(v, wv.x, acc[4 * u + 0]);
-            acc[4 * u + 1] = fmaf(v, wv.y, acc[4 * u + 1]);
-            acc[4 * u + 2] = fmaf(v, wv.z, acc[4 * u + 2]);
-            acc[4 * u + 3] = fmaf(v, wv.w, acc[4 * u + 3]);
-          }
-        }
-#pragma unroll
-    for (int j = 0; j < kFirstCg; ++j) best[j] = fmaxf(best[j], fmaf(acc[j], sScale[j], sShift[j]));
   }
 
-  T* dst = out + (((size_t)b * P + p) * Q + q) * Cout + cg0;
-  if constexpr (sizeof(T) == 2) {
+  float acc[PH][4][8];
 #pragma unroll
-    for (int u = 0; u < kFirstCg / 8; ++u) {
-      uint4 o;
-      o.x = pack_bf16x2(best[8 * u + 0], best[8 * u + 1]); o.y = pack_bf16x2(best[8 * u + 2], best[8 * u + 3]);
-      o.z = pack_bf16x2(best[8 * u + 4], best[8 * u + 5]); o.w = pack_bf16x2(best[8 * u + 6], best[8 * u + 7]);
-      reinterpret_cast<uint4*>(dst)[u] = o;
+  for (int r = 0; r < PH; ++r)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[r][p][j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < CIN; ++c)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float4* wr = reinterpret_cast<const float4*>(&sW[c * 9 + dy * 3 + dx][g * 8]);
+        const float4 w0 = wr[0], w1 = wr[1];
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int r = 0; r < PH; ++r)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float v = in[c][r + dy][p + dx];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r][p][j] = fmaf(v, wv[j], acc[r][p][j]);
+          }
+      }
+
+  float sc[8], sf[8];
+  {
+    const float4 a0 = *reinterpret_cast<const float4*>(&sScale[g * 8]), a1 = *reinterpret_cast<const float4*>(&sScale[g * 8 + 4]);
+    const float4 b0 = *reinterpret_cast<const float4*>(&sShift[g * 8]), b1 = *reinterpret_cast<const float4*>(&sShift[g * 8 + 4]);
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    sf[0] = b0.x; sf[1] = b0.y; sf[2] = b0.z; sf[3] = b0.w; sf[4] = b1.x; sf[5] = b1.y; sf[6] = b1.z; sf[7] = b1.w;
+  }
+  auto store8 = [&](T* dst, const float (&v)[8]) {
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    } else {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  };
+  if constexpr (POOL) {
+    // BN + ReLU, then the 2x2 max: two pooled pixels per thread
+    const int Q = W >> 1;
+    T* dst = out + (((size_t)b * rows + ry) * Q + sx * 2) * Cout + g * 8;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float m = 0.f;   // ReLU output is >= 0: 0 is the identity of the max
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int p = 0; p < 2; ++p) m = fmaxf(m, fmaf(acc[r][2 * q + p][j], sc[j], sf[j]));
+        v[j] = m;
+      }
+      store8(dst + (size_t)q * Cout, v);
     }
   } else {
+    T* dst = out + (((size_t)b * H + ry) * W + sx * 4) * Cout + g * 8;
 #pragma unroll
-    for (int u = 0; u < kFirstCg / 4; ++u)
-      reinterpret_cast<float4*>(dst)[u] = make_float4(best[4 * u], best[4 * u + 1], best[4 * u + 2], best[4 * u + 3]);
+    for (int p = 0; p < 4; ++p) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(acc[0][p][j], sc[j], sf[j]), 0.f);
+      store8(dst + (size_t)p * Cout, v);
+    }
   }
 }
 
@@ -124,15 +155,14 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv3x3_first(const f
   MSTR_REQUIRE(B > 0 && H > 0 && W > 0, MSTR_ERR_BAD_ARG, "mstr_conv3x3_first: bad size");
   MSTR_REQUIRE(C_in >= 1 && C_in <= kFirstMaxCin, MSTR_ERR_UNSUPPORTED,
                "mstr_conv3x3_first: C_in=%d not in [1,%d] (use mstr_conv_gemm_*)", C_in, kFirstMaxCin);
-  const int kFirstCg = pool ? FirstCg<true>::value : FirstCg<false>::value;
-  MSTR_REQUIRE(C_out % kFirstCg == 0, MSTR_ERR_UNSUPPORTED,
-               "mstr_conv3x3_first: C_out=%d must be a multiple of %d", C_out, kFirstCg);
-  MSTR_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), MSTR_ERR_UNSUPPORTED,
-               "mstr_conv3x3_first: pooled variant needs even H, W");
+  MSTR_REQUIRE(C_out % 8 == 0 && C_out <= kFirstMaxCout, MSTR_ERR_UNSUPPORTED,
+               "mstr_conv3x3_first: C_out=%d must be a multiple of 8 and <= %d", C_out, kFirstMaxCout);
+  MSTR_REQUIRE(W % 4 == 0, MSTR_ERR_UNSUPPORTED, "mstr_conv3x3_first: W=%d must be a multiple of 4", W);
+  MSTR_REQUIRE(!pool || H % 2 == 0, MSTR_ERR_UNSUPPORTED, "mstr_conv3x3_first: pooled variant needs even H");
   MSTR_REQUIRE(aligned16(out), MSTR_ERR_BAD_ARG, "mstr_conv3x3_first: out must be 16-byte aligned");
-  const int P = pool ? H / 2 : H, Q = pool ? W / 2 : W;
   MSTR_REQUIRE(B <= 65535, MSTR_ERR_UNSUPPORTED, "mstr_conv3x3_first: batch %d > 65535 (split the batch)", B);
-  dim3 grid(ceil_div(P * Q, 256), B, C_out / kFirstCg);
+  const int rows = pool ? H / 2 : H;
+  dim3 grid(ceil_div(rows * (W / 4) * (C_out / 8), 256), B, 1);
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == MSTR_BF16) {
     if (pool) launch_first<__nv_bfloat16, true>(C_in, grid, st, x, w, scale, shift, (__nv_bfloat16*)out, H, W, C_out);

@@ -20,24 +20,38 @@ class KernelTimer:
     the current stream; ``summary()`` (after a synchronize) aggregates time and work per kernel."""
 
     def __init__(self):
-        self.records = []   # (name, work, start event, end event)
+        self.records = []   # (name, work, start event, end event, unit, desc)
 
     def summary(self):
         out = {}
-        for name, work, s, e in self.records:
+        for name, work, s, e, _unit, _desc in self.records:
             d = out.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
             d["launches"] += 1
             d["ms"] += s.elapsed_time(e)
             d["work"] += work
         return out
 
+    def table(self, steps: int = 1):
+        """Per call site (in launch order of one step): mean duration and achieved rate."""
+        per_step = len(self.records) // max(steps, 1)
+        rows = []
+        for i in range(per_step):
+            recs = self.records[i::per_step] if per_step else []
+            name, work, _, _, unit, desc = recs[0]
+            ms = sum(s.elapsed_time(e) for _, _, s, e, _, _ in recs) / len(recs)
+            rate = work / (ms * 1e-3) if ms > 0 else 0.0
+            rows.append({"kernel": name, "what": desc, "ms": round(ms, 4), "work": work, "unit": unit,
+                         "achieved": round(rate / (1e12 if unit == "flop" else 1e9), 1),
+                         "achieved_unit": "TFLOP/s" if unit == "flop" else "GB/s"})
+        return rows
+
 
 TIMER: Optional[KernelTimer] = None
 
 
 class _timed:
-    def __init__(self, name: str, work: float = 0.0):
-        self.name, self.work = name, work
+    def __init__(self, name: str, work: float = 0.0, unit: str = "flop", desc: str = ""):
+        self.name, self.work, self.unit, self.desc = name, work, unit, desc
 
     def __enter__(self):
         if TIMER is not None:
@@ -49,7 +63,7 @@ class _timed:
         if TIMER is not None and exc[0] is None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
-            TIMER.records.append((self.name, self.work, self.s, e))
+            TIMER.records.append((self.name, self.work, self.s, e, self.unit, self.desc))
         return False
 
 
@@ -92,7 +106,7 @@ def tps_rectify(img: Optional[torch.Tensor], c_prime: torch.Tensor, basis: torch
         assert img.shape[0] == B and H * W == n, (img.shape, basis.shape)
         out = torch.empty_like(img)
     grid = torch.empty((B, n, 2), device=c_prime.device, dtype=torch.float32) if want_grid else None
-    with _timed("tps_rectify", float(B) * C * n * 8):            # work = algorithmic bytes (image in + out)
+    with _timed("tps_rectify", float(B) * C * n * 8, "byte", "B%d %dx%dx%d image in + out" % (B, C, H, W)):
         check(lib().mstr_tps_rectify(ptr(img), ptr(c_prime), ptr(basis), ptr(inv_delta_C), ptr(out), ptr(grid),
                                      B, C, H, W, F, mode, stream_ptr()), "mstr_tps_rectify")
     if img is None:
@@ -110,7 +124,8 @@ def conv3x3_first(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: 
     assert w.shape == (Cout, Cin, 3, 3)
     P, Q = (H // 2, W // 2) if pool else (H, W)
     out = torch.empty((B, P, Q, Cout), device=x.device, dtype=out_dtype)
-    with _timed("conv3x3_first", 2.0 * B * H * W * Cout * 9 * Cin):
+    with _timed("conv3x3_first", float(out.numel() * out.element_size() + x.numel() * 4), "byte",
+                "B%d %dx%d %d->%d%s: NHWC out + image in" % (B, H, W, Cin, Cout, " +pool" if pool else "")):
         check(lib().mstr_conv3x3_first(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(out), _dt(out), B, Cin, H, W,
                                        Cout, int(pool), stream_ptr()), "mstr_conv3x3_first")
     return out
@@ -136,9 +151,10 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
     if residual is not None:
         assert residual.shape == (B, P, Q, Cout)
     flops = 2.0 * B * P * Q * Cout * R * S * Cin
+    desc = "M=%d (B%d %dx%d) %d->%d %dx%d%s" % (B * P * Q, B, P, Q, Cin, Cout, R, S, " +res" if residual is not None else "")
     if x.dtype == torch.float32:
         out = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32)
-        with _timed("conv_gemm_f32", flops):
+        with _timed("conv_gemm_f32", flops, "flop", desc):
             check(lib().mstr_conv_gemm_f32(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out), B, H, W,
                                            Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
                                            stream_ptr()), "mstr_conv_gemm_f32")
@@ -147,7 +163,9 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
         raise TypeError("conv_gemm: unsupported dtype %s" % x.dtype)
     out_b = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     out_f = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32) if want_f32 else None
-    with _timed("conv_gemm_bf16", flops):
+    # which kernel mstr_conv_gemm_bf16 dispatches to (conv_tc.cu): the CTA-pair kernel for C_out % 256 == 0
+    variant = "conv_gemm_bf16_2cta" if (Cin % 64 == 0 and Cout % 256 == 0) else "conv_gemm_bf16_1cta"
+    with _timed(variant, flops, "flop", desc):
         check(lib().mstr_conv_gemm_bf16(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out_b), ptr(out_f),
                                         B, H, W, Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
                                         stream_ptr()), "mstr_conv_gemm_bf16")
@@ -179,7 +197,8 @@ def maxpool_nhwc(x: torch.Tensor, kernel=(2, 2), stride=(2, 2), pad=(0, 0)) -> t
     P = (H + 2 * pad[0] - kernel[0]) // stride[0] + 1
     Q = (W + 2 * pad[1] - kernel[1]) // stride[1] + 1
     out = torch.empty((B, P, Q, C), device=x.device, dtype=x.dtype)
-    with _timed("maxpool_nhwc", float(x.numel() + out.numel()) * x.element_size()):
+    with _timed("maxpool_nhwc", float(x.numel() + out.numel()) * x.element_size(), "byte",
+                "B%d %dx%dx%d -> %dx%d in + out" % (B, H, W, C, P, Q)):
         check(lib().mstr_maxpool_nhwc(ptr(x), ptr(out), _dt(x), B, H, W, C, kernel[0], kernel[1], stride[0], stride[1],
                                       pad[0], pad[1], stream_ptr()), "mstr_maxpool_nhwc")
     return out
@@ -231,7 +250,7 @@ def bilstm_recurrent(gates_x: torch.Tensor, w_hh: torch.Tensor, want_f32: bool, 
     assert gates_x.shape == (B, T, 2, 4 * Hd) and w_hh.shape == (2, 4 * Hd, Hd)
     out_f = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.float32) if want_f32 else None
     out_b = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.bfloat16) if want_bf16 else None
-    with _timed("bilstm_recurrent", 2.0 * B * T * 2 * 4 * Hd * Hd):
+    with _timed("bilstm_recurrent", 2.0 * B * T * 2 * 4 * Hd * Hd, "flop", "B%d T%d both directions (fp32 SIMT)" % (B, T)):
         check(lib().mstr_bilstm_recurrent(ptr(gates_x), ptr(w_hh), ptr(out_f), ptr(out_b), B, T, Hd, stream_ptr()),
               "mstr_bilstm_recurrent")
     if want_f32 and want_bf16:
@@ -255,7 +274,7 @@ def bilstm_recurrent_bf16(gates_x: torch.Tensor, w_hh_packed: torch.Tensor) -> t
     Hd = w_hh_packed.shape[2]
     assert gates_x.shape == (B, T, 2, 4 * Hd) and w_hh_packed.shape == (2, 4 * Hd, Hd)
     out = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.bfloat16)
-    with _timed("bilstm_recurrent_bf16", 2.0 * B * T * 2 * 4 * Hd * Hd):
+    with _timed("bilstm_recurrent_bf16", 2.0 * B * T * 2 * 4 * Hd * Hd, "flop", "B%d T%d both directions (tcgen05)" % (B, T)):
         check(lib().mstr_bilstm_recurrent_bf16(ptr(gates_x), ptr(w_hh_packed), ptr(out), B, T, Hd, stream_ptr()),
               "mstr_bilstm_recurrent_bf16")
     return out
@@ -285,7 +304,7 @@ def attn_decode(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int,
         if text.shape[1] != steps:
             text = text[:, :steps].contiguous()
     macs = Hd * Hd + 2 * T * Hd + 4 * Hd * 2 * Hd + C * Hd      # h2h, score+context, LSTMCell, generator
-    with _timed("attn_decode", 2.0 * B * steps * macs):
+    with _timed("attn_decode", 2.0 * B * steps * macs, "flop", "B%d T%d %d steps (fp32 SIMT, 1 launch)" % (B, T, steps)):
         check(lib().mstr_attn_decode(ptr(enc), ptr(proj), ptr(packed["w_h2h"]), ptr(packed["b_h2h"]),
                                      ptr(packed["w_score"]), ptr(packed["w_ctx"]), ptr(packed["w_tok"]),
                                      ptr(packed["w_hh"]), ptr(packed["bias"]), ptr(packed["w_gen"]),
@@ -321,7 +340,8 @@ def attn_decode_bf16(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps:
         if text.shape[1] != steps:
             text = text[:, :steps].contiguous()
     macs = Hd * Hd + 2 * T * Hd + 4 * Hd * 2 * Hd + C * Hd
-    with _timed("attn_decode_bf16", 2.0 * B * steps * macs):
+    with _timed("attn_decode_bf16", 2.0 * B * steps * macs, "flop",
+                "B%d T%d %d steps (tcgen05, %d launches)" % (B, T, steps, 3 * steps + 2)):
         check(lib().mstr_attn_decode_bf16(ptr(enc), ptr(proj), ptr(packed["w_head"]), ptr(packed["b_h2h"]),
                                           ptr(packed["b_gen"]), ptr(packed["w_score"]), ptr(packed["w_cat"]),
                                           ptr(packed["w_tok"]), ptr(packed["bias"]), ptr(text), ptr(ws), ptr(logits),

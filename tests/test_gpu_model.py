@@ -163,6 +163,27 @@ def test_bf16_matches_quantisation_matched_oracle(sd_cfg_a):
     assert same32.mean() >= 0.35, "greedy ids equal to the fp32 oracle on only %d of %d crops" % (same32.sum(), B)
 
 
+def test_bf16_stress_config_runs_on_tensor_cores(sd_cfg_s, golden_dir):
+    """3x64x256 crops / max length 50 in the bf16 mode (T=65 columns, 51 steps): every tensor-core kernel
+    accepts the geometry; features stay within bf16 storage accuracy of the reference's."""
+    g = np.load(os.path.join(golden_dir, "cfg_s.npz"))
+    wseed, dseed, B = [int(v) for v in g["meta"]]
+    geom = synth.CFG_S
+    x = synth.make_crops(dseed, B, geom)
+    ov, sc, io = synth.make_semantics(dseed + 1, B)
+    m = load_model(sd_cfg_s, geom, precision="bf16", DECODER_EARLY_EXIT=False)
+    st = {}
+    try:
+        out = _run(m, x, ov, sc, io, st)
+    finally:
+        config.MAX_TEXT_LENGTH = 25
+    assert tuple(st["features"].shape) == (B, 3, 65, 512)
+    assert_close(nchw(host(st["features"])), g["features"], 5e-2, "bf16 features (stress)")
+    logits = host(out["logits"])
+    assert logits.shape == (B, 51, 97) and np.isfinite(logits).all()
+    assert (host(out["ids"]) == g["ids"]).mean() > 0.5
+
+
 def test_bf16_properties_at_benchmark_batch(sd_cfg_a):
     """B=4096 (BASELINE.json config 3): results do not depend on how the batch is split or ordered,
     repeated runs are bit-identical, and the decode is not degenerate."""

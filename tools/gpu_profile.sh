@@ -17,4 +17,10 @@ echo "ncu launches exit $?"
 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_bf16 -s $((39 * 3 + 18)) -c 2 \
     -o gpurun_out/${TAG}_conv $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
+# the other kernels of the path, one launch each in a steady-state step: TPS, both BiLSTM layers, decoder head/ctx/cell
+ncu --set full --clock-control none --import-source on -k regex:"tps_rectify|bilstm_tc|attn_context|rnn_gemm" \
+    -s $((3 * 82)) -c 7 -o gpurun_out/${TAG}_seq $CMD > gpurun_out/${TAG}_ncu_seq.log 2>&1
+echo "ncu seq exit $?"
+python bench.py --steps 10 --warmup 3 --kernel-table gpurun_out/${TAG}_kernel_table.json > gpurun_out/${TAG}_bench.log 2>&1
+tail -1 gpurun_out/${TAG}_bench.log > gpurun_out/${TAG}_bench_line.json
 ls -la gpurun_out/

@@ -44,35 +44,45 @@ struct TcParams {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_THREADS = 192;
 
-template <int BLOCK_N, int BLOCK_K>
+// RESB ("resident B"): the whole weight matrix of a small layer (K <= TC_RES_MAX_KB k-blocks, one N tile) is
+// loaded into shared memory ONCE per CTA and stays there for every tile; only the activation tiles stream.
+// For the C_out = 128 layers the 128x128 MMA reads 128 B/clk of shared memory by itself, so also WRITING a
+// fresh 16 KB weight tile per k-block (another 64 B/clk) is what held them at ~45 % of the tensor peak.
+constexpr int TC_RES_MAX_KB = 9;   // 9 x 64 = 576 = 3x3x64: the 64 -> 128 layers (144 KB of weights)
+
+template <int BLOCK_N, int BLOCK_K, bool RESB = false>
 struct TcCfg {
   static constexpr int ROW_BYTES = BLOCK_K * 2;
   static constexpr int A_BYTES = TC_BLOCK_M * ROW_BYTES;
   static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int RES_BYTES = RESB ? TC_RES_MAX_KB * B_BYTES : 0;
+  static constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int RING_BUDGET = RESB ? (227 * 1024 - 4096 - RES_BYTES) : 196608;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 4 * BLOCK_N * 4 /*scale/shift x2*/ +
-                                    (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RES_BYTES + STAGES * STAGE_BYTES +
+                                    4 * BLOCK_N * 4 /*scale/shift x2*/ + (2 * STAGES + 5) * 8 + 16;
 };
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool RESB = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const TcParams p) {
-  using Cfg = TcCfg<BLOCK_N, BLOCK_K>;
+  using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  float* sScale = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BLOCK_N]
+  uint8_t* sRes = smem;                                 // RESB: [num_k][BLOCK_N rows][ROW_BYTES], loaded once
+  uint8_t* sA = smem + Cfg::RES_BYTES;
+  uint8_t* sB = sA + STAGES * Cfg::A_BYTES;             // !RESB: streamed weight tiles
+  float* sScale = reinterpret_cast<float*>(sA + STAGES * Cfg::STAGE_BYTES);    // [2][BLOCK_N]
   float* sShift = sScale + 2 * BLOCK_N;                                        // [2][BLOCK_N]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + 2 * BLOCK_N);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;         // RESB: resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,6 +100,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
+    mbar_init(res_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -101,6 +112,10 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if constexpr (RESB) {   // the whole [BLOCK_N x K] weight matrix, once
+        mbar_arrive_expect_tx(res_bar, (uint32_t)(num_k * Cfg::B_BYTES));
+        for (int kb = 0; kb < num_k; ++kb) tma_load_2d(sRes + kb * Cfg::B_BYTES, &tmB, res_bar, kb * BLOCK_K, 0);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -140,7 +155,8 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                  (uint16_t)s, (uint16_t)r);
             else
               tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cc * BLOCK_K, m0);
-            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], (tap * p.cin_chunks + cc) * BLOCK_K, n0);
+            if constexpr (!RESB)
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], (tap * p.cin_chunks + cc) * BLOCK_K, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -154,6 +170,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if constexpr (RESB) mbar_wait(res_bar, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -162,7 +179,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint32_t b_addr = RESB ? smem_u32(sRes + kb * Cfg::B_BYTES) : smem_u32(sB + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             const uint64_t da = make_smem_desc<Cfg::ROW_BYTES>(a_addr + k * 32);
@@ -266,18 +283,18 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // ---------------------------------------------------------------------------------------------
 static TmaEncoders g_enc;
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool RESB = false>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N, BLOCK_K>;
+  using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB>;
   static bool attr_set = false;
   if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K>,
+    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   MSTR_LAUNCH_CHECK("conv_gemm_bf16_kernel");
   return MSTR_OK;
 }
@@ -386,6 +403,10 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   cudaStream_t st = (cudaStream_t)stream;
   if (block_k == 64) {
     if (block_n == 256) return launch_tc<256, 64>(tmA, tmB, p, st);
+    static const int use_resb = [] { const char* e = getenv("MSTR_CONV_RESB"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (block_n == 128 && use_resb && p.num_n_tiles == 1 && p.taps * p.cin_chunks <= TC_RES_MAX_KB &&
+        p.num_m_tiles >= 4 * sm_count())
+      return launch_tc<128, 64, true>(tmA, tmB, p, st);      // resident weights (64 -> 128 layers)
     if (block_n == 128) return launch_tc<128, 64>(tmA, tmB, p, st);
     return launch_tc<64, 64>(tmA, tmB, p, st);
   } else {

@@ -148,6 +148,20 @@ def test_conv_gemm_bf16_tcgen05(case):
     assert np.array_equal(host(out_b), orc.round_bf16(host(out_f))), "bf16 output is not the rounded f32 output"
 
 
+def test_conv_gemm_bf16_resident_weights():
+    """64 -> 128 layers with >= 4 tiles per SM keep the whole weight matrix resident in shared memory
+    (conv_gemm_bf16_kernel<128, 64, RESB>): M = 96*16*50 = 76800 -> 600 tiles; 3x3 with residual and 1x1."""
+    bf = torch.bfloat16
+    for case in ((96, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), True, True),
+                 (96, 16, 50, 64, 128, 1, 1, (1, 1), (0, 0), False, False)):
+        x, w, scale, shift, res = _conv_inputs(case, 23, True)
+        ref = _conv_ref(x, w, scale, shift, res, case[7], case[8], case[10])
+        out_f = ops.conv_gemm(dev(x, bf), dev(w, bf), dev(scale), dev(shift), None if res is None else dev(res, bf),
+                              stride=case[7], pad=case[8], relu=case[10], want_f32=True, want_bf16=False)
+        torch.cuda.synchronize()
+        assert_close(host(out_f), ref, 2e-5, "conv_gemm_bf16 resident weights %s" % (case,))
+
+
 SWAP_CASES = [
     (5, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), False, True),     # layer1 conv1 geometry, M = 4000 (ragged 256-tile)
     (3, 16, 50, 128, 128, 3, 3, (1, 1), (1, 1), True, True),     # 128 -> 128 with residual

@@ -48,7 +48,8 @@ constexpr int TC_THREADS = 192;
 // loaded into shared memory ONCE per CTA and stays there for every tile; only the activation tiles stream.
 // For the C_out = 128 layers the 128x128 MMA reads 128 B/clk of shared memory by itself, so also WRITING a
 // fresh 16 KB weight tile per k-block (another 64 B/clk) is what held them at ~45 % of the tensor peak.
-constexpr int TC_RES_MAX_KB = 9;   // 9 x 64 = 576 = 3x3x64: the 64 -> 128 layers (144 KB of weights)
+constexpr int TC_RES_MAX_KB = 9;
+constexpr int STAGES_MAX_DUMMY = 8;   // barrier storage is sized for the maximum ring depth   // 9 x 64 = 576 = 3x3x64: the 64 -> 128 layers (144 KB of weights)
 
 template <int BLOCK_N, int BLOCK_K, bool RESB = false>
 struct TcCfg {
@@ -57,16 +58,18 @@ struct TcCfg {
   static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
   static constexpr int RES_BYTES = RESB ? TC_RES_MAX_KB * B_BYTES : 0;
   static constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
-  static constexpr int RING_BUDGET = RESB ? (227 * 1024 - 4096 - RES_BYTES) : 196608;
+  static constexpr int EPI_SLAB = RESB ? EPI_SLAB_BYTES / 2 : EPI_SLAB_BYTES;   // RESB layers store bf16 only
+  static constexpr int TAIL_BYTES = 4 * BLOCK_N * 4 /*scale/shift x2*/ + (2 * STAGES_MAX_DUMMY + 5) * 8 + 16;
+  static constexpr int RING_BUDGET = 227 * 1024 - 1024 /*align slack*/ - RES_BYTES - 2 * EPI_SLAB - TAIL_BYTES;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RES_BYTES + STAGES * STAGE_BYTES +
-                                    4 * BLOCK_N * 4 /*scale/shift x2*/ + (2 * STAGES + 5) * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 + RES_BYTES + STAGES * STAGE_BYTES + 2 * EPI_SLAB + TAIL_BYTES;
 };
 
 template <int BLOCK_N, int BLOCK_K, bool RESB = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmOb, const __grid_constant__ CUtensorMap tmOf,
                       const TcParams p) {
   using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB>;
   constexpr int STAGES = Cfg::STAGES;
@@ -75,11 +78,12 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint8_t* sRes = smem;                                 // RESB: [num_k][BLOCK_N rows][ROW_BYTES], loaded once
   uint8_t* sA = smem + Cfg::RES_BYTES;
   uint8_t* sB = sA + STAGES * Cfg::A_BYTES;             // !RESB: streamed weight tiles
-  float* sScale = reinterpret_cast<float*>(sA + STAGES * Cfg::STAGE_BYTES);    // [2][BLOCK_N]
+  uint8_t* sEpi = sA + STAGES * Cfg::STAGE_BYTES;       // 2 output slabs (1024-byte aligned: every part above is)
+  float* sScale = reinterpret_cast<float*>(sEpi + 2 * Cfg::EPI_SLAB);          // [2][BLOCK_N]
   float* sShift = sScale + 2 * BLOCK_N;                                        // [2][BLOCK_N]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + 2 * BLOCK_N);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
+  uint64_t* empty_bar = full_bar + STAGES_MAX_DUMMY;
+  uint64_t* tfull_bar = empty_bar + STAGES_MAX_DUMMY;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
   uint64_t* res_bar = tempty_bar + 2;         // RESB: resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
@@ -199,6 +203,11 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int ep_tid = threadIdx.x - 64;
+    EpiStage est{sEpi, Cfg::EPI_SLAB, 0};
+    if (ep_tid == 0) {
+      prefetch_tensormap(&tmOb);
+      prefetch_tensormap(&tmOf);
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -221,46 +230,30 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
         tmem_ld_wait();
-        if (valid) {
-          float y[32];
+        float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
-          if (p.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+        for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
+        if (p.residual && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint4 rv = __ldg(rp + u);
-              const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+          for (int u = 0; u < 4; ++u) {
+            const uint4 rv = __ldg(rp + u);
+            const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_bf16x2(w4[e]);
-                y[u * 8 + e * 2] += f.x;
-                y[u * 8 + e * 2 + 1] += f.y;
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(w4[e]);
+              y[u * 8 + e * 2] += f.x;
+              y[u * 8 + e * 2 + 1] += f.y;
             }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
-          }
-          if (p.out_bf16) {
-            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_off + c0);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint4 o;
-              o.x = pack_bf16x2(y[u * 8 + 0], y[u * 8 + 1]);
-              o.y = pack_bf16x2(y[u * 8 + 2], y[u * 8 + 3]);
-              o.z = pack_bf16x2(y[u * 8 + 4], y[u * 8 + 5]);
-              o.w = pack_bf16x2(y[u * 8 + 6], y[u * 8 + 7]);
-              op[u] = o;
-            }
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + row_off + c0);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) op[u] = make_float4(y[u * 4], y[u * 4 + 1], y[u * 4 + 2], y[u * 4 + 3]);
           }
         }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+        }
+        // rows beyond M are clipped by the TMA store
+        if (p.out_f32) epi_stage_store<true>(est, &tmOf, y, row, n0 + c0, m0, ep_tid);
+        if (p.out_bf16) epi_stage_store<false>(est, &tmOb, y, row, n0 + c0, m0, ep_tid);
       }
       tc_fence_before();
       __syncwarp();
@@ -268,6 +261,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (ep_tid == 0) bulk_wait_all();   // the last output slabs have left shared memory and are globally visible
   }
 
   tc_fence_before();
@@ -284,7 +278,8 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 static TmaEncoders g_enc;
 
 template <int BLOCK_N, int BLOCK_K, bool RESB = false>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
+                     const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -294,7 +289,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOb, tmOf, p);
   MSTR_LAUNCH_CHECK("conv_gemm_bf16_kernel");
   return MSTR_OK;
 }
@@ -400,18 +395,24 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
       reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
   }
 
+  // output tensor maps for the epilogue's TMA stores (an absent output gets a copy of the other map; it is never used)
+  alignas(64) CUtensorMap tmOb, tmOf;
+  if (out_bf16) { rc = encode_output_2d(g_enc, &tmOb, out_bf16, false, (uint64_t)C_out, (uint64_t)p.M); if (rc != MSTR_OK) return rc; }
+  if (out_f32) { rc = encode_output_2d(g_enc, &tmOf, out_f32, true, (uint64_t)C_out, (uint64_t)p.M); if (rc != MSTR_OK) return rc; }
+  if (!out_bf16) tmOb = tmOf;
+  if (!out_f32) tmOf = tmOb;
   cudaStream_t st = (cudaStream_t)stream;
   if (block_k == 64) {
-    if (block_n == 256) return launch_tc<256, 64>(tmA, tmB, p, st);
+    if (block_n == 256) return launch_tc<256, 64>(tmA, tmB, tmOb, tmOf, p, st);
     static const int use_resb = [] { const char* e = getenv("MSTR_CONV_RESB"); return (e && e[0] == '0') ? 0 : 1; }();
     if (block_n == 128 && use_resb && p.num_n_tiles == 1 && p.taps * p.cin_chunks <= TC_RES_MAX_KB &&
-        p.num_m_tiles >= 4 * sm_count())
-      return launch_tc<128, 64, true>(tmA, tmB, p, st);      // resident weights (64 -> 128 layers)
-    if (block_n == 128) return launch_tc<128, 64>(tmA, tmB, p, st);
-    return launch_tc<64, 64>(tmA, tmB, p, st);
+        p.num_m_tiles >= 4 * sm_count() && !out_f32)
+      return launch_tc<128, 64, true>(tmA, tmB, tmOb, tmOf, p, st);      // resident weights (64 -> 128 layers)
+    if (block_n == 128) return launch_tc<128, 64>(tmA, tmB, tmOb, tmOf, p, st);
+    return launch_tc<64, 64>(tmA, tmB, tmOb, tmOf, p, st);
   } else {
-    if (block_n == 256) return launch_tc<256, 32>(tmA, tmB, p, st);
-    if (block_n == 128) return launch_tc<128, 32>(tmA, tmB, p, st);
-    return launch_tc<64, 32>(tmA, tmB, p, st);
+    if (block_n == 256) return launch_tc<256, 32>(tmA, tmB, tmOb, tmOf, p, st);
+    if (block_n == 128) return launch_tc<128, 32>(tmA, tmB, tmOb, tmOf, p, st);
+    return launch_tc<64, 32>(tmA, tmB, tmOb, tmOf, p, st);
   }
 }

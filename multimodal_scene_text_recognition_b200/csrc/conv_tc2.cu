@@ -44,9 +44,11 @@ template <int BLOCK_N>
 struct Tc2Cfg {
   static constexpr int B_BYTES = (BLOCK_N / 2) * 128;       // this CTA's half of the weight tile
   static constexpr int STAGE_BYTES = T2_A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int TAIL_BYTES = 4 * BLOCK_N * 4 + (2 * 8 + 4) * 8 + 16;
+  static constexpr int RING_BUDGET = 227 * 1024 - 1024 - 2 * EPI_SLAB_BYTES - TAIL_BYTES;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 4 * BLOCK_N * 4 + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * EPI_SLAB_BYTES + TAIL_BYTES;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -122,6 +124,7 @@ __device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar) {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmOb, const __grid_constant__ CUtensorMap tmOf,
                            const Tc2Params p) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
@@ -130,11 +133,12 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * T2_A_BYTES;
-  float* sScale = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BLOCK_N]
+  uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;                            // 2 output slabs
+  float* sScale = reinterpret_cast<float*>(sEpi + 2 * EPI_SLAB_BYTES);         // [2][BLOCK_N]
   float* sShift = sScale + 2 * BLOCK_N;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + 2 * BLOCK_N);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -232,6 +236,11 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int ep_tid = threadIdx.x - 64;
+    EpiStage est{sEpi, EPI_SLAB_BYTES, 0};
+    if (ep_tid == 0) {
+      prefetch_tensormap(&tmOb);
+      prefetch_tensormap(&tmOf);
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -254,46 +263,30 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
         tmem_ld_wait();
-        if (valid) {
-          float y[32];
+        float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
-          if (p.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+        for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
+        if (p.residual && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint4 rv = __ldg(rp + u);
-              const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+          for (int u = 0; u < 4; ++u) {
+            const uint4 rv = __ldg(rp + u);
+            const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_bf16x2(w4[e]);
-                y[u * 8 + e * 2] += f.x;
-                y[u * 8 + e * 2 + 1] += f.y;
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(w4[e]);
+              y[u * 8 + e * 2] += f.x;
+              y[u * 8 + e * 2 + 1] += f.y;
             }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
-          }
-          if (p.out_bf16) {
-            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_off + c0);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint4 o;
-              o.x = pack_bf16x2(y[u * 8 + 0], y[u * 8 + 1]);
-              o.y = pack_bf16x2(y[u * 8 + 2], y[u * 8 + 3]);
-              o.z = pack_bf16x2(y[u * 8 + 4], y[u * 8 + 5]);
-              o.w = pack_bf16x2(y[u * 8 + 6], y[u * 8 + 7]);
-              op[u] = o;
-            }
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + row_off + c0);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) op[u] = make_float4(y[u * 4], y[u * 4 + 1], y[u * 4 + 2], y[u * 4 + 3]);
           }
         }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+        }
+        // registers -> swizzled smem slab -> TMA store (rows beyond M are clipped by the TMA unit)
+        if (p.out_f32) epi_stage_store<true>(est, &tmOf, y, row, n0 + c0, m0, ep_tid);
+        if (p.out_bf16) epi_stage_store<false>(est, &tmOb, y, row, n0 + c0, m0, ep_tid);
       }
       tc_fence_before();
       __syncwarp();
@@ -301,6 +294,7 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (ep_tid == 0) bulk_wait_all();   // the last output slabs have left shared memory and are globally visible
   }
 
   // neither CTA may leave (or free TMEM) while its peer can still read its shared memory / signal its barriers
@@ -315,7 +309,8 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 static TmaEncoders g_enc2;
 
 template <int BLOCK_N>
-static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Params& p, cudaStream_t st) {
+static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
+                      const Tc2Params& p, cudaStream_t st) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -338,7 +333,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2P
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSTR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_bf16_2cta_kernel<BLOCK_N>, tmA, tmB, p));
+  MSTR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_bf16_2cta_kernel<BLOCK_N>, tmA, tmB, tmOb, tmOf, p));
   MSTR_LAUNCH_CHECK("conv_gemm_bf16_2cta_kernel");
   return MSTR_OK;
 }
@@ -392,8 +387,13 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
     if (drv <= 13010 && (int64_t)B * H * W * C_in * 2 < 131072)
       reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
   }
-  if (block_n == 256) return launch_tc2<256>(tmA, tmB, p, st);
-  return launch_tc2<128>(tmA, tmB, p, st);
+  alignas(64) CUtensorMap tmOb, tmOf;
+  if (out_bf16) { rc = encode_output_2d(g_enc2, &tmOb, out_bf16, false, (uint64_t)C_out, (uint64_t)p.M); if (rc != MSTR_OK) return rc; }
+  if (out_f32) { rc = encode_output_2d(g_enc2, &tmOf, out_f32, true, (uint64_t)C_out, (uint64_t)p.M); if (rc != MSTR_OK) return rc; }
+  if (!out_bf16) tmOb = tmOf;
+  if (!out_f32) tmOf = tmOb;
+  if (block_n == 256) return launch_tc2<256>(tmA, tmB, tmOb, tmOf, p, st);
+  return launch_tc2<128>(tmA, tmB, tmOb, tmOf, p, st);
 }
 
 }  // namespace mstr

@@ -165,6 +165,58 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- epilogue output path: registers -> swizzled shared-memory slab -> TMA store ---------------------
+// The accumulator layout gives every thread one output ROW; storing it directly makes each warp store
+// instruction touch 32 different cache lines with 16 bytes each (ncu: 16.5 of 32 bytes per sector used, and
+// ~2 cycles of LSU time per 16-byte request, which bounded every small-K layer).  Instead the 128 epilogue
+// threads write a [128 rows x 32 columns] slab into shared memory (bank-conflict-free thanks to the TMA
+// swizzle pattern) and one thread hands it to the TMA engine, which writes whole lines and clips the rows
+// beyond M.  Two slabs alternate so the store of slab g overlaps the math of slab g+1.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+constexpr int EPI_SLAB_BYTES = 16384;        // 128 rows x 128 bytes (32 f32 columns); bf16 slabs use half of it
+struct EpiStage {
+  uint8_t* buf;   // 2 slabs, 1024-byte aligned
+  int slab;       // bytes per slab: EPI_SLAB_BYTES, or half of it when only bf16 is ever stored
+  int turn;
+};
+
+// Called by all 128 epilogue threads (named barriers 2 and 3).  y = this thread's row, columns [col0, col0+32).
+template <bool F32>
+__device__ __forceinline__ void epi_stage_store(EpiStage& st, const CUtensorMap* tmO, const float (&y)[32], int row,
+                                                int col0, int m0, int ep_tid) {
+  uint8_t* buf = st.buf + (st.turn & 1) * st.slab;
+  asm volatile("bar.sync 2, 128;" ::: "memory");     // the store that last read this slab has drained it
+  if constexpr (F32) {
+    uint8_t* r = buf + row * 128;                      // 128-byte rows, 128B swizzle: chunk ^= row & 7
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<float4*>(r + ((c ^ (row & 7)) << 4)) = make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
+  } else {
+    uint8_t* r = buf + row * 64;                       // 64-byte rows, 64B swizzle: chunk ^= (row >> 1) & 3
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(r + ((c ^ ((row >> 1) & 3)) << 4)) =
+          make_uint4(pack_bf16x2(y[8 * c], y[8 * c + 1]), pack_bf16x2(y[8 * c + 2], y[8 * c + 3]),
+                     pack_bf16x2(y[8 * c + 4], y[8 * c + 5]), pack_bf16x2(y[8 * c + 6], y[8 * c + 7]));
+  }
+  fence_proxy_async_smem();
+  asm volatile("bar.sync 3, 128;" ::: "memory");     // slab complete
+  if (ep_tid == 0) {
+    tma_store_2d(tmO, buf, col0, m0);
+    bulk_commit();
+    bulk_wait_read<1>();                               // the OTHER slab's store has finished reading shared memory
+  }
+  ++st.turn;
+}
+
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -189,6 +241,22 @@ static inline int load_tma_encoders(TmaEncoders& e) {
   MSTR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
   MSTR_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, MSTR_ERR_CUDA, "cuTensorMapEncodeIm2col not available");
   e.im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+  return MSTR_OK;
+}
+
+// 2-D output tensor [outer][inner] of 2-byte (bf16) or 4-byte (f32) elements for the epilogue's TMA stores:
+// 32-column boxes, i.e. 64-byte (bf16, 64B swizzle) or 128-byte (f32, 128B swizzle) rows x 128 rows.
+static inline int encode_output_2d(const TmaEncoders& e, CUtensorMap* map, const void* base, bool f32, uint64_t inner,
+                                   uint64_t outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = e.tiled(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                       const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed with CUresult %d", (int)r);
   return MSTR_OK;
 }
 

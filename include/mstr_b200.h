@@ -101,6 +101,16 @@ int mstr_conv_gemm_bf16(const void* x, const void* w, const float* scale, const 
                         int C_in, int C_out, int R, int S, int stride_h, int stride_w, int pad_h,
                         int pad_w, int relu, mstr_stream_t stream);
 
+/* TF32 parity mode on the tensor cores (error-compensated 3xTF32, see csrc/conv_tf32.cu): fp32 NHWC
+ * activations and fp32 results like mstr_conv_gemm_f32, ~fp32 accuracy, tcgen05.mma.kind::tf32.
+ *   w_hi = w with the low 13 mantissa bits cleared, w_lo = w - w_hi (both f32, [C_out][R][S][C_in])
+ * Requires C_in % 32 == 0, C_out % 128 == 0.
+ */
+int mstr_conv_gemm_tf32(const float* x, const float* w_hi, const float* w_lo, const float* scale,
+                        const float* shift, const float* residual, float* out, int B, int H, int W, int C_in,
+                        int C_out, int R, int S, int stride_h, int stride_w, int pad_h, int pad_w, int relu,
+                        mstr_stream_t stream);
+
 /* ---- pooling / layout helpers -------------------------------------------------------------
  * mstr_maxpool_nhwc : nn.MaxPool2d with -inf padding (feature_extraction.py:66,72,78).
  * mstr_mean_hw      : AdaptiveAvgPool2d(1) of the localisation net (transformation.py:57):

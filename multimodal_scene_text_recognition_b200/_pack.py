@@ -32,9 +32,17 @@ def cached(module: torch.nn.Module, key, sources: Iterable[torch.Tensor], build:
 def act_dtype(precision: str) -> torch.dtype:
     if precision == 'bf16':
         return torch.bfloat16
-    if precision == 'fp32':
+    if precision in ('fp32', 'tf32'):
         return torch.float32
-    raise ValueError("config.PRECISION must be 'bf16' or 'fp32', got %r" % (precision,))
+    raise ValueError("config.PRECISION must be 'bf16', 'tf32' or 'fp32', got %r" % (precision,))
+
+
+def wrap_weight(w: torch.Tensor, precision: str):
+    """GEMM weight in the activation dtype; for the 'tf32' mode the fp32 weight with its hi/lo split."""
+    if precision == 'tf32':
+        from .ops import SplitWeight
+        return SplitWeight(w.float().contiguous())
+    return w.to(act_dtype(precision)).contiguous()
 
 
 def bn_sources(bn: torch.nn.BatchNorm2d):
@@ -51,7 +59,7 @@ def fold_bn(bn: torch.nn.BatchNorm2d):
 def pack_conv(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, precision: str):
     """-> (w [Cout,R,S,Cin] in the activation dtype, scale, shift)."""
     def build():
-        w = conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(act_dtype(precision))
+        w = wrap_weight(conv.weight.detach().permute(0, 2, 3, 1).contiguous(), precision)
         scale, shift = fold_bn(bn)
         return w, scale, shift
     return cached(conv, ('conv', precision), [conv.weight] + bn_sources(bn), build)

@@ -45,8 +45,10 @@ POST_DECODER_MLP = False
 
 # ---- additions of this implementation -----------------------------------------------------------
 # 'bf16' : throughput mode - tcgen05 tensor-core GEMMs with bf16 operands, fp32 accumulation/epilogues
-# 'fp32' : parity mode - every product in fp32 FMA (stands in for the north star's "TF32 mode",
-#          which is specified by bit-identical ids; single-pass TF32 cannot deliver that here)
+# 'tf32' : parity mode on the tensor cores - error-compensated 3xTF32 (tcgen05.mma.kind::tf32 on hi/lo split
+#          operands, fp32 accumulation) for every conv / linear with C_in % 32 == 0 and C_out % 128 == 0, fp32
+#          elsewhere; single-pass TF32 cannot deliver the north star's "ids identical" on this network
+# 'fp32' : parity mode with every product in fp32 FMA (SIMT kernels only)
 PRECISION = 'bf16'
 # 'folded'    : grid = (P_hat inv_delta_C[:, :F]) C'  with the constant folded in fp64 (more accurate)
 # 'reference' : T = inv_delta_C [C';0] then P' = P_hat T in fp32, the order of transformation.py:161-162

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .. import config, ops
-from .._pack import act_dtype, cached, require_inference
+from .._pack import act_dtype, cached, require_inference, wrap_weight
 
 
 def _cell_pack(cell: "AttentionCell", generator: nn.Linear, precision: str):
@@ -31,7 +31,7 @@ def _cell_pack(cell: "AttentionCell", generator: nn.Linear, precision: str):
         f = lambda t: t.detach().float().contiguous()
         w_ih = cell.rnn.weight_ih.detach().float()
         pk = {
-            "w_i2h": f(cell.i2h.weight).to(act_dtype(precision)).contiguous(),
+            "w_i2h": wrap_weight(f(cell.i2h.weight), precision),
             "w_h2h": f(cell.h2h.weight), "b_h2h": f(cell.h2h.bias),
             "w_score": f(cell.score.weight).view(-1).contiguous(),
             "w_ctx": w_ih[:, :hd].contiguous(),                 # context part of LSTMCell.weight_ih

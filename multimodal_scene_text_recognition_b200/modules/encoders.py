@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import config, ops
-from .._pack import act_dtype, cached, require_inference
+from .._pack import act_dtype, cached, require_inference, wrap_weight
 
 
 class BidirectionalLSTM(nn.Module):
@@ -42,9 +42,9 @@ class BidirectionalLSTM(nn.Module):
             bias = torch.cat([r.bias_ih_l0 + r.bias_hh_l0,
                               r.bias_ih_l0_reverse + r.bias_hh_l0_reverse], 0).detach().float()  # [2*4H]
             w_hh = torch.stack([r.weight_hh_l0, r.weight_hh_l0_reverse], 0).detach().float()     # [2, 4H, H]
-            return {"w_ih": w_ih.to(dt).contiguous(), "bias": bias.contiguous(), "w_hh": w_hh.contiguous(),
+            return {"w_ih": wrap_weight(w_ih, precision), "bias": bias.contiguous(), "w_hh": w_hh.contiguous(),
                     "w_hh_tc": ops.pack_w_hh_bf16(w_hh) if precision == 'bf16' else None,
-                    "w_lin": self.linear.weight.detach().float().to(dt).contiguous(),
+                    "w_lin": wrap_weight(self.linear.weight.detach().float(), precision),
                     "b_lin": self.linear.bias.detach().float().contiguous()}
         return cached(self, ("bilstm", precision), src, build)
 

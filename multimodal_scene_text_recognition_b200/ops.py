@@ -67,6 +67,26 @@ class _timed:
         return False
 
 
+class SplitWeight:
+    """fp32 weight with its TF32 head / tail split (w = hi + lo, hi = w with the low 13 mantissa bits
+    cleared) for the 3xTF32 tensor-core parity mode.  Passing one as ``w`` to conv_gemm / linear selects
+    mstr_conv_gemm_tf32 where the layer qualifies (C_in % 32 == 0, C_out % 128 == 0); other layers use
+    ``full`` with the fp32 SIMT kernel."""
+
+    def __init__(self, w: torch.Tensor, hi: Optional[torch.Tensor] = None, lo: Optional[torch.Tensor] = None):
+        self.full = w.contiguous()
+        if hi is None:
+            hi = (self.full.view(torch.int32) & -8192).view(torch.float32)
+            lo = self.full - hi
+        self.hi, self.lo = hi.contiguous(), lo.contiguous()
+
+    shape = property(lambda self: self.full.shape)
+    dtype = property(lambda self: self.full.dtype)
+
+    def reshape(self, *shape):
+        return SplitWeight(self.full.reshape(*shape), self.hi.reshape(*shape), self.lo.reshape(*shape))
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return MSTR_F32
@@ -141,6 +161,9 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
     kernel and return an f32 tensor; bf16 tensors run the tcgen05 kernel and return
     (out_bf16 or None, out_f32 or None) according to want_bf16 / want_f32.
     """
+    split = w if isinstance(w, SplitWeight) else None
+    if split is not None:
+        w = split.full
     _req(x, "x"); _req(w, "w", x.dtype); _req(scale, "scale", torch.float32); _req(shift, "shift", torch.float32)
     _req(residual, "residual", x.dtype)
     B, H, W, Cin = x.shape
@@ -152,6 +175,13 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
         assert residual.shape == (B, P, Q, Cout)
     flops = 2.0 * B * P * Q * Cout * R * S * Cin
     desc = "M=%d (B%d %dx%d) %d->%d %dx%d%s" % (B * P * Q, B, P, Q, Cin, Cout, R, S, " +res" if residual is not None else "")
+    if x.dtype == torch.float32 and split is not None and Cin % 32 == 0 and Cout % 128 == 0:
+        out = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32)
+        with _timed("conv_gemm_tf32x3", flops, "flop", desc):
+            check(lib().mstr_conv_gemm_tf32(ptr(x), ptr(split.hi), ptr(split.lo), ptr(scale), ptr(shift), ptr(residual),
+                                            ptr(out), B, H, W, Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1],
+                                            int(relu), stream_ptr()), "mstr_conv_gemm_tf32")
+        return out
     if x.dtype == torch.float32:
         out = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32)
         with _timed("conv_gemm_f32", flops, "flop", desc):

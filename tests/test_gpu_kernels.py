@@ -122,6 +122,25 @@ def test_conv_gemm_f32(case):
     assert_close(host(out), ref, 5e-6, "conv_gemm_f32 %s" % (case,))
 
 
+TF32_CASES = [c for c in CONV_CASES if c[3] % 32 == 0 and c[4] % 128 == 0]
+
+
+@pytest.mark.parametrize("case", TF32_CASES)
+def test_conv_gemm_tf32x3_tensor_cores(case):
+    """3xTF32 (hi/lo split operands on tcgen05.mma.kind::tf32) must be as accurate as the fp32 FMA kernel."""
+    stride, pad, relu = case[7], case[8], case[10]
+    x, w, scale, shift, res = _conv_inputs(case, 3, False)
+    ref = _conv_ref(x, w, scale, shift, res, stride, pad, relu)
+    out = ops.conv_gemm(dev(x), ops.SplitWeight(dev(w)), dev(scale), dev(shift), None if res is None else dev(res),
+                        stride=stride, pad=pad, relu=relu)
+    torch.cuda.synchronize()
+    assert_close(host(out), ref, 5e-6, "conv_gemm_tf32x3 %s" % (case,))
+    # and it really is a different code path from the SIMT kernel: many tiles, ragged M
+    if case[4] == 512:
+        sw = ops.SplitWeight(dev(w))
+        assert torch.equal(sw.hi + sw.lo, sw.full) and not torch.equal(sw.hi, sw.full)
+
+
 def test_linear_f32_small_n():
     """nn.Linear with N=40 (localization_fc2) and a bias but no scale."""
     r = rng(4)

@@ -59,6 +59,29 @@ def test_fp32_matches_reference_golden(sd_cfg_a, golden_dir):
     assert_close(host(tf), g["logits_tf"], 3e-4, "teacher-forced logits vs reference")
 
 
+def test_tf32_tensor_core_parity_mode(sd_cfg_a, golden_dir):
+    """config.PRECISION = 'tf32': convs / linears on tcgen05.mma.kind::tf32 with the 3xTF32 split.  North-star
+    tolerance for the TF32 mode: ids bit-identical, logits within 1e-4 relative (the fp32 noise floor of this
+    network is ~2e-4, see test_fp32_matches_reference_golden)."""
+    g = np.load(os.path.join(golden_dir, "cfg_a.npz"))
+    wseed, dseed, B = [int(v) for v in g["meta"]]
+    x, ov, sc, io = _inputs(B, seed=dseed)
+    m = load_model(sd_cfg_a, precision="tf32", TPS_GRID="reference", DECODER_EARLY_EXIT=False)
+    st = {}
+    out = _run(m, x, ov, sc, io, st)
+    assert_close(nchw(host(st["features"])), g["features"], 1e-4, "tf32 ResNet features vs reference")
+    assert_close(host(st["enc1"]), g["enc1"], 1e-4, "tf32 encoder output vs reference")
+    assert np.array_equal(host(out["ids"]), g["ids"]), "decoded ids differ from the reference"
+    assert_close(host(out["logits"]), g["logits"], 3e-4, "tf32 logits vs reference")
+    # a larger batch against the oracle
+    B2 = 24
+    x, ov, sc, io = _inputs(B2, seed=321)
+    ref = orc.forward(sd_cfg_a, x, ov, sc, io, stages=True)
+    out = _run(m, x, ov, sc, io)
+    assert np.array_equal(host(out["ids"]), ref["ids"])
+    assert_close(host(out["logits"]), ref["logits"], 3e-4, "tf32 logits vs oracle")
+
+
 def test_fp32_matches_oracle_batch(sd_cfg_a):
     B = 24
     x, ov, sc, io = _inputs(B, seed=321)

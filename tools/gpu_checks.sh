@@ -18,13 +18,13 @@ PT="python -m pytest -q -m gpu -p no:cacheprovider -x"
 run tps        300 $PT tests/test_gpu_kernels.py -k "tps"
 run first      300 $PT tests/test_gpu_kernels.py -k "conv3x3_first"
 run conv_f32   300 $PT tests/test_gpu_kernels.py -k "conv_gemm_f32 or linear_f32"
-run conv_tc    300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "bf16_tcgen05"
+run conv_tc    300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "bf16_tcgen05 or tf32x3"
 run conv_tc2   300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "many_tiles or swapped or resident"
 run small      300 $PT tests/test_gpu_kernels.py -k "maxpool or mean or embed or errors"
 run bilstm     300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "bilstm"
 run attn       300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "attn and not bf16"
 run attn_tc    300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "attn_decode_bf16"
-run model_fp32 600 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_model.py -k "fp32 or scene"
+run model_fp32 600 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_model.py -k "fp32 or scene or tf32"
 run model_bf16 600 python -m pytest -q -m gpu -p no:cacheprovider -s tests/test_gpu_model.py -k "bf16"
 run smoke      300 python -c "import __graft_entry__ as g; g.smoke()"
 run h2d        120 python tools/diag_h2d.py

@@ -24,7 +24,7 @@ ref64 = orc.forward(sd, x[:16], ov[:16], sc[:16], io[:16], dtype=np.float64, sta
 report = {"B": B}
 print("fp32 oracle vs fp64 oracle (first 16): logits %.2e, ids equal %d/16" % (
     err(ref32["logits"][:16], ref64["logits"])[1], (ref32["ids"][:16] == ref64["ids"]).all(1).sum()))
-for precision, grid in (("fp32", "reference"), ("fp32", "folded"), ("bf16", "folded")):
+for precision, grid in (("fp32", "reference"), ("tf32", "reference"), ("fp32", "folded"), ("bf16", "reference")):
     m = load_model(sd, precision=precision, TPS_GRID=grid, DECODER_EARLY_EXIT=False)
     st = {}
     with torch.no_grad():

@@ -9,6 +9,13 @@
 // tcgen05.mma.kind::tf32 (128x128x8) per K-step instead of one: 1/6 of the bf16 rate, ~10x the fp32
 // SIMT kernel.
 //
+// Accumulation: the tensor core adds into its fp32 accumulator with truncation, so a single TMEM
+// accumulation over K = 4608 drifts by ~2.5e-5 of the result (measured), an order of magnitude more than
+// an fp32 FMA chain.  K is therefore cut into chunks of TF_CHUNK_KB k-blocks (256 values): each chunk
+// accumulates in a fresh TMEM buffer and the epilogue threads add the chunk results into fp32 registers
+// (round-to-nearest), the same two-level scheme fp8 GEMMs use.  The two TMEM buffers alternate per
+// chunk, so the promotion of chunk i overlaps the MMAs of chunk i+1.
+//
 // Operands stay plain fp32 in global memory (NHWC activations, [C_out][R][S][C_in] weights; the
 // weight split is done once on the host).  Per k-block of 32 channels the producer warp TMA-loads
 // the raw fp32 activation tile (im2col map, 128 pixels x 128 bytes) plus the w_hi / w_lo tiles; four
@@ -39,6 +46,7 @@ constexpr int TF_THREADS = 320;           // producer, MMA, 4 epilogue warps, 4 
 constexpr int TF_TILE = 128 * 128;        // 128 rows x 32 fp32 (one 128-byte swizzle span)
 constexpr int TF_STAGE = 5 * TF_TILE;     // x_raw, x_hi, x_lo, w_hi, w_lo
 constexpr int TF_STAGES = 2;
+constexpr int TF_CHUNK_KB = 8;             // k-blocks (of 32 values) per TMEM accumulation chunk
 constexpr int TF_SMEM_BYTES = 1024 + TF_STAGES * TF_STAGE + 2 * EPI_SLAB_BYTES + 4 * 128 * 4 + 16 * 8 + 16;
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -135,29 +143,32 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&ready_bar[stage], phase);
+        for (int kb0 = 0; kb0 < num_k; kb0 += TF_CHUNK_KB) {
+          const int kb1 = min(kb0 + TF_CHUNK_KB, num_k);
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t base = smem_u32(smem + stage * TF_STAGE);
-          const uint32_t x_hi = base + 1 * TF_TILE, x_lo = base + 2 * TF_TILE;
-          const uint32_t w_hi = base + 3 * TF_TILE, w_lo = base + 4 * TF_TILE;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&ready_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t base = smem_u32(smem + stage * TF_STAGE);
+            const uint32_t x_hi = base + 1 * TF_TILE, x_lo = base + 2 * TF_TILE;
+            const uint32_t w_hi = base + 3 * TF_TILE, w_lo = base + 4 * TF_TILE;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 8 fp32 = 32 bytes per K-step
-            const uint64_t dxh = make_smem_desc<128>(x_hi + k * 32), dxl = make_smem_desc<128>(x_lo + k * 32);
-            const uint64_t dwh = make_smem_desc<128>(w_hi + k * 32), dwl = make_smem_desc<128>(w_lo + k * 32);
-            umma_tf32(d_tmem, dxl, dwh, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
-            umma_tf32(d_tmem, dxh, dwl, idesc, 1u);
-            umma_tf32(d_tmem, dxh, dwh, idesc, 1u);
+            for (int k = 0; k < 4; ++k) {   // 8 fp32 = 32 bytes per K-step
+              const uint64_t dxh = make_smem_desc<128>(x_hi + k * 32), dxl = make_smem_desc<128>(x_lo + k * 32);
+              const uint64_t dwh = make_smem_desc<128>(w_hi + k * 32), dwl = make_smem_desc<128>(w_lo + k * 32);
+              umma_tf32(d_tmem, dxl, dwh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);   // small terms first
+              umma_tf32(d_tmem, dxh, dwl, idesc, 1u);
+              umma_tf32(d_tmem, dxh, dwh, idesc, 1u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+            if (++stage == TF_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);
-          if (++stage == TF_STAGES) { stage = 0; phase ^= 1; }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else if (warp >= 6) {
@@ -203,19 +214,35 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         sf[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+      // two-level accumulation: add every K chunk's TMEM result into fp32 registers
+      float sum[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+      for (int kb0 = 0; kb0 < num_k; kb0 += TF_CHUNK_KB) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128 + c0), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
       const int m = m0 + row;
       const bool valid = m < p.M;
       const size_t row_off = (size_t)m * p.Cout + n0;
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128 + c0), v);
-        tmem_ld_wait();
         float y[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
+        for (int j = 0; j < 32; ++j) y[j] = fmaf(sum[c0 + j], sc[c0 + j], sf[c0 + j]);
         if (p.residual && valid) {
           const float4* rp = reinterpret_cast<const float4*>(p.residual + row_off + c0);
 #pragma unroll
@@ -230,11 +257,6 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         }
         epi_stage_store<true>(est, &tmO, y, row, n0 + c0, m0, ep_tid);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
     if (ep_tid == 0) bulk_wait_all();
   }

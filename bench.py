@@ -302,7 +302,8 @@ def run_ours(args):
     value = B * world * args.steps / (total_ms * 1e-3)
     e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
     kern = timer.summary()
-    conv = kern.get("conv_gemm_bf16_2cta" if args.precision == "bf16" else "conv_gemm_f32", {"launches": 0, "ms": 0.0, "work": 0.0})
+    conv = kern.get({"bf16": "conv_gemm_bf16_2cta", "tf32": "conv_gemm_tf32x3"}.get(args.precision, "conv_gemm_f32"),
+                    {"launches": 0, "ms": 0.0, "work": 0.0})
     conv_tflops = conv["work"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
     peak = peaks["bf16_sustained"]
     traffic = None
@@ -320,7 +321,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": {"bf16": "bf16", "tf32": "tf32x3"}.get(args.precision, "f32"), "data": "synthetic",
         "config": {
             "workload": "TPS-ResNet-BiLSTM-Attn greedy forward (BASELINE.json configs[2]): 1x32x100 crops, "
                         "26 decode steps without early exit, 97 classes, overlap semantic vectors, seeded random-init weights",
@@ -360,7 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=4096, help="crops per GPU per step")
-    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--precision", choices=["bf16", "tf32", "fp32"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write the per-call-site kernel table (JSON) to this path")
     args = ap.parse_args()

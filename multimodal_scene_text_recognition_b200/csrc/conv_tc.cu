@@ -51,10 +51,14 @@ constexpr int TC_THREADS = 192;
 constexpr int TC_RES_MAX_KB = 9;
 constexpr int STAGES_MAX_DUMMY = 8;   // barrier storage is sized for the maximum ring depth   // 9 x 64 = 576 = 3x3x64: the 64 -> 128 layers (144 KB of weights)
 
-template <int BLOCK_N, int BLOCK_K, bool RESB = false>
+// MT ("M tiles per CTA"): with MT = 2 a CTA owns 256 output rows as two 128-row accumulators that share every
+// weight tile.  The C_out = 128 layers are bound by operand traffic from L2 (32 KB per 128x128x64 block);
+// sharing the weight tile cuts that by a quarter and doubles the tensor-core work per barrier round trip.
+template <int BLOCK_N, int BLOCK_K, bool RESB = false, int MT = 1>
 struct TcCfg {
   static constexpr int ROW_BYTES = BLOCK_K * 2;
-  static constexpr int A_BYTES = TC_BLOCK_M * ROW_BYTES;
+  static constexpr int A_HALF = TC_BLOCK_M * ROW_BYTES;
+  static constexpr int A_BYTES = MT * A_HALF;
   static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
   static constexpr int RES_BYTES = RESB ? TC_RES_MAX_KB * B_BYTES : 0;
   static constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
@@ -62,17 +66,18 @@ struct TcCfg {
   static constexpr int TAIL_BYTES = 4 * BLOCK_N * 4 /*scale/shift x2*/ + (2 * STAGES_MAX_DUMMY + 5) * 8 + 16;
   static constexpr int RING_BUDGET = 227 * 1024 - 1024 /*align slack*/ - RES_BYTES - 2 * EPI_SLAB - TAIL_BYTES;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
-  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int TMEM_COLS = 2 * MT * BLOCK_N < 32 ? 32 : 2 * MT * BLOCK_N;
   static constexpr int SMEM_BYTES = 1024 + RES_BYTES + STAGES * STAGE_BYTES + 2 * EPI_SLAB + TAIL_BYTES;
 };
 
-template <int BLOCK_N, int BLOCK_K, bool RESB = false>
+template <int BLOCK_N, int BLOCK_K, bool RESB = false, int MT = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOb, const __grid_constant__ CUtensorMap tmOf,
                       const TcParams p) {
-  using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB>;
+  using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB, MT>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int TILE_M = TC_BLOCK_M * MT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sRes = smem;                                 // RESB: [num_k][BLOCK_N rows][ROW_BYTES], loaded once
@@ -124,13 +129,18 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-        const int m0 = (tile / p.num_n_tiles) * TC_BLOCK_M;
-        int cw = 0, chh = 0, cn = 0;
-        if (p.im2col) {
-          const int q = m0 % p.Q, pp = (m0 / p.Q) % p.P;
-          cn = m0 / (p.Q * p.P);
-          cw = q * p.sw - p.pw;
-          chh = pp * p.sh - p.ph;
+        const int m0 = (tile / p.num_n_tiles) * TILE_M;
+        int cw[MT], chh[MT], cn[MT];
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+          cw[h] = chh[h] = cn[h] = 0;
+          if (p.im2col) {
+            const int mh = m0 + h * TC_BLOCK_M;
+            const int q = mh % p.Q, pp = (mh / p.Q) % p.P;
+            cn[h] = mh / (p.Q * p.P);
+            cw[h] = q * p.sw - p.pw;
+            chh[h] = pp * p.sh - p.ph;
+          }
         }
         // While this tile streams, pull the A rows of this CTA's NEXT tile from HBM into L2 (the taps of
         // a tile re-read almost the same pixels, so one tap's worth of prefetch covers the tile): the
@@ -142,7 +152,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const int r = tap / p.S, s = tap - r * p.S;
           for (int cc = 0; cc < p.cin_chunks; ++cc, ++kb_index) {
             if (do_prefetch && kb_index == 2) {
-              const int nm0 = (next_tile / p.num_n_tiles) * TC_BLOCK_M;
+              const int nm0 = (next_tile / p.num_n_tiles) * TILE_M;
               if (p.im2col) {
                 const int nq = nm0 % p.Q, npp = (nm0 / p.Q) % p.P, nn = nm0 / (p.Q * p.P);
                 for (int c2 = 0; c2 < p.cin_chunks; ++c2)
@@ -154,11 +164,15 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            if (p.im2col)
-              tma_load_im2col_4d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cc * BLOCK_K, cw, chh, cn,
-                                 (uint16_t)s, (uint16_t)r);
-            else
-              tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cc * BLOCK_K, m0);
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {
+              uint8_t* dstA = sA + stage * Cfg::A_BYTES + h * Cfg::A_HALF;
+              if (p.im2col)
+                tma_load_im2col_4d(dstA, &tmA, &full_bar[stage], cc * BLOCK_K, cw[h], chh[h], cn[h], (uint16_t)s,
+                                   (uint16_t)r);
+              else
+                tma_load_2d(dstA, &tmA, &full_bar[stage], cc * BLOCK_K, m0 + h * TC_BLOCK_M);
+            }
             if constexpr (!RESB)
               tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], (tap * p.cin_chunks + cc) * BLOCK_K, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -178,7 +192,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * BLOCK_N);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -186,9 +200,12 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t b_addr = RESB ? smem_u32(sRes + kb * Cfg::B_BYTES) : smem_u32(sB + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t da = make_smem_desc<Cfg::ROW_BYTES>(a_addr + k * 32);
             const uint64_t db = make_smem_desc<Cfg::ROW_BYTES>(b_addr + k * 32);
-            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {
+              const uint64_t da = make_smem_desc<Cfg::ROW_BYTES>(a_addr + h * Cfg::A_HALF + k * 32);
+              umma_bf16(d_tmem + (uint32_t)(h * BLOCK_N), da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);                  // frees the smem slot once these MMAs retire
           if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
@@ -212,7 +229,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-      const int m0 = (tile / p.num_n_tiles) * TC_BLOCK_M;
+      const int m0 = (tile / p.num_n_tiles) * TILE_M;
       float* sc = sScale + acc * BLOCK_N;
       float* sf = sShift + acc * BLOCK_N;
       for (int i = ep_tid; i < BLOCK_N; i += 128) {
@@ -222,38 +239,44 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int m = m0 + row;
-      const bool valid = m < p.M;
-      const size_t row_off = (size_t)m * p.Cout + n0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
-        tmem_ld_wait();
-        float y[32];
+      for (int h = 0; h < MT; ++h) {
+        const int mh = m0 + h * TC_BLOCK_M;
+        const int m = mh + row;
+        const bool valid = m < p.M;
+        const size_t row_off = (size_t)m * p.Cout + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * MT + h) * BLOCK_N + c0), v);
+          tmem_ld_wait();
+          float y[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
-        if (p.residual && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+          for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
+          if (p.residual && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint4 rv = __ldg(rp + u);
-            const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+            for (int u = 0; u < 4; ++u) {
+              const uint4 rv = __ldg(rp + u);
+              const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(w4[e]);
-              y[u * 8 + e * 2] += f.x;
-              y[u * 8 + e * 2 + 1] += f.y;
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w4[e]);
+                y[u * 8 + e * 2] += f.x;
+                y[u * 8 + e * 2 + 1] += f.y;
+              }
             }
           }
-        }
-        if (p.relu) {
+          if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+          }
+          // rows beyond M are clipped by the TMA store (a tile that starts beyond M stores nothing)
+          if (mh < p.M) {
+            if (p.out_f32) epi_stage_store<true>(est, &tmOf, y, row, n0 + c0, mh, ep_tid);
+            if (p.out_bf16) epi_stage_store<false>(est, &tmOb, y, row, n0 + c0, mh, ep_tid);
+          }
         }
-        // rows beyond M are clipped by the TMA store
-        if (p.out_f32) epi_stage_store<true>(est, &tmOf, y, row, n0 + c0, m0, ep_tid);
-        if (p.out_bf16) epi_stage_store<false>(est, &tmOb, y, row, n0 + c0, m0, ep_tid);
       }
       tc_fence_before();
       __syncwarp();
@@ -277,19 +300,21 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // ---------------------------------------------------------------------------------------------
 static TmaEncoders g_enc;
 
-template <int BLOCK_N, int BLOCK_K, bool RESB = false>
+template <int BLOCK_N, int BLOCK_K, bool RESB = false, int MT = 1>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
                      const TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB>;
+  using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB>,
+    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB, MT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  TcParams q = p;
+  q.num_m_tiles = ceil_div(p.M, TC_BLOCK_M * MT);
+  const int tiles = q.num_m_tiles * q.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOb, tmOf, p);
+  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOb, tmOf, q);
   MSTR_LAUNCH_CHECK("conv_gemm_bf16_kernel");
   return MSTR_OK;
 }
@@ -404,10 +429,14 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   cudaStream_t st = (cudaStream_t)stream;
   if (block_k == 64) {
     if (block_n == 256) return launch_tc<256, 64>(tmA, tmB, tmOb, tmOf, p, st);
-    static const int use_resb = [] { const char* e = getenv("MSTR_CONV_RESB"); return (e && e[0] == '0') ? 0 : 1; }();
+    static const int use_resb = [] { const char* e = getenv("MSTR_CONV_RESB"); return (e && e[0] == '1') ? 1 : 0; }();
     if (block_n == 128 && use_resb && p.num_n_tiles == 1 && p.taps * p.cin_chunks <= TC_RES_MAX_KB &&
         p.num_m_tiles >= 4 * sm_count() && !out_f32)
       return launch_tc<128, 64, true>(tmA, tmB, tmOb, tmOf, p, st);      // resident weights (64 -> 128 layers)
+    // two 128-row accumulators per CTA sharing each weight tile (MSTR_CONV_MT2=0 disables)
+    static const int use_mt2 = [] { const char* e = getenv("MSTR_CONV_MT2"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (block_n == 128 && use_mt2 && p.num_m_tiles >= 8 * sm_count())
+      return launch_tc<128, 64, false, 2>(tmA, tmB, tmOb, tmOf, p, st);
     if (block_n == 128) return launch_tc<128, 64>(tmA, tmB, tmOb, tmOf, p, st);
     return launch_tc<64, 64>(tmA, tmB, tmOb, tmOf, p, st);
   } else {

@@ -181,6 +181,26 @@ def test_conv_gemm_bf16_resident_weights():
         assert_close(host(out_f), ref, 2e-5, "conv_gemm_bf16 resident weights %s" % (case,))
 
 
+def test_conv_gemm_bf16_two_accumulators_per_cta():
+    """C_out = 128 layers with >= 8 tiles per SM run with two 128-row accumulators per CTA sharing each
+    weight tile (conv_gemm_bf16_kernel<128, 64, false, 2>): M = 193*16*50 = 154400 (ragged: not a multiple of
+    256).  The oracle is evaluated on the first and last crops (convolution is per-crop independent)."""
+    bf = torch.bfloat16
+    for case in ((193, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), True, True),
+                 (193, 16, 50, 128, 128, 3, 3, (1, 1), (1, 1), False, True)):
+        x, w, scale, shift, res = _conv_inputs(case, 29, True)
+        sel = [0, 1, 2, 95, 96, 190, 191, 192]
+        ref = _conv_ref(x[sel], w, scale, shift, None if res is None else res[sel], case[7], case[8], case[10])
+        out_b = ops.conv_gemm(dev(x, bf), dev(w, bf), dev(scale), dev(shift), None if res is None else dev(res, bf),
+                              stride=case[7], pad=case[8], relu=case[10], want_f32=False, want_bf16=True)
+        torch.cuda.synchronize()
+        got = host(out_b)[sel].astype(np.float64)
+        tol = np.maximum(np.abs(ref), 1e-3) * 2.0 ** -7
+        bad = np.abs(got - ref) > tol
+        assert not bad.any(), "%d of %d outputs off by more than a bf16 ulp (max err %.3e) %s" % (
+            bad.sum(), bad.size, np.abs(got - ref).max(), case)
+
+
 SWAP_CASES = [
     (5, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), False, True),     # layer1 conv1 geometry, M = 4000 (ragged 256-tile)
     (3, 16, 50, 128, 128, 3, 3, (1, 1), (1, 1), True, True),     # 128 -> 128 with residual

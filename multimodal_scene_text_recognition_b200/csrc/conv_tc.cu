@@ -14,9 +14,12 @@
 //   warp 0      TMA producer  : STAGES-deep smem ring, mbarrier full/empty
 //   warp 1      MMA issuer    : one thread issues tcgen05.mma.cta_group::1.kind::f16 (128 x BLOCK_N x 16),
 //                               accumulators in TMEM (2 x BLOCK_N fp32 columns, double buffered)
-//   warps 2..5  epilogue      : tcgen05.ld 32x32b.x32 -> folded BN, residual, ReLU -> bf16/f32 NHWC stores,
-//                               overlapped with the next tile's MMAs through the second TMEM buffer
-// Roofline: tensor pipe.  Algorithmic FLOPs = 2 * M * C_out * R*S*C_in per launch.
+//   warps 2..5  epilogue      : tcgen05.ld 32x32b.x32 -> folded BN, residual, ReLU -> swizzled smem slab -> TMA store
+//                               (bf16 and/or f32 NHWC), overlapped with the next tile's MMAs through the second
+//                               TMEM buffer
+// This single-CTA kernel serves the layers the CTA-pair kernel (conv_tc2.cu) does not take: C_out = 128 layers
+// (MT = 2: two 128-row accumulators per CTA share each weight tile) and small / odd shapes.
+// Roofline: tensor pipe, fed from L2.  Algorithmic FLOPs = 2 * M * C_out * R*S*C_in per launch.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -33,7 +36,6 @@ struct TcParams {
   int P, Q, sh, sw, ph, pw;
   int im2col;               // 1: A via im2col map; 0: A via 2-D tiled map [M][K]
   int relu;
-  int prefetch;             // L2-prefetch the next tile's A rows (off: measured -3 %; MSTR_CONV_PREFETCH=1 enables)
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
@@ -44,54 +46,46 @@ struct TcParams {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_THREADS = 192;
 
-// RESB ("resident B"): the whole weight matrix of a small layer (K <= TC_RES_MAX_KB k-blocks, one N tile) is
-// loaded into shared memory ONCE per CTA and stays there for every tile; only the activation tiles stream.
-// For the C_out = 128 layers the 128x128 MMA reads 128 B/clk of shared memory by itself, so also WRITING a
-// fresh 16 KB weight tile per k-block (another 64 B/clk) is what held them at ~45 % of the tensor peak.
-constexpr int TC_RES_MAX_KB = 9;
-constexpr int STAGES_MAX_DUMMY = 8;   // barrier storage is sized for the maximum ring depth   // 9 x 64 = 576 = 3x3x64: the 64 -> 128 layers (144 KB of weights)
+constexpr int TC_MAX_STAGES = 8;   // barrier storage is sized for the maximum ring depth
 
 // MT ("M tiles per CTA"): with MT = 2 a CTA owns 256 output rows as two 128-row accumulators that share every
 // weight tile.  The C_out = 128 layers are bound by operand traffic from L2 (32 KB per 128x128x64 block);
 // sharing the weight tile cuts that by a quarter and doubles the tensor-core work per barrier round trip.
-template <int BLOCK_N, int BLOCK_K, bool RESB = false, int MT = 1>
+template <int BLOCK_N, int BLOCK_K, int MT = 1>
 struct TcCfg {
   static constexpr int ROW_BYTES = BLOCK_K * 2;
   static constexpr int A_HALF = TC_BLOCK_M * ROW_BYTES;
   static constexpr int A_BYTES = MT * A_HALF;
   static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
-  static constexpr int RES_BYTES = RESB ? TC_RES_MAX_KB * B_BYTES : 0;
-  static constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
-  static constexpr int EPI_SLAB = RESB ? EPI_SLAB_BYTES / 2 : EPI_SLAB_BYTES;   // RESB layers store bf16 only
-  static constexpr int TAIL_BYTES = 4 * BLOCK_N * 4 /*scale/shift x2*/ + (2 * STAGES_MAX_DUMMY + 5) * 8 + 16;
-  static constexpr int RING_BUDGET = 227 * 1024 - 1024 /*align slack*/ - RES_BYTES - 2 * EPI_SLAB - TAIL_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_SLAB = EPI_SLAB_BYTES;
+  static constexpr int TAIL_BYTES = 4 * BLOCK_N * 4 /*scale/shift x2*/ + (2 * TC_MAX_STAGES + 5) * 8 + 16;
+  static constexpr int RING_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 2 * EPI_SLAB - TAIL_BYTES;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * MT * BLOCK_N < 32 ? 32 : 2 * MT * BLOCK_N;
-  static constexpr int SMEM_BYTES = 1024 + RES_BYTES + STAGES * STAGE_BYTES + 2 * EPI_SLAB + TAIL_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * EPI_SLAB + TAIL_BYTES;
 };
 
-template <int BLOCK_N, int BLOCK_K, bool RESB = false, int MT = 1>
+template <int BLOCK_N, int BLOCK_K, int MT = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOb, const __grid_constant__ CUtensorMap tmOf,
                       const TcParams p) {
-  using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB, MT>;
+  using Cfg = TcCfg<BLOCK_N, BLOCK_K, MT>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TILE_M = TC_BLOCK_M * MT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sRes = smem;                                 // RESB: [num_k][BLOCK_N rows][ROW_BYTES], loaded once
-  uint8_t* sA = smem + Cfg::RES_BYTES;
-  uint8_t* sB = sA + STAGES * Cfg::A_BYTES;             // !RESB: streamed weight tiles
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * Cfg::A_BYTES;
   uint8_t* sEpi = sA + STAGES * Cfg::STAGE_BYTES;       // 2 output slabs (1024-byte aligned: every part above is)
   float* sScale = reinterpret_cast<float*>(sEpi + 2 * Cfg::EPI_SLAB);          // [2][BLOCK_N]
   float* sShift = sScale + 2 * BLOCK_N;                                        // [2][BLOCK_N]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + 2 * BLOCK_N);
-  uint64_t* empty_bar = full_bar + STAGES_MAX_DUMMY;
-  uint64_t* tfull_bar = empty_bar + STAGES_MAX_DUMMY;   // [2] accumulator ready
+  uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + TC_MAX_STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
-  uint64_t* res_bar = tempty_bar + 2;         // RESB: resident weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,7 +103,6 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
-    mbar_init(res_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -121,10 +114,6 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if constexpr (RESB) {   // the whole [BLOCK_N x K] weight matrix, once
-        mbar_arrive_expect_tx(res_bar, (uint32_t)(num_k * Cfg::B_BYTES));
-        for (int kb = 0; kb < num_k; ++kb) tma_load_2d(sRes + kb * Cfg::B_BYTES, &tmB, res_bar, kb * BLOCK_K, 0);
-      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -142,26 +131,9 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             chh[h] = pp * p.sh - p.ph;
           }
         }
-        // While this tile streams, pull the A rows of this CTA's NEXT tile from HBM into L2 (the taps of
-        // a tile re-read almost the same pixels, so one tap's worth of prefetch covers the tile): the
-        // first k-blocks of a tile otherwise expose DRAM latency that the 4-stage ring cannot hide.
-        const int next_tile = tile + gridDim.x;
-        const bool do_prefetch = p.prefetch && next_tile < num_tiles && (next_tile % p.num_n_tiles) == 0;
-        int kb_index = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int r = tap / p.S, s = tap - r * p.S;
-          for (int cc = 0; cc < p.cin_chunks; ++cc, ++kb_index) {
-            if (do_prefetch && kb_index == 2) {
-              const int nm0 = (next_tile / p.num_n_tiles) * TILE_M;
-              if (p.im2col) {
-                const int nq = nm0 % p.Q, npp = (nm0 / p.Q) % p.P, nn = nm0 / (p.Q * p.P);
-                for (int c2 = 0; c2 < p.cin_chunks; ++c2)
-                  tma_prefetch_im2col_4d(&tmA, c2 * BLOCK_K, nq * p.sw - p.pw, npp * p.sh - p.ph, nn,
-                                         (uint16_t)((p.S - 1) / 2), (uint16_t)((p.taps / p.S - 1) / 2));
-              } else {
-                for (int c2 = 0; c2 < p.cin_chunks; ++c2) tma_prefetch_2d(&tmA, c2 * BLOCK_K, nm0);
-              }
-            }
+          for (int cc = 0; cc < p.cin_chunks; ++cc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
@@ -173,8 +145,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               else
                 tma_load_2d(dstA, &tmA, &full_bar[stage], cc * BLOCK_K, m0 + h * TC_BLOCK_M);
             }
-            if constexpr (!RESB)
-              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], (tap * p.cin_chunks + cc) * BLOCK_K, n0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], (tap * p.cin_chunks + cc) * BLOCK_K, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -188,7 +159,6 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if constexpr (RESB) mbar_wait(res_bar, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -197,7 +167,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = RESB ? smem_u32(sRes + kb * Cfg::B_BYTES) : smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             const uint64_t db = make_smem_desc<Cfg::ROW_BYTES>(b_addr + k * 32);
@@ -300,13 +270,13 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // ---------------------------------------------------------------------------------------------
 static TmaEncoders g_enc;
 
-template <int BLOCK_N, int BLOCK_K, bool RESB = false, int MT = 1>
+template <int BLOCK_N, int BLOCK_K, int MT = 1>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
                      const TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N, BLOCK_K, RESB, MT>;
+  using Cfg = TcCfg<BLOCK_N, BLOCK_K, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB, MT>,
+    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, MT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -314,7 +284,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   q.num_m_tiles = ceil_div(p.M, TC_BLOCK_M * MT);
   const int tiles = q.num_m_tiles * q.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, RESB, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOb, tmOf, q);
+  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOb, tmOf, q);
   MSTR_LAUNCH_CHECK("conv_gemm_bf16_kernel");
   return MSTR_OK;
 }
@@ -323,11 +293,6 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
                         void* out_bf16, float* out_f32, int B, int H, int W, int C_in, int C_out, int R, int S,
                         int stride_h, int stride_w, int pad_h, int pad_w, int relu, cudaStream_t st);
-
-// conv_tc_swap.cu: operand-swapped variant for C_out = 128 layers
-int conv_gemm_bf16_swap(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
-                        void* out_bf16, int B, int H, int W, int C_in, int C_out, int R, int S, int stride_h,
-                        int stride_w, int pad_h, int pad_w, int relu, cudaStream_t st);
 
 }  // namespace mstr
 
@@ -354,15 +319,6 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
     return conv_gemm_bf16_2cta(x, w, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,
                                stride_w, pad_h, pad_w, relu, (cudaStream_t)stream);
   }
-  // operand-swapped kernel for C_out = 128-type layers with bf16 output.  Correct (tests) but measured SLOWER
-  // than the 128x128 kernel (epilogue-bound: 2-byte stores), so it is opt-in: MSTR_CONV_SWAP=1
-  static const int use_swap = [] { const char* e = getenv("MSTR_CONV_SWAP"); return (e && e[0] == '1') ? 1 : 0; }();
-  if (use_swap && C_in % 64 == 0 && C_out % 128 == 0 && C_out % 256 != 0 && out_bf16 && !out_f32) {
-    const int64_t M2 = (int64_t)B * ((H + 2 * pad_h - R) / stride_h + 1) * ((W + 2 * pad_w - S) / stride_w + 1);
-    MSTR_REQUIRE(M2 > 0 && M2 < (1ll << 31), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad output size");
-    return conv_gemm_bf16_swap(x, w, scale, shift, residual, out_bf16, B, H, W, C_in, C_out, R, S, stride_h, stride_w,
-                               pad_h, pad_w, relu, (cudaStream_t)stream);
-  }
   int rc = load_tma_encoders(g_enc);
   if (rc != MSTR_OK) return rc;
 
@@ -384,8 +340,6 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   p.sh = stride_h; p.sw = stride_w; p.ph = pad_h; p.pw = pad_w;
   p.im2col = !(R == 1 && S == 1 && stride_h == 1 && stride_w == 1 && pad_h == 0 && pad_w == 0);
   p.relu = relu;
-  static const int prefetch_on = [] { const char* e = getenv("MSTR_CONV_PREFETCH"); return (e && e[0] == '1') ? 1 : 0; }();
-  p.prefetch = prefetch_on;
   p.scale = scale; p.shift = shift;
   p.residual = (const __nv_bfloat16*)residual;
   p.out_bf16 = (__nv_bfloat16*)out_bf16;
@@ -429,14 +383,10 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   cudaStream_t st = (cudaStream_t)stream;
   if (block_k == 64) {
     if (block_n == 256) return launch_tc<256, 64>(tmA, tmB, tmOb, tmOf, p, st);
-    static const int use_resb = [] { const char* e = getenv("MSTR_CONV_RESB"); return (e && e[0] == '1') ? 1 : 0; }();
-    if (block_n == 128 && use_resb && p.num_n_tiles == 1 && p.taps * p.cin_chunks <= TC_RES_MAX_KB &&
-        p.num_m_tiles >= 4 * sm_count() && !out_f32)
-      return launch_tc<128, 64, true>(tmA, tmB, tmOb, tmOf, p, st);      // resident weights (64 -> 128 layers)
     // two 128-row accumulators per CTA sharing each weight tile (MSTR_CONV_MT2=0 disables)
     static const int use_mt2 = [] { const char* e = getenv("MSTR_CONV_MT2"); return (e && e[0] == '0') ? 0 : 1; }();
     if (block_n == 128 && use_mt2 && p.num_m_tiles >= 8 * sm_count())
-      return launch_tc<128, 64, false, 2>(tmA, tmB, tmOb, tmOf, p, st);
+      return launch_tc<128, 64, 2>(tmA, tmB, tmOb, tmOf, p, st);
     if (block_n == 128) return launch_tc<128, 64>(tmA, tmB, tmOb, tmOf, p, st);
     return launch_tc<64, 64>(tmA, tmB, tmOb, tmOf, p, st);
   } else {

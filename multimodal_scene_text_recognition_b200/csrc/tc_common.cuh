@@ -66,17 +66,6 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
       "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
-// L2 prefetch of the box a later TMA load will fetch (no shared-memory destination, no barrier).
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_im2col_4d(const CUtensorMap* map, int c, int w, int h, int n,
-                                                       uint16_t off_w, uint16_t off_h) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-               : "memory");
-}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

@@ -167,20 +167,6 @@ def test_conv_gemm_bf16_tcgen05(case):
     assert np.array_equal(host(out_b), orc.round_bf16(host(out_f))), "bf16 output is not the rounded f32 output"
 
 
-def test_conv_gemm_bf16_resident_weights():
-    """64 -> 128 layers with >= 4 tiles per SM keep the whole weight matrix resident in shared memory
-    (conv_gemm_bf16_kernel<128, 64, RESB>): M = 96*16*50 = 76800 -> 600 tiles; 3x3 with residual and 1x1."""
-    bf = torch.bfloat16
-    for case in ((96, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), True, True),
-                 (96, 16, 50, 64, 128, 1, 1, (1, 1), (0, 0), False, False)):
-        x, w, scale, shift, res = _conv_inputs(case, 23, True)
-        ref = _conv_ref(x, w, scale, shift, res, case[7], case[8], case[10])
-        out_f = ops.conv_gemm(dev(x, bf), dev(w, bf), dev(scale), dev(shift), None if res is None else dev(res, bf),
-                              stride=case[7], pad=case[8], relu=case[10], want_f32=True, want_bf16=False)
-        torch.cuda.synchronize()
-        assert_close(host(out_f), ref, 2e-5, "conv_gemm_bf16 resident weights %s" % (case,))
-
-
 def test_conv_gemm_bf16_two_accumulators_per_cta():
     """C_out = 128 layers with >= 8 tiles per SM run with two 128-row accumulators per CTA sharing each
     weight tile (conv_gemm_bf16_kernel<128, 64, false, 2>): M = 193*16*50 = 154400 (ragged: not a multiple of
@@ -199,34 +185,6 @@ def test_conv_gemm_bf16_two_accumulators_per_cta():
         bad = np.abs(got - ref) > tol
         assert not bad.any(), "%d of %d outputs off by more than a bf16 ulp (max err %.3e) %s" % (
             bad.sum(), bad.size, np.abs(got - ref).max(), case)
-
-
-SWAP_CASES = [
-    (5, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), False, True),     # layer1 conv1 geometry, M = 4000 (ragged 256-tile)
-    (3, 16, 50, 128, 128, 3, 3, (1, 1), (1, 1), True, True),     # 128 -> 128 with residual
-    (5, 16, 50, 64, 128, 1, 1, (1, 1), (0, 0), False, False),    # 1x1 downsample
-    (2, 8, 25, 64, 384, 3, 3, (1, 1), (1, 1), True, False),      # three 128-channel tiles
-    (40, 32, 50, 64, 128, 3, 3, (1, 1), (1, 1), False, True),    # conv0_2 over pixel pairs: M = 64000 (250 tiles)
-]
-
-
-@pytest.mark.parametrize("case", SWAP_CASES)
-def test_conv_gemm_bf16_swapped_operands(case):
-    """C_out = 128-type layers with bf16-only output: the 128x128 kernel by default, the operand-swapped
-    kernel (conv_tc_swap.cu) when MSTR_CONV_SWAP=1 is set before the library is first used."""
-    stride, pad, relu = case[7], case[8], case[10]
-    x, w, scale, shift, res = _conv_inputs(case, 21, True)
-    ref = _conv_ref(x, w, scale, shift, res, stride, pad, relu)
-    bf = torch.bfloat16
-    out_b = ops.conv_gemm(dev(x, bf), dev(w, bf), dev(scale), dev(shift), None if res is None else dev(res, bf),
-                          stride=stride, pad=pad, relu=relu, want_f32=False, want_bf16=True)
-    torch.cuda.synchronize()
-    got = host(out_b).astype(np.float64)
-    # the bf16 result is the rounding of an fp32 value within ~1e-5 of ref: allow one bf16 ulp
-    tol = np.maximum(np.abs(ref), 1e-3) * 2.0 ** -7
-    bad = np.abs(got - ref) > tol
-    assert not bad.any(), "%d of %d outputs off by more than a bf16 ulp (max err %.3e)" % (
-        bad.sum(), bad.size, np.abs(got - ref).max())
 
 
 def test_conv_gemm_bf16_many_tiles():

@@ -101,6 +101,18 @@ int mstr_conv_gemm_bf16(const void* x, const void* w, const float* scale, const 
                         int C_in, int C_out, int R, int S, int stride_h, int stride_w, int pad_h,
                         int pad_w, int relu, mstr_stream_t stream);
 
+/* Convolution with a fused 1x1 branch (a BasicBlock's conv2/bn2 + downsample conv/bn + add + ReLU,
+ * modules/feature_extraction.py:39-47 with :94-100):
+ *   out = act( conv_RxS(x, w_cat[:, :R*S*C_in]) + x2 . w_cat[:, R*S*C_in:]^T ) * scale + shift [+ residual] )
+ * x2 is NHWC [B][P][Q][C_in2] on the OUTPUT grid; both branches accumulate in one TMEM accumulator, so the two
+ * BatchNorm scales must be folded into w_cat by the caller (scale is then null) and shift = shift_a + shift_b.
+ * Requires C_in % 64 == 0, C_in2 % 64 == 0.
+ */
+int mstr_conv_gemm_bf16_dual(const void* x, const void* x2, const void* w_cat, const float* scale, const float* shift,
+                             const void* residual, void* out_bf16, float* out_f32, int B, int H, int W, int C_in,
+                             int C_in2, int C_out, int R, int S, int stride_h, int stride_w, int pad_h, int pad_w,
+                             int relu, mstr_stream_t stream);
+
 /* TF32 parity mode on the tensor cores (error-compensated 3xTF32, see csrc/conv_tf32.cu): fp32 NHWC
  * activations and fp32 results like mstr_conv_gemm_f32, ~fp32 accuracy, tcgen05.mma.kind::tf32.
  *   w_hi = w with the low 13 mantissa bits cleared, w_lo = w - w_hi (both f32, [C_out][R][S][C_in])

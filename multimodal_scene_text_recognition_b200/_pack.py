@@ -106,3 +106,19 @@ def pack_conv_pixel_pairs(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, preci
         scale, shift = fold_bn(bn)
         return wp, scale.repeat(2).contiguous(), shift.repeat(2).contiguous()
     return cached(conv, ('pairs', precision), [conv.weight] + bn_sources(bn), build)
+
+
+def pack_block_tail(conv2: torch.nn.Conv2d, bn2: torch.nn.BatchNorm2d, ds_conv: torch.nn.Conv2d,
+                    ds_bn: torch.nn.BatchNorm2d):
+    """conv2/bn2 and the 1x1 downsample conv/bn of a BasicBlock as ONE GEMM: both BatchNorm scales folded into
+    the bf16 weights (the two branches share an accumulator), weights concatenated along K, shifts added.
+    -> (w_cat [Cout, R*S*planes + inplanes] bf16, shift [Cout] f32)"""
+    def build():
+        s2, b2 = fold_bn(bn2)
+        sd, bd = fold_bn(ds_bn)
+        w2 = conv2.weight.detach().float().permute(0, 2, 3, 1) * s2[:, None, None, None]     # [Cout, R, S, Cin]
+        wd = ds_conv.weight.detach().float().permute(0, 2, 3, 1) * sd[:, None, None, None]   # [Cout, 1, 1, Cin2]
+        cout = w2.shape[0]
+        w_cat = torch.cat([w2.reshape(cout, -1), wd.reshape(cout, -1)], dim=1).to(torch.bfloat16).contiguous()
+        return w_cat, (b2 + bd).contiguous()
+    return cached(conv2, ('block_tail',), [conv2.weight, ds_conv.weight] + bn_sources(bn2) + bn_sources(ds_bn), build)

@@ -67,3 +67,6 @@ RNN_TENSOR_CORES = True
 # bf16 mode only: run the 32-channel 3x3 convolution (conv0_2) over horizontal pixel pairs
 # (_pack.pack_conv_pixel_pairs): identical results, better tensor-core tile shapes.
 CONV_PIXEL_PAIRS = True
+# bf16 mode only: compute a BasicBlock's conv2/bn2, its 1x1 downsample conv/bn, the residual add and the ReLU as
+# one GEMM (weights concatenated along K, BatchNorm scales folded into the bf16 weights).
+FUSE_DOWNSAMPLE = True

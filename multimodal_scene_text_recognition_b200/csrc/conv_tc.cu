@@ -33,6 +33,7 @@ struct TcParams {
   int M, Cout;
   int num_m_tiles, num_n_tiles;
   int taps, S, cin_chunks;  // K loop = taps x cin_chunks blocks of BLOCK_K channels
+  int cin2_chunks;          // + extra k-blocks from a second [M][C_in2] matrix (fused 1x1 branch), 0 = none
   int P, Q, sh, sw, ph, pw;
   int im2col;               // 1: A via im2col map; 0: A via 2-D tiled map [M][K]
   int relu;
@@ -70,7 +71,7 @@ template <int BLOCK_N, int BLOCK_K, int MT = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOb, const __grid_constant__ CUtensorMap tmOf,
-                      const TcParams p) {
+                      const __grid_constant__ CUtensorMap tmA2, const TcParams p) {
   using Cfg = TcCfg<BLOCK_N, BLOCK_K, MT>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TILE_M = TC_BLOCK_M * MT;
@@ -90,7 +91,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_k = p.taps * p.cin_chunks;
+  const int num_k = p.taps * p.cin_chunks + p.cin2_chunks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -148,6 +149,17 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], (tap * p.cin_chunks + cc) * BLOCK_K, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+        }
+        // fused 1x1 branch: its input rows are the same output pixels, its weights follow in K
+        for (int cc = 0; cc < p.cin2_chunks; ++cc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int h = 0; h < MT; ++h)
+            tma_load_2d(sA + stage * Cfg::A_BYTES + h * Cfg::A_HALF, &tmA2, &full_bar[stage], cc * BLOCK_K,
+                        m0 + h * TC_BLOCK_M);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], (p.taps * p.cin_chunks + cc) * BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -272,7 +284,7 @@ static TmaEncoders g_enc;
 
 template <int BLOCK_N, int BLOCK_K, int MT = 1>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
-                     const TcParams& p, cudaStream_t st) {
+                     const CUtensorMap& tmA2, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, BLOCK_K, MT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -284,7 +296,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   q.num_m_tiles = ceil_div(p.M, TC_BLOCK_M * MT);
   const int tiles = q.num_m_tiles * q.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOb, tmOf, q);
+  conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOb, tmOf, tmA2, q);
   MSTR_LAUNCH_CHECK("conv_gemm_bf16_kernel");
   return MSTR_OK;
 }
@@ -292,16 +304,16 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 // conv_tc2.cu: CTA-pair (cta_group::2) variant
 int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
                         void* out_bf16, float* out_f32, int B, int H, int W, int C_in, int C_out, int R, int S,
-                        int stride_h, int stride_w, int pad_h, int pad_w, int relu, cudaStream_t st);
+                        int stride_h, int stride_w, int pad_h, int pad_w, int relu, const void* x2, int C_in2,
+                        cudaStream_t st);
 
-}  // namespace mstr
-
-extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const void* x, const void* w, const float* scale, const float* shift,
-                                   const void* residual, void* out_bf16, float* out_f32, int B, int H, int W,
-                                   int C_in, int C_out, int R, int S, int stride_h, int stride_w, int pad_h,
-                                   int pad_w, int relu, mstr_stream_t stream) {
-  using namespace mstr;
+static int conv_gemm_bf16_impl(const void* x, const void* w, const float* scale, const float* shift,
+                               const void* residual, void* out_bf16, float* out_f32, int B, int H, int W,
+                               int C_in, int C_out, int R, int S, int stride_h, int stride_w, int pad_h,
+                               int pad_w, int relu, const void* x2, int C_in2, mstr_stream_t stream) {
   MSTR_REQUIRE(x && w && (out_bf16 || out_f32), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: null pointer");
+  MSTR_REQUIRE(!x2 || (C_in2 > 0 && C_in2 % 64 == 0 && C_in % 64 == 0 && aligned16(x2)), MSTR_ERR_UNSUPPORTED,
+               "mstr_conv_gemm_bf16_dual: the fused 1x1 branch needs C_in %% 64 == 0 and C_in2 %% 64 == 0");
   MSTR_REQUIRE(B > 0 && H > 0 && W > 0 && C_in > 0 && C_out > 0 && R > 0 && S > 0 && stride_h > 0 && stride_w > 0 &&
                    pad_h >= 0 && pad_w >= 0,
                MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad size");
@@ -317,7 +329,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
     const int64_t M2 = (int64_t)B * ((H + 2 * pad_h - R) / stride_h + 1) * ((W + 2 * pad_w - S) / stride_w + 1);
     MSTR_REQUIRE(M2 > 0 && M2 < (1ll << 31), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad output size");
     return conv_gemm_bf16_2cta(x, w, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,
-                               stride_w, pad_h, pad_w, relu, (cudaStream_t)stream);
+                               stride_w, pad_h, pad_w, relu, x2, C_in2, (cudaStream_t)stream);
   }
   int rc = load_tma_encoders(g_enc);
   if (rc != MSTR_OK) return rc;
@@ -337,6 +349,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   p.taps = R * S;
   p.S = S;
   p.cin_chunks = C_in / block_k;
+  p.cin2_chunks = x2 ? C_in2 / block_k : 0;
   p.sh = stride_h; p.sw = stride_w; p.ph = pad_h; p.pw = pad_w;
   p.im2col = !(R == 1 && S == 1 && stride_h == 1 && stride_w == 1 && pad_h == 0 && pad_w == 0);
   p.relu = relu;
@@ -347,7 +360,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
 
   const CUtensorMapSwizzle swz = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   alignas(64) CUtensorMap tmA, tmB;
-  const int64_t K = (int64_t)R * S * C_in;
+  const int64_t K = (int64_t)R * S * C_in + (x2 ? C_in2 : 0);
   rc = encode_tiled_2d_bf16(g_enc, &tmB, w, (uint64_t)K, (uint64_t)C_out, (uint32_t)block_k, (uint32_t)block_n, swz);
   if (rc != MSTR_OK) return rc;
   if (!p.im2col) {
@@ -374,6 +387,11 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
       reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
   }
 
+  alignas(64) CUtensorMap tmA2 = tmA;
+  if (x2) {   // [M][C_in2] matrix whose rows are the output pixels
+    rc = encode_tiled_2d_bf16(g_enc, &tmA2, x2, (uint64_t)C_in2, (uint64_t)p.M, (uint32_t)block_k, TC_BLOCK_M, swz);
+    if (rc != MSTR_OK) return rc;
+  }
   // output tensor maps for the epilogue's TMA stores (an absent output gets a copy of the other map; it is never used)
   alignas(64) CUtensorMap tmOb, tmOf;
   if (out_bf16) { rc = encode_output_2d(g_enc, &tmOb, out_bf16, false, (uint64_t)C_out, (uint64_t)p.M); if (rc != MSTR_OK) return rc; }
@@ -382,16 +400,36 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(const 
   if (!out_f32) tmOf = tmOb;
   cudaStream_t st = (cudaStream_t)stream;
   if (block_k == 64) {
-    if (block_n == 256) return launch_tc<256, 64>(tmA, tmB, tmOb, tmOf, p, st);
+    if (block_n == 256) return launch_tc<256, 64>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
     // two 128-row accumulators per CTA sharing each weight tile (MSTR_CONV_MT2=0 disables)
     static const int use_mt2 = [] { const char* e = getenv("MSTR_CONV_MT2"); return (e && e[0] == '0') ? 0 : 1; }();
     if (block_n == 128 && use_mt2 && p.num_m_tiles >= 8 * sm_count())
-      return launch_tc<128, 64, 2>(tmA, tmB, tmOb, tmOf, p, st);
-    if (block_n == 128) return launch_tc<128, 64>(tmA, tmB, tmOb, tmOf, p, st);
-    return launch_tc<64, 64>(tmA, tmB, tmOb, tmOf, p, st);
+      return launch_tc<128, 64, 2>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+    if (block_n == 128) return launch_tc<128, 64>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+    return launch_tc<64, 64>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
   } else {
-    if (block_n == 256) return launch_tc<256, 32>(tmA, tmB, tmOb, tmOf, p, st);
-    if (block_n == 128) return launch_tc<128, 32>(tmA, tmB, tmOb, tmOf, p, st);
-    return launch_tc<64, 32>(tmA, tmB, tmOb, tmOf, p, st);
+    if (block_n == 256) return launch_tc<256, 32>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+    if (block_n == 128) return launch_tc<128, 32>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+    return launch_tc<64, 32>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
   }
+}
+
+}  // namespace mstr
+
+extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16(
+    const void* x, const void* w, const float* scale, const float* shift, const void* residual, void* out_bf16,
+    float* out_f32, int B, int H, int W, int C_in, int C_out, int R, int S, int stride_h, int stride_w, int pad_h,
+    int pad_w, int relu, mstr_stream_t stream) {
+  return mstr::conv_gemm_bf16_impl(x, w, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,
+                                   stride_w, pad_h, pad_w, relu, nullptr, 0, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_bf16_dual(
+    const void* x, const void* x2, const void* w_cat, const float* scale, const float* shift, const void* residual,
+    void* out_bf16, float* out_f32, int B, int H, int W, int C_in, int C_in2, int C_out, int R, int S, int stride_h,
+    int stride_w, int pad_h, int pad_w, int relu, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x2, MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16_dual: null x2");
+  return conv_gemm_bf16_impl(x, w_cat, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,
+                             stride_w, pad_h, pad_w, relu, x2, C_in2, stream);
 }

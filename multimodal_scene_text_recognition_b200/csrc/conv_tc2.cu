@@ -26,6 +26,7 @@ struct Tc2Params {
   int M, Cout;
   int num_m_pairs, num_n_tiles;
   int taps, S, cin_chunks;
+  int cin2_chunks;          // extra k-blocks read from a second [M][C_in2] matrix (fused 1x1 branch), 0 = none
   int P, Q, sh, sw, ph, pw;
   int im2col;
   int relu;
@@ -125,7 +126,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ CUtensorMap tmOb, const __grid_constant__ CUtensorMap tmOf,
-                           const Tc2Params p) {
+                           const __grid_constant__ CUtensorMap tmA2, const Tc2Params p) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -147,7 +148,7 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int num_tiles = p.num_m_pairs * p.num_n_tiles;
-  const int num_k = p.taps * p.cin_chunks;
+  const int num_k = p.taps * p.cin_chunks + p.cin2_chunks;
   const int first_tile = (int)cluster_id_x();
   const int tile_step = (int)num_clusters_x();
 
@@ -199,6 +200,15 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             tma2_load_2d(sB + stage * Cfg::B_BYTES, &tmB, bar, (tap * p.cin_chunks + cc) * T2_BLOCK_K, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+        }
+        // fused 1x1 branch: its input rows are the same output pixels, its weights follow in K
+        for (int cc = 0; cc < p.cin2_chunks; ++cc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          tma2_load_2d(sA + stage * T2_A_BYTES, &tmA2, bar, cc * T2_BLOCK_K, m0);
+          tma2_load_2d(sB + stage * Cfg::B_BYTES, &tmB, bar, (p.taps * p.cin_chunks + cc) * T2_BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -310,7 +320,7 @@ static TmaEncoders g_enc2;
 
 template <int BLOCK_N>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
-                      const Tc2Params& p, cudaStream_t st) {
+                      const CUtensorMap& tmA2, const Tc2Params& p, cudaStream_t st) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -333,7 +343,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSTR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_bf16_2cta_kernel<BLOCK_N>, tmA, tmB, tmOb, tmOf, p));
+  MSTR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_bf16_2cta_kernel<BLOCK_N>, tmA, tmB, tmOb, tmOf, tmA2, p));
   MSTR_LAUNCH_CHECK("conv_gemm_bf16_2cta_kernel");
   return MSTR_OK;
 }
@@ -341,7 +351,8 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 // Called by mstr_conv_gemm_bf16 (conv_tc.cu) when the layer qualifies: C_in % 64 == 0, C_out % 128 == 0.
 int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
                         void* out_bf16, float* out_f32, int B, int H, int W, int C_in, int C_out, int R, int S,
-                        int stride_h, int stride_w, int pad_h, int pad_w, int relu, cudaStream_t st) {
+                        int stride_h, int stride_w, int pad_h, int pad_w, int relu, const void* x2, int C_in2,
+                        cudaStream_t st) {
   int rc = load_tma_encoders(g_enc2);
   if (rc != MSTR_OK) return rc;
   Tc2Params p;
@@ -355,6 +366,7 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
   p.taps = R * S;
   p.S = S;
   p.cin_chunks = C_in / T2_BLOCK_K;
+  p.cin2_chunks = x2 ? C_in2 / T2_BLOCK_K : 0;
   p.sh = stride_h; p.sw = stride_w; p.ph = pad_h; p.pw = pad_w;
   p.im2col = !(R == 1 && S == 1 && stride_h == 1 && stride_w == 1 && pad_h == 0 && pad_w == 0);
   p.relu = relu;
@@ -364,7 +376,7 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
   p.out_f32 = out_f32;
 
   alignas(64) CUtensorMap tmA, tmB;
-  const int64_t K = (int64_t)R * S * C_in;
+  const int64_t K = (int64_t)R * S * C_in + (x2 ? C_in2 : 0);
   rc = encode_tiled_2d_bf16(g_enc2, &tmB, w, (uint64_t)K, (uint64_t)C_out, T2_BLOCK_K, (uint32_t)(block_n / 2),
                             CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != MSTR_OK) return rc;
@@ -387,13 +399,18 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
     if (drv <= 13010 && (int64_t)B * H * W * C_in * 2 < 131072)
       reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
   }
+  alignas(64) CUtensorMap tmA2 = tmA;
+  if (x2) {   // [M][C_in2] matrix whose rows are the output pixels
+    rc = encode_tiled_2d_bf16(g_enc2, &tmA2, x2, (uint64_t)C_in2, (uint64_t)p.M, T2_BLOCK_K, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != MSTR_OK) return rc;
+  }
   alignas(64) CUtensorMap tmOb, tmOf;
   if (out_bf16) { rc = encode_output_2d(g_enc2, &tmOb, out_bf16, false, (uint64_t)C_out, (uint64_t)p.M); if (rc != MSTR_OK) return rc; }
   if (out_f32) { rc = encode_output_2d(g_enc2, &tmOf, out_f32, true, (uint64_t)C_out, (uint64_t)p.M); if (rc != MSTR_OK) return rc; }
   if (!out_bf16) tmOb = tmOf;
   if (!out_f32) tmOf = tmOb;
-  if (block_n == 256) return launch_tc2<256>(tmA, tmB, tmOb, tmOf, p, st);
-  return launch_tc2<128>(tmA, tmB, tmOb, tmOf, p, st);
+  if (block_n == 256) return launch_tc2<256>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+  return launch_tc2<128>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
 }
 
 }  // namespace mstr

@@ -20,7 +20,8 @@ import torch
 import torch.nn as nn
 
 from .. import config, ops
-from .._pack import act_dtype, pack_conv, pack_conv_pixel_pairs, pack_first_conv, require_inference
+from .._pack import (act_dtype, pack_block_tail, pack_conv, pack_conv_pixel_pairs, pack_first_conv,
+                     require_inference)
 
 
 def _conv_bn(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, precision: str, relu: bool, residual=None, **kw):
@@ -79,6 +80,12 @@ class BasicBlock(nn.Module):
         """feature_extraction.py:32-47 on NHWC activations: three (two) fused launches."""
         out = _conv_bn(x, self.conv1, self.bn1, precision, relu=True)
         residual = x
+        if (self.downsample is not None and precision == 'bf16' and config.FUSE_DOWNSAMPLE
+                and x.shape[3] % 64 == 0 and out.shape[3] % 64 == 0 and tuple(self.downsample[0].stride) == (1, 1)):
+            # conv2+bn2, the 1x1 downsample conv+bn, the add and the ReLU as ONE tensor-core GEMM
+            w_cat, shift = pack_block_tail(self.conv2, self.bn2, self.downsample[0], self.downsample[1])
+            return ops.conv_gemm_dual(out, x, w_cat, shift, kernel=tuple(self.conv2.kernel_size),
+                                      pad=tuple(self.conv2.padding), relu=True)
         if self.downsample is not None:
             residual = _conv_bn(x, self.downsample[0], self.downsample[1], precision, relu=False)
         return _conv_bn(out, self.conv2, self.bn2, precision, relu=True, residual=residual)

@@ -204,6 +204,29 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
     return out_f if want_f32 else out_b
 
 
+def conv_gemm_dual(x: torch.Tensor, x2: torch.Tensor, w_cat: torch.Tensor, shift: torch.Tensor, *, kernel: Tuple[int, int],
+                   pad: Tuple[int, int] = (1, 1), relu: bool = True) -> torch.Tensor:
+    """bf16 convolution (stride 1) with a fused 1x1 branch: x NHWC [B,H,W,Cin], x2 NHWC [B,P,Q,Cin2] on the output
+    grid, w_cat [Cout, R*S*Cin + Cin2] bf16 with the BatchNorm scales folded in, shift [Cout] f32."""
+    _req(x, "x", torch.bfloat16); _req(x2, "x2", torch.bfloat16); _req(w_cat, "w_cat", torch.bfloat16)
+    _req(shift, "shift", torch.float32)
+    B, H, W, Cin = x.shape
+    R, S = kernel
+    P, Q = H + 2 * pad[0] - R + 1, W + 2 * pad[1] - S + 1
+    Cin2 = x2.shape[3]
+    Cout = w_cat.shape[0]
+    assert x2.shape == (B, P, Q, Cin2) and w_cat.shape == (Cout, R * S * Cin + Cin2)
+    out = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.bfloat16)
+    flops = 2.0 * B * P * Q * Cout * (R * S * Cin + Cin2)
+    variant = "conv_gemm_bf16_2cta" if Cout % 256 == 0 else "conv_gemm_bf16_1cta"
+    with _timed(variant, flops, "flop", "M=%d (B%d %dx%d) %d->%d %dx%d + fused 1x1 %d->%d" % (
+            B * P * Q, B, P, Q, Cin, Cout, R, S, Cin2, Cout)):
+        check(lib().mstr_conv_gemm_bf16_dual(ptr(x), ptr(x2), ptr(w_cat), 0, ptr(shift), 0, ptr(out), 0, B, H, W, Cin,
+                                             Cin2, Cout, R, S, 1, 1, pad[0], pad[1], int(relu), stream_ptr()),
+              "mstr_conv_gemm_bf16_dual")
+    return out
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
            want_f32: bool = False, want_bf16: bool = True):
     """nn.Linear on the last dimension through the same GEMM kernels (x [..., K], w [N, K])."""

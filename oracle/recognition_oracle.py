@@ -209,14 +209,27 @@ def tps_forward(x, sd, H, W, dt=np.float32, quant=None):
 # --------------------------------------------------------------------------------------
 # ResNet feature extractor (modules/feature_extraction.py)
 # --------------------------------------------------------------------------------------
+def _bn_fold(sd, name, dt):
+    scale = sd[name + ".weight"].astype(dt) / np.sqrt(sd[name + ".running_var"].astype(dt) + dt.type(BN_EPS))
+    return scale, sd[name + ".bias"].astype(dt) - sd[name + ".running_mean"].astype(dt) * scale
+
+
 def _basic_block(x, sd, prefix, dt, quant):
     """BasicBlock.forward (feature_extraction.py:32-47)."""
     out = _q(_conv_bn_relu(x, sd, prefix + ".conv1", prefix + ".bn1", dt, quant=quant), quant)
+    if (prefix + ".downsample.0.weight") in sd and quant:
+        # CUDA bf16 mode: conv2/bn2 + downsample conv/bn + add as ONE GEMM whose bf16 weights carry the folded
+        # BatchNorm scales (both branches share the fp32 accumulator; no intermediate rounding of the residual)
+        s2, b2 = _bn_fold(sd, prefix + ".bn2", dt)
+        sdn, bd = _bn_fold(sd, prefix + ".downsample.1", dt)
+        w2 = _q(sd[prefix + ".conv2.weight"].astype(dt) * s2[:, None, None, None], quant)
+        wd = _q(sd[prefix + ".downsample.0.weight"].astype(dt) * sdn[:, None, None, None], quant)
+        y = conv2d(out, w2, (1, 1), (1, 1)) + conv2d(x, wd, (1, 1), (0, 0)) + (b2 + bd)[None, :, None, None]
+        return _q(relu(y), quant)
     out = _conv_bn_relu(out, sd, prefix + ".conv2", prefix + ".bn2", dt, quant=quant, act=False)
     if (prefix + ".downsample.0.weight") in sd:
         res = _conv_bn_relu(x, sd, prefix + ".downsample.0", prefix + ".downsample.1", dt,
                             pad=(0, 0), quant=quant, act=False)
-        res = _q(res, quant)           # downsample result is stored bf16 before the add
     else:
         res = x
     return _q(relu(out + res), quant)

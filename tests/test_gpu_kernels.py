@@ -187,6 +187,33 @@ def test_conv_gemm_bf16_two_accumulators_per_cta():
             bad.sum(), bad.size, np.abs(got - ref).max(), case)
 
 
+@pytest.mark.parametrize("B,H,W,planes,inplanes", [(3, 8, 25, 256, 128), (5, 4, 26, 512, 256), (3, 16, 50, 128, 64),
+                                                   (193, 16, 50, 128, 64)])
+def test_conv_gemm_bf16_fused_downsample(B, H, W, planes, inplanes):
+    """mstr_conv_gemm_bf16_dual: 3x3 conv + fused 1x1 branch + ReLU in one accumulator (CTA-pair kernel for
+    C_out % 256 == 0, single-CTA kernel with one or two accumulators per CTA for C_out = 128)."""
+    r = rng(31)
+    x = orc.round_bf16(r.standard_normal((B, H, W, planes)).astype(np.float32))
+    x2 = orc.round_bf16(r.standard_normal((B, H, W, inplanes)).astype(np.float32))
+    w2 = orc.round_bf16((r.standard_normal((planes, 3, 3, planes)) / np.sqrt(9 * planes)).astype(np.float32))
+    wd = orc.round_bf16((r.standard_normal((planes, 1, 1, inplanes)) / np.sqrt(inplanes)).astype(np.float32))
+    shift = r.normal(0, 0.2, planes).astype(np.float32)
+    sel = list(range(B)) if B <= 8 else [0, 1, 2, 95, 96, 190, 191, 192]
+    ref = (orc.conv2d(nchw(x[sel]).astype(np.float64), w2.transpose(0, 3, 1, 2).astype(np.float64), (1, 1), (1, 1)) +
+           orc.conv2d(nchw(x2[sel]).astype(np.float64), wd.transpose(0, 3, 1, 2).astype(np.float64), (1, 1), (0, 0)) +
+           shift[None, :, None, None])
+    ref = nhwc(orc.relu(ref))
+    bf = torch.bfloat16
+    w_cat = np.concatenate([w2.reshape(planes, -1), wd.reshape(planes, -1)], axis=1)
+    out = ops.conv_gemm_dual(dev(x, bf), dev(x2, bf), dev(w_cat, bf), dev(shift), kernel=(3, 3), pad=(1, 1), relu=True)
+    torch.cuda.synchronize()
+    got = host(out)[sel].astype(np.float64)
+    tol = np.maximum(np.abs(ref), 1e-3) * 2.0 ** -7
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), "%d of %d outputs off by more than a bf16 ulp (max err %.3e)" % (
+        bad.sum(), bad.size, np.abs(got - ref).max())
+
+
 def test_conv_gemm_bf16_many_tiles():
     """More M tiles than SMs: exercises the persistent tile loop, the smem ring wrap-around and both
     TMEM accumulator buffers.  M = 64*16*50 = 51200 -> 400 M tiles x 1 N tile."""

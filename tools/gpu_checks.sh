@@ -19,7 +19,7 @@ run tps        300 $PT tests/test_gpu_kernels.py -k "tps"
 run first      300 $PT tests/test_gpu_kernels.py -k "conv3x3_first"
 run conv_f32   300 $PT tests/test_gpu_kernels.py -k "conv_gemm_f32 or linear_f32"
 run conv_tc    300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "bf16_tcgen05 or tf32x3"
-run conv_tc2   300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "many_tiles or two_accumulators"
+run conv_tc2   300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "many_tiles or two_accumulators or fused_downsample"
 run small      300 $PT tests/test_gpu_kernels.py -k "maxpool or mean or embed or errors"
 run bilstm     300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "bilstm"
 run attn       300 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu_kernels.py -k "attn and not bf16"

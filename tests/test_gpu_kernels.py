@@ -181,7 +181,8 @@ def test_conv_gemm_bf16_two_accumulators_per_cta():
                               stride=case[7], pad=case[8], relu=case[10], want_f32=False, want_bf16=True)
         torch.cuda.synchronize()
         got = host(out_b)[sel].astype(np.float64)
-        tol = np.maximum(np.abs(ref), 1e-3) * 2.0 ** -7
+        # one bf16 ulp of the result + the fp32 accumulation noise of sums whose terms are O(max |ref|)
+    tol = np.abs(ref) * 2.0 ** -7 + 3e-5 * np.abs(ref).max()
         bad = np.abs(got - ref) > tol
         assert not bad.any(), "%d of %d outputs off by more than a bf16 ulp (max err %.3e) %s" % (
             bad.sum(), bad.size, np.abs(got - ref).max(), case)
@@ -208,7 +209,8 @@ def test_conv_gemm_bf16_fused_downsample(B, H, W, planes, inplanes):
     out = ops.conv_gemm_dual(dev(x, bf), dev(x2, bf), dev(w_cat, bf), dev(shift), kernel=(3, 3), pad=(1, 1), relu=True)
     torch.cuda.synchronize()
     got = host(out)[sel].astype(np.float64)
-    tol = np.maximum(np.abs(ref), 1e-3) * 2.0 ** -7
+    # one bf16 ulp of the result + the fp32 accumulation noise of sums whose terms are O(max |ref|)
+    tol = np.abs(ref) * 2.0 ** -7 + 3e-5 * np.abs(ref).max()
     bad = np.abs(got - ref) > tol
     assert not bad.any(), "%d of %d outputs off by more than a bf16 ulp (max err %.3e)" % (
         bad.sum(), bad.size, np.abs(got - ref).max())

@@ -182,7 +182,7 @@ def test_conv_gemm_bf16_two_accumulators_per_cta():
         torch.cuda.synchronize()
         got = host(out_b)[sel].astype(np.float64)
         # one bf16 ulp of the result + the fp32 accumulation noise of sums whose terms are O(max |ref|)
-    tol = np.abs(ref) * 2.0 ** -7 + 3e-5 * np.abs(ref).max()
+        tol = np.abs(ref) * 2.0 ** -7 + 3e-5 * np.abs(ref).max()
         bad = np.abs(got - ref) > tol
         assert not bad.any(), "%d of %d outputs off by more than a bf16 ulp (max err %.3e) %s" % (
             bad.sum(), bad.size, np.abs(got - ref).max(), case)

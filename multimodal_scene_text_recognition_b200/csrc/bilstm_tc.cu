@@ -32,7 +32,7 @@ constexpr int LT_STAGES = 4;
 constexpr int LT_W_TILE_BYTES = 128 * 128;         // [128 gate rows][64 k] bf16
 constexpr int LT_H_KB_BYTES = LT_M * 128;          // one k-block of h: 128 rows x 128 bytes
 constexpr int LT_H_BUF_BYTES = LT_KB * LT_H_KB_BYTES;  // 64 KB
-constexpr int LT_THREADS = 608;            // producer, MMA, 16 epilogue warps, 1 L2-prefetch warp
+constexpr int LT_THREADS = 576;            // producer, MMA, 16 epilogue warps
 constexpr int LT_EPI_WARPS = 16;
 constexpr int LT_SMEM_BYTES = 1024 + 2 * LT_H_BUF_BYTES + LT_STAGES * LT_W_TILE_BYTES + 256;
 constexpr uint32_t LT_ACC_COL0 = 256;  // TMEM: [0,256) cell state, [256,384) / [384,512) accumulators
@@ -125,21 +125,6 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
         }
       }
     }
-  } else if (warp == 2 + LT_EPI_WARPS) {
-    // ===================== L2 prefetch of the next step's gates_x rows =====================
-    // gates_x (872 MB per layer) streams from HBM exactly once; the epilogue threads need 128 bytes per gate of
-    // it right after every MMA chunk, so its DRAM latency sat on the per-step critical path.  This warp pulls
-    // the 4 KB row of every crop for step s+1 into L2 while step s computes (paced by the hready barrier).
-    for (int step = 0; step + 1 < T; ++step) {
-      if (step > 0) mbar_wait(&hready_bar[LT_KB - 1], (step - 1) & 1);   // step-1 finished: stay one step ahead
-      const int t = dir ? (T - 2 - step) : (step + 1);
-      for (int r = 0; r < LT_M; ++r) {
-        const int crop = crop0 + r;
-        if (crop >= p.B) break;
-        const char* rowp = reinterpret_cast<const char*>(p.gates_x + (((size_t)crop * T + t) * 2 + dir) * (4 * LT_H));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + lane * 128));   // 32 lanes x 128 B = the 4 KB row
-      }
-    }
   } else {
     // ===================== epilogue: gate math, c in TMEM, h -> smem (next A operand) + global ===========
     const int ew = warp - 2;                 // 0..15
@@ -155,6 +140,15 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
       uint8_t* h_next = sH + ((step + 1) & 1) * LT_H_BUF_BYTES;
       const float* gx_row = p.gates_x + (((size_t)(valid ? crop : 0) * T + t) * 2 + dir) * (4 * LT_H);
       __nv_bfloat16* out_row = p.out + ((size_t)(valid ? crop : 0) * T + t) * (2 * LT_H) + dir * LT_H;
+      // gates_x (872 MB per layer) streams from HBM exactly once and is needed right after every MMA chunk, so
+      // its DRAM latency sat on the per-step critical path: pull the NEXT step's 4 KB row of this crop into L2
+      // now (the four threads that share the row take a quarter each)
+      if (valid && step + 1 < T) {
+        const int tn = dir ? (t - 1) : (t + 1);
+        const char* nxt = reinterpret_cast<const char*>(p.gates_x + (((size_t)crop * T + tn) * 2 + dir) * (4 * LT_H));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (uq * 8 + i) * 128));
+      }
       for (int chunk = 0; chunk < LT_CHUNKS; ++chunk, ++n) {
         const int buf = n & 1;
         const int unit0 = chunk * LT_CHUNK_UNITS + uq * 8;       // first of this thread's 8 hidden units

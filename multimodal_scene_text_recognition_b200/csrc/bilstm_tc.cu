@@ -32,7 +32,7 @@ constexpr int LT_STAGES = 4;
 constexpr int LT_W_TILE_BYTES = 128 * 128;         // [128 gate rows][64 k] bf16
 constexpr int LT_H_KB_BYTES = LT_M * 128;          // one k-block of h: 128 rows x 128 bytes
 constexpr int LT_H_BUF_BYTES = LT_KB * LT_H_KB_BYTES;  // 64 KB
-constexpr int LT_THREADS = 576;            // producer, MMA, 16 epilogue warps
+constexpr int LT_THREADS = 576;
 constexpr int LT_EPI_WARPS = 16;
 constexpr int LT_SMEM_BYTES = 1024 + 2 * LT_H_BUF_BYTES + LT_STAGES * LT_W_TILE_BYTES + 256;
 constexpr uint32_t LT_ACC_COL0 = 256;  // TMEM: [0,256) cell state, [256,384) / [384,512) accumulators
@@ -140,15 +140,6 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
       uint8_t* h_next = sH + ((step + 1) & 1) * LT_H_BUF_BYTES;
       const float* gx_row = p.gates_x + (((size_t)(valid ? crop : 0) * T + t) * 2 + dir) * (4 * LT_H);
       __nv_bfloat16* out_row = p.out + ((size_t)(valid ? crop : 0) * T + t) * (2 * LT_H) + dir * LT_H;
-      // gates_x (872 MB per layer) streams from HBM exactly once and is needed right after every MMA chunk, so
-      // its DRAM latency sat on the per-step critical path: pull the NEXT step's 4 KB row of this crop into L2
-      // now (the four threads that share the row take a quarter each)
-      if (valid && step + 1 < T) {
-        const int tn = dir ? (t - 1) : (t + 1);
-        const char* nxt = reinterpret_cast<const char*>(p.gates_x + (((size_t)crop * T + tn) * 2 + dir) * (4 * LT_H));
-#pragma unroll
-        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (uq * 8 + i) * 128));
-      }
       for (int chunk = 0; chunk < LT_CHUNKS; ++chunk, ++n) {
         const int buf = n & 1;
         const int unit0 = chunk * LT_CHUNK_UNITS + uq * 8;       // first of this thread's 8 hidden units

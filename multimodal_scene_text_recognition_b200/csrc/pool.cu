@@ -10,56 +10,43 @@
 
 namespace mstr {
 
-// one thread = one output pixel x 8 (bf16) or 4 (f32) channels per item, two items per loop trip so that all
-// (up to 8) 16-byte window loads of both are in flight together
+// one thread = one output pixel x 8 (bf16) or 4 (f32) channels
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int P,
                     int Q, int kh, int kw, int sh, int sw, int ph, int pw) {
   const int cv = C / VEC;
   const int64_t total = (int64_t)B * P * Q * cv;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
-    float m[2][VEC];
-    bool any[2] = {false, false};
-    int64_t oidx[2];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * VEC;
+    int64_t r = i / cv;
+    const int q = (int)(r % Q); r /= Q;
+    const int p = (int)(r % P);
+    const int b = (int)(r / P);
+    float m[VEC];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int64_t i = i0 + u * stride;
-      oidx[u] = -1;
+    for (int v = 0; v < VEC; ++v) m[v] = -FLT_MAX;
+    bool any = false;
+    for (int dy = 0; dy < kh; ++dy) {
+      const int y = p * sh - ph + dy;
+      if (y < 0 || y >= H) continue;
+      for (int dx = 0; dx < kw; ++dx) {
+        const int xx = q * sw - pw + dx;
+        if (xx < 0 || xx >= W) continue;
+        any = true;
+        const T* src = x + (((int64_t)b * H + y) * W + xx) * C + c;
+        uint4 raw = *reinterpret_cast<const uint4*>(src);
+        const T* e = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) m[u][v] = -FLT_MAX;
-      if (i >= total) continue;
-      const int c = (int)(i % cv) * VEC;
-      int64_t r = i / cv;
-      const int q = (int)(r % Q); r /= Q;
-      const int p = (int)(r % P);
-      const int b = (int)(r / P);
-      oidx[u] = (((int64_t)b * P + p) * Q + q) * C + c;
-      for (int dy = 0; dy < kh; ++dy) {
-        const int y = p * sh - ph + dy;
-        if (y < 0 || y >= H) continue;
-        for (int dx = 0; dx < kw; ++dx) {
-          const int xx = q * sw - pw + dx;
-          if (xx < 0 || xx >= W) continue;
-          any[u] = true;
-          const T* src = x + (((int64_t)b * H + y) * W + xx) * C + c;
-          uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
-          const T* e = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) m[u][v] = fmaxf(m[u][v], Elem<T>::load(e + v));
-        }
+        for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], Elem<T>::load(e + v));
       }
     }
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (oidx[u] < 0) continue;
-      uint4 o;
-      T* oe = reinterpret_cast<T*>(&o);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) Elem<T>::store(oe + v, any[u] ? m[u][v] : -INFINITY);
-      *reinterpret_cast<uint4*>(out + oidx[u]) = o;
-    }
+    for (int v = 0; v < VEC; ++v) Elem<T>::store(oe + v, any ? m[v] : -INFINITY);
+    *reinterpret_cast<uint4*>(out + (((int64_t)b * P + p) * Q + q) * C + c) = o;
   }
 }
 

@@ -215,6 +215,14 @@ int mstr_attn_decode_bf16(const void* enc_bf16, const void* proj_bf16, const voi
                           int32_t* lengths, float* alpha_out, int B, int T, int Hd, int C, int steps,
                           int early_exit, mstr_stream_t stream);
 
+/* Crops never interact in the decoder, so mstr_attn_decode_bf16 can split a large batch into contiguous crop
+ * groups whose launch chains run concurrently on internal side streams forked from / joined into the
+ * caller's stream (ordinary stream semantics for the caller).  max_groups = 1 (the default: measured fastest
+ * on B200, see csrc/attn_tc.cu) runs one chain; 0 = automatic (up to 4 groups of at least
+ * min_crops_per_group crops, 0 -> 1024); 2..4 = at most that many groups.
+ * Call mstr_attn_decode_bf16_workspace_bytes AFTER changing this setting. */
+int mstr_set_decode_groups(int max_groups, int min_crops_per_group);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,9 @@
 // times W_ih is a row gather of W_tok).  proj = i2h(enc) is loop invariant (:81) and computed once by
 // the caller.  Differences to the fp32 SIMT kernel (attn_decode.cu): proj / enc / h / ctx are bf16
 // operands (fp32 accumulation everywhere), tanh.approx in the attention scores.
+#include <atomic>
+#include <mutex>
+
 #include "tc_common.cuh"
 
 namespace mstr {
@@ -345,11 +348,144 @@ __global__ void decode_init_kernel(const DecodeState s) {
 
 static TmaEncoders g_attn_enc;
 
+// ---- crop groups on forked streams ---------------------------------------------------------------
+// A decode step is a chain of three short launches (head GEMM -> attention -> cell GEMM), and crops never
+// interact.  The batch can therefore be split into contiguous crop groups whose chains run on side streams forked
+// from / joined back into the caller's stream with events (the caller still sees ordinary stream semantics).
+// MEASURED (B200, B=4096, 26 steps): 1 chain 1.81 ms, 2 groups 2.03 ms, 3 groups 2.37 ms, 4 groups 2.55 ms -
+// the kernels are throughput bound (attention on HBM, the cell epilogue on its token-row gathers), not latency
+// bound, and more launches only add front-end cost.  Grouping is therefore OFF by default (one chain) and kept
+// as an opt-in (mstr_set_decode_groups) for small-SM-count parts / future tuning.
+constexpr int AT_MAX_GROUPS = 4;
+struct ForkJoin {
+  cudaStream_t side[AT_MAX_GROUPS - 1] = {};
+  cudaEvent_t fork = nullptr;
+  cudaEvent_t join[AT_MAX_GROUPS - 1] = {};
+  bool ready = false;
+};
+static ForkJoin g_fj[64];          // per device ordinal
+static std::mutex g_fj_mutex;
+static std::mutex g_enqueue_mutex;
+
+static int fork_join_for_device(ForkJoin** out) {
+  int dev = 0;
+  MSTR_CUDA(cudaGetDevice(&dev));
+  MSTR_REQUIRE(dev >= 0 && dev < 64, MSTR_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_fj_mutex);
+  ForkJoin& f = g_fj[dev];
+  if (!f.ready) {
+    MSTR_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
+    for (int i = 0; i < AT_MAX_GROUPS - 1; ++i) {
+      MSTR_CUDA(cudaStreamCreateWithFlags(&f.side[i], cudaStreamNonBlocking));
+      MSTR_CUDA(cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming));
+    }
+    f.ready = true;
+  }
+  *out = &f;
+  return MSTR_OK;
+}
+
+static inline size_t group_ws_bytes(int Bg) {
+  // xh[2][Bg][2H] bf16 | hp [Bg][H] f32 | c [Bg][H] f32 | tok [Bg] | done [Bg] | live, rounded to 256 bytes
+  size_t b = (size_t)Bg * AT_H * (2 * 2 * 2 + 4 + 4) + (size_t)Bg * 8 + 16;
+  return (b + 255) & ~(size_t)255;
+}
+
+struct DecodeArgs {
+  const __nv_bfloat16* enc; const __nv_bfloat16* proj; const void* w_head; const void* w_cat;
+  const float* b_h2h; const float* b_gen; const float* w_score; const float* w_tok; const float* bias;
+  const int64_t* text; float* logits; int32_t* ids; int32_t* lengths; float* alpha_out;
+  int T, C, steps, early_exit;
+};
+
+// One crop group [g0, g0 + Bg): its own state block and the whole chain of launches on `st`.
+static int decode_group(const DecodeArgs& a, uint8_t* ws, int g0, int Bg, cudaStream_t st) {
+  DecodeState s;
+  const size_t xh_bytes = (size_t)Bg * 2 * AT_H * 2;
+  s.xh[0] = reinterpret_cast<__nv_bfloat16*>(ws);
+  s.xh[1] = reinterpret_cast<__nv_bfloat16*>(ws + xh_bytes);
+  s.hp = reinterpret_cast<float*>(ws + 2 * xh_bytes);
+  s.cst = s.hp + (size_t)Bg * AT_H;
+  s.tok = reinterpret_cast<int32_t*>(s.cst + (size_t)Bg * AT_H);
+  s.done = s.tok + Bg;
+  s.live = s.done + Bg;
+  s.b_h2h = a.b_h2h; s.b_gen = a.b_gen; s.w_score = a.w_score; s.w_tok = a.w_tok; s.bias = a.bias;
+  s.text = a.text ? a.text + (size_t)g0 * a.steps : nullptr;
+  s.logits = a.logits + (size_t)g0 * a.steps * a.C;
+  s.ids = a.ids + (size_t)g0 * a.steps;
+  s.lengths = a.lengths ? a.lengths + g0 : nullptr;
+  s.alpha_out = a.alpha_out ? a.alpha_out + (size_t)g0 * a.steps * a.T : nullptr;
+  s.B = Bg; s.T = a.T; s.C = a.C; s.steps = a.steps; s.early_exit = a.early_exit;
+  // h_0 = c_0 = 0 (decoders.py:36-38); ctx halves are overwritten before use
+  MSTR_CUDA(cudaMemsetAsync(ws, 0, 2 * xh_bytes + (size_t)Bg * AT_H * 8, st));
+  decode_init_kernel<<<ceil_div(Bg, 256), 256, 0, st>>>(s);
+  MSTR_LAUNCH_CHECK("decode_init_kernel");
+
+  // tensor maps: h view [Bg][256] with row stride 512 elements; [ctx|h] view [Bg][512]; weights
+  alignas(64) CUtensorMap tmH[2], tmXH[2], tmHead, tmCat;
+  int rc;
+  for (int p = 0; p < 2; ++p) {
+    cuuint64_t dims[2] = {(cuuint64_t)AT_H, (cuuint64_t)Bg};
+    cuuint64_t strides[1] = {(cuuint64_t)(2 * AT_H * 2)};
+    cuuint32_t box[2] = {64, AT_BLOCK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_attn_enc.tiled(&tmH[p], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, s.xh[p] + AT_H, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled(h) failed with CUresult %d", (int)r);
+    rc = encode_tiled_2d_bf16(g_attn_enc, &tmXH[p], s.xh[p], 2 * AT_H, Bg, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != MSTR_OK) return rc;
+  }
+  rc = encode_tiled_2d_bf16(g_attn_enc, &tmHead, a.w_head, AT_H, 3 * AT_BLOCK, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != MSTR_OK) return rc;
+  rc = encode_tiled_2d_bf16(g_attn_enc, &tmCat, a.w_cat, 2 * AT_H, 4 * AT_H, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != MSTR_OK) return rc;
+
+  const int m_tiles = ceil_div(Bg, AT_BLOCK);
+  const __nv_bfloat16* enc = a.enc + (size_t)g0 * a.T * AT_H;
+  const __nv_bfloat16* proj = a.proj + (size_t)g0 * a.T * AT_H;
+  for (int i = 0; i <= a.steps; ++i) {
+    // head_i: hp_i (tiles 0,1) and logits_{i-1} (tile 2); the last iteration only needs the logits tile
+    rnn_gemm_kernel<0><<<dim3(3, m_tiles), AT_THREADS, AT_SMEM_BYTES, st>>>(tmH[i & 1], tmHead, s, i, AT_H / 64);
+    MSTR_LAUNCH_CHECK("rnn_gemm_kernel<head>");
+    if (i == a.steps) break;
+    attn_context_kernel<<<ceil_div(Bg, 8), 256, 0, st>>>(enc, proj, s, i);
+    MSTR_LAUNCH_CHECK("attn_context_kernel");
+    rnn_gemm_kernel<1><<<dim3(4 * AT_H / AT_BLOCK, m_tiles), AT_THREADS, AT_SMEM_BYTES, st>>>(tmXH[i & 1], tmCat, s, i,
+                                                                                           2 * AT_H / 64);
+    MSTR_LAUNCH_CHECK("rnn_gemm_kernel<cell>");
+  }
+  return MSTR_OK;
+}
+
+// Number of crop groups for a batch: groups of at least 1024 crops (8 M-tiles), at most AT_MAX_GROUPS.
+static std::atomic<int> g_group_limit{1};    // 1 = one chain (default); 0 = automatic; see mstr_set_decode_groups
+static std::atomic<int> g_group_min_crops{1024};
+static inline int decode_groups(int B) {
+  const int limit = g_group_limit.load(std::memory_order_relaxed);
+  if (limit == 1) return 1;
+  int g = B / g_group_min_crops.load(std::memory_order_relaxed);
+  const int cap = (limit > 0 && limit < AT_MAX_GROUPS) ? limit : AT_MAX_GROUPS;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
 }  // namespace mstr
 
+extern "C" __attribute__((visibility("default"))) int mstr_set_decode_groups(int max_groups, int min_crops_per_group) {
+  using namespace mstr;
+  MSTR_REQUIRE(max_groups >= 0 && max_groups <= AT_MAX_GROUPS && min_crops_per_group >= 0, MSTR_ERR_BAD_ARG,
+               "mstr_set_decode_groups: max_groups must be 0 (automatic) .. %d", AT_MAX_GROUPS);
+  g_group_limit.store(max_groups);
+  g_group_min_crops.store(min_crops_per_group > 0 ? min_crops_per_group : 1024);
+  return MSTR_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int64_t mstr_attn_decode_bf16_workspace_bytes(int B, int Hd) {
-  // xh[2][B][2H] bf16 | hp [B][H] f32 | c [B][H] f32 | tok [B] | done [B] | live (16 bytes)
-  return (int64_t)B * Hd * (2 * 2 * 2 + 4 + 4) + (int64_t)B * 8 + 16;
+  (void)Hd;
+  using namespace mstr;
+  const int G = decode_groups(B);
+  const int per = (ceil_div(B, G) + AT_BLOCK - 1) / AT_BLOCK * AT_BLOCK;
+  return (int64_t)G * (int64_t)group_ws_bytes(per);
 }
 
 extern "C" __attribute__((visibility("default"))) int mstr_attn_decode_bf16(
@@ -372,63 +508,47 @@ extern "C" __attribute__((visibility("default"))) int mstr_attn_decode_bf16(
   int rc = load_tma_encoders(g_attn_enc);
   if (rc != MSTR_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(rnn_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rnn_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+  });
+  MSTR_REQUIRE(attr_err == cudaSuccess, MSTR_ERR_CUDA, "cudaFuncSetAttribute(rnn_gemm_kernel) failed: %s",
+               cudaGetErrorString(attr_err));
 
-  DecodeState s;
+  DecodeArgs a{static_cast<const __nv_bfloat16*>(enc_bf16), static_cast<const __nv_bfloat16*>(proj_bf16), w_head, w_cat,
+               b_h2h, b_gen, w_score, w_tok, bias, text, logits, ids, lengths, alpha_out, T, C, steps, early_exit};
+  const int G = decode_groups(B);
+  const int per = (ceil_div(B, G) + AT_BLOCK - 1) / AT_BLOCK * AT_BLOCK;   // crops per group, whole M-tiles
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  const size_t xh_bytes = (size_t)B * 2 * AT_H * 2;
-  s.xh[0] = reinterpret_cast<__nv_bfloat16*>(ws);
-  s.xh[1] = reinterpret_cast<__nv_bfloat16*>(ws + xh_bytes);
-  s.hp = reinterpret_cast<float*>(ws + 2 * xh_bytes);
-  s.cst = s.hp + (size_t)B * AT_H;
-  s.tok = reinterpret_cast<int32_t*>(s.cst + (size_t)B * AT_H);
-  s.done = s.tok + B;
-  s.live = s.done + B;
-  s.b_h2h = b_h2h; s.b_gen = b_gen; s.w_score = w_score; s.w_tok = w_tok; s.bias = bias; s.text = text;
-  s.logits = logits; s.ids = ids; s.lengths = lengths; s.alpha_out = alpha_out;
-  s.B = B; s.T = T; s.C = C; s.steps = steps; s.early_exit = early_exit;
-  // h_0 = c_0 = 0 (decoders.py:36-38); ctx halves are overwritten before use
-  MSTR_CUDA(cudaMemsetAsync(ws, 0, 2 * xh_bytes + (size_t)B * AT_H * 8, st));
-  decode_init_kernel<<<ceil_div(B, 256), 256, 0, st>>>(s);
-  MSTR_LAUNCH_CHECK("decode_init_kernel");
+  if (G == 1) return decode_group(a, ws, 0, B, st);
 
-  // tensor maps: h view [B][256] with row stride 512 elements; [ctx|h] view [B][512]; weights
-  alignas(64) CUtensorMap tmH[2], tmXH[2], tmHead, tmCat;
-  for (int p = 0; p < 2; ++p) {
-    cuuint64_t dims[2] = {(cuuint64_t)AT_H, (cuuint64_t)B};
-    cuuint64_t strides[1] = {(cuuint64_t)(2 * AT_H * 2)};
-    cuuint32_t box[2] = {64, AT_BLOCK};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_attn_enc.tiled(&tmH[p], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, s.xh[p] + AT_H, dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled(h) failed with CUresult %d", (int)r);
-    rc = encode_tiled_2d_bf16(g_attn_enc, &tmXH[p], s.xh[p], 2 * AT_H, B, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc != MSTR_OK) return rc;
-  }
-  rc = encode_tiled_2d_bf16(g_attn_enc, &tmHead, w_head, AT_H, 3 * AT_BLOCK, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
+  ForkJoin* fj = nullptr;
+  rc = fork_join_for_device(&fj);
   if (rc != MSTR_OK) return rc;
-  rc = encode_tiled_2d_bf16(g_attn_enc, &tmCat, w_cat, 2 * AT_H, 4 * AT_H, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc != MSTR_OK) return rc;
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(rnn_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-    MSTR_CUDA(cudaFuncSetAttribute(rnn_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-    attr_set = true;
+  std::lock_guard<std::mutex> enqueue_lock(g_enqueue_mutex);   // the fork / join events are shared per device
+  MSTR_CUDA(cudaEventRecord(fj->fork, st));
+  int result = MSTR_OK;
+  int forked = 0;
+  for (int g = 0; g < G; ++g) {
+    const int g0 = g * per;
+    if (g0 >= B) break;
+    const int Bg = (B - g0 < per) ? (B - g0) : per;
+    cudaStream_t gs = st;
+    if (g > 0) {
+      gs = fj->side[g - 1];
+      MSTR_CUDA(cudaStreamWaitEvent(gs, fj->fork, 0));
+      forked = g;
+    }
+    rc = decode_group(a, ws + (size_t)g * group_ws_bytes(per), g0, Bg, gs);
+    if (rc != MSTR_OK) { result = rc; break; }
   }
-  const int m_tiles = ceil_div(B, AT_BLOCK);
-  const __nv_bfloat16* enc = static_cast<const __nv_bfloat16*>(enc_bf16);
-  const __nv_bfloat16* proj = static_cast<const __nv_bfloat16*>(proj_bf16);
-  for (int i = 0; i <= steps; ++i) {
-    // head_i: hp_i (tiles 0,1) and logits_{i-1} (tile 2); the last iteration only needs the logits tile
-    rnn_gemm_kernel<0><<<dim3(3, m_tiles), AT_THREADS, AT_SMEM_BYTES, st>>>(tmH[i & 1], tmHead, s, i, AT_H / 64);
-    MSTR_LAUNCH_CHECK("rnn_gemm_kernel<head>");
-    if (i == steps) break;
-    attn_context_kernel<<<ceil_div(B, 8), 256, 0, st>>>(enc, proj, s, i);
-    MSTR_LAUNCH_CHECK("attn_context_kernel");
-    rnn_gemm_kernel<1><<<dim3(4 * AT_H / AT_BLOCK, m_tiles), AT_THREADS, AT_SMEM_BYTES, st>>>(tmXH[i & 1], tmCat, s, i,
-                                                                                           2 * AT_H / 64);
-    MSTR_LAUNCH_CHECK("rnn_gemm_kernel<cell>");
+  // always join what was forked, also on error, so the caller's stream order stays intact
+  for (int g = 1; g <= forked; ++g) {
+    MSTR_CUDA(cudaEventRecord(fj->join[g - 1], fj->side[g - 1]));
+    MSTR_CUDA(cudaStreamWaitEvent(st, fj->join[g - 1], 0));
   }
-  return MSTR_OK;
+  return result;
 }

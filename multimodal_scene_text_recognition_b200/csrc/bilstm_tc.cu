@@ -3,22 +3,39 @@
 // Replaces the recurrent half of nn.LSTM(bidirectional=True, batch_first=True)
 // (modules/encoders.py:14,24; gate order i,f,g,o, zero initial state, the reverse direction runs
 // t = T-1..0 with the *_reverse parameters).  The input projection x W_ih^T + b_ih + b_hh is a
-// separate tcgen05 GEMM (mstr_conv_gemm_bf16); its fp32 result `gates_x` is added in the epilogue.
+// separate tcgen05 GEMM (mstr_conv_gemm_bf16); its fp32 result `gates_x` is the initial value of the
+// gate accumulators.
 //
 // One CTA owns a tile of 128 crops of one direction for ALL T steps (grid = ceil(B/128) x 2):
 //   h_t   [128 crops x 256] bf16 lives in shared memory in the UMMA K-major 128B-swizzled layout
 //         (double buffered), written by the epilogue threads and read by tcgen05.mma as operand A;
+//         the same tiles are the kernel's output: the MMA thread hands each finished k-block tile to a
+//         TMA store (rows beyond B clipped by the tensor map);
 //   c_t   [128 x 256] fp32 lives in TMEM columns 0..255 for the whole sequence;
-//   W_hh  (bf16, 512 KB per direction, L2 resident) is streamed by TMA through a 4-stage ring in
+//   W_hh  (bf16, 512 KB per direction, L2 resident) is streamed by TMA through a 3-stage ring in
 //         tiles of [128 gate rows x 64 k]; rows are pre-packed so that one 128-column accumulator
 //         chunk holds the i,f,g,o gates of the same 32 hidden units;
 //   gates [128 x 128] fp32 accumulators are double buffered in TMEM columns 256..511, so the MMAs
-//         of chunk c+1 overlap the gate math of chunk c.
-// Per step: 8 chunks x 4 k-blocks x 4 tcgen05.mma (128x128x16).  Warp roles: warp 0 = TMA producer,
-// warp 1 = MMA issuer, warps 2..17 = epilogue (four warps per TMEM lane quarter, 8 units each: 16 warps
-// hide the latency of the gates_x loads and TMEM round trips better than 8 did, 0.65 -> see profiles/).
-// The gate non-linearities use tanh.approx (1 MUFU each; sigmoid(x) = 0.5 tanh(x/2) + 0.5), which is
-// what bounds the kernel: 5 MUFU per hidden unit per crop per step at 16 MUFU/clk/SM.
+//         of chunk c+1 overlap the gate math of chunk c;
+//   gates_x tiles [128 crops x 32 f32] (one gate of one chunk, 16 KB) arrive by TMA through their own
+//         3-stage ring; four loader warps (one per TMEM lane quarter) copy them shared memory ->
+//         registers -> tcgen05.st into the accumulator buffer BEFORE the chunk's MMAs, which then
+//         accumulate on top (the epilogue never touches gates_x).
+// Per step: 8 chunks x 4 k-blocks x 4 tcgen05.mma (128x128x16).  Warp roles: warp 0 = W_hh TMA producer,
+// warp 1 = MMA issuer + output TMA stores, warps 2..17 = epilogue (four per TMEM lane quarter, 8 units
+// each), warps 18..21 = gates_x loaders, warp 22 = gates_x TMA producer.
+//
+// Why this shape (B200, B=4096, T=26, both directions; ncu stall sampling + elimination runs):
+// the first version let every epilogue thread (TMEM lane = crop) read its own gates_x values and write its
+// own h values with 16-byte global accesses.  The rows of 32 lanes are 4 KB (gates_x) / 1 KB (out) apart,
+// so EVERY such warp instruction costs 32 L1 wavefronts: ~4k L1 cycles per chunk, 0.40 of the kernel's
+// 0.68 ms (0.33 ms with the loads removed), and prefetching (registers or L2) could not help because the
+// cost is L1 throughput, not latency.  A load still in flight also stalls the epilogue's
+// fence.proxy.async (needed before h can be handed to tcgen05.mma).  Moving both streams to TMA (whole
+// 128-byte segments, conflict-free swizzled shared-memory reads) gives 0.47 ms; what remains is the TMA
+// feed of 128 KB per chunk per SM (gates_x + W_hh: 0.34 ms without the gates_x loads) on top of a
+// 0.21 ms barrier / TMEM round-trip skeleton.  The gate non-linearities use tanh.approx (1 MUFU each;
+// sigmoid(x) = 0.5 tanh(x/2) + 0.5): 5 MUFU per hidden unit per crop per step - not the limiter.
 #include "tc_common.cuh"
 
 namespace mstr {
@@ -28,13 +45,17 @@ constexpr int LT_M = 128;          // crops per CTA
 constexpr int LT_CHUNK_UNITS = 32; // hidden units per accumulator chunk (x 4 gates = 128 columns)
 constexpr int LT_CHUNKS = LT_H / LT_CHUNK_UNITS;   // 8
 constexpr int LT_KB = LT_H / 64;   // 4 k-blocks of 64 bf16 (one 128-byte swizzle span)
-constexpr int LT_STAGES = 4;
+constexpr int LT_STAGES = 3;          // W_hh ring: 3 x 16 KB (2 starves the MMAs, 4 leaves too little for gates_x)
 constexpr int LT_W_TILE_BYTES = 128 * 128;         // [128 gate rows][64 k] bf16
 constexpr int LT_H_KB_BYTES = LT_M * 128;          // one k-block of h: 128 rows x 128 bytes
 constexpr int LT_H_BUF_BYTES = LT_KB * LT_H_KB_BYTES;  // 64 KB
-constexpr int LT_THREADS = 576;
 constexpr int LT_EPI_WARPS = 16;
-constexpr int LT_SMEM_BYTES = 1024 + 2 * LT_H_BUF_BYTES + LT_STAGES * LT_W_TILE_BYTES + 256;
+constexpr int LT_LOAD_WARPS = 4;
+constexpr int LT_THREADS = 32 * (2 + LT_EPI_WARPS + LT_LOAD_WARPS + 1);   // 736: + gates_x TMA producer warp
+constexpr int LT_GX_STAGES = 3;
+constexpr int LT_GX_TILE_BYTES = LT_M * 128;        // one pass: 128 crops x 32 f32 columns (one gate of a chunk)
+constexpr int LT_SMEM_BYTES =
+    1024 + 2 * LT_H_BUF_BYTES + LT_STAGES * LT_W_TILE_BYTES + LT_GX_STAGES * LT_GX_TILE_BYTES + 256;
 constexpr uint32_t LT_ACC_COL0 = 256;  // TMEM: [0,256) cell state, [256,384) / [384,512) accumulators
 
 struct LstmTcParams {
@@ -44,17 +65,22 @@ struct LstmTcParams {
 };
 
 __global__ void __launch_bounds__(LT_THREADS, 1)
-bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) {
+bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmGx,
+                 const __grid_constant__ CUtensorMap tmOut, const LstmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sH = smem;                                   // [2][LT_KB][128 rows][128 B]
   uint8_t* sW = smem + 2 * LT_H_BUF_BYTES;              // [STAGES][128 rows][128 B]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sW + LT_STAGES * LT_W_TILE_BYTES);
+  uint8_t* sG = sW + LT_STAGES * LT_W_TILE_BYTES;       // [GX_STAGES][128 rows][128 B] f32, 128B swizzle
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sG + LT_GX_STAGES * LT_GX_TILE_BYTES);
   uint64_t* empty_bar = full_bar + LT_STAGES;
   uint64_t* tfull_bar = empty_bar + LT_STAGES;          // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                 // [2]
   uint64_t* hready_bar = tempty_bar + 2;                // [LT_KB]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hready_bar + LT_KB);
+  uint64_t* tinit_bar = hready_bar + LT_KB;             // [2] accumulator buffer holds its gates_x tile
+  uint64_t* gfull_bar = tinit_bar + 2;                  // [LT_GX_STAGES]
+  uint64_t* gempty_bar = gfull_bar + LT_GX_STAGES;      // [LT_GX_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gempty_bar + LT_GX_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dir = blockIdx.y;
@@ -67,8 +93,15 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
   fence_proxy_async_smem();
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmW);
+    prefetch_tensormap(&tmGx);
+    prefetch_tensormap(&tmOut);
     for (int i = 0; i < LT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], LT_EPI_WARPS); }
+    for (int i = 0; i < LT_GX_STAGES; ++i) { mbar_init(&gfull_bar[i], 1); mbar_init(&gempty_bar[i], LT_LOAD_WARPS); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], LT_EPI_WARPS);
+      mbar_init(&tinit_bar[i], LT_LOAD_WARPS);
+    }
     for (int i = 0; i < LT_KB; ++i) mbar_init(&hready_bar[i], 2 * LT_EPI_WARPS);  // 2 chunks x 16 warps per k-block
     fence_barrier_init();
   }
@@ -86,7 +119,7 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
       for (int step = 0; step < T; ++step)
         for (int chunk = 0; chunk < LT_CHUNKS; ++chunk)
           for (int kb = 0; kb < LT_KB; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_quiet(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], LT_W_TILE_BYTES);
             tma_load_2d(sW + stage * LT_W_TILE_BYTES, &tmW, &full_bar[stage], kb * 64,
                         dir * 4 * LT_H + chunk * 128);
@@ -101,57 +134,65 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
       uint32_t phase = 0;
       int n = 0;  // running chunk counter
       for (int step = 0; step < T; ++step) {
-        const uint32_t h_addr = smem_u32(sH + (step & 1) * LT_H_BUF_BYTES);
+        uint8_t* h_buf = sH + (step & 1) * LT_H_BUF_BYTES;
+        const uint32_t h_addr = smem_u32(h_buf);
+        // the TMA stores issued one step ago have finished reading the buffer the epilogue of this step
+        // (which cannot start before this step's first MMA commits) is going to overwrite
+        bulk_wait_read<0>();
         for (int chunk = 0; chunk < LT_CHUNKS; ++chunk, ++n) {
           const int buf = n & 1;
-          mbar_wait(&tempty_bar[buf], ((n >> 1) & 1) ^ 1);
+          mbar_wait_quiet(&tinit_bar[buf], (n >> 1) & 1);     // the loaders have written gates_x into this buffer
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + LT_ACC_COL0 + (uint32_t)(buf * 128);
           for (int kb = 0; kb < LT_KB; ++kb) {
             // h_t k-block kb is complete once both chunks of step t-1 that produce it have been written
-            if (step > 0 && chunk == 0) mbar_wait(&hready_bar[kb], (step - 1) & 1);
-            mbar_wait(&full_bar[stage], phase);
+            if (step > 0 && chunk == 0) {
+              mbar_wait_quiet(&hready_bar[kb], (step - 1) & 1);
+              // ... which also makes it the output of step-1: [128 crops x 64 units] bf16, already in the
+              // 128B-swizzled layout a TMA store expects; rows beyond B are clipped by the tensor map
+              const int t_prev = dir ? (T - step) : (step - 1);
+              tma_store_2d(&tmOut, h_buf + kb * LT_H_KB_BYTES, t_prev * 2 * LT_H + dir * LT_H + kb * 64, crop0);
+              if (kb == LT_KB - 1) bulk_commit();
+            }
+            mbar_wait_quiet(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = h_addr + kb * LT_H_KB_BYTES;
             const uint32_t b_addr = smem_u32(sW + stage * LT_W_TILE_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, make_smem_desc<128>(a_addr + k * 32), make_smem_desc<128>(b_addr + k * 32), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, make_smem_desc<128>(a_addr + k * 32), make_smem_desc<128>(b_addr + k * 32), idesc, 1u);
             umma_commit(&empty_bar[stage]);
             if (kb == LT_KB - 1) umma_commit(&tfull_bar[buf]);
             if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
+      // h_T, the output of the last step
+      {
+        uint8_t* h_buf = sH + (T & 1) * LT_H_BUF_BYTES;
+        const int t_prev = dir ? 0 : (T - 1);
+        for (int kb = 0; kb < LT_KB; ++kb) {
+          mbar_wait_quiet(&hready_bar[kb], (T - 1) & 1);
+          tma_store_2d(&tmOut, h_buf + kb * LT_H_KB_BYTES, t_prev * 2 * LT_H + dir * LT_H + kb * 64, crop0);
+        }
+        bulk_commit();
+        bulk_wait_all();
+      }
     }
-  } else {
-    // ===================== epilogue: gate math, c in TMEM, h -> smem (next A operand) + global ===========
+  } else if (warp < 2 + LT_EPI_WARPS) {
+    // ===================== epilogue: gate math, c in TMEM, h -> smem (next A operand and output tile) =====
     const int ew = warp - 2;                 // 0..15
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int uq = ew >> 2;                  // which 8 of the chunk's 32 units
     const int row = quarter * 32 + lane;     // crop row within the tile
-    const int crop = crop0 + row;
-    const bool valid = crop < p.B;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int n = 0;
     for (int step = 0; step < T; ++step) {
-      const int t = dir ? (T - 1 - step) : step;
       uint8_t* h_next = sH + ((step + 1) & 1) * LT_H_BUF_BYTES;
-      const float* gx_row = p.gates_x + (((size_t)(valid ? crop : 0) * T + t) * 2 + dir) * (4 * LT_H);
-      __nv_bfloat16* out_row = p.out + ((size_t)(valid ? crop : 0) * T + t) * (2 * LT_H) + dir * LT_H;
       for (int chunk = 0; chunk < LT_CHUNKS; ++chunk, ++n) {
         const int buf = n & 1;
         const int unit0 = chunk * LT_CHUNK_UNITS + uq * 8;       // first of this thread's 8 hidden units
-        // input-projection gates for these units: issued before waiting for the MMA
-        float4 gx[4][2];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int v = 0; v < 2; ++v)
-            gx[g][v] = valid ? __ldg(reinterpret_cast<const float4*>(gx_row + g * LT_H + unit0) + v)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-        mbar_wait(&tfull_bar[buf], (n >> 1) & 1);
+        mbar_wait_quiet(&tfull_bar[buf], (n >> 1) & 1);
         tc_fence_after();
         const uint32_t acc_addr = lane_addr + LT_ACC_COL0 + (uint32_t)(buf * 128 + uq * 8);
         uint32_t a[4][8], cst[8];
@@ -159,18 +200,15 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
         for (int g = 0; g < 4; ++g) tmem_ld8(acc_addr + (uint32_t)(g * 32), a[g]);
         if (step > 0) tmem_ld8(lane_addr + (uint32_t)unit0, cst);
         tmem_ld_wait();
-        // accumulator values are in registers: hand the buffer back to the MMA warp
+        // gate pre-activations (gates_x + h W_hh^T) are in registers: hand the buffer back to the loaders
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         float hv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int v = j >> 2;
-          const float gi = reinterpret_cast<const float*>(&gx[0][v])[j & 3] + __uint_as_float(a[0][j]);
-          const float gf = reinterpret_cast<const float*>(&gx[1][v])[j & 3] + __uint_as_float(a[1][j]);
-          const float gg = reinterpret_cast<const float*>(&gx[2][v])[j & 3] + __uint_as_float(a[2][j]);
-          const float go = reinterpret_cast<const float*>(&gx[3][v])[j & 3] + __uint_as_float(a[3][j]);
+          const float gi = __uint_as_float(a[0][j]), gf = __uint_as_float(a[1][j]);
+          const float gg = __uint_as_float(a[2][j]), go = __uint_as_float(a[3][j]);
           const float c_prev = step > 0 ? __uint_as_float(cst[j]) : 0.f;
           const float c_new = fmaf(sigmoid_approx(gf), c_prev, sigmoid_approx(gi) * tanh_approx(gg));
           cst[j] = __float_as_uint(c_new);
@@ -183,11 +221,76 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmTcParams p) 
         const int kb = unit0 >> 6;
         const int c0 = (unit0 & 63) >> 3;
         *reinterpret_cast<uint4*>(h_next + kb * LT_H_KB_BYTES + row * 128 + ((c0 ^ (row & 7)) << 4)) = hpk;
-        if (valid) *reinterpret_cast<uint4*>(out_row + unit0) = hpk;
         tmem_st_wait();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hready_bar[kb]);
+      }
+    }
+  } else if (warp < 2 + LT_EPI_WARPS + LT_LOAD_WARPS) {
+    // ===================== gates_x loaders: shared-memory tile -> registers -> accumulator buffer ==========
+    // One pass = one gate of one chunk = 32 accumulator columns.  The tile arrives by TMA (whole 128-byte
+    // segments; per-lane global loads of rows 4 KB apart cost 32 L1 wavefronts per instruction, which was
+    // the kernel's bottleneck), lane = crop row reads its 128 bytes with the 128B swizzle (conflict free).
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int crop = crop0 + row;
+    const float* gx_crop = p.gates_x + ((size_t)(crop < p.B ? crop : 0) * T * 2 + dir) * (4 * LT_H);
+    const ptrdiff_t t_stride = (ptrdiff_t)(dir ? -1 : 1) * (2 * 4 * LT_H);
+    const float* grow = gx_crop + (size_t)(dir ? T - 1 : 0) * (2 * 4 * LT_H);
+    // L2 prefetch of this crop's 4 KB row, two steps ahead of the TMA loads
+    prefetch_l2_bulk(grow, 4 * LT_H * 4);
+    if (T > 1) prefetch_l2_bulk(grow + t_stride, 4 * LT_H * 4);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + LT_ACC_COL0;
+    const uint32_t srow = smem_u32(sG) + (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    int stage = 0;
+    uint32_t phase = 0;
+    int n = 0;
+    for (int step = 0; step < T; ++step, grow += t_stride) {
+      if (step + 2 < T) prefetch_l2_bulk(grow + 2 * t_stride, 4 * LT_H * 4);
+      for (int chunk = 0; chunk < LT_CHUNKS; ++chunk, ++n) {
+        const int buf = n & 1;
+        const uint32_t acc = lane_addr + (uint32_t)(buf * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t r[32];
+          if (g == 0) {
+            mbar_wait_quiet(&tempty_bar[buf], ((n >> 1) & 1) ^ 1);   // the epilogue has drained this buffer
+            tc_fence_after();
+          }
+          mbar_wait_quiet(&gfull_bar[stage], phase);
+          const uint32_t base = srow + (uint32_t)stage * LT_GX_TILE_BYTES;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            lds_v4(base + (((uint32_t)c ^ sw) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+          tmem_st32(acc + (uint32_t)(g * 32), r);
+          // the store has issued, so the shared-memory reads that feed it have completed: release the stage
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&gempty_bar[stage]);
+          if (++stage == LT_GX_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tinit_bar[buf]);
+      }
+    }
+  } else {
+    // ===================== gates_x TMA producer: (step, chunk, gate) order =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int step = 0; step < T; ++step) {
+        const int t = dir ? (T - 1 - step) : step;
+        for (int chunk = 0; chunk < LT_CHUNKS; ++chunk)
+          for (int g = 0; g < 4; ++g) {
+            mbar_wait_quiet(&gempty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&gfull_bar[stage], LT_GX_TILE_BYTES);
+            tma_load_2d(sG + stage * LT_GX_TILE_BYTES, &tmGx, &gfull_bar[stage],
+                        (t * 2 + dir) * 4 * LT_H + g * LT_H + chunk * LT_CHUNK_UNITS, crop0);
+            if (++stage == LT_GX_STAGES) { stage = 0; phase ^= 1; }
+          }
       }
     }
   }
@@ -217,6 +320,23 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   alignas(64) CUtensorMap tmW;
   rc = encode_tiled_2d_bf16(g_lstm_enc, &tmW, w_hh_packed, LT_H, 2 * 4 * LT_H, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != MSTR_OK) return rc;
+  // gates_x viewed as [B rows][T*2*4H f32 columns]; box = 32 columns x 128 crops, rows beyond B are zero filled
+  alignas(64) CUtensorMap tmGx;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)T * 2 * 4 * LT_H, (cuuint64_t)B};
+    cuuint64_t strides[1] = {(cuuint64_t)T * 2 * 4 * LT_H * 4};
+    cuuint32_t box[2] = {32, LT_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_lstm_enc.tiled(&tmGx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(gates_x), dims, strides,
+                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled(gates_x) failed with CUresult %d", (int)r);
+  }
+  // output viewed as [B rows][T*2H bf16 columns]; box = 64 units x 128 crops (one k-block tile of h)
+  alignas(64) CUtensorMap tmOut;
+  rc = encode_tiled_2d_bf16(g_lstm_enc, &tmOut, out_bf16, (uint64_t)T * 2 * LT_H, (uint64_t)B, 64, LT_M,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != MSTR_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MSTR_CUDA(cudaFuncSetAttribute(bilstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES));
@@ -224,7 +344,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   }
   LstmTcParams p{gates_x, (__nv_bfloat16*)out_bf16, B, T};
   dim3 grid(ceil_div(B, LT_M), 2);
-  bilstm_tc_kernel<<<grid, LT_THREADS, LT_SMEM_BYTES, (cudaStream_t)stream>>>(tmW, p);
+  bilstm_tc_kernel<<<grid, LT_THREADS, LT_SMEM_BYTES, (cudaStream_t)stream>>>(tmW, tmGx, tmOut, p);
   MSTR_LAUNCH_CHECK("bilstm_tc_kernel");
   return MSTR_OK;
 }

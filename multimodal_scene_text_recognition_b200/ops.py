@@ -375,6 +375,12 @@ def pack_gate_rows_bf16(w: torch.Tensor) -> torch.Tensor:
     return w.reshape(4, hd // 32, 32, k).permute(1, 0, 2, 3).reshape(four_h, k).to(torch.bfloat16).contiguous()
 
 
+def set_decode_groups(max_groups: int = 1, min_crops_per_group: int = 0) -> None:
+    """Crop groups of the tensor-core decoder (mstr_set_decode_groups): 1 = a single chain on the caller's
+    stream (default, measured fastest), 0 = automatic (<= 4 groups of >= 1024 crops), 2..4 = at most that many."""
+    check(lib().mstr_set_decode_groups(int(max_groups), int(min_crops_per_group)), "mstr_set_decode_groups")
+
+
 def attn_decode_bf16(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int, text: Optional[torch.Tensor],
                      early_exit: bool, want_alpha: bool = False) -> dict:
     """Tensor-core greedy / teacher-forced attention decode (bf16 mode).  enc, proj [B,T,H] bf16;

@@ -403,6 +403,43 @@ def _decoder_pack_bf16(sd, Hd=256):
             "w_score": t(p + "score.weight").view(-1).contiguous()}
 
 
+def test_attn_decode_bf16_crop_groups_match_single_chain(sd_cfg_a):
+    """The decoder's crop groups (chains on forked side streams) must give exactly the single-chain result,
+    including ragged last groups, teacher forcing, early exit and work queued behind the call."""
+    Hd, B, T, steps = 256, 300, 26, 26
+    enc = orc.round_bf16((rng(28).standard_normal((B, T, Hd)) * 0.5).astype(np.float32))
+    w_i2h = orc.round_bf16(sd_cfg_a["decoder.attention_cell.i2h.weight"])
+    proj = orc.round_bf16((enc.astype(np.float64) @ w_i2h.astype(np.float64).T).astype(np.float32))
+    pk = _decoder_pack_bf16(sd_cfg_a)
+    bf = torch.bfloat16
+    text = rng(29).integers(0, 97, (B, steps)).astype(np.int64)
+    text[:, 0] = 0
+    e, p_ = dev(enc, bf), dev(proj, bf)
+
+    def run():
+        out = []
+        for txt, ee in ((None, False), (None, True), (dev(text), False)):
+            r = ops.attn_decode_bf16(e, p_, pk, steps, txt, early_exit=ee, want_alpha=True)
+            # consumer on the caller's stream right behind the call: must see the joined result
+            out.append((r["logits"].clone(), r["ids"].clone(), r["lengths"].clone(), r["alpha"].clone()))
+        torch.cuda.synchronize()
+        return [[host(t) for t in r] for r in out]
+
+    try:
+        ops.set_decode_groups(1, 0)
+        single = run()
+        ops.set_decode_groups(3, 100)       # groups of 128 crops: [0,128) [128,256) [256,300)
+        grouped = run()
+        ops.set_decode_groups(4, 64)        # 128, 128, 44 (a fourth group would be empty)
+        grouped4 = run()
+    finally:
+        ops.set_decode_groups(1, 0)
+    for other in (grouped, grouped4):
+        for a, b in zip(single, other):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+
+
 @pytest.mark.parametrize("B,T,steps", [(37, 26, 26), (130, 26, 26), (5, 65, 51)])
 def test_attn_decode_bf16_tensor_cores(sd_cfg_a, B, T, steps):
     """Tensor-core decode vs the oracle with bf16 rounding at the same operands.  Teacher-forced logits

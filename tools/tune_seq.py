@@ -1,0 +1,48 @@
+"""Timing of the sequence-stage kernels in isolation (BiLSTM recurrence, tensor-core decoder with 1..4 crop
+groups) at the bench geometry.  Usage (GPU box): python tools/tune_seq.py [B]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from multimodal_scene_text_recognition_b200 import ops, synth
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+T, H, steps = 26, 256, 26
+dev = torch.device("cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, reps=10):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return float(np.median(ts)), float(min(ts))
+
+
+gx = torch.randn(B, T, 2, 4 * H, device=dev)
+w = torch.randn(2, 4 * H, H, device=dev) / 16
+wp = ops.pack_w_hh_bf16(w)
+print("bilstm_recurrent_bf16 B=%d: median %.3f ms, best %.3f ms" % ((B,) + timeit(lambda: ops.bilstm_recurrent_bf16(gx, wp))))
+
+sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(999).items() if k.startswith("decoder.")}
+p = "decoder.attention_cell."
+w_ih = sd[p + "rnn.weight_ih"]
+C = sd["decoder.generator.weight"].shape[0]
+head = torch.zeros((384, H), device=dev)
+head[:H] = sd[p + "h2h.weight"]; head[H:H + C] = sd["decoder.generator.weight"]
+pk = {"w_head": head.to(torch.bfloat16).contiguous(),
+      "w_cat": ops.pack_gate_rows_bf16(torch.cat([w_ih[:, :H], sd[p + "rnn.weight_hh"]], 1)),
+      "w_tok": w_ih[:, H:].t().contiguous(), "bias": (sd[p + "rnn.bias_ih"] + sd[p + "rnn.bias_hh"]).contiguous(),
+      "b_h2h": sd[p + "h2h.bias"], "b_gen": sd["decoder.generator.bias"],
+      "w_score": sd[p + "score.weight"].view(-1).contiguous()}
+enc = (torch.randn(B, T, H, device=dev) * 0.5).to(torch.bfloat16)
+proj = (enc.float() @ sd[p + "i2h.weight"].t()).to(torch.bfloat16)
+for groups, minc in ((1, 0), (2, 1024), (3, 1024), (4, 1024), (4, 512)):
+    ops.set_decode_groups(groups, minc)
+    med, best = timeit(lambda: ops.attn_decode_bf16(enc, proj, pk, steps, None, early_exit=False))
+    print("attn_decode_bf16 B=%d groups<=%d (min %d crops): median %.3f ms, best %.3f ms" % (B, groups, minc or 1024, med, best))
+ops.set_decode_groups(1, 0)

@@ -50,6 +50,41 @@ maxpool_nhwc_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, 
   }
 }
 
+// Fast path for the network's pools (bf16, 2x2 window, any stride / padding): one thread = one output pixel x
+// 8 channels; the four 16-byte taps are ALL issued before the first max (the generic kernel's runtime loops
+// serialise load -> max -> load, four DRAM latencies per item: 4.2 TB/s), out-of-range taps read as -inf.
+// bf16 max is exact, so the packed HMNMX2 path gives the same bits as the fp32 path.
+__global__ void __launch_bounds__(256)
+maxpool2x2_bf16_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H, int W, int cv, int P, int Q,
+                       int sh, int sw, int ph, int pw, int total) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int c = i % cv;
+  int r = i / cv;
+  const int q = r % Q; r /= Q;
+  const int p = r % P;
+  const int b = r / P;
+  const int y0 = p * sh - ph, x0 = q * sw - pw;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+  uint4 v[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int y = y0 + (t >> 1), xx = x0 + (t & 1);
+    const bool ok = (y >= 0) && (y < H) && (xx >= 0) && (xx < W);
+    v[t] = ok ? __ldg(x + ((size_t)(b * H + y) * W + xx) * cv + c) : ninf;
+  }
+  auto mx = [](uint32_t a, uint32_t bb) {
+    __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&bb));
+    return *reinterpret_cast<uint32_t*>(&r2);
+  };
+  uint4 o;
+  o.x = mx(mx(v[0].x, v[1].x), mx(v[2].x, v[3].x));
+  o.y = mx(mx(v[0].y, v[1].y), mx(v[2].y, v[3].y));
+  o.z = mx(mx(v[0].z, v[1].z), mx(v[2].z, v[3].z));
+  o.w = mx(mx(v[0].w, v[1].w), mx(v[2].w, v[3].w));
+  out[i] = o;
+}
+
 // [B][HW][C] -> [B][C] f32 mean; one thread per (b, c), coalesced across c.
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -109,8 +144,14 @@ extern "C" __attribute__((visibility("default"))) int mstr_maxpool_nhwc(const vo
   if (dtype == MSTR_BF16) {
     MSTR_REQUIRE(C % 8 == 0, MSTR_ERR_UNSUPPORTED, "mstr_maxpool_nhwc: C %% 8 != 0 for bf16");
     const int64_t items = (int64_t)B * P * Q * (C / 8);
-    maxpool_nhwc_kernel<__nv_bfloat16, 8><<<grid_for(items, 256), 256, 0, st>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, P, Q, kh, kw, sh, sw, ph, pw);
+    if (kh == 2 && kw == 2 && ph <= 1 && pw <= 1 && items < (int64_t)1 << 31 && (int64_t)B * H * W * (C / 8) < (int64_t)1 << 31) {
+      // every window has at least one in-range tap when the padding is smaller than the window
+      maxpool2x2_bf16_kernel<<<(int)ceil_div64(items, 256), 256, 0, st>>>(
+          (const uint4*)x, (uint4*)out, H, W, C / 8, P, Q, sh, sw, ph, pw, (int)items);
+    } else {
+      maxpool_nhwc_kernel<__nv_bfloat16, 8><<<grid_for(items, 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, P, Q, kh, kw, sh, sw, ph, pw);
+    }
   } else if (dtype == MSTR_F32) {
     MSTR_REQUIRE(C % 4 == 0, MSTR_ERR_UNSUPPORTED, "mstr_maxpool_nhwc: C %% 4 != 0 for f32");
     const int64_t items = (int64_t)B * P * Q * (C / 4);

@@ -15,6 +15,12 @@ Cases
   cfg_a_tf   same weights, teacher-forced branch (is_train=True) with a seeded text
   scene      Linear_Embedding in 'scene' mode
   cfg_s      3x64x256 crops, MAX_TEXT_LENGTH=50, B=1 (modules built directly, model.py hard-codes cfg-A)
+  default_init  the reference's OWN random init: torch.manual_seed(config.RANDOM_SEED) then Model() - no
+             synthetic recipe.  The mirror's constructor consumes the RNG identically, so the GPU test
+             rebuilds the same 253 tensors from the seed alone (tests/test_gpu_model.py).  This
+             network is degenerate (zero fc2.weight, 0/1 BatchNorm statistics: every crop yields the same
+             logits), which is why the other cases use synth.make_state_dict - it is kept because it is the
+             literal "random-init weights" configuration of the reference.
 """
 import os
 import sys
@@ -128,9 +134,36 @@ def case_cfg_s():
     print("cfg_s feat", tuple(feat.shape), "ids:", logits.argmax(2)[:, :12].tolist())
 
 
+def case_default_init():
+    torch.manual_seed(WEIGHT_SEED)            # config.RANDOM_SEED (config.py:16)
+    m = ref_model.Model().eval()
+    B = 4
+    x = torch.from_numpy(synth.make_crops(DATA_SEED, B))
+    ov, sc, io = [torch.from_numpy(a) for a in synth.make_semantics(DATA_SEED + 1, B)]
+    text = torch.zeros(B, 26, dtype=torch.long)
+    with torch.no_grad():
+        rect = m.Transformation(x)
+        feat = m.FeatureExtraction(rect)
+        enc1 = m.encoder(m.AdaptiveAvgPool(feat.permute(0, 3, 1, 2)).squeeze(3))
+        logits = m(x, text, ov, sc, io, is_train=False)
+    # a checksum of the freshly initialised parameters pins "same weights" without storing 200 MB
+    sd = m.state_dict()
+    names = sorted(k for k in sd if sd[k].dtype.is_floating_point)
+    sums = np.array([float(sd[k].double().sum()) for k in names])
+    abss = np.array([float(sd[k].double().abs().sum()) for k in names])
+    np.savez_compressed(
+        os.path.join(HERE, "default_init.npz"),
+        rectified=rect.numpy()[:, :, ::4, ::4], enc1=enc1.numpy(), logits=logits.numpy(),
+        ids=logits.argmax(2).numpy(), param_sums=sums, param_abs_sums=abss,
+        meta=np.array([WEIGHT_SEED, DATA_SEED, B]),
+    )
+    print("default_init ids:", logits.argmax(2)[:, :12].tolist())
+
+
 if __name__ == "__main__":
     case_cfg_a()
     case_cfg_s()
+    case_default_init()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

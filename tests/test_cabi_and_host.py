@@ -140,3 +140,22 @@ def test_shard_bounds_cover_batch():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     with pytest.raises(ValueError):
         shard_bounds(8, 2, 2)
+
+
+def test_default_init_matches_reference_constructor():
+    """Same seed -> same 253 tensors as the reference's Model() (checksums stored by
+    tests/golden/make_golden.py:case_default_init): the mirror registers and initialises its parameters
+    in the reference's order (model.py:34-83)."""
+    import os
+    import numpy as np
+    import torch
+    from multimodal_scene_text_recognition_b200 import config, model as M
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "default_init.npz"))
+    config.MAX_TEXT_LENGTH = 25
+    torch.manual_seed(int(g["meta"][0]))
+    sd = M.Model().state_dict()
+    names = sorted(k for k in sd if sd[k].dtype.is_floating_point)
+    assert len(sd) == 253 and len(names) == len(g["param_sums"])
+    sums = np.array([float(sd[k].double().sum()) for k in names])
+    abss = np.array([float(sd[k].double().abs().sum()) for k in names])
+    assert np.array_equal(sums, g["param_sums"]) and np.array_equal(abss, g["param_abs_sums"])

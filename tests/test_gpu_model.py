@@ -59,6 +59,28 @@ def test_fp32_matches_reference_golden(sd_cfg_a, golden_dir):
     assert_close(host(tf), g["logits_tf"], 3e-4, "teacher-forced logits vs reference")
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tf32", 1e-4), ("bf16", 2e-2)])
+def test_reference_default_init_golden(golden_dir, precision, tol):
+    """The reference's own random init (torch.manual_seed(config.RANDOM_SEED); Model()) rebuilt from the seed
+    by the mirror's constructor, against what the reference's Model.forward produced for it
+    (tests/golden/default_init.npz).  North-star tolerances: ids identical, logits 1e-4 (tf32) / 2e-2 (bf16)
+    relative."""
+    from multimodal_scene_text_recognition_b200 import model as M
+    g = np.load(os.path.join(golden_dir, "default_init.npz"))
+    wseed, dseed, B = [int(v) for v in g["meta"]]
+    config.PRECISION = precision
+    config.MAX_TEXT_LENGTH = 25
+    config.TPS_GRID, config.DECODER_EARLY_EXIT, config.SEMANTIC_VECTOR = "reference", False, "overlap"
+    torch.manual_seed(wseed)
+    m = M.Model().eval().to(DEV)
+    x, ov, sc, io = _inputs(B, seed=dseed)
+    st = {}
+    out = _run(m, x, ov, sc, io, st)
+    assert_close(host(st["enc1"]), g["enc1"], tol, "encoder output vs reference (default init)")
+    assert_close(host(out["logits"]), g["logits"], tol, "logits vs reference (default init)")
+    assert np.array_equal(host(out["ids"]), g["ids"]), "decoded ids differ from the reference (default init)"
+
+
 def test_tf32_tensor_core_parity_mode(sd_cfg_a, golden_dir):
     """config.PRECISION = 'tf32': convs / linears on tcgen05.mma.kind::tf32 with the 3xTF32 split.  North-star
     tolerance for the TF32 mode: ids bit-identical, logits within 1e-4 relative (the fp32 noise floor of this

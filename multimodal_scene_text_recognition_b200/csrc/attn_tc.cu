@@ -37,7 +37,7 @@ struct DecodeState {
   // operand / state buffers (device)
   __nv_bfloat16* xh[2];   // [B][512]: cols 0..255 ctx_i, cols 256..511 h_i   (double buffered by step parity)
   float* hp;              // [B][256]
-  float* cst;             // [B][256]
+  float* cst;             // [256][B] (transposed: the cell epilogue's lane = crop accesses are coalesced)
   int32_t* tok;           // [B] token fed to the current step
   int32_t* done;          // [B] crop has emitted [s]
   int32_t* live;          // [1] number of crops still decoding (early exit)
@@ -49,6 +49,13 @@ struct DecodeState {
   int B, T, C, steps, early_exit;
 };
 
+// Programmatic dependent launch: every kernel of the decode chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may be scheduled (and run their prologue:
+// barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel drains; griddep_wait() blocks
+// until the previous grid has completed and its writes are visible, and must precede every dependent access.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float at_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float at_tanh(float x) { return fmaf(2.f, at_sigmoid(2.f * x), -1.f); }
 
@@ -57,7 +64,6 @@ template <int EPI>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const DecodeState s, const int step, const int num_k) {
-  if (s.early_exit && *s.live == 0) return;   // every crop has emitted [s]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -82,8 +88,13 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                                        // the previous kernel of the chain has completed
+  griddep_launch();
+  const bool idle = s.early_exit && *s.live == 0;        // every crop has emitted [s]
 
-  if (warp == 0) {
+  if (idle) {
+    // nothing to do for this step
+  } else if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < num_k; ++kb) {
@@ -122,31 +133,44 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     if constexpr (EPI == 0) {
+      // The accumulator layout gives every thread one crop ROW, and rows are 1 KB (hp) / 10 KB (logits) apart in
+      // global memory: a direct store costs 32 L1 wavefronts per instruction (an elimination run priced these
+      // stores at 0.35 of the decoder's 1.9 ms).  The tile is therefore transposed through the (now idle)
+      // operand stages: row-wise writes with an odd stride (conflict free), then each warp copies whole rows
+      // with 128-byte coalesced stores.
+      float* stg = reinterpret_cast<float*>(smem);
+      const int ew = warp - 2;               // 0..3
       if (n_tile < 2) {
         // hp_i = h_i W_h2h^T + b_h2h  (consumed by attn_context_kernel of this step)
+        constexpr int LD = AT_BLOCK + 1;
 #pragma unroll 1
         for (int c0 = 0; c0 < AT_BLOCK; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
-          if (valid) {
-            float4* dst = reinterpret_cast<float4*>(s.hp + (size_t)crop * AT_H + n_tile * AT_BLOCK + c0);
-            const float4* bb = reinterpret_cast<const float4*>(s.b_h2h + n_tile * AT_BLOCK + c0);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float4 b4 = __ldg(bb + u);
-              dst[u] = make_float4(__uint_as_float(v[4 * u]) + b4.x, __uint_as_float(v[4 * u + 1]) + b4.y,
-                                   __uint_as_float(v[4 * u + 2]) + b4.z, __uint_as_float(v[4 * u + 3]) + b4.w);
-            }
-          }
+          for (int j = 0; j < 32; ++j) stg[row * LD + c0 + j] = __uint_as_float(v[j]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float bias4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bias4[q] = __ldg(s.b_h2h + n_tile * AT_BLOCK + q * 32 + lane);
+#pragma unroll 4
+        for (int r = ew * 32; r < ew * 32 + 32; ++r) {
+          if (m0 + r >= s.B) break;
+          float* dst = s.hp + (size_t)(m0 + r) * AT_H + n_tile * AT_BLOCK;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q * 32 + lane] = stg[r * LD + q * 32 + lane] + bias4[q];
         }
       } else if (step > 0) {
         // logits of decode step (step-1) = h_step W_gen^T + b_gen; argmax feeds the token of `step`
+        constexpr int LD = 101;              // >= num_classes rounded up to odd; C <= 128 is checked by the host
+        const int ld = (s.C | 1) > LD ? (s.C | 1) : LD;
+        int* skip = reinterpret_cast<int*>(stg + AT_BLOCK * 129);   // per row: do not store (crop finished / out of range)
         const int ls = step - 1;
         const bool was_done = valid && s.early_exit && s.done[crop];
         float best = -INFINITY;
         int besti = 0;
-        float* lrow = s.logits + ((size_t)(valid ? crop : 0) * s.steps + ls) * s.C;
 #pragma unroll 1
         for (int c0 = 0; c0 < AT_BLOCK; c0 += 32) {
           uint32_t v[32];
@@ -157,11 +181,12 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int cls = c0 + j;
             if (cls < s.C) {
               const float y = __uint_as_float(v[j]) + __ldg(s.b_gen + cls);
-              if (valid && !was_done) lrow[cls] = y;
+              stg[row * ld + cls] = y;
               if (y > best) { best = y; besti = cls; }      // ascending: the lowest index wins ties
             }
           }
         }
+        skip[row] = (!valid || was_done) ? 1 : 0;
         if (valid) {
           if (was_done) {
             s.ids[(size_t)crop * s.steps + ls] = 0;          // argmax of the zero-initialised logits row
@@ -177,13 +202,20 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (step < s.steps) s.tok[crop] = s.text ? (int)s.text[(size_t)crop * s.steps + step] : besti;
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 2
+        for (int r = ew * 32; r < ew * 32 + 32; ++r) {
+          if (skip[r]) continue;
+          float* lrow = s.logits + ((size_t)(m0 + r) * s.steps + ls) * s.C;
+          for (int cls = lane; cls < s.C; cls += 32) lrow[cls] = stg[r * ld + cls];
+        }
       }
     } else {
       // LSTM cell: this tile = 32 hidden units x 4 gates of 128 crops
       const int unit0 = n_tile * 32;
       const int tok = valid ? s.tok[crop] : 0;
       const float* wt = s.w_tok + (size_t)tok * (4 * AT_H);
-      float* crow = s.cst + (size_t)(valid ? crop : 0) * AT_H + unit0;
+      float* ccol = s.cst + (size_t)unit0 * s.B + (valid ? crop : 0);   // cell state is kept [H][B]: lane = crop is coalesced
       __nv_bfloat16* hrow = s.xh[(step + 1) & 1] + (size_t)(valid ? crop : 0) * (2 * AT_H) + AT_H + unit0;
 #pragma unroll 1
       for (int sub = 0; sub < 4; ++sub) {            // 8 units at a time
@@ -203,9 +235,9 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             add[g][0] = t0.x + b0.x; add[g][1] = t0.y + b0.y; add[g][2] = t0.z + b0.z; add[g][3] = t0.w + b0.w;
             add[g][4] = t1.x + b1.x; add[g][5] = t1.y + b1.y; add[g][6] = t1.z + b1.z; add[g][7] = t1.w + b1.w;
           }
-          float4 c0v = reinterpret_cast<const float4*>(crow + sub * 8)[0];
-          float4 c1v = reinterpret_cast<const float4*>(crow + sub * 8)[1];
-          float cp[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+          float cp[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cp[j] = ccol[(size_t)(sub * 8 + j) * s.B];
           float hv[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -217,8 +249,8 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             cp[j] = cn;
             hv[j] = at_sigmoid(go) * at_tanh(cn);
           }
-          reinterpret_cast<float4*>(crow + sub * 8)[0] = make_float4(cp[0], cp[1], cp[2], cp[3]);
-          reinterpret_cast<float4*>(crow + sub * 8)[1] = make_float4(cp[4], cp[5], cp[6], cp[7]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ccol[(size_t)(sub * 8 + j) * s.B] = cp[j];
           *reinterpret_cast<uint4*>(hrow + sub * 8) =
               make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]),
                          pack_bf16x2(hv[6], hv[7]));
@@ -239,6 +271,8 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 __global__ void __launch_bounds__(256)
 attn_context_kernel(const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ proj,
                     const DecodeState s, const int step) {
+  griddep_wait();
+  griddep_launch();
   if (s.early_exit && *s.live == 0) return;
   const int lane = threadIdx.x & 31;
   const int crop = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -444,16 +478,33 @@ static int decode_group(const DecodeArgs& a, uint8_t* ws, int g0, int Bg, cudaSt
   const int m_tiles = ceil_div(Bg, AT_BLOCK);
   const __nv_bfloat16* enc = a.enc + (size_t)g0 * a.T * AT_H;
   const __nv_bfloat16* proj = a.proj + (size_t)g0 * a.T * AT_H;
+  cudaLaunchAttribute pdl[1];
+  pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  auto config = [&](dim3 grid, int threads, size_t smem) {
+    cudaLaunchConfig_t c = {};
+    c.gridDim = grid; c.blockDim = dim3(threads); c.dynamicSmemBytes = smem; c.stream = st;
+    c.attrs = pdl; c.numAttrs = 1;
+    return c;
+  };
   for (int i = 0; i <= a.steps; ++i) {
     // head_i: hp_i (tiles 0,1) and logits_{i-1} (tile 2); the last iteration only needs the logits tile
-    rnn_gemm_kernel<0><<<dim3(3, m_tiles), AT_THREADS, AT_SMEM_BYTES, st>>>(tmH[i & 1], tmHead, s, i, AT_H / 64);
-    MSTR_LAUNCH_CHECK("rnn_gemm_kernel<head>");
+    {
+      cudaLaunchConfig_t c = config(dim3(3, m_tiles), AT_THREADS, AT_SMEM_BYTES);
+      MSTR_CUDA(cudaLaunchKernelEx(&c, rnn_gemm_kernel<0>, tmH[i & 1], tmHead, s, i, AT_H / 64));
+      MSTR_LAUNCH_CHECK("rnn_gemm_kernel<head>");
+    }
     if (i == a.steps) break;
-    attn_context_kernel<<<ceil_div(Bg, 8), 256, 0, st>>>(enc, proj, s, i);
-    MSTR_LAUNCH_CHECK("attn_context_kernel");
-    rnn_gemm_kernel<1><<<dim3(4 * AT_H / AT_BLOCK, m_tiles), AT_THREADS, AT_SMEM_BYTES, st>>>(tmXH[i & 1], tmCat, s, i,
-                                                                                           2 * AT_H / 64);
-    MSTR_LAUNCH_CHECK("rnn_gemm_kernel<cell>");
+    {
+      cudaLaunchConfig_t c = config(dim3(ceil_div(Bg, 8)), 256, 0);
+      MSTR_CUDA(cudaLaunchKernelEx(&c, attn_context_kernel, enc, proj, s, i));
+      MSTR_LAUNCH_CHECK("attn_context_kernel");
+    }
+    {
+      cudaLaunchConfig_t c = config(dim3(4 * AT_H / AT_BLOCK, m_tiles), AT_THREADS, AT_SMEM_BYTES);
+      MSTR_CUDA(cudaLaunchKernelEx(&c, rnn_gemm_kernel<1>, tmXH[i & 1], tmCat, s, i, 2 * AT_H / 64));
+      MSTR_LAUNCH_CHECK("rnn_gemm_kernel<cell>");
+    }
   }
   return MSTR_OK;
 }

@@ -229,6 +229,24 @@ def test_conv_gemm_bf16_many_tiles():
     assert_close(host(out_f), ref, 2e-5, "conv_gemm_bf16 400 tiles")
 
 
+def test_conv_gemm_bf16_wide_tile_opt_in(monkeypatch):
+    """256 x 512 CTA-pair tiles (single TMEM accumulator, two tcgen05.mma per k-step; MSTR_CONV_N512=1) must give the
+    same bits as the default 256 x 256 tiles: C_out = 512, residual + ReLU, several tiles per CTA pair."""
+    case = (8, 4, 26, 256, 512, 3, 3, (1, 1), (1, 1), True, True)
+    x, w, scale, shift, res = _conv_inputs(case, 7, True)
+    bf = torch.bfloat16
+    args = (dev(x, bf), dev(w, bf), dev(scale), dev(shift), dev(res, bf))
+    kw = dict(stride=(1, 1), pad=(1, 1), relu=True, want_f32=False, want_bf16=True)
+    monkeypatch.delenv("MSTR_CONV_N512", raising=False)
+    base = ops.conv_gemm(*args, **kw)
+    monkeypatch.setenv("MSTR_CONV_N512", "1")
+    wide = ops.conv_gemm(*args, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(base, wide)
+    ref = _conv_ref(x, w, scale, shift, res, (1, 1), (1, 1), True)
+    assert_close(host(wide), orc.round_bf16(ref.astype(np.float32)), 1e-2, "conv_gemm_bf16 wide tile")
+
+
 # ------------------------------------------------------------------------------------------------
 # pooling / reductions / cast / embedding
 # ------------------------------------------------------------------------------------------------

@@ -223,6 +223,19 @@ int mstr_attn_decode_bf16(const void* enc_bf16, const void* proj_bf16, const voi
  * Call mstr_attn_decode_bf16_workspace_bytes AFTER changing this setting. */
 int mstr_set_decode_groups(int max_groups, int min_crops_per_group);
 
+/* Input side of the path: the loader's transforms.Resize((32,100)) + ToTensor()
+ * (coco_dataset.py:27,40-41) on a ragged batch of grayscale uint8 crops, bit-exact with Pillow's antialiased
+ * fixed-point bilinear resample (what torchvision's Resize calls for PIL images).
+ *   pixels    packed uint8 crops (row-major, no padding), device memory
+ *   offsets   [B] int64 byte offset of each crop in `pixels`; sizes_hw [B][2] int32 (height, width), device
+ *   out       [B][1][out_h][out_w] float32 in [0,1], device
+ *   status    optional device int: set to (crop index + 1) if a crop is empty or larger than
+ *             max_in_h x max_in_w (its output is then filled with NaN); may be NULL
+ *   max_in_h, max_in_w  upper bounds of the crop sizes (they size the coefficient tables) */
+int mstr_resize_to_tensor_u8(const void* pixels, const int64_t* offsets, const int32_t* sizes_hw, float* out,
+                             int* status, int B, int out_h, int out_w, int max_in_h, int max_in_w,
+                             mstr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,7 @@ SIGNATURES = {
     "mstr_attn_decode_bf16_workspace_bytes": (c_int64, [_I, _I]),
     "mstr_attn_decode_bf16": (c_int, [_P] * 15 + [_I] * 6 + [_P]),
     "mstr_set_decode_groups": (c_int, [_I, _I]),
+    "mstr_resize_to_tensor_u8": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -375,6 +375,24 @@ def pack_gate_rows_bf16(w: torch.Tensor) -> torch.Tensor:
     return w.reshape(4, hd // 32, 32, k).permute(1, 0, 2, 3).reshape(four_h, k).to(torch.bfloat16).contiguous()
 
 
+def resize_to_tensor_u8(pixels: torch.Tensor, offsets: torch.Tensor, sizes_hw: torch.Tensor, max_in_hw,
+                        out_hw=(32, 100)) -> torch.Tensor:
+    """Ragged batch of grayscale uint8 crops -> [B, 1, out_h, out_w] f32 in [0, 1]: transforms.Resize + ToTensor of
+    the reference's loaders (coco_dataset.py:27,40-41), bit-exact with Pillow's bilinear resample.
+    pixels: packed uint8 crops (device), offsets [B] int64, sizes_hw [B, 2] int32 (height, width)."""
+    _req(pixels, "pixels", torch.uint8); _req(offsets, "offsets", torch.int64); _req(sizes_hw, "sizes_hw", torch.int32)
+    B = offsets.shape[0]
+    assert sizes_hw.shape == (B, 2)
+    out = torch.empty((B, 1, out_hw[0], out_hw[1]), device=pixels.device, dtype=torch.float32)
+    status = torch.zeros((1,), device=pixels.device, dtype=torch.int32)
+    with _timed("resize_to_tensor_u8", float(pixels.numel() + out.numel() * 4), "byte",
+                "B%d ragged u8 crops -> %dx%d f32" % (B, out_hw[0], out_hw[1])):
+        check(lib().mstr_resize_to_tensor_u8(ptr(pixels), ptr(offsets), ptr(sizes_hw), ptr(out), ptr(status), B,
+                                             int(out_hw[0]), int(out_hw[1]), int(max_in_hw[0]), int(max_in_hw[1]),
+                                             stream_ptr()), "mstr_resize_to_tensor_u8")
+    return out
+
+
 def set_decode_groups(max_groups: int = 1, min_crops_per_group: int = 0) -> None:
     """Crop groups of the tensor-core decoder (mstr_set_decode_groups): 1 = a single chain on the caller's
     stream (default, measured fastest), 0 = automatic (<= 4 groups of >= 1024 crops), 2..4 = at most that many."""

@@ -65,3 +65,45 @@ class HostBatchPrefetcher:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._free[sid] = ev
+
+
+# ---------------------------------------------------------------------------------------------------
+# crops -> model input
+# ---------------------------------------------------------------------------------------------------
+def pack_crops(crops) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Tuple[int, int]]:
+    """Pack a ragged list of grayscale uint8 crops ([H_i, W_i] numpy arrays or tensors - what
+    ``Image.open(path).convert('L').crop(bbox)`` yields, coco_dataset.py:239-243) into pinned host buffers:
+    (pixels uint8 [sum H_i W_i], offsets int64 [B], sizes int32 [B, 2], (max H, max W))."""
+    import numpy as np
+    arrs = []
+    for c in crops:
+        a = c.numpy() if isinstance(c, torch.Tensor) else np.asarray(c)
+        if a.dtype != np.uint8 or a.ndim != 2 or a.shape[0] < 1 or a.shape[1] < 1:
+            raise ValueError("crops must be non-empty 2-D uint8 arrays (grayscale), got %s %s" % (a.dtype, a.shape))
+        arrs.append(np.ascontiguousarray(a))
+    if not arrs:
+        raise ValueError("empty crop list")
+    sizes = np.array([a.shape for a in arrs], dtype=np.int32)
+    counts = sizes[:, 0].astype(np.int64) * sizes[:, 1]
+    offsets = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+    pin = torch.cuda.is_available()
+    pixels = torch.empty((int(counts.sum()),), dtype=torch.uint8, pin_memory=pin)
+    flat = pixels.numpy()
+    for a, o, n in zip(arrs, offsets, counts):
+        flat[o:o + n] = a.reshape(-1)
+    off_t = torch.from_numpy(offsets)
+    size_t = torch.from_numpy(sizes)
+    if pin:
+        off_t, size_t = off_t.pin_memory(), size_t.pin_memory()
+    return pixels, off_t, size_t, (int(sizes[:, 0].max()), int(sizes[:, 1].max()))
+
+
+def crops_to_input(crops, device, out_hw=(32, 100)) -> torch.Tensor:
+    """The loader's ``Resize((32, 100))`` + ``ToTensor()`` (coco_dataset.py:27,40-41) for a whole batch of
+    ragged grayscale crops on the GPU: [B, 1, 32, 100] f32 in [0, 1], bit-exact with the PIL path, ready for
+    ``Model.forward`` / ``Model.recognize``.  uint8 pixels cross PCIe instead of resized fp32 images."""
+    from . import ops
+    pixels, offsets, sizes, max_hw = pack_crops(crops)
+    dev = torch.device(device)
+    return ops.resize_to_tensor_u8(pixels.to(dev, non_blocking=True), offsets.to(dev, non_blocking=True),
+                                   sizes.to(dev, non_blocking=True), max_hw, out_hw)

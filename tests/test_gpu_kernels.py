@@ -1,5 +1,7 @@
 """Per-kernel parity: every C-ABI entry point (called through ops.py -> ctypes -> libmstr_b200.so)
 against the numpy oracle on the same seeded inputs.  GPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -516,3 +518,41 @@ def test_errors_are_loud():
         ops.conv_gemm(x, w, None, None, pad=(1, 1))
     with pytest.raises(MstrError, match="CUDA tensor"):
         ops.maxpool_nhwc(torch.zeros(1, 4, 4, 8))
+
+
+# ------------------------------------------------------------------------------------------------
+# input side: Resize((32,100)) + ToTensor on ragged uint8 crops
+# ------------------------------------------------------------------------------------------------
+def test_resize_to_tensor_bit_exact_with_pillow_restatement(golden_dir):
+    """CUDA kernel vs oracle/resize_oracle.py (pinned to Pillow) and vs the committed Pillow outputs: ragged
+    batch incl. 1x1, identity (32x100), single-axis, strongly minified crops; bit-exact."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import make_resize_golden as mg
+    from oracle import resize_oracle as ro
+    from multimodal_scene_text_recognition_b200 import pipeline
+    g = np.load(os.path.join(golden_dir, "resize_cases.npz"))
+    crops = [mg.make_crop(1000 + i, int(h), int(w)) for i, (h, w) in enumerate(g["shapes"])]
+    out = pipeline.crops_to_input(crops, DEV)
+    torch.cuda.synchronize()
+    got = host(out)
+    assert got.shape == (len(crops), 1, 32, 100) and got.dtype == np.float32
+    for i, c in enumerate(crops):
+        assert np.array_equal(got[i], ro.resize_to_tensor(c)), "crop %d %s" % (i, c.shape)
+        assert np.array_equal(np.rint(got[i, 0] * 255.0).astype(np.uint8), g["resized_%d" % i])
+    assert np.array_equal(got[0], g["to_tensor_0"])
+    # a larger ragged batch with random sizes
+    rs = np.random.RandomState(9)
+    many = [(rs.rand(int(rs.randint(1, 120)), int(rs.randint(1, 500))) * 256).astype(np.uint8) for _ in range(300)]
+    got = host(pipeline.crops_to_input(many, DEV))
+    for i in range(0, 300, 7):
+        assert np.array_equal(got[i], ro.resize_to_tensor(many[i]))
+
+
+def test_resize_to_tensor_flags_oversized_crop():
+    px = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    off = torch.zeros(1, dtype=torch.int64, device=DEV)
+    sz = torch.tensor([[8, 8]], dtype=torch.int32, device=DEV)
+    out = ops.resize_to_tensor_u8(px, off, sz, (4, 4))      # crop larger than the declared bound: NaN, no overrun
+    torch.cuda.synchronize()
+    assert torch.isnan(out).all()

@@ -36,6 +36,14 @@ for (H, W, C, k, s, p) in ((32, 100, 64, (2, 2), (2, 2), (0, 0)), (16, 50, 128, 
     P = (H + 2 * p[0] - 2) // s[0] + 1; Q = (W + 2 * p[1] - 2) // s[1] + 1
     timeit("maxpool %dx%dx%d s%s p%s" % (H, W, C, s, p), lambda: ops.maxpool_nhwc(x, k, s, p), 2 * B * C * (H * W + P * Q))
     del x
+# input side: 4096 ragged grayscale crops (heights 16..96, widths 40..400) -> [B,1,32,100] f32
+from multimodal_scene_text_recognition_b200 import pipeline
+rs = np.random.RandomState(0)
+crops = [(rs.rand(int(rs.randint(16, 97)), int(rs.randint(40, 401))) * 256).astype(np.uint8) for _ in range(B)]
+pixels, offsets, sizes, max_hw = pipeline.pack_crops(crops)
+pd, od, sd_ = pixels.to(dev), offsets.to(dev), sizes.to(dev)
+timeit("resize_to_tensor_u8 (%.1f MB of crops)" % (pixels.numel() / 1e6),
+       lambda: ops.resize_to_tensor_u8(pd, od, sd_, max_hw), pixels.numel() + B * 3200 * 4)
 F = 20
 from multimodal_scene_text_recognition_b200.modules.transformation import GridGenerator
 gg = GridGenerator(F, (32, 100)).to(dev)

@@ -160,8 +160,9 @@ int mstr_embed_semantics(const float* ids, const float* table, const float* ious
 int mstr_bilstm_recurrent(const float* gates_x, const float* w_hh, float* out_f32, void* out_bf16,
                           int B, int T, int Hd, mstr_stream_t stream);
 /* Tensor-core variant for the bf16 throughput mode: h_t is kept in shared memory as bf16 (the
- * operand of tcgen05.mma), c_t in TMEM as f32, W_hh streamed by TMA; gate non-linearities use
- * tanh.approx.  One launch for all T steps of both directions.
+ * operand of tcgen05.mma), c_t in TMEM as f32, W_hh AND the gates_x tiles streamed by TMA (gates_x is
+ * written into the TMEM accumulators before each chunk's MMAs), the output leaves by TMA store; gate
+ * non-linearities use tanh.approx.  One launch for all T steps of both directions.
  *   w_hh_packed [2][4*Hd][Hd] bf16 with the rows of each direction re-ordered so that packed row
  *               chunk*128 + g*32 + j  holds original row  g*Hd + chunk*32 + j  (chunk = 0..7,
  *               g = gate i,f,g,o, j = 0..31): one 128-column accumulator chunk then carries all four

@@ -325,7 +325,11 @@ static int conv_gemm_bf16_impl(const void* x, const void* w, const float* scale,
   // CTA-pair kernel for C_out % 256 == 0 (measured: +9 % on the 512->512 layers, -8 % on C_out = 128 layers,
   // which therefore stay on the single-CTA kernel); MSTR_CONV_2CTA=0 forces the single-CTA kernel
   static const int use_2cta = [] { const char* e = getenv("MSTR_CONV_2CTA"); return (e && e[0] == '0') ? 0 : 1; }();
-  if (use_2cta && C_in % 64 == 0 && C_out % 256 == 0 && (int64_t)B * H * W < (1ll << 31) && sm_count() >= 2) {
+  // opt-in (MSTR_CONV_PAIR_MT2=1): C_out % 128 == 0 layers with bf16 output on the pair kernel's MT = 2 variant.
+  // MEASURED slower than the single-CTA MT = 2 kernel below (4.70 vs 4.47 ms per step over the five such layers)
+  const char* pair128_env = getenv("MSTR_CONV_PAIR_MT2");
+  const bool pair128 = C_out % 128 == 0 && !out_f32 && pair128_env && pair128_env[0] == '1';
+  if (use_2cta && C_in % 64 == 0 && (C_out % 256 == 0 || pair128) && (int64_t)B * H * W < (1ll << 31) && sm_count() >= 2) {
     const int64_t M2 = (int64_t)B * ((H + 2 * pad_h - R) / stride_h + 1) * ((W + 2 * pad_w - S) / stride_w + 1);
     MSTR_REQUIRE(M2 > 0 && M2 < (1ll << 31), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad output size");
     return conv_gemm_bf16_2cta(x, w, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,

@@ -51,18 +51,27 @@ constexpr int T2_A_BYTES = 128 * 128;   // 128 rows x 64 bf16
 // tiles (+11 % = exactly the exposed epilogue, ~8k of ~74k cycles per tile): the main loop did not get faster with
 // 25 % less L2 traffic, i.e. the kernel is NOT L2-feed bound but at the tensor / power limit (1.55 GHz under
 // sw_power_cap).  The wide tile therefore stays opt-in (MSTR_CONV_N512=1) as a tested negative result.
-template <int BLOCK_N>
+// MT = 2 (BLOCK_N = 128, bf16 output only): the pair owns 512 output rows as two 256-row accumulators that share
+// every weight tile, for the C_out = 128 layers.  Per CTA and k-block that is 32 KB of activations + 8 KB of
+// weights for 256x128x64 MACs (52 MAC per operand byte; the single-CTA MT = 2 kernel needs 48 KB: 44 MAC/B).
+// MEASURED (bench step, five C_out = 128 layers): 4.70 ms against 4.47 ms for the single-CTA MT = 2 kernel - 17 %
+// fewer operand bytes did not pay for the pair protocol, so this variant is opt-in (MSTR_CONV_PAIR_MT2=1).  The
+// K = 576 layers move 432 KB of operands per 256-row tile in ~11.8k cycles (9 TB/s chip-wide, close to the
+// ~12.5 TB/s the L2 delivers to the SMs) for 4.6k cycles of MMA work.
+template <int BLOCK_N, int MT = 1>
 struct Tc2Cfg {
   static constexpr int UMMA_N = BLOCK_N > 256 ? 256 : BLOCK_N;    // columns per tcgen05.mma
-  static constexpr int NH = BLOCK_N / UMMA_N;                       // MMAs per k-step
-  static constexpr int NUM_ACC = (2 * BLOCK_N <= 512) ? 2 : 1;      // accumulator buffers in TMEM
+  static constexpr int NH = BLOCK_N / UMMA_N;                       // MMAs per k-step and accumulator
+  static constexpr int NUM_ACC = (2 * MT * BLOCK_N <= 512) ? 2 : 1; // accumulator buffers in TMEM
+  static constexpr int A_BYTES = MT * T2_A_BYTES;            // this CTA's 128 rows of each of the MT accumulators
   static constexpr int B_BYTES = (BLOCK_N / 2) * 128;       // this CTA's half of the weight tile
-  static constexpr int STAGE_BYTES = T2_A_BYTES + B_BYTES;
-  static constexpr int EPI_SLAB = BLOCK_N > 256 ? EPI_SLAB_BYTES / 2 : EPI_SLAB_BYTES;   // 512: bf16 slabs only
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr bool BF16_ONLY = BLOCK_N > 256 || MT > 1;
+  static constexpr int EPI_SLAB = BF16_ONLY ? EPI_SLAB_BYTES / 2 : EPI_SLAB_BYTES;
   static constexpr int TAIL_BYTES = 4 * BLOCK_N * 4 + (2 * 8 + 4) * 8 + 16;
   static constexpr int RING_BUDGET = 227 * 1024 - 1024 - 2 * EPI_SLAB - TAIL_BYTES;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
-  static constexpr int TMEM_COLS = NUM_ACC * BLOCK_N;
+  static constexpr int TMEM_COLS = NUM_ACC * MT * BLOCK_N;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * EPI_SLAB + TAIL_BYTES;
 };
 
@@ -136,18 +145,19 @@ __device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar) {
       : "memory");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT = 1>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ CUtensorMap tmOb, const __grid_constant__ CUtensorMap tmOf,
                            const __grid_constant__ CUtensorMap tmA2, const Tc2Params p) {
-  using Cfg = Tc2Cfg<BLOCK_N>;
+  using Cfg = Tc2Cfg<BLOCK_N, MT>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int PAIR_M = 256 * MT;         // output rows per pair and tile
   extern __shared__ uint8_t smem_raw[];
   // the dynamic smem base has the same offset in both CTAs, so this rounding is identical in both
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * T2_A_BYTES;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
   uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;                            // 2 output slabs
   float* sScale = reinterpret_cast<float*>(sEpi + 2 * Cfg::EPI_SLAB);          // [2][BLOCK_N]
   float* sShift = sScale + 2 * BLOCK_N;
@@ -193,13 +203,19 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         // this CTA stages rows [h * UMMA_N + rank * UMMA_N/2, + UMMA_N/2) of the weight tile for MMA h
         const int n0 = (tile % p.num_n_tiles) * BLOCK_N + (int)rank * (Cfg::UMMA_N / 2);
-        const int m0 = (tile / p.num_n_tiles) * 256 + (int)rank * 128;
-        int cw = 0, chh = 0, cn = 0;
-        if (p.im2col) {
-          const int q = m0 % p.Q, pp = (m0 / p.Q) % p.P;
-          cn = m0 / (p.Q * p.P);
-          cw = q * p.sw - p.pw;
-          chh = pp * p.sh - p.ph;
+        // accumulator a covers rows [tile_m0 + a * 256, + 256); this CTA stages its 128 rows of each
+        const int m0 = (tile / p.num_n_tiles) * PAIR_M + (int)rank * 128;
+        int cw[MT], chh[MT], cn[MT];
+#pragma unroll
+        for (int a = 0; a < MT; ++a) {
+          cw[a] = chh[a] = cn[a] = 0;
+          if (p.im2col) {
+            const int ma = m0 + a * 256;
+            const int q = ma % p.Q, pp = (ma / p.Q) % p.P;
+            cn[a] = ma / (p.Q * p.P);
+            cw[a] = q * p.sw - p.pw;
+            chh[a] = pp * p.sh - p.ph;
+          }
         }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int r = tap / p.S, s = tap - r * p.S;
@@ -207,11 +223,14 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
-            if (p.im2col)
-              tma2_load_im2col_4d(sA + stage * T2_A_BYTES, &tmA, bar, cc * T2_BLOCK_K, cw, chh, cn, (uint16_t)s,
-                                  (uint16_t)r);
-            else
-              tma2_load_2d(sA + stage * T2_A_BYTES, &tmA, bar, cc * T2_BLOCK_K, m0);
+#pragma unroll
+            for (int a = 0; a < MT; ++a) {
+              uint8_t* dstA = sA + stage * Cfg::A_BYTES + a * T2_A_BYTES;
+              if (p.im2col)
+                tma2_load_im2col_4d(dstA, &tmA, bar, cc * T2_BLOCK_K, cw[a], chh[a], cn[a], (uint16_t)s, (uint16_t)r);
+              else
+                tma2_load_2d(dstA, &tmA, bar, cc * T2_BLOCK_K, m0 + a * 256);
+            }
 #pragma unroll
             for (int h = 0; h < Cfg::NH; ++h)
               tma2_load_2d(sB + stage * Cfg::B_BYTES + h * (Cfg::UMMA_N / 2) * 128, &tmB, bar,
@@ -224,7 +243,9 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
-          tma2_load_2d(sA + stage * T2_A_BYTES, &tmA2, bar, cc * T2_BLOCK_K, m0);
+#pragma unroll
+          for (int a = 0; a < MT; ++a)
+            tma2_load_2d(sA + stage * Cfg::A_BYTES + a * T2_A_BYTES, &tmA2, bar, cc * T2_BLOCK_K, m0 + a * 256);
 #pragma unroll
           for (int h = 0; h < Cfg::NH; ++h)
             tma2_load_2d(sB + stage * Cfg::B_BYTES + h * (Cfg::UMMA_N / 2) * 128, &tmB, bar,
@@ -244,19 +265,22 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * BLOCK_N);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * T2_A_BYTES);
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < T2_BLOCK_K / 16; ++k)
 #pragma unroll
-            for (int h = 0; h < Cfg::NH; ++h)
-              umma2_bf16(d_tmem + (uint32_t)(h * Cfg::UMMA_N), make_smem_desc<128>(a_addr + k * 32),
-                         make_smem_desc<128>(b_addr + h * (Cfg::UMMA_N / 2) * 128 + k * 32), idesc,
-                         (kb > 0 || k > 0) ? 1u : 0u);
+            for (int a = 0; a < MT; ++a)
+#pragma unroll
+              for (int h = 0; h < Cfg::NH; ++h)
+                umma2_bf16(d_tmem + (uint32_t)(a * BLOCK_N + h * Cfg::UMMA_N),
+                           make_smem_desc<128>(a_addr + a * T2_A_BYTES + k * 32),
+                           make_smem_desc<128>(b_addr + h * (Cfg::UMMA_N / 2) * 128 + k * 32), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
           umma2_commit_multicast(&empty_bar[stage]);
           if (kb == num_k - 1) umma2_commit_multicast(&tfull_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -278,7 +302,7 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-      const int m0 = (tile / p.num_n_tiles) * 256 + (int)rank * 128;
+      const int m_tile = (tile / p.num_n_tiles) * PAIR_M + (int)rank * 128;
       float* sc = sScale + acc * BLOCK_N;
       float* sf = sShift + acc * BLOCK_N;
       for (int i = ep_tid; i < BLOCK_N; i += 128) {
@@ -288,38 +312,47 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int m = m0 + row;
-      const bool valid = m < p.M;
-      const size_t row_off = (size_t)m * p.Cout + n0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
-        tmem_ld_wait();
-        float y[32];
+      for (int a = 0; a < MT; ++a) {
+        const int m0 = m_tile + a * 256;
+        const int m = m0 + row;
+        const bool valid = m < p.M;
+        const size_t row_off = (size_t)m * p.Cout + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * MT + a) * BLOCK_N + c0), v);
+          tmem_ld_wait();
+          float y[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
-        if (p.residual && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+          for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[c0 + j], sf[c0 + j]);
+          if (p.residual && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint4 rv = __ldg(rp + u);
-            const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+            for (int u = 0; u < 4; ++u) {
+              const uint4 rv = __ldg(rp + u);
+              const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(w4[e]);
-              y[u * 8 + e * 2] += f.x;
-              y[u * 8 + e * 2 + 1] += f.y;
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w4[e]);
+                y[u * 8 + e * 2] += f.x;
+                y[u * 8 + e * 2 + 1] += f.y;
+              }
             }
           }
-        }
-        if (p.relu) {
+          if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+          }
+          // registers -> swizzled smem slab -> TMA store (rows beyond M are clipped by the TMA unit; a slab that
+          // starts beyond M stores nothing - every thread still takes part in the slab barriers)
+          if (m0 < p.M) {
+            if constexpr (!Cfg::BF16_ONLY) {
+              if (p.out_f32) epi_stage_store<true>(est, &tmOf, y, row, n0 + c0, m0, ep_tid);
+            }
+            if (p.out_bf16) epi_stage_store<false>(est, &tmOb, y, row, n0 + c0, m0, ep_tid);
+          }
         }
-        // registers -> swizzled smem slab -> TMA store (rows beyond M are clipped by the TMA unit)
-        if (p.out_f32) epi_stage_store<true>(est, &tmOf, y, row, n0 + c0, m0, ep_tid);
-        if (p.out_bf16) epi_stage_store<false>(est, &tmOb, y, row, n0 + c0, m0, ep_tid);
       }
       tc_fence_before();
       __syncwarp();
@@ -340,13 +373,13 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
 static TmaEncoders g_enc2;
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT = 1>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
                       const CUtensorMap& tmA2, const Tc2Params& p, cudaStream_t st) {
-  using Cfg = Tc2Cfg<BLOCK_N>;
+  using Cfg = Tc2Cfg<BLOCK_N, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_2cta_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_2cta_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -365,7 +398,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSTR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_bf16_2cta_kernel<BLOCK_N>, tmA, tmB, tmOb, tmOf, tmA2, p));
+  MSTR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_bf16_2cta_kernel<BLOCK_N, MT>, tmA, tmB, tmOb, tmOf, tmA2, p));
   MSTR_LAUNCH_CHECK("conv_gemm_bf16_2cta_kernel");
   return MSTR_OK;
 }
@@ -386,7 +419,10 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
   const char* wide_env = getenv("MSTR_CONV_N512");
   const bool wide = wide_env && wide_env[0] == '1';
   const int block_n = (C_out % 512 == 0 && !out_f32 && wide) ? 512 : (C_out % 256 == 0) ? 256 : 128;
-  p.num_m_pairs = ceil_div(p.M, 256);
+  // C_out = 128 layers with bf16 output: two 256-row accumulators per pair (opt-in, MSTR_CONV_PAIR_MT2=1)
+  const char* mt_env = getenv("MSTR_CONV_PAIR_MT2");
+  const int mt = (block_n == 128 && !out_f32 && mt_env && mt_env[0] == '1') ? 2 : 1;
+  p.num_m_pairs = ceil_div(p.M, 256 * mt);
   p.num_n_tiles = C_out / block_n;
   p.taps = R * S;
   p.S = S;
@@ -436,6 +472,7 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
   if (!out_bf16) tmOb = tmOf;
   if (!out_f32) tmOf = tmOb;
   if (block_n == 512) return launch_tc2<512>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+  if (block_n == 128 && mt == 2) return launch_tc2<128, 2>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
   if (block_n == 256) return launch_tc2<256>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
   return launch_tc2<128>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
 }

@@ -249,6 +249,22 @@ def test_conv_gemm_bf16_wide_tile_opt_in(monkeypatch):
     assert_close(host(wide), orc.round_bf16(ref.astype(np.float32)), 1e-2, "conv_gemm_bf16 wide tile")
 
 
+def test_conv_gemm_bf16_pair_two_accumulators_opt_in(monkeypatch):
+    """C_out = 128 on the CTA-pair kernel with two 256-row accumulators per pair (MSTR_CONV_PAIR_MT2=1) must give
+    the same bits as the default single-CTA kernel; ragged M (not a multiple of 512), several tiles per pair."""
+    case = (37, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), False, True)
+    x, w, scale, shift, res = _conv_inputs(case, 8, True)
+    bf = torch.bfloat16
+    args = (dev(x, bf), dev(w, bf), dev(scale), dev(shift), None)
+    kw = dict(stride=(1, 1), pad=(1, 1), relu=True, want_f32=False, want_bf16=True)
+    monkeypatch.delenv("MSTR_CONV_PAIR_MT2", raising=False)
+    base = ops.conv_gemm(*args, **kw)
+    monkeypatch.setenv("MSTR_CONV_PAIR_MT2", "1")
+    pair = ops.conv_gemm(*args, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(base, pair)
+
+
 # ------------------------------------------------------------------------------------------------
 # pooling / reductions / cast / embedding
 # ------------------------------------------------------------------------------------------------

@@ -45,7 +45,7 @@ struct TcParams {
 };
 
 constexpr int TC_BLOCK_M = 128;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;     // producer, MMA issuer, 2 x 4 epilogue warps
 
 constexpr int TC_MAX_STAGES = 8;   // barrier storage is sized for the maximum ring depth
 
@@ -102,7 +102,7 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -201,8 +201,15 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int ep_tid = threadIdx.x - 64;
-    EpiStage est{sEpi, Cfg::EPI_SLAB, 0};
+    // Two groups of four warps (TMEM lane quarters 2,3,0,1 each) split the tile: with MT = 2 group g drains
+    // accumulator g, otherwise column half g.  One group needed ~10k cycles per 256-row tile (ncu: TMEM load
+    // latency, fence.proxy.async, the slab barriers and the per-tile fences add up to ~1.2k cycles per 32-column
+    // step), more than the MMAs of every K <= 1152 layer; each group has its own slab ring and named barriers.
+    const int eg = (warp - 2) >> 2;
+    const int ep_tid = (threadIdx.x - 64) & 127;
+    const int ep_all = threadIdx.x - 64;
+    EpiStage est = make_epi_stage(sEpi + eg * Cfg::EPI_SLAB, Cfg::EPI_SLAB, p.out_f32 != nullptr);   // 1 f32 / 2 bf16 slabs
+    est.bar = 2 + 2 * eg;
     if (ep_tid == 0) {
       prefetch_tensormap(&tmOb);
       prefetch_tensormap(&tmOf);
@@ -214,21 +221,23 @@ conv_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int m0 = (tile / p.num_n_tiles) * TILE_M;
       float* sc = sScale + acc * BLOCK_N;
       float* sf = sShift + acc * BLOCK_N;
-      for (int i = ep_tid; i < BLOCK_N; i += 128) {
+      for (int i = ep_all; i < BLOCK_N; i += 256) {
         sc[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
         sf[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      const int h_begin = MT == 2 ? eg : 0, h_end = MT == 2 ? eg + 1 : MT;
+      const int c_begin = MT == 2 ? 0 : eg * (BLOCK_N / 2), c_end = MT == 2 ? BLOCK_N : (eg + 1) * (BLOCK_N / 2);
 #pragma unroll 1
-      for (int h = 0; h < MT; ++h) {
+      for (int h = h_begin; h < h_end; ++h) {
         const int mh = m0 + h * TC_BLOCK_M;
         const int m = mh + row;
         const bool valid = m < p.M;
         const size_t row_off = (size_t)m * p.Cout + n0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * MT + h) * BLOCK_N + c0), v);
           tmem_ld_wait();

@@ -37,7 +37,7 @@ struct Tc2Params {
   float* out_f32;
 };
 
-constexpr int T2_THREADS = 192;
+constexpr int T2_THREADS = 320;      // producer, MMA issuer, 2 x 4 epilogue warps
 constexpr int T2_BLOCK_K = 64;
 constexpr int T2_A_BYTES = 128 * 128;   // 128 rows x 64 bf16
 
@@ -58,7 +58,7 @@ constexpr int T2_A_BYTES = 128 * 128;   // 128 rows x 64 bf16
 // fewer operand bytes did not pay for the pair protocol, so this variant is opt-in (MSTR_CONV_PAIR_MT2=1).  The
 // K = 576 layers move 432 KB of operands per 256-row tile in ~11.8k cycles (9 TB/s chip-wide, close to the
 // ~12.5 TB/s the L2 delivers to the SMs) for 4.6k cycles of MMA work.
-template <int BLOCK_N, int MT = 1>
+template <int BLOCK_N, int MT = 1, bool F32OUT = false>
 struct Tc2Cfg {
   static constexpr int UMMA_N = BLOCK_N > 256 ? 256 : BLOCK_N;    // columns per tcgen05.mma
   static constexpr int NH = BLOCK_N / UMMA_N;                       // MMAs per k-step and accumulator
@@ -67,12 +67,16 @@ struct Tc2Cfg {
   static constexpr int B_BYTES = (BLOCK_N / 2) * 128;       // this CTA's half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr bool BF16_ONLY = BLOCK_N > 256 || MT > 1;
-  static constexpr int EPI_SLAB = BF16_ONLY ? EPI_SLAB_BYTES / 2 : EPI_SLAB_BYTES;
+  // output slab rings (tc_common.cuh), one per epilogue warp group: 24 KB each (3 bf16 slabs) for the common tile,
+  // which has the room next to 5 operand stages; 32 KB each (2 f32 slabs) for the f32-output instantiation (the
+  // BiLSTM input projections: K <= 512, 4 stages are plenty); 16 KB each (2 bf16 slabs) for the bf16-only variants
+  static constexpr int EPI_GROUP_BYTES = BF16_ONLY ? EPI_SLAB_BYTES : (F32OUT ? 2 * EPI_SLAB_BYTES : 3 * EPI_SLAB_BYTES / 2);
+  static constexpr int EPI_REGION = 2 * EPI_GROUP_BYTES;
   static constexpr int TAIL_BYTES = 4 * BLOCK_N * 4 + (2 * 8 + 4) * 8 + 16;
-  static constexpr int RING_BUDGET = 227 * 1024 - 1024 - 2 * EPI_SLAB - TAIL_BYTES;
+  static constexpr int RING_BUDGET = 227 * 1024 - 1024 - EPI_REGION - TAIL_BYTES;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = NUM_ACC * MT * BLOCK_N;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * EPI_SLAB + TAIL_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_REGION + TAIL_BYTES;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -145,12 +149,12 @@ __device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar) {
       : "memory");
 }
 
-template <int BLOCK_N, int MT = 1>
+template <int BLOCK_N, int MT = 1, bool F32OUT = false>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ CUtensorMap tmOb, const __grid_constant__ CUtensorMap tmOf,
                            const __grid_constant__ CUtensorMap tmA2, const Tc2Params p) {
-  using Cfg = Tc2Cfg<BLOCK_N, MT>;
+  using Cfg = Tc2Cfg<BLOCK_N, MT, F32OUT>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int PAIR_M = 256 * MT;         // output rows per pair and tile
   extern __shared__ uint8_t smem_raw[];
@@ -158,8 +162,8 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;                            // 2 output slabs
-  float* sScale = reinterpret_cast<float*>(sEpi + 2 * Cfg::EPI_SLAB);          // [2][BLOCK_N]
+  uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;                            // output slab ring
+  float* sScale = reinterpret_cast<float*>(sEpi + Cfg::EPI_REGION);            // [2][BLOCK_N]
   float* sShift = sScale + 2 * BLOCK_N;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + 2 * BLOCK_N);
   uint64_t* empty_bar = full_bar + 8;
@@ -185,7 +189,7 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);   // one multicast commit
-      mbar_init(&tempty_bar[i], 8);  // leader's: 4 epilogue warps x 2 CTAs
+      mbar_init(&tempty_bar[i], 16); // leader's: 8 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -292,8 +296,13 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     // ===================== epilogue (both CTAs; warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int ep_tid = threadIdx.x - 64;
-    EpiStage est{sEpi, Cfg::EPI_SLAB, 0};
+    // two groups of four warps split the tile (MT = 2: accumulator g, otherwise column half g), each with its own
+    // slab ring and named barriers - see conv_tc.cu
+    const int eg = (warp - 2) >> 2;
+    const int ep_tid = (threadIdx.x - 64) & 127;
+    const int ep_all = threadIdx.x - 64;
+    EpiStage est = make_epi_stage(sEpi + eg * Cfg::EPI_GROUP_BYTES, Cfg::EPI_GROUP_BYTES, F32OUT && p.out_f32 != nullptr);
+    est.bar = 2 + 2 * eg;
     if (ep_tid == 0) {
       prefetch_tensormap(&tmOb);
       prefetch_tensormap(&tmOf);
@@ -305,21 +314,23 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const int m_tile = (tile / p.num_n_tiles) * PAIR_M + (int)rank * 128;
       float* sc = sScale + acc * BLOCK_N;
       float* sf = sShift + acc * BLOCK_N;
-      for (int i = ep_tid; i < BLOCK_N; i += 128) {
+      for (int i = ep_all; i < BLOCK_N; i += 256) {
         sc[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
         sf[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      const int a_begin = MT == 2 ? eg : 0, a_end = MT == 2 ? eg + 1 : MT;
+      const int c_begin = MT == 2 ? 0 : eg * (BLOCK_N / 2), c_end = MT == 2 ? BLOCK_N : (eg + 1) * (BLOCK_N / 2);
 #pragma unroll 1
-      for (int a = 0; a < MT; ++a) {
+      for (int a = a_begin; a < a_end; ++a) {
         const int m0 = m_tile + a * 256;
         const int m = m0 + row;
         const bool valid = m < p.M;
         const size_t row_off = (size_t)m * p.Cout + n0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * MT + a) * BLOCK_N + c0), v);
           tmem_ld_wait();
@@ -347,7 +358,7 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           // registers -> swizzled smem slab -> TMA store (rows beyond M are clipped by the TMA unit; a slab that
           // starts beyond M stores nothing - every thread still takes part in the slab barriers)
           if (m0 < p.M) {
-            if constexpr (!Cfg::BF16_ONLY) {
+            if constexpr (F32OUT) {
               if (p.out_f32) epi_stage_store<true>(est, &tmOf, y, row, n0 + c0, m0, ep_tid);
             }
             if (p.out_bf16) epi_stage_store<false>(est, &tmOb, y, row, n0 + c0, m0, ep_tid);
@@ -373,13 +384,13 @@ conv_gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
 static TmaEncoders g_enc2;
 
-template <int BLOCK_N, int MT = 1>
+template <int BLOCK_N, int MT = 1, bool F32OUT = false>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
                       const CUtensorMap& tmA2, const Tc2Params& p, cudaStream_t st) {
-  using Cfg = Tc2Cfg<BLOCK_N, MT>;
+  using Cfg = Tc2Cfg<BLOCK_N, MT, F32OUT>;
   static bool attr_set = false;
   if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_2cta_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_2cta_kernel<BLOCK_N, MT, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -398,7 +409,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSTR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_bf16_2cta_kernel<BLOCK_N, MT>, tmA, tmB, tmOb, tmOf, tmA2, p));
+  MSTR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_bf16_2cta_kernel<BLOCK_N, MT, F32OUT>, tmA, tmB, tmOb, tmOf, tmA2, p));
   MSTR_LAUNCH_CHECK("conv_gemm_bf16_2cta_kernel");
   return MSTR_OK;
 }
@@ -473,7 +484,11 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
   if (!out_f32) tmOf = tmOb;
   if (block_n == 512) return launch_tc2<512>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
   if (block_n == 128 && mt == 2) return launch_tc2<128, 2>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
-  if (block_n == 256) return launch_tc2<256>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+  if (block_n == 256) {
+    if (out_f32) return launch_tc2<256, 1, true>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+    return launch_tc2<256>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+  }
+  if (out_f32) return launch_tc2<128, 1, true>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
   return launch_tc2<128>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
 }
 

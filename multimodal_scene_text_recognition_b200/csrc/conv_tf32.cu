@@ -202,7 +202,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int ep_tid = threadIdx.x - 64;
-    EpiStage est{sEpi, EPI_SLAB_BYTES, 0};
+    EpiStage est = make_epi_stage(sEpi, 2 * EPI_SLAB_BYTES, true);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n0 = (tile % p.num_n_tiles) * 128;

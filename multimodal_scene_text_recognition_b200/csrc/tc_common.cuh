@@ -180,7 +180,10 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // ~2 cycles of LSU time per 16-byte request, which bounded every small-K layer).  Instead the 128 epilogue
 // threads write a [128 rows x 32 columns] slab into shared memory (bank-conflict-free thanks to the TMA
 // swizzle pattern) and one thread hands it to the TMA engine, which writes whole lines and clips the rows
-// beyond M.  Two slabs alternate so the store of slab g overlaps the math of slab g+1.
+// beyond M.  The slabs form a ring of `nslabs` (2..6): the thread that issued a store only waits until at most
+// nslabs-1 stores are still reading shared memory, i.e. until the slab that is written NEXT has been drained.
+// With two slabs every 32-column step waited for the previous store's read (~1.4k cycles: the C_out = 128, K = 576
+// layers and the f32-output GEMMs spent 11.7k cycles per 256-row tile in their epilogue against 4-5k of MMA work).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
@@ -192,17 +195,27 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 constexpr int EPI_SLAB_BYTES = 16384;        // 128 rows x 128 bytes (32 f32 columns); bf16 slabs use half of it
 struct EpiStage {
-  uint8_t* buf;   // 2 slabs, 1024-byte aligned
+  uint8_t* buf;   // slab ring, 1024-byte aligned
   int slab;       // bytes per slab: EPI_SLAB_BYTES, or half of it when only bf16 is ever stored
-  int turn;
+  int nslabs;     // 1, 2, 3, 4 or 6 slabs in the ring
+  int turn;       // slab written next
+  int bar;        // named barriers bar and bar+1 belong to the 128 threads that share this ring
 };
+// ring of `region_bytes` for a kernel call that does / does not store f32
+__device__ __forceinline__ EpiStage make_epi_stage(uint8_t* buf, int region_bytes, bool stores_f32) {
+  const int slab = stores_f32 ? EPI_SLAB_BYTES : EPI_SLAB_BYTES / 2;
+  int n = region_bytes / slab;
+  n = n >= 6 ? 6 : (n == 5 ? 4 : (n < 1 ? 1 : n));          // the wait below exists for 1, 2, 3, 4 and 6
+  return EpiStage{buf, slab, n, 0, 2};
+}
 
-// Called by all 128 epilogue threads (named barriers 2 and 3).  y = this thread's row, columns [col0, col0+32).
+// Called by the 128 epilogue threads that share the ring (named barriers st.bar and st.bar + 1).  y = this
+// thread's row, columns [col0, col0+32); ep_tid = 0..127 within that group.
 template <bool F32>
 __device__ __forceinline__ void epi_stage_store(EpiStage& st, const CUtensorMap* tmO, const float (&y)[32], int row,
                                                 int col0, int m0, int ep_tid) {
-  uint8_t* buf = st.buf + (st.turn & 1) * st.slab;
-  asm volatile("bar.sync 2, 128;" ::: "memory");     // the store that last read this slab has drained it
+  uint8_t* buf = st.buf + st.turn * st.slab;
+  asm volatile("bar.sync %0, 128;" ::"r"(st.bar) : "memory");     // the store that last read this slab has drained it
   if constexpr (F32) {
     uint8_t* r = buf + row * 128;                      // 128-byte rows, 128B swizzle: chunk ^= row & 7
 #pragma unroll
@@ -217,13 +230,18 @@ __device__ __forceinline__ void epi_stage_store(EpiStage& st, const CUtensorMap*
                      pack_bf16x2(y[8 * c + 4], y[8 * c + 5]), pack_bf16x2(y[8 * c + 6], y[8 * c + 7]));
   }
   fence_proxy_async_smem();
-  asm volatile("bar.sync 3, 128;" ::: "memory");     // slab complete
+  asm volatile("bar.sync %0, 128;" ::"r"(st.bar + 1) : "memory");     // slab complete
   if (ep_tid == 0) {
     tma_store_2d(tmO, buf, col0, m0);
     bulk_commit();
-    bulk_wait_read<1>();                               // the OTHER slab's store has finished reading shared memory
+    // the store that read the slab written NEXT (nslabs - 1 stores ago) has finished reading shared memory
+    if (st.nslabs == 6) bulk_wait_read<5>();
+    else if (st.nslabs == 4) bulk_wait_read<3>();
+    else if (st.nslabs == 3) bulk_wait_read<2>();
+    else if (st.nslabs == 2) bulk_wait_read<1>();
+    else bulk_wait_read<0>();
   }
-  ++st.turn;
+  if (++st.turn == st.nslabs) st.turn = 0;
 }
 
 // Read-only 16-byte load whose position in the instruction stream is pinned (asm volatile): used to issue

@@ -56,11 +56,12 @@ def test_tps_rectify(geom, B):
 # ------------------------------------------------------------------------------------------------
 # first-layer conv
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [5, 19])      # the kernel walks 8 images per block: partial and several groups
 @pytest.mark.parametrize("cin,cout,pool,dtype", [(1, 32, False, torch.bfloat16), (1, 64, True, torch.bfloat16),
                                                  (3, 32, False, torch.float32), (3, 64, True, torch.float32)])
-def test_conv3x3_first(cin, cout, pool, dtype):
+def test_conv3x3_first(cin, cout, pool, dtype, B):
     r = rng(2)
-    B, H, W = 5, 32, 100
+    H, W = 32, 100
     x = r.uniform(0, 1, (B, cin, H, W)).astype(np.float32)
     w = (r.standard_normal((cout, cin, 3, 3)) * 0.3).astype(np.float32)
     scale = r.uniform(0.5, 1.5, cout).astype(np.float32)

@@ -268,14 +268,20 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // Bahdanau attention of one decode step: one warp per crop, lane = 8 channels.
-__global__ void __launch_bounds__(256)
+// Single pass with an online softmax: every iteration loads four time steps of BOTH proj and enc (eight 16-byte
+// loads in flight per lane), scores them and folds them into a running (max, denominator, context).  The earlier
+// two-pass version (scores over all of proj, softmax, then enc) was a chain of 14 dependent memory round trips per
+// warp; with all 4096 warps resident at once that chain IS the kernel time (26 us at 52 % of the HBM peak).
+// 4 warps per block, 7 blocks per SM (72 registers): 28 warps x 148 SMs hold all 4096 crops of the bench batch at once.
+constexpr int AT_CTX_WARPS = 4;
+__global__ void __launch_bounds__(32 * AT_CTX_WARPS, 7)
 attn_context_kernel(const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ proj,
                     const DecodeState s, const int step) {
   griddep_wait();
   griddep_launch();
   if (s.early_exit && *s.live == 0) return;
   const int lane = threadIdx.x & 31;
-  const int crop = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int crop = blockIdx.x * AT_CTX_WARPS + (threadIdx.x >> 5);
   if (crop >= s.B) return;
   const int T = s.T;
   float hp[8], ws[8];
@@ -289,16 +295,25 @@ attn_context_kernel(const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* 
   const uint4* pj = reinterpret_cast<const uint4*>(proj + (size_t)crop * T * AT_H) + lane;   // 32 uint4 per time step
   const uint4* en = reinterpret_cast<const uint4*>(enc + (size_t)crop * T * AT_H) + lane;
   constexpr int MAX_SLOTS = 3;   // T <= 96
-  float e_slot[MAX_SLOTS];
+  float e_slot[MAX_SLOTS];       // score of time step t lives in lane t % 32, slot t / 32 (for alpha_out)
 #pragma unroll
   for (int k = 0; k < MAX_SLOTS; ++k) e_slot[k] = -INFINITY;
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    uint4 v[4];
+  float mx = -INFINITY, den = 0.f;
+  float cx[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = (t0 + u < T) ? __ldg(pj + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
+  for (int q = 0; q < 8; ++q) cx[q] = 0.f;
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    uint4 vp[4], ve[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      const bool in = t0 + u < T;
+      vp[u] = in ? __ldg(pj + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
+      ve[u] = in ? __ldg(en + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t w4[4] = {vp[u].x, vp[u].y, vp[u].z, vp[u].w};
       float part = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -309,52 +324,24 @@ attn_context_kernel(const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* 
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
       const int t = t0 + u;
+      e[u] = t < T ? part : -INFINITY;
       if (t < T && (t & 31) == lane) {
 #pragma unroll
         for (int k = 0; k < MAX_SLOTS; ++k)
           if ((t >> 5) == k) e_slot[k] = part;
       }
     }
-  }
-  float mx = -INFINITY;
+    // online softmax update with the four new scores (all lanes hold the same e[], mx, den)
+    const float m_new = fmaxf(fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])), mx);
+    const float rescale = __expf(mx - m_new);          // 0 on the first iteration (mx = -inf)
+    den *= rescale;
 #pragma unroll
-  for (int k = 0; k < MAX_SLOTS; ++k) mx = fmaxf(mx, e_slot[k]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float den = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAX_SLOTS; ++k) {
-    e_slot[k] = (e_slot[k] == -INFINITY) ? 0.f : __expf(e_slot[k] - mx);
-    den += e_slot[k];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
-  const float inv = 1.f / den;
-  if (s.alpha_out) {
-#pragma unroll
-    for (int k = 0; k < MAX_SLOTS; ++k) {
-      const int t = k * 32 + lane;
-      if (t < T) s.alpha_out[((size_t)crop * s.steps + step) * T + t] = e_slot[k] * inv;
-    }
-  }
-  float cx[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) cx[q] = 0.f;
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = (t0 + u < T) ? __ldg(en + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
+    for (int q = 0; q < 8; ++q) cx[q] *= rescale;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int t = t0 + u;
-      float a = 0.f;
-#pragma unroll
-      for (int k = 0; k < MAX_SLOTS; ++k) {
-        const float cand = __shfl_sync(0xffffffffu, e_slot[k], t & 31);
-        if ((t >> 5) == k) a = cand;
-      }
-      a = (t < T) ? a * inv : 0.f;
-      const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      const float a = __expf(e[u] - m_new);            // 0 for padded time steps (e = -inf)
+      den += a;
+      const uint32_t w4[4] = {ve[u].x, ve[u].y, ve[u].z, ve[u].w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 f = unpack_bf16x2(w4[q]);
@@ -362,10 +349,19 @@ attn_context_kernel(const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* 
         cx[2 * q + 1] = fmaf(a, f.y, cx[2 * q + 1]);
       }
     }
+    mx = m_new;
+  }
+  const float inv = 1.f / den;
+  if (s.alpha_out) {
+#pragma unroll
+    for (int k = 0; k < MAX_SLOTS; ++k) {
+      const int t = k * 32 + lane;
+      if (t < T) s.alpha_out[((size_t)crop * s.steps + step) * T + t] = __expf(e_slot[k] - mx) * inv;
+    }
   }
   __nv_bfloat16* dst = s.xh[step & 1] + (size_t)crop * (2 * AT_H) + lane * 8;
-  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(cx[0], cx[1]), pack_bf16x2(cx[2], cx[3]),
-                                              pack_bf16x2(cx[4], cx[5]), pack_bf16x2(cx[6], cx[7]));
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(cx[0] * inv, cx[1] * inv), pack_bf16x2(cx[2] * inv, cx[3] * inv),
+                                              pack_bf16x2(cx[4] * inv, cx[5] * inv), pack_bf16x2(cx[6] * inv, cx[7] * inv));
 }
 
 // token_0 = [GO] (0) or text[:, 0]; lengths = steps; done = 0; live = B; ids zero-filled.
@@ -496,7 +492,7 @@ static int decode_group(const DecodeArgs& a, uint8_t* ws, int g0, int Bg, cudaSt
     }
     if (i == a.steps) break;
     {
-      cudaLaunchConfig_t c = config(dim3(ceil_div(Bg, 8)), 256, 0);
+      cudaLaunchConfig_t c = config(dim3(ceil_div(Bg, AT_CTX_WARPS)), 32 * AT_CTX_WARPS, 0);
       MSTR_CUDA(cudaLaunchKernelEx(&c, attn_context_kernel, enc, proj, s, i));
       MSTR_LAUNCH_CHECK("attn_context_kernel");
     }

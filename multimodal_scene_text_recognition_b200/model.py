@@ -14,7 +14,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import config, ops
+from . import _cabi, config, ops
 from ._pack import act_dtype
 from .utils import AttnLabelConverter
 from .modules.transformation import TPS_SpatialTransformerNetwork
@@ -84,6 +84,16 @@ class Model(nn.Module):
     def _run(self, input, text, overlap, scene, ious, is_train, stages=None):
         if config.ENCODER != 'LSTM':
             raise NotImplementedError("only config.ENCODER == 'LSTM' is implemented (model.py:99)")
+        if input.shape[0] == 0:
+            # empty batch (e.g. the last, empty shard of a rank): the reference returns an empty
+            # [0, steps, classes] tensor from Attention.forward; nothing is launched here
+            if not input.is_cuda:
+                raise _cabi.MstrError("the recognition path has no CPU implementation: move the inputs to a CUDA device")
+            steps = config.MAX_TEXT_LENGTH + 1
+            dev = input.device
+            return {"logits": torch.zeros((0, steps, self.decoder.num_classes), device=dev),
+                    "ids": torch.zeros((0, steps), device=dev, dtype=torch.int32),
+                    "lengths": torch.zeros((0,), device=dev, dtype=torch.int32)}
         # Transformation (model.py:88)
         rect = self.Transformation(input)
         # Feature extraction (model.py:91-93): NHWC result; permute + AdaptiveAvgPool2d((None,1)) +

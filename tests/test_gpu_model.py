@@ -81,6 +81,17 @@ def test_reference_default_init_golden(golden_dir, precision, tol):
     assert np.array_equal(host(out["ids"]), g["ids"]), "decoded ids differ from the reference (default init)"
 
 
+def test_empty_batch_returns_empty_result(sd_cfg_a):
+    m = load_model(sd_cfg_a, precision="bf16")
+    x = torch.zeros((0, 1, 32, 100), device=DEV)
+    z = torch.zeros((0, 15), device=DEV), torch.zeros((0, 52), device=DEV), torch.zeros((0, 52), device=DEV)
+    with torch.no_grad():
+        out = m.recognize(x, *z)
+        logits = m(x, torch.zeros((0, 26), dtype=torch.long, device=DEV), *z, is_train=False)
+    assert out["logits"].shape == (0, 26, 97) and out["ids"].shape == (0, 26) and out["lengths"].shape == (0,)
+    assert logits.shape == (0, 26, 97)
+
+
 def test_tf32_tensor_core_parity_mode(sd_cfg_a, golden_dir):
     """config.PRECISION = 'tf32': convs / linears on tcgen05.mma.kind::tf32 with the 3xTF32 split.  North-star
     tolerance for the TF32 mode: ids bit-identical, logits within 1e-4 relative (the fp32 noise floor of this

@@ -43,6 +43,32 @@ for precision, grid in (("fp32", "reference"), ("tf32", "reference"), ("fp32", "
         }
     report["%s/%s" % (precision, grid)] = row
     print(precision, grid, json.dumps(row))
+
+# The reference's OWN random init (torch.manual_seed(config.RANDOM_SEED); Model()): the mirror consumes the RNG
+# identically, so the same seed rebuilds the same 253 tensors; oracle = the torch CPU port on those weights.
+from multimodal_scene_text_recognition_b200 import model as M  # noqa: E402
+from oracle import torch_port as tp  # noqa: E402
+config.MAX_TEXT_LENGTH = 25
+torch.manual_seed(999)
+cpu_model = M.Model().eval()
+sd_def = {k: v.clone() for k, v in cpu_model.state_dict().items()}
+ref_def = tp.forward(sd_def, torch.from_numpy(x), torch.from_numpy(ov), torch.from_numpy(sc), torch.from_numpy(io))
+ref_logits = ref_def["logits"].numpy() if isinstance(ref_def, dict) else ref_def.numpy()
+ref_ids = ref_logits.argmax(2)
+row = {}
+for precision in ("fp32", "tf32", "bf16"):
+    config.PRECISION = precision
+    config.TPS_GRID, config.DECODER_EARLY_EXIT, config.SEMANTIC_VECTOR = "reference", False, "overlap"
+    torch.manual_seed(999)
+    m = M.Model().eval().to("cuda:0")
+    with torch.no_grad():
+        out = m.recognize(dev(x), dev(ov), dev(sc), dev(io))
+    torch.cuda.synchronize()
+    ids = host(out["ids"])
+    row[precision] = {"logits": err(host(out["logits"]), ref_logits)[1],
+                      "ids_equal_crops": int((ids == ref_ids).all(1).sum()), "crops": B}
+report["reference_default_init_seed999"] = row
+print("default init", json.dumps(row))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
     json.dump(report, f, indent=1)

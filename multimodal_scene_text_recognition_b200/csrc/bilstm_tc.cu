@@ -36,6 +36,8 @@
 // feed of 128 KB per chunk per SM (gates_x + W_hh: 0.34 ms without the gates_x loads) on top of a
 // 0.21 ms barrier / TMEM round-trip skeleton.  The gate non-linearities use tanh.approx (1 MUFU each;
 // sigmoid(x) = 0.5 tanh(x/2) + 0.5): 5 MUFU per hidden unit per crop per step - not the limiter.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace mstr {
@@ -305,6 +307,11 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 
 static TmaEncoders g_lstm_enc;
 
+// bilstm_cluster.cu: cluster-cooperative variant (W_hh stationary in shared memory, h exchanged through DSMEM)
+int bilstm_recurrent_bf16_cluster(const float* gates_x, const void* w_hh_packed, void* out_bf16, int B, int T,
+                                  cudaStream_t stream);
+int bilstm_cluster_capacity();
+
 }  // namespace mstr
 
 extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16(
@@ -315,6 +322,14 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   MSTR_REQUIRE(Hd == LT_H, MSTR_ERR_UNSUPPORTED, "mstr_bilstm_recurrent_bf16: hidden size %d != %d", Hd, LT_H);
   MSTR_REQUIRE(aligned16(gates_x) && aligned16(w_hh_packed) && aligned16(out_bf16), MSTR_ERR_BAD_ARG,
                "mstr_bilstm_recurrent_bf16: pointers must be 16-byte aligned");
+  // Two kernels, chosen by occupancy.  The cluster-cooperative kernel (bilstm_cluster.cu: W_hh stationary, 8 CTAs per
+  // crop tile) has a ~3x shorter step (6 us vs 17.7 us) but the device holds only ~13 of its clusters at once, so it
+  // wins while all (crop tile, direction) pairs fit in one wave - batches up to ~800 crops (B=256: 0.156 vs 0.347 ms);
+  // beyond that this kernel's 64+ independent CTAs win (B=4096: 0.46 vs 1.03 ms).  MSTR_BILSTM_CLUSTER=0 / 1 forces one.
+  const char* cl_env = getenv("MSTR_BILSTM_CLUSTER");
+  const int tiles = ceil_div(B, LT_M) * 2;
+  const bool use_cluster = cl_env ? cl_env[0] == '1' : (tiles <= bilstm_cluster_capacity());
+  if (use_cluster) return bilstm_recurrent_bf16_cluster(gates_x, w_hh_packed, out_bf16, B, T, (cudaStream_t)stream);
   int rc = load_tma_encoders(g_lstm_enc);
   if (rc != MSTR_OK) return rc;
   alignas(64) CUtensorMap tmW;

@@ -328,9 +328,13 @@ def test_bilstm_recurrent(B, T):
     assert np.array_equal(host(out_b), orc.round_bf16(host(out_f)))
 
 
+@pytest.mark.parametrize("kernel", ["single", "cluster"])
 @pytest.mark.parametrize("B,T", [(1, 26), (130, 26), (128, 5), (3, 65)])
-def test_bilstm_recurrent_bf16_tensor_cores(B, T):
-    """tcgen05 recurrence (h_t in bf16, tanh.approx gates) vs the oracle with bf16-rounded W_hh / h_t."""
+def test_bilstm_recurrent_bf16_tensor_cores(B, T, kernel, monkeypatch):
+    """tcgen05 recurrence (h_t in bf16, tanh.approx gates) vs the oracle with bf16-rounded W_hh / h_t, for both
+    kernels: one CTA per crop tile streaming W_hh (bilstm_tc.cu) and the 8-CTA cluster with stationary W_hh
+    slices and the DSMEM exchange of h (bilstm_cluster.cu); the dispatcher picks by occupancy."""
+    monkeypatch.setenv("MSTR_BILSTM_CLUSTER", "1" if kernel == "cluster" else "0")
     r = rng(17)
     Hd = 256
     gx = r.standard_normal((B, T, 2, 4 * Hd)).astype(np.float32)

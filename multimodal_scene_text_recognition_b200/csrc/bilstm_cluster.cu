@@ -8,13 +8,15 @@
 // A cluster of 8 CTAs owns one tile of 128 crops of one direction for all T steps; CTA `rank` owns the gate
 // chunk `rank` = hidden units [rank*32, rank*32+32) x gates i,f,g,o (128 gate rows):
 //   W slice  [128 gate rows x 256 k] bf16 = 64 KB, loaded ONCE by TMA (bilstm_tc.cu streams all 512 KB of W_hh of
-//            a direction from L2 every step);
-//   h_t      [128 crops x 256] bf16, the A operand, double buffered in EVERY CTA of the cluster; each CTA's epilogue
-//            writes its 32 new hidden units (16 bytes per thread) into the h_{t+1} buffer of all 8 CTAs with
-//            st.shared::cluster, fences (fence.proxy.async: the consumers are tcgen05.mma) and arrives on every
-//            CTA's `hfull` mbarrier (release.cluster, one arrival per CTA after a CTA-local barrier of the epilogue
-//            threads); the MMA thread of each CTA waits (acquire.cluster) for the 8 arrivals before it issues the
-//            step's 16 tcgen05.mma;
+//            a direction from L2 every step), as 8 k-blocks of 32 (64-byte rows, 64B swizzle);
+//   h_t      [128 crops x 256] bf16, the A operand, double buffered in EVERY CTA of the cluster, in the same k-blocks
+//            of 32 units: k-block j IS the 8 KB slice CTA j produces.  The epilogue threads write their 16 bytes
+//            into the local copy of the slice, fence (fence.proxy.async), meet at a CTA-local barrier, and seven
+//            threads then push the slice to the seven peers with cp.async.bulk.shared::cluster, each completing
+//            8 KB of transaction count on the PEER's `hfull` mbarrier; the CTA's own arrive.expect_tx(7 x 8 KB)
+//            covers the local slice.  The MMA thread waits for `hfull` (acquire.cluster) and issues the step's 16
+//            tcgen05.mma.  (A first version wrote 16 bytes per thread into all 8 CTAs with st.shared::cluster -
+//            4096 remote stores per CTA and step plus a cluster-scope fence: 6 us per step.)
 //   gates    three [128 x 128] f32 accumulator buffers in TMEM (step % 3).  gates_x does not depend on h, so the
 //            loader warps pre-fill the accumulators up to two steps AHEAD (TMA tile -> shared memory -> registers ->
 //            tcgen05.st); the MMAs accumulate on top;
@@ -32,15 +34,16 @@ namespace mstr {
 constexpr int LC_H = 256;
 constexpr int LC_M = 128;                      // crops per cluster
 constexpr int LC_CLUSTER = 8;                  // CTAs per cluster = gate chunks of 32 hidden units
-constexpr int LC_KB = LC_H / 64;               // 4 k-blocks of 64 bf16
-constexpr int LC_TILE_BYTES = 128 * 128;       // [128 rows][128 B]: W k-block, h k-block, gates_x pass
-constexpr int LC_H_BUF_BYTES = LC_KB * LC_TILE_BYTES;   // 64 KB
+constexpr int LC_KB = LC_H / 32;               // 8 k-blocks of 32 bf16: k-block j = the hidden units CTA j produces
+constexpr int LC_KTILE_BYTES = 128 * 64;       // [128 rows][64 B], 64B swizzle: one k-block of W or of h (8 KB)
+constexpr int LC_TILE_BYTES = 128 * 128;       // [128 rows][128 B] f32, 128B swizzle: one gates_x pass (16 KB)
+constexpr int LC_H_BUF_BYTES = LC_KB * LC_KTILE_BYTES;   // 64 KB
 constexpr int LC_GX_STAGES = 2;
 constexpr int LC_ACC = 3;                      // accumulator buffers in TMEM
 constexpr int LC_EPI_WARPS = 16;
 constexpr int LC_LOAD_WARPS = 4;
 constexpr int LC_THREADS = 32 * (2 + LC_EPI_WARPS + LC_LOAD_WARPS);   // 704
-constexpr int LC_SMEM_BYTES = 1024 + LC_KB * LC_TILE_BYTES + 2 * LC_H_BUF_BYTES + LC_GX_STAGES * LC_TILE_BYTES + 256;
+constexpr int LC_SMEM_BYTES = 1024 + LC_KB * LC_KTILE_BYTES + 2 * LC_H_BUF_BYTES + LC_GX_STAGES * LC_TILE_BYTES + 256;
 
 struct LstmClusterParams {
   const float* gates_x;         // [B][T][2][4H]
@@ -66,14 +69,6 @@ __device__ __forceinline__ uint32_t lc_map_to_cta(uint32_t local_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void lc_st_cluster_v4(uint32_t cluster_addr, const uint4& v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z),
-               "r"(v.w)
-               : "memory");
-}
-__device__ __forceinline__ void lc_mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 // wait with cluster-scope acquire: the arrivals come from the other CTAs of the cluster
 __device__ __forceinline__ void lc_mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -93,8 +88,14 @@ __device__ __forceinline__ void lc_mbar_wait_cluster(uint64_t* bar, uint32_t par
     if (clock64() - t0 > 4000000000ll) __trap();     // a protocol bug must surface as a trapped launch, not a hang
   }
 }
-// generic-proxy writes (incl. st.shared::cluster) -> async proxy (tcgen05.mma of any CTA of the cluster)
-__device__ __forceinline__ void lc_fence_proxy_async_all() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
+// bulk copy of `bytes` from this CTA's shared memory into a peer CTA's shared memory (async proxy), completing
+// `bytes` of transaction count on the PEER's mbarrier
+__device__ __forceinline__ void lc_bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                     uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(bar_cluster_addr)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(LC_THREADS, 1)
 bilstm_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmGx,
@@ -102,8 +103,8 @@ bilstm_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   // the dynamic smem base has the same offset in every CTA of the cluster, so this rounding is identical in all of them
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sW = smem;                                    // [LC_KB][128 gate rows][128 B]
-  uint8_t* sH = sW + LC_KB * LC_TILE_BYTES;              // [2][LC_KB][128 crops][128 B]
+  uint8_t* sW = smem;                                    // [LC_KB][128 gate rows][64 B]
+  uint8_t* sH = sW + LC_KB * LC_KTILE_BYTES;             // [2][LC_KB][128 crops][64 B]
   uint8_t* sG = sH + 2 * LC_H_BUF_BYTES;                 // [LC_GX_STAGES][128 crops][128 B] f32
   uint64_t* wfull_bar = reinterpret_cast<uint64_t*>(sG + LC_GX_STAGES * LC_TILE_BYTES);
   uint64_t* gfull_bar = wfull_bar + 1;                   // [LC_GX_STAGES]
@@ -135,7 +136,7 @@ bilstm_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], LC_EPI_WARPS);
     }
-    for (int i = 0; i < 2; ++i) mbar_init(&hfull_bar[i], LC_CLUSTER);   // one arrival per CTA of the cluster
+    for (int i = 0; i < 2; ++i) mbar_init(&hfull_bar[i], 1);   // own arrive.expect_tx; the 7 peer slices complete_tx
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -147,9 +148,9 @@ bilstm_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer: W slice once, then gates_x tiles (step, gate) =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(wfull_bar, LC_KB * LC_TILE_BYTES);
+      mbar_arrive_expect_tx(wfull_bar, LC_KB * LC_KTILE_BYTES);
       for (int kb = 0; kb < LC_KB; ++kb)
-        tma_load_2d(sW + kb * LC_TILE_BYTES, &tmW, wfull_bar, kb * 64, dir * 4 * LC_H + (int)rank * 128);
+        tma_load_2d(sW + kb * LC_KTILE_BYTES, &tmW, wfull_bar, kb * 32, dir * 4 * LC_H + (int)rank * 128);
       int stage = 0;
       uint32_t phase = 0;
       for (int step = 0; step < T; ++step) {
@@ -179,11 +180,11 @@ bilstm_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
 #pragma unroll
         for (int kb = 0; kb < LC_KB; ++kb) {
-          const uint32_t a_addr = h_addr + kb * LC_TILE_BYTES;
-          const uint32_t b_addr = smem_u32(sW + kb * LC_TILE_BYTES);
+          const uint32_t a_addr = h_addr + kb * LC_KTILE_BYTES;
+          const uint32_t b_addr = smem_u32(sW + kb * LC_KTILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, make_smem_desc<128>(a_addr + k * 32), make_smem_desc<128>(b_addr + k * 32), idesc, 1u);
+          for (int k = 0; k < 2; ++k)
+            umma_bf16(d_tmem, make_smem_desc<64>(a_addr + k * 32), make_smem_desc<64>(b_addr + k * 32), idesc, 1u);
         }
         umma_commit(&tfull_bar[acc]);
       }
@@ -198,11 +199,11 @@ bilstm_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     const bool valid = crop < p.B;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int unit0 = (int)rank * 32 + uq * 8;            // first of this thread's 8 hidden units
-    // where this thread's 16 bytes go inside an h buffer: k-block unit0/64, row, 16-byte chunk (128B swizzle)
-    const int c0 = (unit0 & 63) >> 3;
-    const uint32_t h_off = (uint32_t)((unit0 >> 6) * LC_TILE_BYTES + row * 128 + ((c0 ^ (row & 7)) << 4));
-    const uint32_t h_local = smem_u32(sH) + h_off;          // + nb * LC_H_BUF_BYTES, mapped to every CTA with mapa
-    const uint32_t bar_local = smem_u32(hfull_bar);
+    // this CTA's slice of h is k-block `rank` of the buffer: [128 rows][64 B], 64B swizzle (chunk ^= (row >> 1) & 3);
+    // this thread owns 16-byte chunk uq of its row
+    const uint32_t slice_off = (uint32_t)((int)rank * LC_KTILE_BYTES);
+    const uint32_t h_off = slice_off + (uint32_t)(row * 64 + ((uq ^ ((row >> 1) & 3)) << 4));
+    const uint32_t ep_tid = (uint32_t)(threadIdx.x - 64);   // 0..511
     float cst[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) cst[j] = 0.f;
@@ -232,17 +233,29 @@ bilstm_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                                    pack_bf16x2(hv[6], hv[7]));
       if (step + 1 < T) {
         const int nb = (step + 1) & 1;
-#pragma unroll
-        for (int d = 0; d < LC_CLUSTER; ++d)
-          lc_st_cluster_v4(lc_map_to_cta(h_local + (uint32_t)(nb * LC_H_BUF_BYTES), (uint32_t)d), hpk);
-        lc_fence_proxy_async_all();
-        // all 512 epilogue threads have written and fenced their pieces; one thread then signals the 8 CTAs
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (ew == 0 && lane < LC_CLUSTER) lc_mbar_arrive_cluster(lc_map_to_cta(bar_local + (uint32_t)(nb * 8), (uint32_t)lane));
+        uint8_t* hb = sH + nb * LC_H_BUF_BYTES;
+        *reinterpret_cast<uint4*>(hb + h_off) = hpk;           // own copy of the slice (also the source of the bulk copies)
+        fence_proxy_async_smem();
+        // the bulk copies this thread issued one step ago (from the OTHER buffer, which is rewritten next step) have
+        // finished reading shared memory: every thread passes the barrier below only after this
+        if (ep_tid < LC_CLUSTER) bulk_wait_read<0>();
+        asm volatile("bar.sync 1, 512;" ::: "memory");         // the whole 8 KB slice is written and fenced
+        if (ep_tid < LC_CLUSTER) {
+          const uint32_t src = smem_u32(hb) + slice_off;
+          if (ep_tid == rank) {
+            // own barrier: the local slice is in place, and 7 peer slices of 8 KB are expected
+            mbar_arrive_expect_tx(&hfull_bar[nb], (LC_CLUSTER - 1) * LC_KTILE_BYTES);
+          } else {
+            lc_bulk_copy_to_peer(lc_map_to_cta(src, ep_tid), src, LC_KTILE_BYTES,
+                                 lc_map_to_cta(smem_u32(&hfull_bar[nb]), ep_tid));
+            bulk_commit();
+          }
+        }
       }
       // the output copy goes out after the slice has been published (a store in flight would stall the fence)
       if (valid) *reinterpret_cast<uint4*>(p.out + ((size_t)crop * T + t) * (2 * LC_H) + dir * LC_H + unit0) = hpk;
     }
+    if (ep_tid < LC_CLUSTER) bulk_wait_read<0>();   // this CTA's shared memory is no longer being read by a bulk copy
   } else {
     // ===================== gates_x loaders: shared-memory tile -> registers -> accumulator buffer ==========
     const int quarter = warp & 3;
@@ -338,7 +351,7 @@ int bilstm_recurrent_bf16_cluster(const float* gates_x, const void* w_hh_packed,
   int rc = load_tma_encoders(g_lstm_cluster_enc);
   if (rc != MSTR_OK) return rc;
   alignas(64) CUtensorMap tmW, tmGx;
-  rc = encode_tiled_2d_bf16(g_lstm_cluster_enc, &tmW, w_hh_packed, LC_H, 2 * 4 * LC_H, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = encode_tiled_2d_bf16(g_lstm_cluster_enc, &tmW, w_hh_packed, LC_H, 2 * 4 * LC_H, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != MSTR_OK) return rc;
   {
     // gates_x viewed as [B rows][T*2*4H f32 columns]; box = 32 columns x 128 crops, rows beyond B are zero filled

@@ -323,9 +323,10 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   MSTR_REQUIRE(aligned16(gates_x) && aligned16(w_hh_packed) && aligned16(out_bf16), MSTR_ERR_BAD_ARG,
                "mstr_bilstm_recurrent_bf16: pointers must be 16-byte aligned");
   // Two kernels, chosen by occupancy.  The cluster-cooperative kernel (bilstm_cluster.cu: W_hh stationary, 8 CTAs per
-  // crop tile) has a ~3x shorter step (6 us vs 17.7 us) but the device holds only ~13 of its clusters at once, so it
-  // wins while all (crop tile, direction) pairs fit in one wave - batches up to ~800 crops (B=256: 0.156 vs 0.347 ms);
-  // beyond that this kernel's 64+ independent CTAs win (B=4096: 0.46 vs 1.03 ms).  MSTR_BILSTM_CLUSTER=0 / 1 forces one.
+  // crop tile) has a 4.5x shorter step (3.9 us vs 17.7 us) but the device holds only ~13 of its clusters at once, so it
+  // wins while all (crop tile, direction) pairs fit in one wave - batches up to ~800 crops (B=256: 0.101 vs 0.347 ms);
+  // beyond that this kernel's 64+ independent CTAs are level or ahead (B=4096: 0.463 vs 0.482 ms).
+  // MSTR_BILSTM_CLUSTER=0 / 1 forces one.
   const char* cl_env = getenv("MSTR_BILSTM_CLUSTER");
   const int tiles = ceil_div(B, LT_M) * 2;
   const bool use_cluster = cl_env ? cl_env[0] == '1' : (tiles <= bilstm_cluster_capacity());

@@ -365,11 +365,11 @@ extern "C" __attribute__((visibility("default"))) int mstr_attn_decode(const flo
   cudaStream_t st = (cudaStream_t)stream;
   attn_decode_init_kernel<<<ceil_div(B, 256), 256, 0, st>>>(lengths, ids, B, steps, early_exit);
   MSTR_LAUNCH_CHECK("attn_decode_init_kernel");
-  static bool attr_set = false;
+  static unsigned long long smem_set = 0;
   const int smem = AD_SMEM_FLOATS * (int)sizeof(float);
-  if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  {
+    const int rc_attr = ensure_dynamic_smem((const void*)attn_decode_kernel, smem, &smem_set);
+    if (rc_attr != MSTR_OK) return rc_attr;
   }
   AttnParams p{enc, proj, w_h2h, b_h2h, w_score, w_ctx, w_tok, w_hh, bias, w_gen, b_gen, text, h0, c0,
                logits, ids, lengths, alpha_out, h_out, c_out, B, T, C, steps, early_exit};

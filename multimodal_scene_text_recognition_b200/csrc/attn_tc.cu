@@ -555,15 +555,11 @@ extern "C" __attribute__((visibility("default"))) int mstr_attn_decode_bf16(
   int rc = load_tma_encoders(g_attn_enc);
   if (rc != MSTR_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(rnn_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(rnn_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-  });
-  MSTR_REQUIRE(attr_err == cudaSuccess, MSTR_ERR_CUDA, "cudaFuncSetAttribute(rnn_gemm_kernel) failed: %s",
-               cudaGetErrorString(attr_err));
+  static unsigned long long smem_set_head = 0, smem_set_cell = 0;
+  rc = ensure_dynamic_smem((const void*)rnn_gemm_kernel<0>, AT_SMEM_BYTES, &smem_set_head);
+  if (rc != MSTR_OK) return rc;
+  rc = ensure_dynamic_smem((const void*)rnn_gemm_kernel<1>, AT_SMEM_BYTES, &smem_set_cell);
+  if (rc != MSTR_OK) return rc;
 
   DecodeArgs a{static_cast<const __nv_bfloat16*>(enc_bf16), static_cast<const __nv_bfloat16*>(proj_bf16), w_head, w_cat,
                b_h2h, b_gen, w_score, w_tok, bias, text, logits, ids, lengths, alpha_out, T, C, steps, early_exit};

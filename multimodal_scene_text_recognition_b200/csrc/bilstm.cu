@@ -128,11 +128,11 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent(cons
   MSTR_REQUIRE(B > 0 && T > 0, MSTR_ERR_BAD_ARG, "mstr_bilstm_recurrent: bad size");
   MSTR_REQUIRE(Hd == LS_H, MSTR_ERR_UNSUPPORTED, "mstr_bilstm_recurrent: hidden size %d != %d", Hd, LS_H);
   MSTR_REQUIRE(aligned16(w_hh), MSTR_ERR_BAD_ARG, "mstr_bilstm_recurrent: w_hh must be 16-byte aligned");
-  static bool attr_set = false;
+  static unsigned long long smem_set = 0;
   const int smem = LS_SMEM_FLOATS * (int)sizeof(float);
-  if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(bilstm_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  {
+    const int rc_attr = ensure_dynamic_smem((const void*)bilstm_recurrent_kernel, smem, &smem_set);
+    if (rc_attr != MSTR_OK) return rc_attr;
   }
   dim3 grid(ceil_div(B, LS_BT), 2);
   bilstm_recurrent_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(gates_x, w_hh, out_f32,

@@ -321,12 +321,8 @@ static cudaLaunchConfig_t lc_launch_config(int tiles, cudaStream_t stream, cudaL
 }
 
 static int lc_prepare() {
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(bilstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES));
-    attr_set = true;
-  }
-  return MSTR_OK;
+  static unsigned long long smem_set = 0;
+  return ensure_dynamic_smem((const void*)bilstm_cluster_kernel, LC_SMEM_BYTES, &smem_set);
 }
 
 // How many 8-CTA clusters of this kernel the device can hold at once (each CTA takes a whole SM and the 8 SMs of a

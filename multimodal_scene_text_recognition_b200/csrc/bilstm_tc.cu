@@ -353,11 +353,9 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   rc = encode_tiled_2d_bf16(g_lstm_enc, &tmOut, out_bf16, (uint64_t)T * 2 * LT_H, (uint64_t)B, 64, LT_M,
                             CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != MSTR_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(bilstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES));
-    attr_set = true;
-  }
+  static unsigned long long smem_set = 0;
+  rc = ensure_dynamic_smem((const void*)bilstm_tc_kernel, LT_SMEM_BYTES, &smem_set);
+  if (rc != MSTR_OK) return rc;
   LstmTcParams p{gates_x, (__nv_bfloat16*)out_bf16, B, T};
   dim3 grid(ceil_div(B, LT_M), 2);
   bilstm_tc_kernel<<<grid, LT_THREADS, LT_SMEM_BYTES, (cudaStream_t)stream>>>(tmW, tmGx, tmOut, p);

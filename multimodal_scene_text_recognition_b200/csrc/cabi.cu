@@ -31,6 +31,16 @@ int sm_count() {
   return cached;
 }
 
+int ensure_dynamic_smem(const void* kernel, int bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  MSTR_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return MSTR_OK;
+  MSTR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));   // idempotent
+  __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+  return MSTR_OK;
+}
+
 }  // namespace mstr
 
 extern "C" __attribute__((visibility("default"))) int mstr_version(void) { return 1000; }

@@ -47,6 +47,9 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device), thread safe.
+// `done_mask` is a per-kernel bit mask of the device ordinals already configured.
+int ensure_dynamic_smem(const void* kernel, int bytes, unsigned long long* done_mask);
 
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t hi16) { return __uint_as_float(hi16 << 16); }

@@ -295,11 +295,10 @@ template <int BLOCK_N, int BLOCK_K, int MT = 1>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
                      const CUtensorMap& tmA2, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, BLOCK_K, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, MT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+  static unsigned long long smem_set = 0;     // one per template instantiation
+  {
+    const int rc_attr = ensure_dynamic_smem((const void*)conv_gemm_bf16_kernel<BLOCK_N, BLOCK_K, MT>, Cfg::SMEM_BYTES, &smem_set);
+    if (rc_attr != MSTR_OK) return rc_attr;
   }
   TcParams q = p;
   q.num_m_tiles = ceil_div(p.M, TC_BLOCK_M * MT);

@@ -388,11 +388,10 @@ template <int BLOCK_N, int MT = 1, bool F32OUT = false>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOb, const CUtensorMap& tmOf,
                       const CUtensorMap& tmA2, const Tc2Params& p, cudaStream_t st) {
   using Cfg = Tc2Cfg<BLOCK_N, MT, F32OUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_bf16_2cta_kernel<BLOCK_N, MT, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::SMEM_BYTES));
-    attr_set = true;
+  static unsigned long long smem_set = 0;     // one per template instantiation
+  {
+    const int rc_attr = ensure_dynamic_smem((const void*)conv_gemm_bf16_2cta_kernel<BLOCK_N, MT, F32OUT>, Cfg::SMEM_BYTES, &smem_set);
+    if (rc_attr != MSTR_OK) return rc_attr;
   }
   const int tiles = p.num_m_pairs * p.num_n_tiles;
   int clusters = sm_count() / 2;

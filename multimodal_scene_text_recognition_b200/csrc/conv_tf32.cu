@@ -346,10 +346,10 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv_gemm_tf32(
     if (drv <= 13010 && (int64_t)B * H * W * C_in * 4 < 131072)
       reinterpret_cast<uint64_t*>(&tmX)[1] &= ~(1ull << 21);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSTR_CUDA(cudaFuncSetAttribute(conv_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES));
-    attr_set = true;
+  static unsigned long long smem_set = 0;
+  {
+    const int rc_attr = ensure_dynamic_smem((const void*)conv_gemm_tf32x3_kernel, TF_SMEM_BYTES, &smem_set);
+    if (rc_attr != MSTR_OK) return rc_attr;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();

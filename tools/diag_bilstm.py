@@ -1,3 +1,4 @@
+"""One launch of the bf16 BiLSTM recurrence (for ncu).  Usage: python tools/diag_bilstm.py B T"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

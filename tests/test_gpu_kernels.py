@@ -329,7 +329,7 @@ def test_bilstm_recurrent(B, T):
 
 
 @pytest.mark.parametrize("kernel", ["single", "cluster"])
-@pytest.mark.parametrize("B,T", [(1, 26), (130, 26), (128, 5), (3, 65)])
+@pytest.mark.parametrize("B,T", [(1, 26), (130, 26), (128, 5), (3, 65), (2, 1), (5, 2), (700, 3)])
 def test_bilstm_recurrent_bf16_tensor_cores(B, T, kernel, monkeypatch):
     """tcgen05 recurrence (h_t in bf16, tanh.approx gates) vs the oracle with bf16-rounded W_hh / h_t, for both
     kernels: one CTA per crop tile streaming W_hh (bilstm_tc.cu) and the 8-CTA cluster with stationary W_hh

@@ -349,6 +349,22 @@ def test_bilstm_recurrent_bf16_tensor_cores(B, T, kernel, monkeypatch):
     assert d.mean() < 2e-3, "mean abs error %.3e" % d.mean()
 
 
+def test_bilstm_cluster_kernel_bit_identical_to_single_cta_kernel(monkeypatch):
+    """Both tensor-core recurrences feed the same bf16 operands to the MMAs in the same k order, so the cluster
+    kernel (DSMEM exchange of h) must reproduce the single-CTA kernel bit for bit: a race detector for the
+    cross-CTA protocol (tools/soak_bilstm.py runs it longer)."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    for i, (B, T) in enumerate([(768, 26), (129, 65), (1, 3), (640, 26), (257, 10), (300, 26)]):
+        gx = torch.randn(B, T, 2, 1024, device=DEV, generator=g) * (1.0 + (i % 3))
+        w = ops.pack_w_hh_bf16(torch.randn(2, 1024, 256, device=DEV, generator=g) / 16)
+        monkeypatch.setenv("MSTR_BILSTM_CLUSTER", "0")
+        a = ops.bilstm_recurrent_bf16(gx, w)
+        monkeypatch.setenv("MSTR_BILSTM_CLUSTER", "1")
+        b = ops.bilstm_recurrent_bf16(gx, w)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b), "B=%d T=%d" % (B, T)
+
+
 # ------------------------------------------------------------------------------------------------
 # attention decoder
 # ------------------------------------------------------------------------------------------------

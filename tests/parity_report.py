@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # gpu_util
 from multimodal_scene_text_recognition_b200 import config, synth  # noqa: E402
 from oracle import recognition_oracle as orc  # noqa: E402
 from gpu_util import dev, err, host, load_model, nchw  # noqa: E402

@@ -28,7 +28,7 @@ run model_fp32 600 python -m pytest -q -m gpu -p no:cacheprovider tests/test_gpu
 run model_bf16 600 python -m pytest -q -m gpu -p no:cacheprovider -s tests/test_gpu_model.py -k "bf16"
 run smoke      300 python -c "import __graft_entry__ as g; g.smoke()"
 run h2d        120 python tools/diag_h2d.py
-run parity     600 python tools/parity_report.py 64
+run parity     600 python tests/parity_report.py 64
 if [ "${1:-}" = "bench" ]; then
   run bench 900 python bench.py --steps 5 --warmup 3
   grep -h '^{' $OUT | tail -1 > gpurun_out/bench_line.json

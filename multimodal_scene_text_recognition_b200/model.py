@@ -23,62 +23,61 @@ from .modules.semantic_vectors import Linear_Embedding, Bert_Embedding, Zero, Ra
 from .modules.encoders import BidirectionalLSTM, TF_Encoder, Oscar_Bert
 from .modules.decoders import Attention, TF_Decoder, Linear_Decoder
 
+# module-level names the reference exposes (model.py:17-32)
 character = config.CHARS
 converter = AttnLabelConverter(character)
 num_classes = len(converter.character)
-
-# model.py:21-32
-imgH = 32
-imgW = 100
-num_fiducial = 20
-input_channel = 1
-output_channel = 512
+imgH, imgW = 32, 100          # crop geometry
+num_fiducial = 20             # TPS control points
+input_channel, output_channel = 1, 512
 hidden_size = 256
 
 
+def _pick(kind: str, key, table):
+    """Constructor for the configured variant ``key`` of a model part, or the reference's error."""
+    try:
+        return table[key]
+    except KeyError:
+        raise Exception("Model.py %s Error: '%s' not recognized" % (kind, key)) from None
+
+
+def _semantic_vector_module():
+    """config.SEMANTIC_SOURCE wins over config.SEMANTIC_EMBEDDING, like the if-chain of model.py:50-59."""
+    by_source = {'zero': Zero, 'rand': Random}
+    by_embedding = {'bert': Bert_Embedding, 'linear': Linear_Embedding}
+    cls = by_source.get(config.SEMANTIC_SOURCE) or by_embedding.get(config.SEMANTIC_EMBEDDING)
+    if cls is None:
+        raise Exception("Model.py Semantic vector error: check config.SEMANTIC_SOURCE and config.SEMANTIC_EMBEDDING")
+    return cls()
+
+
 class Model(nn.Module):
+    """Sub-modules are created in the reference's order (rectifier, feature extractor, pooling, semantic vectors,
+    encoder, decoder): the parameter initialisers then consume the RNG identically, so ``torch.manual_seed(s);
+    Model()`` yields the reference's weights (tests/test_cabi_and_host.py)."""
 
     def __init__(self, imgH=imgH, imgW=imgW, input_channel=input_channel):
         """The reference hard-codes 1x32x100 (model.py:21-32); the keyword arguments exist for the
         3x64x256 stress configuration and default to the reference's values."""
-        super(Model, self).__init__()
-        self.Transformation = TPS_SpatialTransformerNetwork(
-            F=num_fiducial, I_size=(imgH, imgW), I_r_size=(imgH, imgW), I_channel_num=input_channel)
-
+        super().__init__()
+        size = (imgH, imgW)
+        self.Transformation = TPS_SpatialTransformerNetwork(F=num_fiducial, I_size=size, I_r_size=size,
+                                                            I_channel_num=input_channel)
         self.FeatureExtraction = ResNet_FeatureExtractor(input_channel, output_channel)
         self.FeatureExtraction_output = output_channel
-        self.AdaptiveAvgPool = nn.AdaptiveAvgPool2d((None, 1))   # kept for attribute parity; see forward
-
-        if config.SEMANTIC_SOURCE == 'zero':
-            self.get_semantic_vectors = Zero()
-        elif config.SEMANTIC_SOURCE == 'rand':
-            self.get_semantic_vectors = Random()
-        elif config.SEMANTIC_EMBEDDING == 'bert':
-            self.get_semantic_vectors = Bert_Embedding()
-        elif config.SEMANTIC_EMBEDDING == 'linear':
-            self.get_semantic_vectors = Linear_Embedding()
-        else:
-            raise Exception("Model.py Semantic vector error: check config.SEMANTIC_SOURCE and config.SEMANTIC_EMBEDDING")
-
-        if config.ENCODER == 'LSTM':
-            self.encoder = nn.Sequential(
-                BidirectionalLSTM(self.FeatureExtraction_output, hidden_size, hidden_size),
-                BidirectionalLSTM(hidden_size, hidden_size, hidden_size))
-        elif config.ENCODER == 'Transformer':
-            self.encoder = TF_Encoder()
-        elif config.ENCODER == 'Oscar':
-            self.encoder = Oscar_Bert()
-        else:
-            raise Exception("Model.py Encoder Error: '" + config.ENCODER + "' not recognized")
-
-        if config.DECODER == "LSTM":
-            self.decoder = Attention(256, 256, num_classes)
-        elif config.DECODER == "Transformer":
-            self.decoder = TF_Decoder(num_classes)
-        elif config.DECODER == "Linear":
-            self.decoder = Linear_Decoder(num_classes)
-        else:
-            raise Exception("Model.py Decoder Error: '" + config.DECODER + "' not recognized")
+        self.AdaptiveAvgPool = nn.AdaptiveAvgPool2d((None, 1))   # attribute parity only: _run averages over H itself
+        self.get_semantic_vectors = _semantic_vector_module()
+        self.encoder = _pick("Encoder", config.ENCODER, {
+            'LSTM': lambda: nn.Sequential(BidirectionalLSTM(output_channel, hidden_size, hidden_size),
+                                          BidirectionalLSTM(hidden_size, hidden_size, hidden_size)),
+            'Transformer': TF_Encoder,
+            'Oscar': Oscar_Bert,
+        })()
+        self.decoder = _pick("Decoder", config.DECODER, {
+            'LSTM': lambda: Attention(hidden_size, hidden_size, num_classes),
+            'Transformer': lambda: TF_Decoder(num_classes),
+            'Linear': lambda: Linear_Decoder(num_classes),
+        })()
 
     # ---------------------------------------------------------------------------------------
     def _run(self, input, text, overlap, scene, ious, is_train, stages=None):
@@ -131,23 +130,19 @@ class Model(nn.Module):
 
 
 def get_model(saved_model=None):
-    '''
-    input: saved_model = the path to pretrained weights to load model from, if None then wont load any weights
-    return: model  (nn.DataParallel-wrapped on config.PRIMARY_DEVICE, like model.py:109-128)
-    '''
-    model = Model()
-    model = torch.nn.DataParallel(model, device_ids=config.DEVICE_IDS)
-    model = model.to(config.PRIMARY_DEVICE)
-    model.eval()   # the kernels implement eval-mode BatchNorm only
-
-    if saved_model:
-        print('  - Loading model from:', saved_model)
-        pretrained_dict = torch.load(saved_model, map_location=lambda storage, loc: storage)
-        pretrained_dict.pop('module.get_semantic_vectors.embed.weight', None)   # model.py:121
-        model.load_state_dict(pretrained_dict, strict=False)
-    else:
+    """``saved_model``: optional path of a checkpoint.  Returns the model wrapped in ``nn.DataParallel`` over
+    ``config.DEVICE_IDS`` on ``config.PRIMARY_DEVICE`` like the reference's get_model (model.py:109-128); the wrapper
+    is what gives every state-dict key its ``module.`` prefix.  The model is put in eval mode: the kernels implement
+    eval-mode BatchNorm only."""
+    model = torch.nn.DataParallel(Model(), device_ids=config.DEVICE_IDS).to(config.PRIMARY_DEVICE).eval()
+    if not saved_model:
         print('  - Training from scratch (no pretrained weights provided)')
-
+        return model
+    print('  - Loading model from:', saved_model)
+    state = torch.load(saved_model, map_location='cpu')
+    # the reference drops the embedding table of a checkpoint before loading (model.py:121): it is re-initialised
+    state.pop('module.get_semantic_vectors.embed.weight', None)
+    model.load_state_dict(state, strict=False)
     return model
 
 

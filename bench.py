@@ -2,23 +2,32 @@
 """Benchmark of the batched word-crop recognition forward pass (BASELINE.json's metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 4096]
+                    [--scaling strong|weak] [--no-extras]
 
-A "step" is one pass of the whole hot path - TPS rectification, ResNet, 2x BiLSTM, attention
-greedy decode (all MAX_TEXT_LENGTH+1 steps, no early exit, every logit the reference computes) and
-the semantic-vector embedding - over one batch of synthetic 1x32x100 crops with seeded random-init
-weights.  One process per GPU; each rank owns ``--batch`` crops (weak scaling) and, when N > 1, the
-only collective is one NCCL allgather of the decoded ids.
+A "step" is one pass of the whole hot path - TPS rectification, ResNet, 2x BiLSTM, attention greedy decode (all
+MAX_TEXT_LENGTH+1 steps, no early exit, every logit the reference computes) and the semantic-vector embedding - over
+ONE GLOBAL BATCH of ``--batch`` (4096) synthetic 1x32x100 crops with seeded random-init weights: BASELINE.json
+configs[2].  One process per GPU; with N > 1 the global batch is sharded ``--batch / N`` crops per rank (the
+replacement of the reference's ``nn.DataParallel`` split of one batch, model.py:115; "strong" scaling) and the only
+collective is one NCCL allgather of the decoded ids.  ``--scaling weak`` gives every rank ``--batch`` crops instead;
+the default run reports that number too, as ``weak_scaling``.
 
 One JSON line on stdout (rank 0):
   value         crops/s, inputs resident in HBM, timed on the device with CUDA events, max over ranks
-  e2e           same metric through Model.recognize with HOST buffers: every step copies its crops and
-                semantic ids from pinned host memory (pipeline.HostBatchPrefetcher: on a copy stream, one step
-                ahead) and reads the decoded ids / lengths back; all copies inside the timed region
-  roofline      dominant kernel (tcgen05 implicit-GEMM convolutions): algorithmic FLOPs / per-launch
-                CUDA-event time, against the measured cuBLAS bf16 peak of MEASURED_PEAKS.json
-  cpu_baseline  the CPU port of the reference forward (oracle/torch_port.py: ATen CPU kernels, all
-                host threads) on a bounded sample of the same workload (rank 0, N=1)
-``--impl reference`` times only that CPU port and prints the same line shape with impl=reference.
+  e2e           same metric through Model.recognize with HOST buffers: every step copies its crops and semantic ids from
+                pinned host memory (pipeline.HostBatchPrefetcher: on a copy stream, one step ahead) and reads the
+                decoded ids / lengths back; all copies inside the timed region
+  roofline      dominant kernel (tcgen05 implicit-GEMM convolutions): algorithmic FLOPs / per-launch CUDA-event time,
+                against the measured cuBLAS bf16 peak of MEASURED_PEAKS.json
+  ranks         per-rank device time of the timed steps (min / max over ranks) and the allgather's own CUDA-event time
+  other_configs the other BASELINE.json configurations under the same clock sampler (N = 1): batch 256 in bf16 and
+                3xTF32, scene-mode semantic vectors, the 3x64x256 / 51-step stress geometry
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref: its own Model.forward, fp32, all host threads; kind
+                "reference") on a bounded sample of the same workload - or the CPU port (oracle/torch_port.py, kind
+                "port") where baseline/_ref is absent
+  gpu_eager_baseline   the unmodified reference run eagerly on this same GPU with cuDNN disabled as it sets it
+                (model.py:6): the like-for-like speed-up denominator
+``--impl reference`` times only the reference's CPU forward and prints the same line shape with impl=reference.
 """
 from __future__ import annotations
 
@@ -40,7 +49,10 @@ import torch
 METRIC = "crops/sec TPS-ResNet-BiLSTM-Attn 32x100 bs4096"
 UNIT = "crops/s"
 WEIGHT_SEED, DATA_SEED = 999, 123
-CONV_FLOP_PER_CROP = 10.443e9   # all convolutions, SURVEY.md 8d (ResNet 10.090 + LocNet 0.353)
+CONV_FLOP_PER_CROP = 10.443e9     # all convolutions, SURVEY.md 8d (ResNet 10.090 + LocNet 0.353), cfg-A
+CONV_FLOP_PER_CROP_S = 52.676e9   # cfg-S 3x64x256 (ResNet 50.807 + LocNet 1.869)
+WORKLOAD = ("TPS-ResNet-BiLSTM-Attn greedy forward (BASELINE.json configs[2]): 1x32x100 crops, 26 decode steps without "
+            "early exit, 97 classes, overlap semantic vectors, seeded random-init weights")
 
 
 def _peaks():
@@ -100,71 +112,107 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU port of the reference (cpu_baseline and --impl reference)
+# the reference on the host cores (cpu_baseline and --impl reference) and on the GPU (gpu_eager_baseline)
 # --------------------------------------------------------------------------------------------
-def cpu_port_setup():
-    from multimodal_scene_text_recognition_b200 import synth
-    from oracle import torch_port as tp
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = tp.to_torch(synth.make_state_dict(WEIGHT_SEED))
-    return tp, sd, synth, cores
+class CpuReference:
+    """The unmodified reference from baseline/_ref (kind "reference"); the CPU port of oracle/ (kind "port") only
+    where that copy is absent."""
 
+    def __init__(self):
+        from multimodal_scene_text_recognition_b200 import synth
+        self.synth = synth
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        sd = synth.make_state_dict(WEIGHT_SEED)
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import ref_runner
+        if ref_runner.available():
+            self.kind = "reference"
+            self.ref = ref_runner.ReferenceModel(sd, device="cpu")
+            self.what = "unmodified reference Model.forward (baseline/_ref), torch %s CPU, fp32" % torch.__version__
+        else:
+            from oracle import torch_port as tp
+            self.kind = "port"
+            self.tp, self.sd = tp, tp.to_torch(sd)
+            self.what = "CPU port of the reference forward (oracle/torch_port.py; baseline/_ref absent), torch %s, fp32" % torch.__version__
 
-def cpu_port_step(tp, sd, crops, sem):
-    t0 = time.perf_counter()
-    tp.forward(sd, crops, *sem)
-    return time.perf_counter() - t0
+    def inputs(self, n):
+        x = torch.from_numpy(self.synth.make_crops(DATA_SEED, n))
+        sem = [torch.from_numpy(a) for a in self.synth.make_semantics(DATA_SEED + 1, n)]
+        return x, sem
 
+    def step(self, x, sem):
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            self.ref.forward(x, *sem)
+        else:
+            self.tp.forward(self.sd, x, *sem)
+        return time.perf_counter() - t0
 
-def cpu_sample_inputs(synth, n):
-    x = torch.from_numpy(synth.make_crops(DATA_SEED, n))
-    sem = [torch.from_numpy(a) for a in synth.make_semantics(DATA_SEED + 1, n)]
-    return x, sem
+    def sample_size(self, budget_s, cap):
+        x, sem = self.inputs(32)
+        self.step(x, sem)                       # warm-up (thread pool, oneDNN primitives)
+        t = self.step(x, sem)
+        n = int(min(cap, max(32, budget_s * 32 / t)))
+        return n - n % 32
 
 
 def cpu_baseline(budget_s: float = 15.0):
-    """Port timed on the host cores on a bounded sample (~budget_s of CPU work)."""
-    tp, sd, synth, cores = cpu_port_setup()
-    x, sem = cpu_sample_inputs(synth, 32)
-    cpu_port_step(tp, sd, x, sem)                      # warm-up (thread pool, oneDNN primitives)
-    t = cpu_port_step(tp, sd, x, sem)
-    n = int(min(1024, max(32, (budget_s * 0.6) * 32 / t)))
-    n -= n % 32
-    x, sem = cpu_sample_inputs(synth, n)
-    best = min(cpu_port_step(tp, sd, x, sem) for _ in range(2))
-    return {"value": round(n / best, 2), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of the 4096 crops of one step, best of 2 passes, torch %s CPU (oracle/torch_port.py), "
-                      "fp32, all 26 decode steps" % (n, torch.__version__)}
+    """Reference timed on the host cores on a bounded sample (~budget_s of CPU work)."""
+    cpu = CpuReference()
+    n = cpu.sample_size(budget_s * 0.6, 1024)
+    x, sem = cpu.inputs(n)
+    best = min(cpu.step(x, sem) for _ in range(2))
+    return {"value": round(n / best, 2), "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
+            "sample": "%d of the 4096 crops of one step, best of 2 passes, all 26 decode steps; %s" % (n, cpu.what)}
+
+
+def gpu_eager_baseline(dev, batch=512, reps=3):
+    """The unmodified reference executed eagerly by PyTorch on this GPU (fp32, cuDNN disabled as model.py:6 sets
+    it, torch.no_grad / eval), on a bounded sample of the step's crops."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_runner
+    if not ref_runner.available():
+        return {"unavailable": "baseline/_ref is not installed"}
+    from multimodal_scene_text_recognition_b200 import synth
+    try:
+        ref = ref_runner.ReferenceModel(synth.make_state_dict(WEIGHT_SEED), device=str(dev))
+        x = torch.from_numpy(synth.make_crops(DATA_SEED, batch)).to(dev)
+        sem = [torch.from_numpy(a).to(dev) for a in synth.make_semantics(DATA_SEED + 1, batch)]
+        ref_runner.time_forward(ref, x, *sem)                       # warm-up
+        t = ref_runner.time_forward(ref, x, *sem, reps=reps)
+        ref.to("cpu")
+        del ref
+        torch.cuda.empty_cache()
+        return {"value": round(batch / t, 1), "unit": UNIT, "ms_per_batch": round(1e3 * t, 2), "batch": batch,
+                "what": "unmodified reference Model.forward (baseline/_ref) eager on this GPU, fp32, cuDNN disabled "
+                        "(model.py:6), best of %d, torch %s" % (reps, torch.__version__),
+                "cudnn_enabled": bool(torch.backends.cudnn.enabled)}
+    except Exception as exc:   # a baseline must never take the bench line down
+        return {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    tp, sd, synth, cores = cpu_port_setup()
-    x, sem = cpu_sample_inputs(synth, 32)
-    cpu_port_step(tp, sd, x, sem)
-    t = cpu_port_step(tp, sd, x, sem)
+    cpu = CpuReference()
     total_steps = args.steps + args.warmup
     per_step_budget = max(0.5, 120.0 / total_steps)     # whole run ~2 minutes
-    n = int(min(4096, max(32, per_step_budget * 32 / t)))
-    n -= n % 32
-    x, sem = cpu_sample_inputs(synth, n)
+    n = cpu.sample_size(per_step_budget, args.batch)
+    x, sem = cpu.inputs(n)
     for _ in range(args.warmup):
-        cpu_port_step(tp, sd, x, sem)
-    times = [cpu_port_step(tp, sd, x, sem) for _ in range(args.steps)]
+        cpu.step(x, sem)
+    times = [cpu.step(x, sem) for _ in range(args.steps)]
     total = sum(times)
     value = n * args.steps / total
-    sample = "%d-crop sample of the 4096-crop step per timed step, torch %s CPU port of the reference forward" % (
-        n, torch.__version__)
+    sample = "%d-crop sample of the %d-crop step per timed step; %s" % (n, args.batch, cpu.what)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "TPS-ResNet-BiLSTM-Attn greedy forward, 1x32x100 crops, 26 decode steps, "
-                               "seeded random-init weights", "batch_per_gpu": args.batch, "sample_crops_per_step": n},
-        "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": args.batch, "sample_crops_per_step": n},
+        "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,14 +222,51 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+def build_model(geom, precision, dev, semantic="overlap"):
+    from multimodal_scene_text_recognition_b200 import config, model as M, synth
+    config.PRECISION = precision
+    config.MAX_TEXT_LENGTH = geom.max_len
+    config.DECODER_EARLY_EXIT = False      # every step and logit the reference computes
+    config.TPS_GRID = "reference"
+    config.SEMANTIC_VECTOR = semantic
+    sd = synth.make_state_dict(WEIGHT_SEED, geom)
+    return M.load_numpy_state_dict(M.Model(imgH=geom.H, imgW=geom.W, input_channel=geom.in_ch).eval(), sd).to(dev)
+
+
+def other_config(geom, B, precision, dev, peaks, semantic="overlap", reps=5):
+    """Device-timed crops/s of another BASELINE.json configuration (inputs resident, CUDA events, median of reps)."""
+    from multimodal_scene_text_recognition_b200 import config, synth
+    model = build_model(geom, precision, dev, semantic)
+    x = torch.from_numpy(synth.make_crops(DATA_SEED, B, geom)).to(dev)
+    sem = [torch.from_numpy(a).to(dev) for a in synth.make_semantics(DATA_SEED + 1, B)]
+    ts = []
+    with torch.no_grad():
+        for _ in range(3):
+            model.recognize(x, *sem)
+        torch.cuda.synchronize()
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); model.recognize(x, *sem); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+    ms = float(np.median(ts))
+    flop = CONV_FLOP_PER_CROP_S if geom.H == 64 else CONV_FLOP_PER_CROP
+    peak = peaks["bf16_sustained"] * {"bf16": 1.0, "tf32": 1.0 / 6.0}.get(precision, 1.0)   # 3xTF32: half rate, 3 products
+    config.MAX_TEXT_LENGTH = 25
+    config.SEMANTIC_VECTOR = "overlap"
+    return {"geometry": "%dx%dx%d, %d decode steps" % (geom.in_ch, geom.H, geom.W, geom.steps), "batch": B,
+            "precision": precision, "semantic_vectors": semantic, "ms": round(ms, 3),
+            "crops_per_s": round(B / ms * 1e3, 1),
+            "whole_step_frac": round(B / (ms * 1e-3) * flop / 1e12 / peak, 4)}
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from multimodal_scene_text_recognition_b200 import _cabi, config, model as M, ops, parallel, synth
+    from multimodal_scene_text_recognition_b200 import _cabi, config, ops, parallel, synth
     from multimodal_scene_text_recognition_b200.pipeline import HostBatchPrefetcher
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the recognition path has no CPU implementation "
-                         "(use --impl reference for the CPU port)")
+                         "(use --impl reference for the reference's CPU forward)")
     _cabi.lib()   # fail loudly if the extension is missing
     rank, local_rank, world = parallel.init_from_env()
     if world != args.gpus:
@@ -192,115 +277,149 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     peaks = _peaks()
-
-    config.PRECISION = args.precision
-    config.DECODER_EARLY_EXIT = False      # every step and logit the reference computes
-    config.TPS_GRID = "reference"
-    config.SEMANTIC_VECTOR = "overlap"
-    B = args.batch
-    sd = synth.make_state_dict(WEIGHT_SEED)
-    model = M.load_numpy_state_dict(M.Model().eval(), sd).to(dev)
-
-    # per-rank shard of the global batch (weak scaling): seeded by rank, two alternating host batches
-    host_sets = []
-    for k in range(2):
-        x = torch.from_numpy(synth.make_crops(DATA_SEED + 17 * rank + 1000 * k, B)).pin_memory()
-        sem = [torch.from_numpy(a).pin_memory() for a in synth.make_semantics(DATA_SEED + 1 + 17 * rank + 1000 * k, B)]
-        host_sets.append((x, sem))
-    dev_sets = [(x.to(dev), [s.to(dev) for s in sem]) for x, sem in host_sets]
+    model = build_model(synth.CFG_A, args.precision, dev)
     steps_out = config.MAX_TEXT_LENGTH + 1
-    ids_host = torch.empty((B * world, steps_out), dtype=torch.int32).pin_memory()
-    len_host = torch.empty((B * world,), dtype=torch.int32).pin_memory()
 
-    def step_device(k):
-        x, sem = dev_sets[k % 2]
-        with torch.no_grad():
-            out = model.recognize(x, *sem)
-        if world > 1:
-            return parallel.allgather_ids(out["ids"], out["lengths"], B * world)
-        return out["ids"], out["lengths"]
+    def make_workload(global_batch, sharded):
+        """This rank's crops: two alternating host sets (pinned) and their device copies.  ``sharded``: every rank
+        regenerates the GLOBAL batch from the seed and slices its shard, so results do not depend on N; otherwise
+        (weak scaling) every rank draws its own global_batch / world crops from a rank-dependent seed."""
+        lo, hi = parallel.shard_bounds(global_batch, rank, world)
+        host_sets = []
+        for k in range(2):
+            if sharded:
+                xs = synth.make_crops(DATA_SEED + 1000 * k, global_batch)[lo:hi]
+                sems = [a[lo:hi] for a in synth.make_semantics(DATA_SEED + 1 + 1000 * k, global_batch)]
+            else:
+                xs = synth.make_crops(DATA_SEED + 17 * rank + 1000 * k, hi - lo)
+                sems = synth.make_semantics(DATA_SEED + 1 + 17 * rank + 1000 * k, hi - lo)
+            x = torch.from_numpy(np.ascontiguousarray(xs)).pin_memory()
+            sem = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in sems]
+            host_sets.append((x, sem))
+        dev_sets = [(x.to(dev), [s.to(dev) for s in sem]) for x, sem in host_sets]
+        return {"global": global_batch, "local": hi - lo, "host": host_sets, "dev": dev_sets,
+                "ids_host": torch.empty((global_batch, steps_out), dtype=torch.int32).pin_memory(),
+                "len_host": torch.empty((global_batch,), dtype=torch.int32).pin_memory()}
 
-    prefetcher = HostBatchPrefetcher(dev, depth=2)
-    staged = {}
+    gather_events = []
 
-    def stage(k):
-        hx, hsem = host_sets[k % 2]
-        staged[k] = prefetcher.stage([hx] + hsem)
+    def gather(ids, lengths, global_batch):
+        if world == 1:
+            return ids, lengths
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = parallel.allgather_ids(ids, lengths, global_batch)
+        e.record()
+        gather_events.append((s, e))
+        return out
 
-    def step_e2e(k):
-        # every step copies its crops + semantic ids from pinned host memory (on the copy stream, enqueued
-        # one step ahead so that it overlaps the previous step's compute) and reads the decoded ids back
-        if k not in staged:
-            stage(k)
-        t0 = time.perf_counter()
-        tensors, ready, sid = staged.pop(k)
-        torch.cuda.current_stream().wait_event(ready)
-        with torch.no_grad():
-            out = model.recognize(tensors[0], *tensors[1:])
-        prefetcher.release(sid)
-        t1 = time.perf_counter()
-        stage(k + 1)                                    # H2D of the next step's inputs, overlapped
-        t2 = time.perf_counter()
-        ids, lengths = out["ids"], out["lengths"]
-        if world > 1:
-            ids, lengths = parallel.allgather_ids(ids, lengths, B * world)
-        ids_host.copy_(ids, non_blocking=True)
-        len_host.copy_(lengths, non_blocking=True)
-        t3 = time.perf_counter()
-        torch.cuda.current_stream().synchronize()      # the caller needs the decoded ids of this step
-        if os.environ.get("MSTR_BENCH_TRACE"):
-            print("rank %d e2e step %d: launch %.1f stage %.1f gather+d2h %.1f sync %.1f ms" % (
-                rank, k, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (time.perf_counter() - t3)),
-                file=sys.stderr)
+    def make_steps(wl):
+        def step_device(k):
+            x, sem = wl["dev"][k % 2]
+            with torch.no_grad():
+                out = model.recognize(x, *sem)
+            return gather(out["ids"], out["lengths"], wl["global"])
+
+        prefetcher = HostBatchPrefetcher(dev, depth=2)
+        staged = {}
+
+        def stage(k):
+            hx, hsem = wl["host"][k % 2]
+            staged[k] = prefetcher.stage([hx] + hsem)
+
+        def step_e2e(k):
+            # every step copies its crops + semantic ids from pinned host memory (on the copy stream, enqueued one
+            # step ahead so that it overlaps the previous step's compute) and reads the decoded ids back
+            if k not in staged:
+                stage(k)
+            tensors, ready, sid = staged.pop(k)
+            torch.cuda.current_stream().wait_event(ready)
+            with torch.no_grad():
+                out = model.recognize(tensors[0], *tensors[1:])
+            prefetcher.release(sid)
+            stage(k + 1)                                    # H2D of the next step's inputs, overlapped
+            ids, lengths = gather(out["ids"], out["lengths"], wl["global"])
+            wl["ids_host"].copy_(ids, non_blocking=True)
+            wl["len_host"].copy_(lengths, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the caller needs the decoded ids of this step
+        return step_device, step_e2e, staged
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, trace=None):
+    def timed(fn, steps):
+        """-> (max over ranks of the device time of ``steps`` steps, [per-rank device times])."""
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for k in range(steps):
-            t0 = time.perf_counter()
             fn(k)
-            if trace is not None:
-                trace.append(round(1e3 * (time.perf_counter() - t0), 2))
         e.record()
         barrier()
-        ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+        mine = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            per_rank = [float(t.item()) for t in every]
+        else:
+            per_rank = [float(mine.item())]
+        return max(per_rank), per_rank
 
-    for k in range(max(args.warmup, 3)):
-        step_device(k)
-    torch.cuda.synchronize()
+    def measure(global_batch, with_timer, sharded):
+        wl = make_workload(global_batch, sharded)
+        step_device, step_e2e, staged = make_steps(wl)
+        for k in range(max(args.warmup, 3)):
+            step_device(k)
+        torch.cuda.synchronize()
+        gather_events.clear()
+        launches0 = _cabi.launch_count()
+        ops.TIMER = ops.KernelTimer() if (with_timer and rank == 0) else None
+        total_ms, per_rank = timed(step_device, args.steps)
+        timer, ops.TIMER = ops.TIMER, None
+        launches = _cabi.launch_count() - launches0
+        gather_ms = sum(s.elapsed_time(e) for s, e in gather_events) / max(args.steps, 1)
+        for k in range(2):                     # the host-buffer path has its own allocation pattern: warm it up too
+            step_e2e(k)
+        torch.cuda.synchronize()
+        staged.clear()                         # the timed region starts with nothing staged: step 0 pays its copy in full
+        e2e_ms, _ = timed(step_e2e, args.steps)
+        h2d = sum(t.numel() * t.element_size() for t in [wl["host"][0][0]] + wl["host"][0][1]) * world
+        d2h = (wl["ids_host"].numel() + wl["len_host"].numel()) * 4 * world
+        return {"global": global_batch, "local": wl["local"], "total_ms": total_ms, "per_rank_ms": per_rank,
+                "gather_ms_per_step": gather_ms, "e2e_ms": e2e_ms, "launches": launches, "timer": timer,
+                "h2d": h2d, "d2h": d2h}
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = _cabi.launch_count()
-    ops.TIMER = ops.KernelTimer() if rank == 0 else None
-    total_ms = timed(step_device, args.steps)
-    timer, ops.TIMER = ops.TIMER, None
-    launches = _cabi.launch_count() - launches0
-    for k in range(2):                     # the host-buffer path has its own allocation pattern: warm it up too
-        step_e2e(k)
-    torch.cuda.synchronize()
-    staged.clear()                         # the timed region starts with nothing staged: step 0 pays its copy in full
-    e2e_trace = []
-    e2e_ms = timed(step_e2e, args.steps, e2e_trace)
-    if rank == 0:
-        print("e2e per-step host wall ms: %s" % e2e_trace, file=sys.stderr)
+    strong = args.scaling == "strong"
+    main = measure(args.batch if strong else args.batch * world, with_timer=True, sharded=strong)
+    other = None
+    if world > 1 and not args.no_extras:
+        # the other scaling mode as an extra key (same code path, other shard size)
+        other = measure(args.batch * world if strong else args.batch, with_timer=False, sharded=not strong)
+    extras = {}
+    if world == 1 and rank == 0 and not args.no_extras and args.precision == "bf16":
+        extras["other_configs"] = [
+            other_config(synth.CFG_A, 256, "bf16", dev, peaks),
+            other_config(synth.CFG_A, 256, "tf32", dev, peaks, reps=3),
+            other_config(synth.CFG_A, 4096, "bf16", dev, peaks, semantic="scene", reps=3),
+            other_config(synth.CFG_S, 1024, "bf16", dev, peaks, reps=3),
+        ]
     clocks = sampler.stop() if sampler else None
+    if world == 1 and rank == 0 and not args.no_extras:
+        extras["gpu_eager_baseline"] = gpu_eager_baseline(dev)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    value = B * world * args.steps / (total_ms * 1e-3)
-    e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
+    def rate(m, key):
+        return m["global"] * args.steps / (m[key] * 1e-3)
+
+    value, e2e_value = rate(main, "total_ms"), rate(main, "e2e_ms")
+    timer = main["timer"]
     kern = timer.summary()
     conv = kern.get({"bf16": "conv_gemm_bf16_2cta", "tf32": "conv_gemm_tf32x3"}.get(args.precision, "conv_gemm_f32"),
                     {"launches": 0, "ms": 0.0, "work": 0.0})
@@ -315,23 +434,28 @@ def run_ours(args):
     if args.kernel_table:
         with open(args.kernel_table, "w") as f:
             json.dump(timer.table(args.steps), f, indent=1)
-    h2d = sum(t.numel() * t.element_size() for t in [host_sets[0][0]] + host_sets[0][1])
-    d2h = ids_host.numel() * 4 + len_host.numel() * 4
+    gemm_ms = sum(v["ms"] for k, v in kern.items() if k.startswith("conv_gemm_bf16"))
+    gemm_work = sum(v["work"] for k, v in kern.items() if k.startswith("conv_gemm_bf16"))
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(main["total_ms"] / args.steps, 3), "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None,
         "dtype": {"bf16": "bf16", "tf32": "tf32x3"}.get(args.precision, "f32"), "data": "synthetic",
         "config": {
-            "workload": "TPS-ResNet-BiLSTM-Attn greedy forward (BASELINE.json configs[2]): 1x32x100 crops, "
-                        "26 decode steps without early exit, 97 classes, overlap semantic vectors, seeded random-init weights",
-            "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision,
-            "parallelism": "batch-sharded, 1 process/GPU, allgather(ids) only" if world > 1 else "single GPU",
-            "l2": "two alternating input batches; per-step activation traffic (>1 GB) exceeds the 126 MB L2",
+            "workload": WORKLOAD, "global_batch": main["global"], "batch_per_gpu": main["local"],
+            "precision": args.precision,
+            "parallelism": ("one global batch sharded %d crops per rank, 1 process/GPU, allgather(ids) only" % main["local"]
+                            if strong else "%d crops per rank, 1 process/GPU, allgather(ids) only" % main["local"])
+            if world > 1 else "single GPU",
+            "l2": "two alternating input batches; per-step activation traffic exceeds the 126 MB L2 (%.1f GB at %d crops "
+                  "per GPU)" % (main["local"] * 0.29e-3, main["local"]),
         },
-        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(e2e_ms / args.steps, 3)},
-        "gpu_launches": int(launches),
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": main["h2d"],
+                "d2h_bytes_per_step": main["d2h"], "ms_per_step": round(main["e2e_ms"] / args.steps, 3)},
+        "gpu_launches": int(main["launches"]),
+        "ranks": {"ms_per_step_min": round(min(main["per_rank_ms"]) / args.steps, 3),
+                  "ms_per_step_max": round(max(main["per_rank_ms"]) / args.steps, 3),
+                  "allgather_ms_per_step_rank0": round(main["gather_ms_per_step"], 4)},
         "roofline": {
             "bound": "tensor", "kernel": "conv_gemm_bf16_2cta_kernel<256> (tcgen05 cta_group::2 implicit GEMM; %d launches per step, "
                       "%.2f TFLOP and %.3f ms per launch on average)" % (
@@ -341,12 +465,19 @@ def run_ours(args):
             "frac": round(conv_tflops / peak, 4) if peak else None, "traffic": traffic,
             "peak_source": peaks["source"] + ", sustained cuBLAS bf16",
             "whole_step_frac": round(value / world * CONV_FLOP_PER_CROP / 1e12 / peak, 4),
-            "all_conv_gemm_tflops": round(sum(v["work"] for k, v in kern.items() if k.startswith("conv_gemm_bf16")) /
-                                          max(sum(v["ms"] for k, v in kern.items() if k.startswith("conv_gemm_bf16")), 1e-9) / 1e9, 1),
+            "all_conv_gemm_tflops": round(gemm_work / max(gemm_ms, 1e-9) / 1e9, 1),
         },
         "stage_ms_per_step": stage_ms,
         "clocks": clocks,
     }
+    if other is not None:
+        key = "weak_scaling" if strong else "strong_scaling"
+        line[key] = {"value": round(rate(other, "total_ms"), 1), "unit": UNIT, "global_batch": other["global"],
+                     "batch_per_gpu": other["local"], "ms_per_step": round(other["total_ms"] / args.steps, 3),
+                     "e2e_value": round(rate(other, "e2e_ms"), 1),
+                     "ms_per_step_min_rank": round(min(other["per_rank_ms"]) / args.steps, 3),
+                     "allgather_ms_per_step_rank0": round(other["gather_ms_per_step"], 4)}
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)
@@ -360,9 +491,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--batch", type=int, default=4096, help="crops per GPU per step")
+    ap.add_argument("--batch", type=int, default=4096, help="crops of the global batch (strong) / per GPU (weak)")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
     ap.add_argument("--precision", choices=["bf16", "tf32", "fp32"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_configs / gpu_eager_baseline / the other scaling mode")
     ap.add_argument("--kernel-table", default=None, help="write the per-call-site kernel table (JSON) to this path")
     args = ap.parse_args()
     if args.impl == "reference":

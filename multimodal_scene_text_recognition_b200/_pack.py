@@ -51,6 +51,7 @@ def bn_sources(bn: torch.nn.BatchNorm2d):
 
 def fold_bn(bn: torch.nn.BatchNorm2d):
     """scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (fp32, eval-mode BN)."""
+    require_eval(bn)
     scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
     shift = bn.bias.float() - bn.running_mean.float() * scale
     return scale.contiguous(), shift.contiguous()
@@ -78,6 +79,16 @@ def require_inference(*tensors) -> None:
         raise RuntimeError(
             "the B200 kernels implement the inference forward only (SURVEY.md 8b): call under "
             "torch.no_grad() / model.eval(); autograd through them is not supported")
+
+
+def require_eval(module: torch.nn.Module) -> None:
+    """BatchNorm is folded from the running statistics (eval mode).  In train mode the reference normalises with batch
+    statistics and updates the running ones (feature_extraction.py:20, transformation.py:50): refuse instead of
+    silently returning eval-mode results."""
+    if module.training:
+        raise RuntimeError(
+            "%s is in train mode: the B200 kernels implement eval-mode BatchNorm only - call model.eval() "
+            "(get_model() does)" % type(module).__name__)
 
 
 def pack_conv_pixel_pairs(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, precision: str):

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from .. import config, ops
 from .._pack import (act_dtype, pack_block_tail, pack_conv, pack_conv_pixel_pairs, pack_first_conv,
-                     require_inference)
+                     require_eval, require_inference)
 
 
 def _conv_bn(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, precision: str, relu: bool, residual=None, **kw):
@@ -92,6 +92,7 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         require_inference(x)
+        require_eval(self)
         precision = config.PRECISION
         return _to_nchw(self.forward_nhwc(_to_nhwc(x, precision), precision))
 
@@ -154,6 +155,7 @@ class ResNet(nn.Module):
         """x [B, C, H, W] f32 (NCHW image) -> NHWC [B, H', W', C_out] in the activation dtype
         (feature_extraction.py:109-150)."""
         require_inference(x)
+        require_eval(self)
         precision = config.PRECISION
         x = x.contiguous()
         if x.shape[1] <= 4:

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .. import config, ops
-from .._pack import cached, fold_bn, pack_conv, pack_first_conv, act_dtype, require_inference
+from .._pack import cached, fold_bn, pack_conv, pack_first_conv, act_dtype, require_eval, require_inference
 from ..synth import rare_fiducial_bias, tps_constants
 
 
@@ -73,6 +73,7 @@ class LocalizationNetwork(nn.Module):
 
     def forward(self, batch_I):
         require_inference(batch_I)
+        require_eval(self)
         precision = config.PRECISION
         batch_I = batch_I.contiguous()
         B = batch_I.size(0)

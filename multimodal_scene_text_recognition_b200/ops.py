@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import MSTR_BF16, MSTR_F32, check, lib, ptr, stream_ptr
+from ._cabi import MSTR_BF16, MSTR_F32, check, lib, ptr
 
 
 class KernelTimer:
@@ -87,6 +87,39 @@ class SplitWeight:
         return SplitWeight(self.full.reshape(*shape), self.hi.reshape(*shape), self.lo.reshape(*shape))
 
 
+class _on:
+    """Device guard of one launch: every tensor handed to the kernel must live on ONE CUDA device; that device is made
+    current for the duration of the call (the C side launches, encodes TMA descriptors and sets function attributes on
+    the current device) and the stream is that device's current stream.  A model on cuda:1 while the process's current
+    device is cuda:0 - the reference's default is DEVICE_IDS = [1] (config.py:4) - therefore runs on cuda:1."""
+
+    def __init__(self, *tensors):
+        dev = None
+        for t in tensors:
+            if t is None or isinstance(t, SplitWeight):
+                continue
+            if not t.is_cuda:
+                raise _cabi.MstrError("this path has no CPU implementation: got a %s tensor" % t.device)
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise _cabi.MstrError("tensors of one launch live on different devices: %s and %s" % (dev, t.device))
+        self.index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self) -> int:
+        cur = torch.cuda.current_device()
+        if cur != self.index:
+            self.prev = cur
+            torch.cuda.set_device(self.index)
+        return torch.cuda.current_stream(self.index).cuda_stream
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return MSTR_F32
@@ -126,9 +159,9 @@ def tps_rectify(img: Optional[torch.Tensor], c_prime: torch.Tensor, basis: torch
         assert img.shape[0] == B and H * W == n, (img.shape, basis.shape)
         out = torch.empty_like(img)
     grid = torch.empty((B, n, 2), device=c_prime.device, dtype=torch.float32) if want_grid else None
-    with _timed("tps_rectify", float(B) * C * n * 8, "byte", "B%d %dx%dx%d image in + out" % (B, C, H, W)):
+    with _timed("tps_rectify", float(B) * C * n * 8, "byte", "B%d %dx%dx%d image in + out" % (B, C, H, W)), _on(img, c_prime, basis, inv_delta_C) as st:
         check(lib().mstr_tps_rectify(ptr(img), ptr(c_prime), ptr(basis), ptr(inv_delta_C), ptr(out), ptr(grid),
-                                     B, C, H, W, F, mode, stream_ptr()), "mstr_tps_rectify")
+                                     B, C, H, W, F, mode, st), "mstr_tps_rectify")
     if img is None:
         return grid
     return (out, grid) if want_grid else out
@@ -145,9 +178,9 @@ def conv3x3_first(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: 
     P, Q = (H // 2, W // 2) if pool else (H, W)
     out = torch.empty((B, P, Q, Cout), device=x.device, dtype=out_dtype)
     with _timed("conv3x3_first", float(out.numel() * out.element_size() + x.numel() * 4), "byte",
-                "B%d %dx%d %d->%d%s: NHWC out + image in" % (B, H, W, Cin, Cout, " +pool" if pool else "")):
+                "B%d %dx%d %d->%d%s: NHWC out + image in" % (B, H, W, Cin, Cout, " +pool" if pool else "")), _on(x, w, scale, shift) as st:
         check(lib().mstr_conv3x3_first(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(out), _dt(out), B, Cin, H, W,
-                                       Cout, int(pool), stream_ptr()), "mstr_conv3x3_first")
+                                       Cout, int(pool), st), "mstr_conv3x3_first")
     return out
 
 
@@ -177,17 +210,17 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
     desc = "M=%d (B%d %dx%d) %d->%d %dx%d%s" % (B * P * Q, B, P, Q, Cin, Cout, R, S, " +res" if residual is not None else "")
     if x.dtype == torch.float32 and split is not None and Cin % 32 == 0 and Cout % 128 == 0:
         out = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32)
-        with _timed("conv_gemm_tf32x3", flops, "flop", desc):
+        with _timed("conv_gemm_tf32x3", flops, "flop", desc), _on(x, split.hi, split.lo, scale, shift, residual) as st:
             check(lib().mstr_conv_gemm_tf32(ptr(x), ptr(split.hi), ptr(split.lo), ptr(scale), ptr(shift), ptr(residual),
                                             ptr(out), B, H, W, Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1],
-                                            int(relu), stream_ptr()), "mstr_conv_gemm_tf32")
+                                            int(relu), st), "mstr_conv_gemm_tf32")
         return out
     if x.dtype == torch.float32:
         out = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32)
-        with _timed("conv_gemm_f32", flops, "flop", desc):
+        with _timed("conv_gemm_f32", flops, "flop", desc), _on(x, w, scale, shift, residual) as st:
             check(lib().mstr_conv_gemm_f32(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out), B, H, W,
                                            Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
-                                           stream_ptr()), "mstr_conv_gemm_f32")
+                                           st), "mstr_conv_gemm_f32")
         return out
     if x.dtype != torch.bfloat16:
         raise TypeError("conv_gemm: unsupported dtype %s" % x.dtype)
@@ -195,10 +228,10 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
     out_f = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32) if want_f32 else None
     # which kernel mstr_conv_gemm_bf16 dispatches to (conv_tc.cu): the CTA-pair kernel for C_out % 256 == 0
     variant = "conv_gemm_bf16_2cta" if (Cin % 64 == 0 and Cout % 256 == 0) else "conv_gemm_bf16_1cta"
-    with _timed(variant, flops, "flop", desc):
+    with _timed(variant, flops, "flop", desc), _on(x, w, scale, shift, residual) as st:
         check(lib().mstr_conv_gemm_bf16(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out_b), ptr(out_f),
                                         B, H, W, Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
-                                        stream_ptr()), "mstr_conv_gemm_bf16")
+                                        st), "mstr_conv_gemm_bf16")
     if want_f32 and want_bf16:
         return out_b, out_f
     return out_f if want_f32 else out_b
@@ -220,9 +253,9 @@ def conv_gemm_dual(x: torch.Tensor, x2: torch.Tensor, w_cat: torch.Tensor, shift
     flops = 2.0 * B * P * Q * Cout * (R * S * Cin + Cin2)
     variant = "conv_gemm_bf16_2cta" if Cout % 256 == 0 else "conv_gemm_bf16_1cta"
     with _timed(variant, flops, "flop", "M=%d (B%d %dx%d) %d->%d %dx%d + fused 1x1 %d->%d" % (
-            B * P * Q, B, P, Q, Cin, Cout, R, S, Cin2, Cout)):
+            B * P * Q, B, P, Q, Cin, Cout, R, S, Cin2, Cout)), _on(x, x2, w_cat, shift) as st:
         check(lib().mstr_conv_gemm_bf16_dual(ptr(x), ptr(x2), ptr(w_cat), 0, ptr(shift), 0, ptr(out), 0, B, H, W, Cin,
-                                             Cin2, Cout, R, S, 1, 1, pad[0], pad[1], int(relu), stream_ptr()),
+                                             Cin2, Cout, R, S, 1, 1, pad[0], pad[1], int(relu), st),
               "mstr_conv_gemm_bf16_dual")
     return out
 
@@ -251,9 +284,9 @@ def maxpool_nhwc(x: torch.Tensor, kernel=(2, 2), stride=(2, 2), pad=(0, 0)) -> t
     Q = (W + 2 * pad[1] - kernel[1]) // stride[1] + 1
     out = torch.empty((B, P, Q, C), device=x.device, dtype=x.dtype)
     with _timed("maxpool_nhwc", float(x.numel() + out.numel()) * x.element_size(), "byte",
-                "B%d %dx%dx%d -> %dx%d in + out" % (B, H, W, C, P, Q)):
+                "B%d %dx%dx%d -> %dx%d in + out" % (B, H, W, C, P, Q)), _on(x) as st:
         check(lib().mstr_maxpool_nhwc(ptr(x), ptr(out), _dt(x), B, H, W, C, kernel[0], kernel[1], stride[0], stride[1],
-                                      pad[0], pad[1], stream_ptr()), "mstr_maxpool_nhwc")
+                                      pad[0], pad[1], st), "mstr_maxpool_nhwc")
     return out
 
 
@@ -262,7 +295,8 @@ def mean_hw(x: torch.Tensor) -> torch.Tensor:
     _req(x, "x")
     B, H, W, C = x.shape
     out = torch.empty((B, C), device=x.device, dtype=torch.float32)
-    check(lib().mstr_mean_hw(ptr(x), ptr(out), _dt(x), B, H, W, C, stream_ptr()), "mstr_mean_hw")
+    with _on(x) as st:
+        check(lib().mstr_mean_hw(ptr(x), ptr(out), _dt(x), B, H, W, C, st), "mstr_mean_hw")
     return out
 
 
@@ -272,7 +306,8 @@ def mean_h(x: torch.Tensor, want_f32: bool = False):
     B, H, W, C = x.shape
     out = torch.empty((B, W, C), device=x.device, dtype=x.dtype)
     out_f = torch.empty((B, W, C), device=x.device, dtype=torch.float32) if want_f32 else None
-    check(lib().mstr_mean_h(ptr(x), ptr(out), ptr(out_f), _dt(x), B, H, W, C, stream_ptr()), "mstr_mean_h")
+    with _on(x) as st:
+        check(lib().mstr_mean_h(ptr(x), ptr(out), ptr(out_f), _dt(x), B, H, W, C, st), "mstr_mean_h")
     return (out, out_f) if want_f32 else out
 
 
@@ -281,7 +316,8 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     if x.dtype == dtype:
         return x
     out = torch.empty(x.shape, device=x.device, dtype=dtype)
-    check(lib().mstr_cast(ptr(x), ptr(out), _dt(x), _dt(out), x.numel(), stream_ptr()), "mstr_cast")
+    with _on(x) as st:
+        check(lib().mstr_cast(ptr(x), ptr(out), _dt(x), _dt(out), x.numel(), st), "mstr_cast")
     return out
 
 
@@ -290,8 +326,9 @@ def embed_semantics(ids: torch.Tensor, table: torch.Tensor, ious: Optional[torch
     B, n = ids.shape
     rows, D = table.shape
     out = torch.empty((B, n, D), device=ids.device, dtype=torch.float32)
-    check(lib().mstr_embed_semantics(ptr(ids), ptr(table), ptr(ious), ptr(out), B, n, D, rows, mode, stream_ptr()),
-          "mstr_embed_semantics")
+    with _on(ids, table, ious) as st:
+        check(lib().mstr_embed_semantics(ptr(ids), ptr(table), ptr(ious), ptr(out), B, n, D, rows, mode, st),
+              "mstr_embed_semantics")
     return out
 
 
@@ -303,8 +340,8 @@ def bilstm_recurrent(gates_x: torch.Tensor, w_hh: torch.Tensor, want_f32: bool, 
     assert gates_x.shape == (B, T, 2, 4 * Hd) and w_hh.shape == (2, 4 * Hd, Hd)
     out_f = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.float32) if want_f32 else None
     out_b = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.bfloat16) if want_bf16 else None
-    with _timed("bilstm_recurrent", 2.0 * B * T * 2 * 4 * Hd * Hd, "flop", "B%d T%d both directions (fp32 SIMT)" % (B, T)):
-        check(lib().mstr_bilstm_recurrent(ptr(gates_x), ptr(w_hh), ptr(out_f), ptr(out_b), B, T, Hd, stream_ptr()),
+    with _timed("bilstm_recurrent", 2.0 * B * T * 2 * 4 * Hd * Hd, "flop", "B%d T%d both directions (fp32 SIMT)" % (B, T)), _on(gates_x, w_hh) as st:
+        check(lib().mstr_bilstm_recurrent(ptr(gates_x), ptr(w_hh), ptr(out_f), ptr(out_b), B, T, Hd, st),
               "mstr_bilstm_recurrent")
     if want_f32 and want_bf16:
         return out_f, out_b
@@ -327,8 +364,8 @@ def bilstm_recurrent_bf16(gates_x: torch.Tensor, w_hh_packed: torch.Tensor) -> t
     Hd = w_hh_packed.shape[2]
     assert gates_x.shape == (B, T, 2, 4 * Hd) and w_hh_packed.shape == (2, 4 * Hd, Hd)
     out = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.bfloat16)
-    with _timed("bilstm_recurrent_bf16", 2.0 * B * T * 2 * 4 * Hd * Hd, "flop", "B%d T%d both directions (tcgen05)" % (B, T)):
-        check(lib().mstr_bilstm_recurrent_bf16(ptr(gates_x), ptr(w_hh_packed), ptr(out), B, T, Hd, stream_ptr()),
+    with _timed("bilstm_recurrent_bf16", 2.0 * B * T * 2 * 4 * Hd * Hd, "flop", "B%d T%d both directions (tcgen05)" % (B, T)), _on(gates_x, w_hh_packed) as st:
+        check(lib().mstr_bilstm_recurrent_bf16(ptr(gates_x), ptr(w_hh_packed), ptr(out), B, T, Hd, st),
               "mstr_bilstm_recurrent_bf16")
     return out
 
@@ -357,13 +394,13 @@ def attn_decode(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int,
         if text.shape[1] != steps:
             text = text[:, :steps].contiguous()
     macs = Hd * Hd + 2 * T * Hd + 4 * Hd * 2 * Hd + C * Hd      # h2h, score+context, LSTMCell, generator
-    with _timed("attn_decode", 2.0 * B * steps * macs, "flop", "B%d T%d %d steps (fp32 SIMT, 1 launch)" % (B, T, steps)):
+    with _timed("attn_decode", 2.0 * B * steps * macs, "flop", "B%d T%d %d steps (fp32 SIMT, 1 launch)" % (B, T, steps)), _on(enc, proj, text, h0, c0, *[v for v in packed.values() if isinstance(v, torch.Tensor)]) as st:
         check(lib().mstr_attn_decode(ptr(enc), ptr(proj), ptr(packed["w_h2h"]), ptr(packed["b_h2h"]),
                                      ptr(packed["w_score"]), ptr(packed["w_ctx"]), ptr(packed["w_tok"]),
                                      ptr(packed["w_hh"]), ptr(packed["bias"]), ptr(packed["w_gen"]),
                                      ptr(packed["b_gen"]), ptr(text), ptr(h0), ptr(c0), ptr(logits), ptr(ids),
                                      ptr(lengths), ptr(alpha), ptr(h_out), ptr(c_out),
-                                     B, T, Hd, C, steps, int(early_exit), stream_ptr()), "mstr_attn_decode")
+                                     B, T, Hd, C, steps, int(early_exit), st), "mstr_attn_decode")
     return {"logits": logits, "ids": ids, "lengths": lengths, "alpha": alpha, "h": h_out, "c": c_out}
 
 
@@ -386,10 +423,10 @@ def resize_to_tensor_u8(pixels: torch.Tensor, offsets: torch.Tensor, sizes_hw: t
     out = torch.empty((B, 1, out_hw[0], out_hw[1]), device=pixels.device, dtype=torch.float32)
     status = torch.zeros((1,), device=pixels.device, dtype=torch.int32)
     with _timed("resize_to_tensor_u8", float(pixels.numel() + out.numel() * 4), "byte",
-                "B%d ragged u8 crops -> %dx%d f32" % (B, out_hw[0], out_hw[1])):
+                "B%d ragged u8 crops -> %dx%d f32" % (B, out_hw[0], out_hw[1])), _on(pixels, offsets, sizes_hw) as st:
         check(lib().mstr_resize_to_tensor_u8(ptr(pixels), ptr(offsets), ptr(sizes_hw), ptr(out), ptr(status), B,
                                              int(out_hw[0]), int(out_hw[1]), int(max_in_hw[0]), int(max_in_hw[1]),
-                                             stream_ptr()), "mstr_resize_to_tensor_u8")
+                                             st), "mstr_resize_to_tensor_u8")
     return out
 
 
@@ -418,10 +455,10 @@ def attn_decode_bf16(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps:
             text = text[:, :steps].contiguous()
     macs = Hd * Hd + 2 * T * Hd + 4 * Hd * 2 * Hd + C * Hd
     with _timed("attn_decode_bf16", 2.0 * B * steps * macs, "flop",
-                "B%d T%d %d steps (tcgen05, %d launches)" % (B, T, steps, 3 * steps + 2)):
+                "B%d T%d %d steps (tcgen05, %d launches)" % (B, T, steps, 3 * steps + 2)), _on(enc, proj, text, *[v for v in packed.values() if isinstance(v, torch.Tensor)]) as st:
         check(lib().mstr_attn_decode_bf16(ptr(enc), ptr(proj), ptr(packed["w_head"]), ptr(packed["b_h2h"]),
                                           ptr(packed["b_gen"]), ptr(packed["w_score"]), ptr(packed["w_cat"]),
                                           ptr(packed["w_tok"]), ptr(packed["bias"]), ptr(text), ptr(ws), ptr(logits),
                                           ptr(ids), ptr(lengths), ptr(alpha), B, T, Hd, C, steps, int(early_exit),
-                                          stream_ptr()), "mstr_attn_decode_bf16")
+                                          st), "mstr_attn_decode_bf16")
     return {"logits": logits, "ids": ids, "lengths": lengths, "alpha": alpha, "h": None, "c": None}

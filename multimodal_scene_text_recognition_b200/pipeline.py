@@ -32,12 +32,29 @@ class HostBatchPrefetcher:
         for t in host_tensors:
             if not t.is_pinned():
                 raise ValueError("HostBatchPrefetcher needs pinned host tensors (torch.Tensor.pin_memory())")
+        for t in host_tensors:
+            if not t.is_contiguous():
+                raise ValueError("HostBatchPrefetcher needs contiguous host tensors")
         sid = self._next % self.depth
         self._next += 1
         if sid >= len(self._slots):
             self._slots.append([torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_tensors])
             self._free.append(None)
         slot = self._slots[sid]
+        if len(slot) != len(host_tensors):
+            raise ValueError("HostBatchPrefetcher: a batch has %d tensors, the slot was set up for %d" %
+                             (len(host_tensors), len(slot)))
+        # every batch is checked against the slot: same dtype and trailing dimensions; a SHORTER batch (the last one of
+        # a dataset) is copied into the head of the buffers and handed out as views of its own length, so that stale rows
+        # of the previous batch are never recognised; a LONGER one re-allocates the slot once its last consumer is done
+        for i, (d, h) in enumerate(zip(slot, host_tensors)):
+            if h.dtype != d.dtype or tuple(h.shape[1:]) != tuple(d.shape[1:]):
+                raise ValueError("HostBatchPrefetcher: tensor %d is %s %s, the slot holds %s [*, %s]" % (
+                    i, h.dtype, tuple(h.shape), d.dtype, ", ".join(str(v) for v in d.shape[1:])))
+            if h.shape[0] > d.shape[0]:
+                if self._free[sid] is not None:
+                    self._free[sid].synchronize()
+                slot[i] = torch.empty(h.shape, dtype=h.dtype, device=self.device)
         import os, sys, time
         trace = os.environ.get("MSTR_BENCH_TRACE")
         ts = [time.perf_counter()]
@@ -45,20 +62,20 @@ class HostBatchPrefetcher:
             if self._free[sid] is not None:          # do not overwrite a slot its last consumer may still read
                 self.stream.wait_event(self._free[sid])
             ts.append(time.perf_counter())
+            views = []
             for d, h in zip(slot, host_tensors):
                 # one cudaMemcpyAsync per tensor through the C ABI (torch's copy_ was measured to block the host
                 # for the duration of a CPU-side pass over the 52 MB batch in this configuration)
-                if not h.is_contiguous():
-                    raise ValueError("HostBatchPrefetcher needs contiguous host tensors")
                 _cabi.check(_cabi.lib().mstr_copy_h2d_async(d.data_ptr(), h.data_ptr(), h.numel() * h.element_size(),
                                                             self.stream.cuda_stream), "mstr_copy_h2d_async")
+                views.append(d[:h.shape[0]])
                 ts.append(time.perf_counter())
             ready = torch.cuda.Event()
             ready.record(self.stream)
         ts.append(time.perf_counter())
         if trace:
             print("stage: " + " ".join("%.2f" % (1e3 * (b - a)) for a, b in zip(ts, ts[1:])), file=sys.stderr)
-        return slot, ready, sid
+        return views, ready, sid
 
     def release(self, sid: int) -> None:
         """Call after enqueuing the consumer's work on slot ``sid`` (on the current stream)."""

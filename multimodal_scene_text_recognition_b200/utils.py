@@ -45,3 +45,21 @@ class AttnLabelConverter(object):
             s = ''.join(self.character[i] for i in row)
             out.append(s[:s.find('[s]')])
         return out
+
+
+class Averager(object):
+    """Running mean over tensor elements (interface of utils.py:151-172: add / reset / val); the reference's
+    training loop imports it next to the converter, so the name has to resolve for training_functions.py."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.n_count, self.sum = 0, 0
+
+    def add(self, v):
+        self.n_count += v.data.numel()
+        self.sum += v.data.sum()
+
+    def val(self):
+        return self.sum / float(self.n_count) if self.n_count else 0

@@ -214,9 +214,18 @@ def _bn_fold(sd, name, dt):
     return scale, sd[name + ".bias"].astype(dt) - sd[name + ".running_mean"].astype(dt) * scale
 
 
-def _basic_block(x, sd, prefix, dt, quant):
+def _basic_block(x, sd, prefix, dt, quant, trace=None):
     """BasicBlock.forward (feature_extraction.py:32-47)."""
+    y = _basic_block_body(x, sd, prefix, dt, quant, trace)
+    if trace is not None:
+        trace.append((prefix.split("ConvNet.")[-1], y))
+    return y
+
+
+def _basic_block_body(x, sd, prefix, dt, quant, trace):
     out = _q(_conv_bn_relu(x, sd, prefix + ".conv1", prefix + ".bn1", dt, quant=quant), quant)
+    if trace is not None:
+        trace.append((prefix.split("ConvNet.")[-1] + ".conv1", out))
     if (prefix + ".downsample.0.weight") in sd and quant:
         # CUDA bf16 mode: conv2/bn2 + downsample conv/bn + add as ONE GEMM whose bf16 weights carry the folded
         # BatchNorm scales (both branches share the fp32 accumulator; no intermediate rounding of the residual)
@@ -235,33 +244,40 @@ def _basic_block(x, sd, prefix, dt, quant):
     return _q(relu(out + res), quant)
 
 
-def resnet_forward(x, sd, dt=np.float32, quant=None, taps: Optional[dict] = None):
-    """ResNet.forward (feature_extraction.py:109-150). x [B,C,H,W] -> [B,512,H',W']."""
+def resnet_forward(x, sd, dt=np.float32, quant=None, taps: Optional[dict] = None, trace: Optional[list] = None):
+    """ResNet.forward (feature_extraction.py:109-150). x [B,C,H,W] -> [B,512,H',W'].
+    ``trace``: list that receives (layer name, output) of every conv group / block / pool in execution order
+    (the per-layer parity tests compare them with the CUDA path's launches one to one)."""
     n = "FeatureExtraction.ConvNet."
+
+    def tr(name, v):
+        if trace is not None:
+            trace.append((name, v))
+        return v
     # conv0_1: C_in = input_channel, fp32 SIMT on the GPU (weights not quantised), output bf16
-    h = _q(_conv_bn_relu(x.astype(dt), sd, n + "conv0_1", n + "bn0_1", dt, quant=quant,
-                         quant_weight=False), quant)
-    h = _q(_conv_bn_relu(h, sd, n + "conv0_2", n + "bn0_2", dt, quant=quant), quant)
-    h = maxpool2d(h)
-    h = _basic_block(h, sd, n + "layer1.0", dt, quant)
-    h = _q(_conv_bn_relu(h, sd, n + "conv1", n + "bn1", dt, quant=quant), quant)
-    h = maxpool2d(h)
+    h = tr("conv0_1", _q(_conv_bn_relu(x.astype(dt), sd, n + "conv0_1", n + "bn0_1", dt, quant=quant,
+                                       quant_weight=False), quant))
+    h = tr("conv0_2", _q(_conv_bn_relu(h, sd, n + "conv0_2", n + "bn0_2", dt, quant=quant), quant))
+    h = tr("maxpool1", maxpool2d(h))
+    h = _basic_block(h, sd, n + "layer1.0", dt, quant, trace)
+    h = tr("conv1", _q(_conv_bn_relu(h, sd, n + "conv1", n + "bn1", dt, quant=quant), quant))
+    h = tr("maxpool2", maxpool2d(h))
     for b in range(2):
-        h = _basic_block(h, sd, f"{n}layer2.{b}", dt, quant)
-    h = _q(_conv_bn_relu(h, sd, n + "conv2", n + "bn2", dt, quant=quant), quant)
-    h = maxpool2d(h, (2, 2), (2, 1), (0, 1))
+        h = _basic_block(h, sd, f"{n}layer2.{b}", dt, quant, trace)
+    h = tr("conv2", _q(_conv_bn_relu(h, sd, n + "conv2", n + "bn2", dt, quant=quant), quant))
+    h = tr("maxpool3", maxpool2d(h, (2, 2), (2, 1), (0, 1)))
     if taps is not None:
         taps["after_maxpool3"] = h
     for b in range(5):
-        h = _basic_block(h, sd, f"{n}layer3.{b}", dt, quant)
-    h = _q(_conv_bn_relu(h, sd, n + "conv3", n + "bn3", dt, quant=quant), quant)
+        h = _basic_block(h, sd, f"{n}layer3.{b}", dt, quant, trace)
+    h = tr("conv3", _q(_conv_bn_relu(h, sd, n + "conv3", n + "bn3", dt, quant=quant), quant))
     for b in range(3):
-        h = _basic_block(h, sd, f"{n}layer4.{b}", dt, quant)
+        h = _basic_block(h, sd, f"{n}layer4.{b}", dt, quant, trace)
     if taps is not None:
         taps["after_layer4"] = h
-    h = _q(_conv_bn_relu(h, sd, n + "conv4_1", n + "bn4_1", dt, stride=(2, 1), pad=(0, 1),
-                         quant=quant), quant)
-    h = _q(_conv_bn_relu(h, sd, n + "conv4_2", n + "bn4_2", dt, pad=(0, 0), quant=quant), quant)
+    h = tr("conv4_1", _q(_conv_bn_relu(h, sd, n + "conv4_1", n + "bn4_1", dt, stride=(2, 1), pad=(0, 1),
+                                       quant=quant), quant))
+    h = tr("conv4_2", _q(_conv_bn_relu(h, sd, n + "conv4_2", n + "bn4_2", dt, pad=(0, 0), quant=quant), quant))
     return h
 
 

@@ -103,20 +103,14 @@ def _lstm_cell(g, c):
 
 
 def bidirectional_lstm(x, sd, pre):
+    """encoders.py:17-30 through ATen's native (fused, multi-threaded) CPU LSTM, the path ``nn.LSTM`` takes in the
+    reference: ``torch.lstm`` with the flat weight list of a bidirectional single-layer LSTM, batch_first."""
     B, T, _ = x.shape
-    outs = []
-    for sfx, rev in (("", False), ("_reverse", True)):
-        gx = F.linear(x, sd[f"{pre}.rnn.weight_ih_l0{sfx}"],
-                      sd[f"{pre}.rnn.bias_ih_l0{sfx}"] + sd[f"{pre}.rnn.bias_hh_l0{sfx}"])
-        w_hh = sd[f"{pre}.rnn.weight_hh_l0{sfx}"]
-        Hd = w_hh.shape[1]
-        h = torch.zeros(B, Hd, dtype=x.dtype); c = torch.zeros(B, Hd, dtype=x.dtype)
-        out = torch.empty(B, T, Hd, dtype=x.dtype)
-        for t in (range(T - 1, -1, -1) if rev else range(T)):
-            h, c = _lstm_cell(gx[:, t] + F.linear(h, w_hh), c)
-            out[:, t] = h
-        outs.append(out)
-    return F.linear(torch.cat(outs, dim=2), sd[pre + ".linear.weight"], sd[pre + ".linear.bias"])
+    Hd = sd[pre + ".rnn.weight_hh_l0"].shape[1]
+    flat = [sd[f"{pre}.rnn.{n}_l0{sfx}"] for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    zeros = torch.zeros(2, B, Hd, dtype=x.dtype)
+    rec = torch.lstm(x, (zeros, zeros), flat, True, 1, 0.0, False, True, True)[0]
+    return F.linear(rec, sd[pre + ".linear.weight"], sd[pre + ".linear.bias"])
 
 
 def attention_decode(enc, sd, steps, text=None):

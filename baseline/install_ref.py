@@ -82,8 +82,12 @@ def load(device: str = "cpu", device_ids=(0,), dst: str = REF_DST):
     verify(dst)
     for name in MODULE_NAMES:
         mod = sys.modules.get(name)
-        if mod is not None and not os.path.abspath(getattr(mod, "__file__", "") or "").startswith(dst):
-            raise RuntimeError("module %r is already imported from %s" % (name, getattr(mod, "__file__", None)))
+        if mod is None:
+            continue
+        # `modules` has no __init__.py in the reference: a namespace package, located by __path__ instead of __file__
+        where = getattr(mod, "__file__", None) or next(iter(getattr(mod, "__path__", [])), "")
+        if not os.path.abspath(where).startswith(dst):
+            raise RuntimeError("module %r is already imported from %s" % (name, where))
     if dst not in sys.path:
         sys.path.insert(0, dst)
     cfg = importlib.import_module("config")

@@ -479,7 +479,10 @@ def run_ours(args):
                      "allgather_ms_per_step_rank0": round(other["gather_ms_per_step"], 4)}
     line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline()
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as exc:   # a baseline must never take the bench line down
+            line["cpu_baseline"] = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -46,7 +46,7 @@ constexpr int TF_THREADS = 320;           // producer, MMA, 4 epilogue warps, 4 
 constexpr int TF_TILE = 128 * 128;        // 128 rows x 32 fp32 (one 128-byte swizzle span)
 constexpr int TF_STAGE = 5 * TF_TILE;     // x_raw, x_hi, x_lo, w_hi, w_lo
 constexpr int TF_STAGES = 2;
-constexpr int TF_CHUNK_KB = 8;             // k-blocks (of 32 values) per TMEM accumulation chunk
+constexpr int TF_CHUNK_KB = 2;             // k-blocks (of 32 values) per TMEM accumulation chunk
 constexpr int TF_SMEM_BYTES = 1024 + TF_STAGES * TF_STAGE + 2 * EPI_SLAB_BYTES + 4 * 128 * 4 + 16 * 8 + 16;
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,

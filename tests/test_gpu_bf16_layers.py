@@ -40,7 +40,8 @@ def _t(a):   # NHWC numpy -> NCHW float64
 def _replay(name, args, kw, out):
     """(what, got, exact_reference_before_rounding) of one recorded launch, or None if it is not a bf16 launch."""
     if name == "conv3x3_first":
-        x, w, scale, shift, out_dtype, pool = args
+        x, w, scale, shift = args[:4]
+        pool = kw["pool"] if "pool" in kw else args[5]
         y = orc.conv2d(host(x).astype(F64), host(w).astype(F64), (1, 1), (1, 1))
         y = orc.relu(y * host(scale).astype(F64)[None, :, None, None] + host(shift).astype(F64)[None, :, None, None])
         if pool:

@@ -130,13 +130,15 @@ def test_stages_against_live_reference_b128(sd_cfg_a, g128, live_ref):
         assert_close(nchw(host(st["features"])), rs["features"].numpy(), 1e-4, "%s ResNet features vs live reference" % precision)
         assert_close(host(st["enc1"]), rs["enc1"].numpy(), 2e-4, "%s encoder output vs live reference" % precision)
         assert_close(host(out["logits"]), rl, 3.0 * floor, "%s logits vs live reference" % precision)
-        sem_ref = ref.model.get_semantic_vectors(*[torch.from_numpy(a) for a in inputs[1:]])
+        with torch.no_grad():
+            sem_ref = ref.model.get_semantic_vectors(*[torch.from_numpy(a) for a in inputs[1:]])
         assert np.array_equal(host(st["semantics"]), sem_ref.numpy()), "overlap semantic vectors"
     # 'scene' mode: softmax(ious)-weighted embeddings; the logits must not move (decoders.py:79-101 ignores them)
     ref.config.SEMANTIC_VECTOR = "scene"
     try:
         io2 = np.random.Generator(np.random.PCG64(5)).uniform(0, 1, inputs[3].shape).astype(np.float32)
-        sem_ref = ref.model.get_semantic_vectors(torch.from_numpy(inputs[1]), torch.from_numpy(inputs[2]), torch.from_numpy(io2))
+        with torch.no_grad():
+            sem_ref = ref.model.get_semantic_vectors(torch.from_numpy(inputs[1]), torch.from_numpy(inputs[2]), torch.from_numpy(io2))
         m = load_model(sd_cfg_a, precision="fp32", SEMANTIC_VECTOR="scene", DECODER_EARLY_EXIT=False)
         st = {}
         out2 = _recognize(m, (inputs[0], inputs[1], inputs[2], io2), st)

@@ -171,6 +171,10 @@ int mstr_bilstm_recurrent(const float* gates_x, const float* w_hh, float* out_f3
  */
 int mstr_bilstm_recurrent_bf16(const float* gates_x, const void* w_hh_packed, void* out_bf16, int B, int T,
                                int Hd, mstr_stream_t stream);
+/* Two kernels implement mstr_bilstm_recurrent_bf16 with bit-identical results: one CTA per crop tile streaming W_hh
+ * (csrc/bilstm_tc.cu) and a cluster of 8 CTAs per crop tile with stationary W_hh slices (csrc/bilstm_cluster.cu).
+ * which = 0 (default) picks by occupancy, 1 / 2 force the first / second (used by the parity tests). */
+int mstr_set_bilstm_kernel(int which);
 
 /* ---- attention decoder ---------------------------------------------------------------------
  * Replaces Attention.forward (modules/decoders.py:26-64) with AttentionCell.forward (:79-101),
@@ -196,11 +200,11 @@ int mstr_attn_decode(const float* enc, const float* proj, const float* w_h2h, co
                      int32_t* ids, int32_t* lengths, float* alpha_out, float* h_out, float* c_out,
                      int B, int T, int Hd, int C, int steps, int early_exit, mstr_stream_t stream);
 
-/* Tensor-core variant for the bf16 throughput mode: ONE call enqueues the whole greedy (or
- * teacher-forced) loop as three launches per step - a tcgen05 GEMM for [h2h | generator] with the
- * argmax in its epilogue, the attention-context kernel, and a tcgen05 GEMM for the LSTMCell gates with
- * the cell update in its epilogue.  bf16 operands (enc, proj, h, ctx, weights), f32 accumulation,
- * cell state, logits.
+/* Tensor-core variant for the bf16 throughput mode (modules/decoders.py:26-64, :79-101).  ONE call = ONE
+ * persistent cooperative launch that runs every step of the greedy (or teacher-forced) loop: per step a tcgen05 GEMM
+ * for [h2h | generator] with the argmax in its epilogue, the Bahdanau attention over all SMs, and a tcgen05 GEMM for
+ * the LSTMCell gates with the cell update in its epilogue, separated by grid-wide barriers (csrc/attn_tc.cu).
+ * bf16 operands (enc, proj, h, ctx, weights), f32 accumulation, cell state, logits.
  *   enc_bf16, proj_bf16 [B][T][Hd] bf16
  *   w_head [384][Hd] bf16: rows 0..255 = h2h.weight, rows 256..256+C-1 = generator.weight, rest zero
  *   w_cat  [4*Hd][2*Hd] bf16: [rnn.weight_ih[:, :Hd] | rnn.weight_hh] with rows re-ordered like
@@ -216,13 +220,13 @@ int mstr_attn_decode_bf16(const void* enc_bf16, const void* proj_bf16, const voi
                           int32_t* lengths, float* alpha_out, int B, int T, int Hd, int C, int steps,
                           int early_exit, mstr_stream_t stream);
 
-/* Crops never interact in the decoder, so mstr_attn_decode_bf16 can split a large batch into contiguous crop
- * groups whose launch chains run concurrently on internal side streams forked from / joined into the
- * caller's stream (ordinary stream semantics for the caller).  max_groups = 1 (the default: measured fastest
- * on B200, see csrc/attn_tc.cu) runs one chain; 0 = automatic (up to 4 groups of at least
- * min_crops_per_group crops, 0 -> 1024); 2..4 = at most that many groups.
- * Call mstr_attn_decode_bf16_workspace_bytes AFTER changing this setting. */
-int mstr_set_decode_groups(int max_groups, int min_crops_per_group);
+/* mstr_attn_decode_bf16 runs as one persistent launch (on = 1, the default).  on = 0 selects the same phases as a
+ * chain of three launches per step (programmatic dependent launch); both give bit-identical results - the chain is
+ * kept as the cross-check of the persistent kernel's barriers (tests/test_gpu_kernels.py). */
+int mstr_set_decode_persistent(int on);
+/* Diagnostic: %globaltimer (ns) of CTA 0 at the start of the last persistent decode on the current device and at
+ * every grid-barrier entry and exit (two values per barrier, three barriers per step); synchronises the device. */
+int mstr_debug_decode_trace(unsigned long long* out_host, int n);
 
 /* Input side of the path: the loader's transforms.Resize((32,100)) + ToTensor()
  * (coco_dataset.py:27,40-41) on a ragged batch of grayscale uint8 crops, bit-exact with Pillow's antialiased

@@ -37,10 +37,12 @@ SIGNATURES = {
     "mstr_embed_semantics": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mstr_bilstm_recurrent": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "mstr_bilstm_recurrent_bf16": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
+    "mstr_set_bilstm_kernel": (c_int, [_I]),
     "mstr_attn_decode": (c_int, [_P] * 20 + [_I] * 6 + [_P]),
     "mstr_attn_decode_bf16_workspace_bytes": (c_int64, [_I, _I]),
     "mstr_attn_decode_bf16": (c_int, [_P] * 15 + [_I] * 6 + [_P]),
-    "mstr_set_decode_groups": (c_int, [_I, _I]),
+    "mstr_set_decode_persistent": (c_int, [_I]),
+    "mstr_debug_decode_trace": (c_int, [_P, _I]),
     "mstr_resize_to_tensor_u8": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

@@ -27,6 +27,8 @@
 //
 // Warp roles: warp 0 = TMA producer (W slice once, then the gates_x tiles), warp 1 = MMA issuer, warps 2..17 =
 // epilogue (four per TMEM lane quarter, 8 units each), warps 18..21 = gates_x loaders (one per lane quarter).
+#include <atomic>
+
 #include "tc_common.cuh"
 
 namespace mstr {
@@ -328,17 +330,22 @@ static int lc_prepare() {
 // How many 8-CTA clusters of this kernel the device can hold at once (each CTA takes a whole SM and the 8 SMs of a
 // cluster must sit in one GPC): 13 on the B200s of this pool.  0 if the query fails.
 int bilstm_cluster_capacity() {
-  static int cached = -1;
-  if (cached >= 0) return cached;
-  if (lc_prepare() != MSTR_OK) return cached = 0;
-  cudaLaunchAttribute attr[1];
-  cudaLaunchConfig_t cfg = lc_launch_config(64, nullptr, attr);
+  static std::atomic<int> cached[64];             // per device ordinal; value + 1 (0 = not queried yet)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  const int have = cached[dev].load(std::memory_order_relaxed);
+  if (have > 0) return have - 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, bilstm_cluster_kernel, &cfg) != cudaSuccess) {
-    cudaGetLastError();
-    n = 0;
+  if (lc_prepare() == MSTR_OK) {
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = lc_launch_config(64, nullptr, attr);
+    if (cudaOccupancyMaxActiveClusters(&n, bilstm_cluster_kernel, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
   }
-  return cached = n;
+  cached[dev].store(n + 1, std::memory_order_relaxed);
+  return n;
 }
 
 // Called by mstr_bilstm_recurrent_bf16 (bilstm_tc.cu).

@@ -36,7 +36,7 @@
 // feed of 128 KB per chunk per SM (gates_x + W_hh: 0.34 ms without the gates_x loads) on top of a
 // 0.21 ms barrier / TMEM round-trip skeleton.  The gate non-linearities use tanh.approx (1 MUFU each;
 // sigmoid(x) = 0.5 tanh(x/2) + 0.5): 5 MUFU per hidden unit per crop per step - not the limiter.
-#include <stdlib.h>
+#include <atomic>
 
 #include "tc_common.cuh"
 
@@ -311,8 +311,15 @@ static TmaEncoders g_lstm_enc;
 int bilstm_recurrent_bf16_cluster(const float* gates_x, const void* w_hh_packed, void* out_bf16, int B, int T,
                                   cudaStream_t stream);
 int bilstm_cluster_capacity();
+static std::atomic<int> g_bilstm_kernel{0};   // 0 = by occupancy, 1 = one CTA per tile, 2 = cluster per tile
 
 }  // namespace mstr
+
+extern "C" __attribute__((visibility("default"))) int mstr_set_bilstm_kernel(int which) {
+  MSTR_REQUIRE(which >= 0 && which <= 2, MSTR_ERR_BAD_ARG, "mstr_set_bilstm_kernel: 0 (automatic), 1 (single CTA) or 2 (cluster)");
+  mstr::g_bilstm_kernel.store(which);
+  return MSTR_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16(
     const float* gates_x, const void* w_hh_packed, void* out_bf16, int B, int T, int Hd, mstr_stream_t stream) {
@@ -326,10 +333,10 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   // crop tile) has a 4.5x shorter step (3.9 us vs 17.7 us) but the device holds only ~13 of its clusters at once, so it
   // wins while all (crop tile, direction) pairs fit in one wave - batches up to ~800 crops (B=256: 0.101 vs 0.347 ms);
   // beyond that this kernel's 64+ independent CTAs are level or ahead (B=4096: 0.463 vs 0.482 ms).
-  // MSTR_BILSTM_CLUSTER=0 / 1 forces one.
-  const char* cl_env = getenv("MSTR_BILSTM_CLUSTER");
+  // mstr_set_bilstm_kernel forces one (the parity tests run both on the same inputs).
+  const int forced = g_bilstm_kernel.load(std::memory_order_relaxed);
   const int tiles = ceil_div(B, LT_M) * 2;
-  const bool use_cluster = cl_env ? cl_env[0] == '1' : (tiles <= bilstm_cluster_capacity());
+  const bool use_cluster = forced ? forced == 2 : (tiles <= bilstm_cluster_capacity());
   if (use_cluster) return bilstm_recurrent_bf16_cluster(gates_x, w_hh_packed, out_bf16, B, T, (cudaStream_t)stream);
   int rc = load_tma_encoders(g_lstm_enc);
   if (rc != MSTR_OK) return rc;

@@ -330,14 +330,9 @@ static int conv_gemm_bf16_impl(const void* x, const void* w, const float* scale,
   MSTR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(residual) && aligned16(out_bf16) && aligned16(out_f32),
                MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: pointers must be 16-byte aligned");
   MSTR_REQUIRE(R <= 16 && S <= 16 && pad_h < 16 && pad_w < 16, MSTR_ERR_UNSUPPORTED, "mstr_conv_gemm_bf16: filter too large");
-  // CTA-pair kernel for C_out % 256 == 0 (measured: +9 % on the 512->512 layers, -8 % on C_out = 128 layers,
-  // which therefore stay on the single-CTA kernel); MSTR_CONV_2CTA=0 forces the single-CTA kernel
-  static const int use_2cta = [] { const char* e = getenv("MSTR_CONV_2CTA"); return (e && e[0] == '0') ? 0 : 1; }();
-  // opt-in (MSTR_CONV_PAIR_MT2=1): C_out % 128 == 0 layers with bf16 output on the pair kernel's MT = 2 variant.
-  // MEASURED slower than the single-CTA MT = 2 kernel below (4.70 vs 4.47 ms per step over the five such layers)
-  const char* pair128_env = getenv("MSTR_CONV_PAIR_MT2");
-  const bool pair128 = C_out % 128 == 0 && !out_f32 && pair128_env && pair128_env[0] == '1';
-  if (use_2cta && C_in % 64 == 0 && (C_out % 256 == 0 || pair128) && (int64_t)B * H * W < (1ll << 31) && sm_count() >= 2) {
+  // CTA-pair kernel (conv_tc2.cu) for C_out % 256 == 0: +9 % on the 512->512 layers.  C_out = 128 layers stay on the
+  // single-CTA kernel below (pairs measured 8 % slower there; DESIGN.md 4 lists the variants that were tried and removed)
+  if (C_in % 64 == 0 && C_out % 256 == 0 && (int64_t)B * H * W < (1ll << 31) && sm_count() >= 2) {
     const int64_t M2 = (int64_t)B * ((H + 2 * pad_h - R) / stride_h + 1) * ((W + 2 * pad_w - S) / stride_w + 1);
     MSTR_REQUIRE(M2 > 0 && M2 < (1ll << 31), MSTR_ERR_BAD_ARG, "mstr_conv_gemm_bf16: bad output size");
     return conv_gemm_bf16_2cta(x, w, scale, shift, residual, out_bf16, out_f32, B, H, W, C_in, C_out, R, S, stride_h,
@@ -391,12 +386,7 @@ static int conv_gemm_bf16_impl(const void* x, const void* w, const float* scale,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
-    // Drivers up to CUDA 13.1 set a descriptor flag that must be cleared for im2col tensors smaller
-    // than 128 KiB (same guard as the vendor's own GEMM library applies).
-    int drv = 0;
-    cudaDriverGetVersion(&drv);
-    if (drv <= 13010 && (int64_t)B * H * W * C_in * 2 < 131072)
-      reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
+    fix_small_im2col_map(&tmA, (int64_t)B * H * W * C_in * 2);
   }
 
   alignas(64) CUtensorMap tmA2 = tmA;
@@ -413,9 +403,8 @@ static int conv_gemm_bf16_impl(const void* x, const void* w, const float* scale,
   cudaStream_t st = (cudaStream_t)stream;
   if (block_k == 64) {
     if (block_n == 256) return launch_tc<256, 64>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
-    // two 128-row accumulators per CTA sharing each weight tile (MSTR_CONV_MT2=0 disables)
-    static const int use_mt2 = [] { const char* e = getenv("MSTR_CONV_MT2"); return (e && e[0] == '0') ? 0 : 1; }();
-    if (block_n == 128 && use_mt2 && p.num_m_tiles >= 8 * sm_count())
+    // two 128-row accumulators per CTA sharing each weight tile, once there are enough tiles to fill the device
+    if (block_n == 128 && p.num_m_tiles >= 8 * sm_count())
       return launch_tc<128, 64, 2>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
     if (block_n == 128) return launch_tc<128, 64>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
     return launch_tc<64, 64>(tmA, tmB, tmOb, tmOf, tmA2, p, st);

@@ -41,23 +41,10 @@ constexpr int T2_THREADS = 320;      // producer, MMA issuer, 2 x 4 epilogue war
 constexpr int T2_BLOCK_K = 64;
 constexpr int T2_A_BYTES = 128 * 128;   // 128 rows x 64 bf16
 
-// BLOCK_N = 512 (C_out % 512 == 0, bf16 output only): one 256 x 512 tile per pair, issued as two UMMA_N = 256
-// instructions per k-step.  ncu on the 256 x 256 version: 16.2 GB of L2 -> SM operand traffic per 512->512 launch at
-// 12.5 TB/s - the measured L2 throughput ceiling of the part (B300_MICROARCH: ~6300 B/clk) - with the tensor pipe
-// 66 % active: the kernel is L2-feed bound at 64 MAC per operand byte.  The wider tile reads every activation tile
-// once for 512 instead of 256 output channels: 96 KB instead of 128 KB per 256x512x64 block (-25 % L2 traffic).
-// Price: the accumulator takes all 512 TMEM columns, so the epilogue of a tile is no longer hidden behind the
-// next tile's MMAs.  MEASURED (B200, bench step): conv stage 27.4 ms with 256-wide tiles, 30.3 ms with 512-wide
-// tiles (+11 % = exactly the exposed epilogue, ~8k of ~74k cycles per tile): the main loop did not get faster with
-// 25 % less L2 traffic, i.e. the kernel is NOT L2-feed bound but at the tensor / power limit (1.55 GHz under
-// sw_power_cap).  The wide tile therefore stays opt-in (MSTR_CONV_N512=1) as a tested negative result.
-// MT = 2 (BLOCK_N = 128, bf16 output only): the pair owns 512 output rows as two 256-row accumulators that share
-// every weight tile, for the C_out = 128 layers.  Per CTA and k-block that is 32 KB of activations + 8 KB of
-// weights for 256x128x64 MACs (52 MAC per operand byte; the single-CTA MT = 2 kernel needs 48 KB: 44 MAC/B).
-// MEASURED (bench step, five C_out = 128 layers): 4.70 ms against 4.47 ms for the single-CTA MT = 2 kernel - 17 %
-// fewer operand bytes did not pay for the pair protocol, so this variant is opt-in (MSTR_CONV_PAIR_MT2=1).  The
-// K = 576 layers move 432 KB of operands per 256-row tile in ~11.8k cycles (9 TB/s chip-wide, close to the
-// ~12.5 TB/s the L2 delivers to the SMs) for 4.6k cycles of MMA work.
+// Only BLOCK_N = 256, MT = 1 is instantiated.  The template also expresses 256 x 512 pair tiles (BLOCK_N = 512) and two
+// 256-row accumulators per pair for C_out = 128 (BLOCK_N = 128, MT = 2); both were built, verified bit-identical and
+// measured SLOWER on the bench step (conv stage 27.4 -> 30.3 ms; five C_out = 128 layers 4.47 -> 4.70 ms) and have been
+// removed from the library - the measurements and what they say about the limiter are in DESIGN.md 4.
 template <int BLOCK_N, int MT = 1, bool F32OUT = false>
 struct Tc2Cfg {
   static constexpr int UMMA_N = BLOCK_N > 256 ? 256 : BLOCK_N;    // columns per tcgen05.mma
@@ -413,7 +400,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   return MSTR_OK;
 }
 
-// Called by mstr_conv_gemm_bf16 (conv_tc.cu) when the layer qualifies: C_in % 64 == 0, C_out % 128 == 0.
+// Called by mstr_conv_gemm_bf16 (conv_tc.cu) when the layer qualifies: C_in % 64 == 0, C_out % 256 == 0.
 int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
                         void* out_bf16, float* out_f32, int B, int H, int W, int C_in, int C_out, int R, int S,
                         int stride_h, int stride_w, int pad_h, int pad_w, int relu, const void* x2, int C_in2,
@@ -425,13 +412,7 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
   p.Q = (W + 2 * pad_w - S) / stride_w + 1;
   p.M = (int)((int64_t)B * p.P * p.Q);
   p.Cout = C_out;
-  // 256 x 512 tiles are opt-in (MSTR_CONV_N512=1): measured slower, see Tc2Cfg
-  const char* wide_env = getenv("MSTR_CONV_N512");
-  const bool wide = wide_env && wide_env[0] == '1';
-  const int block_n = (C_out % 512 == 0 && !out_f32 && wide) ? 512 : (C_out % 256 == 0) ? 256 : 128;
-  // C_out = 128 layers with bf16 output: two 256-row accumulators per pair (opt-in, MSTR_CONV_PAIR_MT2=1)
-  const char* mt_env = getenv("MSTR_CONV_PAIR_MT2");
-  const int mt = (block_n == 128 && !out_f32 && mt_env && mt_env[0] == '1') ? 2 : 1;
+  const int block_n = 256, mt = 1;
   p.num_m_pairs = ceil_div(p.M, 256 * mt);
   p.num_n_tiles = C_out / block_n;
   p.taps = R * S;
@@ -466,10 +447,7 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
                                upper, T2_BLOCK_K, 128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
-    int drv = 0;
-    cudaDriverGetVersion(&drv);
-    if (drv <= 13010 && (int64_t)B * H * W * C_in * 2 < 131072)
-      reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
+    fix_small_im2col_map(&tmA, (int64_t)B * H * W * C_in * 2);
   }
   alignas(64) CUtensorMap tmA2 = tmA;
   if (x2) {   // [M][C_in2] matrix whose rows are the output pixels
@@ -481,14 +459,8 @@ int conv_gemm_bf16_2cta(const void* x, const void* w, const float* scale, const 
   if (out_f32) { rc = encode_output_2d(g_enc2, &tmOf, out_f32, true, (uint64_t)C_out, (uint64_t)p.M); if (rc != MSTR_OK) return rc; }
   if (!out_bf16) tmOb = tmOf;
   if (!out_f32) tmOf = tmOb;
-  if (block_n == 512) return launch_tc2<512>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
-  if (block_n == 128 && mt == 2) return launch_tc2<128, 2>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
-  if (block_n == 256) {
-    if (out_f32) return launch_tc2<256, 1, true>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
-    return launch_tc2<256>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
-  }
-  if (out_f32) return launch_tc2<128, 1, true>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
-  return launch_tc2<128>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+  if (out_f32) return launch_tc2<256, 1, true>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
+  return launch_tc2<256>(tmA, tmB, tmOb, tmOf, tmA2, p, st);
 }
 
 }  // namespace mstr

@@ -370,6 +370,12 @@ def bilstm_recurrent_bf16(gates_x: torch.Tensor, w_hh_packed: torch.Tensor) -> t
     return out
 
 
+def set_bilstm_kernel(which: str = "auto") -> None:
+    """Tensor-core BiLSTM recurrence: "auto" picks by occupancy (the cluster kernel while every crop tile fits in one
+    wave of clusters, the one-CTA-per-tile kernel beyond); "single" / "cluster" force one (parity tests)."""
+    check(lib().mstr_set_bilstm_kernel({"auto": 0, "single": 1, "cluster": 2}[which]), "mstr_set_bilstm_kernel")
+
+
 def attn_decode(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int, text: Optional[torch.Tensor],
                 early_exit: bool, h0: Optional[torch.Tensor] = None, c0: Optional[torch.Tensor] = None,
                 want_alpha: bool = False, want_state: bool = False) -> dict:
@@ -430,10 +436,10 @@ def resize_to_tensor_u8(pixels: torch.Tensor, offsets: torch.Tensor, sizes_hw: t
     return out
 
 
-def set_decode_groups(max_groups: int = 1, min_crops_per_group: int = 0) -> None:
-    """Crop groups of the tensor-core decoder (mstr_set_decode_groups): 1 = a single chain on the caller's
-    stream (default, measured fastest), 0 = automatic (<= 4 groups of >= 1024 crops), 2..4 = at most that many."""
-    check(lib().mstr_set_decode_groups(int(max_groups), int(min_crops_per_group)), "mstr_set_decode_groups")
+def set_decode_persistent(on: bool = True) -> None:
+    """Tensor-core decoder as ONE persistent cooperative launch (default) or as the chain of three launches per step
+    (bit-identical results; the chain is the cross-check of the persistent kernel)."""
+    check(lib().mstr_set_decode_persistent(int(bool(on))), "mstr_set_decode_persistent")
 
 
 def attn_decode_bf16(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int, text: Optional[torch.Tensor],
@@ -455,7 +461,7 @@ def attn_decode_bf16(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps:
             text = text[:, :steps].contiguous()
     macs = Hd * Hd + 2 * T * Hd + 4 * Hd * 2 * Hd + C * Hd
     with _timed("attn_decode_bf16", 2.0 * B * steps * macs, "flop",
-                "B%d T%d %d steps (tcgen05, %d launches)" % (B, T, steps, 3 * steps + 2)), _on(enc, proj, text, *[v for v in packed.values() if isinstance(v, torch.Tensor)]) as st:
+                "B%d T%d %d steps (tcgen05, 1 persistent launch)" % (B, T, steps)), _on(enc, proj, text, *[v for v in packed.values() if isinstance(v, torch.Tensor)]) as st:
         check(lib().mstr_attn_decode_bf16(ptr(enc), ptr(proj), ptr(packed["w_head"]), ptr(packed["b_h2h"]),
                                           ptr(packed["b_gen"]), ptr(packed["w_score"]), ptr(packed["w_cat"]),
                                           ptr(packed["w_tok"]), ptr(packed["bias"]), ptr(text), ptr(ws), ptr(logits),

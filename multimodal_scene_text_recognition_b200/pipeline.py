@@ -124,3 +124,76 @@ def crops_to_input(crops, device, out_hw=(32, 100)) -> torch.Tensor:
     dev = torch.device(device)
     return ops.resize_to_tensor_u8(pixels.to(dev, non_blocking=True), offsets.to(dev, non_blocking=True),
                                    sizes.to(dev, non_blocking=True), max_hw, out_hw)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CUDA graph replay of the whole forward
+# ---------------------------------------------------------------------------------------------------
+class GraphedRecognizer:
+    """``Model.recognize`` captured ONCE per batch geometry into a CUDA graph and replayed.
+
+    A step of the path is ~50 kernel launches plus their output allocations, issued from Python through ctypes:
+    ~1 ms of host time per step.  At 4096 crops (38 ms of GPU work) that is hidden, at the 512-crop shards of an
+    8-GPU run (~5 ms) it is not - and eight ranks share the host's cores.  Every launch of the path is capturable
+    (no host synchronisation, no allocation inside the C side; tensor maps travel as kernel parameters; the decoder's
+    cooperative launch is a graph kernel node), so the whole forward is recorded on a side stream into a graph whose
+    activations live in the graph's private memory pool, and a step becomes ONE ``cudaGraphLaunch``.
+
+    ``__call__(image, overlap, scene, ious)`` copies the inputs into the graph's static input tensors (device to
+    device, on the current stream) and replays.  The returned dict holds the graph's STATIC output tensors
+    (``logits``, ``ids``, ``lengths``): consume or copy them before the next call with the same geometry.
+    ``config`` is read at capture time; changing ``config.PRECISION`` etc. afterwards needs ``reset()``.
+    """
+
+    def __init__(self, model, warmup: int = 2):
+        self.model = model
+        self.warmup = warmup
+        self._graphs = {}
+
+    def reset(self) -> None:
+        self._graphs.clear()
+
+    @staticmethod
+    def _key(tensors) -> tuple:
+        return tuple((tuple(t.shape), t.dtype, str(t.device)) for t in tensors)
+
+    def _capture(self, tensors):
+        dev = tensors[0].device
+        static_in = [torch.empty_like(t) for t in tensors]
+        for d, s in zip(static_in, tensors):
+            d.copy_(s)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self.warmup):           # weight packing, function attributes, allocator warm-up
+                self.model.recognize(*static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            out = self.model.recognize(*static_in)
+        static_out = {k: out[k] for k in ("logits", "ids", "lengths")}
+        return graph, static_in, static_out
+
+    def __call__(self, image, overlap, scene, ious):
+        tensors = [image, overlap, scene, ious]
+        if image.shape[0] == 0:
+            return self.model.recognize(*tensors)
+        key = self._key(tensors)
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._graphs[key] = self._capture(tensors)
+        graph, static_in, static_out = entry
+        for d, s in zip(static_in, tensors):
+            if d.data_ptr() != s.data_ptr():
+                d.copy_(s, non_blocking=True)
+        graph.replay()
+        return static_out
+
+    def static_inputs(self, image, overlap, scene, ious):
+        """The graph's own input tensors for this geometry (capturing it if needed): a producer (e.g. the host
+        prefetcher) may write them directly and then call with exactly these tensors, which skips the copies."""
+        tensors = [image, overlap, scene, ious]
+        key = self._key(tensors)
+        if key not in self._graphs:
+            self._graphs[key] = self._capture(tensors)
+        return self._graphs[key][1]

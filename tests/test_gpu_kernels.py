@@ -232,38 +232,29 @@ def test_conv_gemm_bf16_many_tiles():
     assert_close(host(out_f), ref, 2e-5, "conv_gemm_bf16 400 tiles")
 
 
-def test_conv_gemm_bf16_wide_tile_opt_in(monkeypatch):
-    """256 x 512 CTA-pair tiles (single TMEM accumulator, two tcgen05.mma per k-step; MSTR_CONV_N512=1) must give the
-    same bits as the default 256 x 256 tiles: C_out = 512, residual + ReLU, several tiles per CTA pair."""
-    case = (8, 4, 26, 256, 512, 3, 3, (1, 1), (1, 1), True, True)
-    x, w, scale, shift, res = _conv_inputs(case, 7, True)
+def test_small_im2col_tensor_map():
+    """im2col tensor maps over tensors smaller than 128 KiB need the descriptor fix of tc_common.cuh
+    (fix_small_im2col_map; drivers <= CUDA 13.1).  3x3 convolutions over 20 KiB .. 100 KiB activations on every
+    tensor-core kernel that builds such a map - single-CTA bf16, CTA-pair bf16, 3xTF32 - against the oracle: if a
+    driver changes the descriptor layout this fails loudly instead of the model drifting."""
     bf = torch.bfloat16
-    args = (dev(x, bf), dev(w, bf), dev(scale), dev(shift), dev(res, bf))
-    kw = dict(stride=(1, 1), pad=(1, 1), relu=True, want_f32=False, want_bf16=True)
-    monkeypatch.delenv("MSTR_CONV_N512", raising=False)
-    base = ops.conv_gemm(*args, **kw)
-    monkeypatch.setenv("MSTR_CONV_N512", "1")
-    wide = ops.conv_gemm(*args, **kw)
+    for case in ((1, 4, 10, 64, 128, 3, 3, (1, 1), (1, 1), False, True),      # 5 KiB, single-CTA kernel
+                 (2, 4, 13, 128, 256, 3, 3, (1, 1), (1, 1), True, True),      # 26 KiB, CTA-pair kernel
+                 (3, 4, 26, 64, 256, 3, 3, (1, 1), (1, 1), False, False)):    # 39 KiB, CTA-pair kernel
+        assert case[0] * case[1] * case[2] * case[3] * 2 < 131072
+        x, w, scale, shift, res = _conv_inputs(case, 41, True)
+        ref = _conv_ref(x, w, scale, shift, res, case[7], case[8], case[10])
+        out_f = ops.conv_gemm(dev(x, bf), dev(w, bf), dev(scale), dev(shift), None if res is None else dev(res, bf),
+                              stride=case[7], pad=case[8], relu=case[10], want_f32=True, want_bf16=False)
+        torch.cuda.synchronize()
+        assert_close(host(out_f), ref, 2e-5, "small im2col tensor (bf16) %s" % (case,))
+    case = (2, 4, 13, 64, 128, 3, 3, (1, 1), (1, 1), False, True)             # 26 KiB of fp32, 3xTF32 kernel
+    x, w, scale, shift, res = _conv_inputs(case, 43, False)
+    ref = _conv_ref(x, w, scale, shift, res, case[7], case[8], case[10])
+    out = ops.conv_gemm(dev(x), ops.SplitWeight(dev(w)), dev(scale), dev(shift), None, stride=case[7], pad=case[8],
+                        relu=case[10])
     torch.cuda.synchronize()
-    assert torch.equal(base, wide)
-    ref = _conv_ref(x, w, scale, shift, res, (1, 1), (1, 1), True)
-    assert_close(host(wide), orc.round_bf16(ref.astype(np.float32)), 1e-2, "conv_gemm_bf16 wide tile")
-
-
-def test_conv_gemm_bf16_pair_two_accumulators_opt_in(monkeypatch):
-    """C_out = 128 on the CTA-pair kernel with two 256-row accumulators per pair (MSTR_CONV_PAIR_MT2=1) must give
-    the same bits as the default single-CTA kernel; ragged M (not a multiple of 512), several tiles per pair."""
-    case = (37, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), False, True)
-    x, w, scale, shift, res = _conv_inputs(case, 8, True)
-    bf = torch.bfloat16
-    args = (dev(x, bf), dev(w, bf), dev(scale), dev(shift), None)
-    kw = dict(stride=(1, 1), pad=(1, 1), relu=True, want_f32=False, want_bf16=True)
-    monkeypatch.delenv("MSTR_CONV_PAIR_MT2", raising=False)
-    base = ops.conv_gemm(*args, **kw)
-    monkeypatch.setenv("MSTR_CONV_PAIR_MT2", "1")
-    pair = ops.conv_gemm(*args, **kw)
-    torch.cuda.synchronize()
-    assert torch.equal(base, pair)
+    assert_close(host(out), ref, 5e-6, "small im2col tensor (3xTF32)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -330,26 +321,29 @@ def test_bilstm_recurrent(B, T):
 
 @pytest.mark.parametrize("kernel", ["single", "cluster"])
 @pytest.mark.parametrize("B,T", [(1, 26), (130, 26), (128, 5), (3, 65), (2, 1), (5, 2), (700, 3)])
-def test_bilstm_recurrent_bf16_tensor_cores(B, T, kernel, monkeypatch):
+def test_bilstm_recurrent_bf16_tensor_cores(B, T, kernel):
     """tcgen05 recurrence (h_t in bf16, tanh.approx gates) vs the oracle with bf16-rounded W_hh / h_t, for both
     kernels: one CTA per crop tile streaming W_hh (bilstm_tc.cu) and the 8-CTA cluster with stationary W_hh
     slices and the DSMEM exchange of h (bilstm_cluster.cu); the dispatcher picks by occupancy."""
-    monkeypatch.setenv("MSTR_BILSTM_CLUSTER", "1" if kernel == "cluster" else "0")
     r = rng(17)
     Hd = 256
     gx = r.standard_normal((B, T, 2, 4 * Hd)).astype(np.float32)
     w_hh = (r.uniform(-1, 1, (2, 4 * Hd, Hd)) / 16).astype(np.float32)
     ref = np.concatenate([orc._lstm_direction(gx[:, :, d].astype(np.float64), w_hh[d].astype(np.float64), bool(d),
                                               quant="bf16") for d in range(2)], axis=2)
-    out = ops.bilstm_recurrent_bf16(dev(gx), ops.pack_w_hh_bf16(dev(w_hh)))
-    torch.cuda.synchronize()
+    try:
+        ops.set_bilstm_kernel(kernel)
+        out = ops.bilstm_recurrent_bf16(dev(gx), ops.pack_w_hh_bf16(dev(w_hh)))
+        torch.cuda.synchronize()
+    finally:
+        ops.set_bilstm_kernel("auto")
     # tanh.approx (2^-11) and bf16 storage of h (2^-9): a rounding flip of h_t moves later steps by ~1 ulp
     assert_close(host(out), ref, 2e-2, "bilstm_recurrent_bf16")
     d = np.abs(host(out).astype(np.float64) - ref)
     assert d.mean() < 2e-3, "mean abs error %.3e" % d.mean()
 
 
-def test_bilstm_cluster_kernel_bit_identical_to_single_cta_kernel(monkeypatch):
+def test_bilstm_cluster_kernel_bit_identical_to_single_cta_kernel():
     """Both tensor-core recurrences feed the same bf16 operands to the MMAs in the same k order, so the cluster
     kernel (DSMEM exchange of h) must reproduce the single-CTA kernel bit for bit: a race detector for the
     cross-CTA protocol (tools/soak_bilstm.py runs it longer)."""
@@ -357,11 +351,14 @@ def test_bilstm_cluster_kernel_bit_identical_to_single_cta_kernel(monkeypatch):
     for i, (B, T) in enumerate([(768, 26), (129, 65), (1, 3), (640, 26), (257, 10), (300, 26)]):
         gx = torch.randn(B, T, 2, 1024, device=DEV, generator=g) * (1.0 + (i % 3))
         w = ops.pack_w_hh_bf16(torch.randn(2, 1024, 256, device=DEV, generator=g) / 16)
-        monkeypatch.setenv("MSTR_BILSTM_CLUSTER", "0")
-        a = ops.bilstm_recurrent_bf16(gx, w)
-        monkeypatch.setenv("MSTR_BILSTM_CLUSTER", "1")
-        b = ops.bilstm_recurrent_bf16(gx, w)
-        torch.cuda.synchronize()
+        try:
+            ops.set_bilstm_kernel("single")
+            a = ops.bilstm_recurrent_bf16(gx, w)
+            ops.set_bilstm_kernel("cluster")
+            b = ops.bilstm_recurrent_bf16(gx, w)
+            torch.cuda.synchronize()
+        finally:
+            ops.set_bilstm_kernel("auto")
         assert torch.equal(a, b), "B=%d T=%d" % (B, T)
 
 
@@ -460,10 +457,12 @@ def _decoder_pack_bf16(sd, Hd=256):
             "w_score": t(p + "score.weight").view(-1).contiguous()}
 
 
-def test_attn_decode_bf16_crop_groups_match_single_chain(sd_cfg_a):
-    """The decoder's crop groups (chains on forked side streams) must give exactly the single-chain result,
-    including ragged last groups, teacher forcing, early exit and work queued behind the call."""
-    Hd, B, T, steps = 256, 300, 26, 26
+@pytest.mark.parametrize("B,T,steps", [(300, 26, 26), (1100, 26, 26), (9, 65, 51)])
+def test_attn_decode_bf16_persistent_kernel_matches_launch_chain(sd_cfg_a, B, T, steps):
+    """The persistent decoder (one cooperative launch, grid barriers between the phases of a step) must give exactly
+    the result of the chain of three launches per step: greedy, early exit, teacher forcing; ragged crop tiles; more
+    tiles than SMs (B = 1100: 72 cell tiles + several crops per warp); work queued behind the call."""
+    Hd = 256
     enc = orc.round_bf16((rng(28).standard_normal((B, T, Hd)) * 0.5).astype(np.float32))
     w_i2h = orc.round_bf16(sd_cfg_a["decoder.attention_cell.i2h.weight"])
     proj = orc.round_bf16((enc.astype(np.float64) @ w_i2h.astype(np.float64).T).astype(np.float32))
@@ -477,22 +476,21 @@ def test_attn_decode_bf16_crop_groups_match_single_chain(sd_cfg_a):
         out = []
         for txt, ee in ((None, False), (None, True), (dev(text), False)):
             r = ops.attn_decode_bf16(e, p_, pk, steps, txt, early_exit=ee, want_alpha=True)
-            # consumer on the caller's stream right behind the call: must see the joined result
+            # consumer on the caller's stream right behind the call
             out.append((r["logits"].clone(), r["ids"].clone(), r["lengths"].clone(), r["alpha"].clone()))
         torch.cuda.synchronize()
         return [[host(t) for t in r] for r in out]
 
     try:
-        ops.set_decode_groups(1, 0)
-        single = run()
-        ops.set_decode_groups(3, 100)       # groups of 128 crops: [0,128) [128,256) [256,300)
-        grouped = run()
-        ops.set_decode_groups(4, 64)        # 128, 128, 44 (a fourth group would be empty)
-        grouped4 = run()
+        ops.set_decode_persistent(False)
+        chain = run()
+        ops.set_decode_persistent(True)
+        persistent = run()
+        again = run()
     finally:
-        ops.set_decode_groups(1, 0)
-    for other in (grouped, grouped4):
-        for a, b in zip(single, other):
+        ops.set_decode_persistent(True)
+    for other in (persistent, again):
+        for a, b in zip(chain, other):
             for x, y in zip(a, b):
                 assert np.array_equal(x, y)
 

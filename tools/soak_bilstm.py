@@ -12,9 +12,9 @@ for i in range(reps):
     T = [26, 65, 3, 26, 10][i % 5]
     gx = torch.randn(B, T, 2, 1024, device="cuda", generator=g) * (1.0 + (i % 3))
     w = ops.pack_w_hh_bf16(torch.randn(2, 1024, 256, device="cuda", generator=g) / 16)
-    os.environ["MSTR_BILSTM_CLUSTER"] = "0"
+    ops.set_bilstm_kernel("single")
     a = ops.bilstm_recurrent_bf16(gx, w)
-    os.environ["MSTR_BILSTM_CLUSTER"] = "1"
+    ops.set_bilstm_kernel("cluster")
     b = ops.bilstm_recurrent_bf16(gx, w)
     torch.cuda.synchronize()
     if not torch.equal(a, b):

@@ -1,12 +1,12 @@
-"""Timing of the sequence-stage kernels in isolation (BiLSTM recurrence, tensor-core decoder with 1..4 crop
-groups) at the bench geometry.  Usage (GPU box): python tools/tune_seq.py [B]"""
+"""Timing of the sequence-stage kernels in isolation (BiLSTM recurrence; tensor-core decoder as one persistent
+launch and as the launch chain) at the bench geometry.  Usage (GPU box): python tools/tune_seq.py [B ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from multimodal_scene_text_recognition_b200 import ops, synth
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+BATCHES = [int(a) for a in sys.argv[1:]] or [4096]
 T, H, steps = 26, 256, 26
 dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -23,11 +23,6 @@ def timeit(fn, reps=10):
     return float(np.median(ts)), float(min(ts))
 
 
-gx = torch.randn(B, T, 2, 4 * H, device=dev)
-w = torch.randn(2, 4 * H, H, device=dev) / 16
-wp = ops.pack_w_hh_bf16(w)
-print("bilstm_recurrent_bf16 B=%d: median %.3f ms, best %.3f ms" % ((B,) + timeit(lambda: ops.bilstm_recurrent_bf16(gx, wp))))
-
 sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(999).items() if k.startswith("decoder.")}
 p = "decoder.attention_cell."
 w_ih = sd[p + "rnn.weight_ih"]
@@ -39,10 +34,34 @@ pk = {"w_head": head.to(torch.bfloat16).contiguous(),
       "w_tok": w_ih[:, H:].t().contiguous(), "bias": (sd[p + "rnn.bias_ih"] + sd[p + "rnn.bias_hh"]).contiguous(),
       "b_h2h": sd[p + "h2h.bias"], "b_gen": sd["decoder.generator.bias"],
       "w_score": sd[p + "score.weight"].view(-1).contiguous()}
-enc = (torch.randn(B, T, H, device=dev) * 0.5).to(torch.bfloat16)
-proj = (enc.float() @ sd[p + "i2h.weight"].t()).to(torch.bfloat16)
-for groups, minc in ((1, 0), (2, 1024), (3, 1024), (4, 1024), (4, 512)):
-    ops.set_decode_groups(groups, minc)
-    med, best = timeit(lambda: ops.attn_decode_bf16(enc, proj, pk, steps, None, early_exit=False))
-    print("attn_decode_bf16 B=%d groups<=%d (min %d crops): median %.3f ms, best %.3f ms" % (B, groups, minc or 1024, med, best))
-ops.set_decode_groups(1, 0)
+w = torch.randn(2, 4 * H, H, device=dev) / 16
+wp = ops.pack_w_hh_bf16(w)
+for B in BATCHES:
+    gx = torch.randn(B, T, 2, 4 * H, device=dev)
+    print("bilstm_recurrent_bf16 B=%d: median %.3f ms, best %.3f ms" % ((B,) + timeit(lambda: ops.bilstm_recurrent_bf16(gx, wp))))
+    enc = (torch.randn(B, T, H, device=dev) * 0.5).to(torch.bfloat16)
+    proj = (enc.float() @ sd[p + "i2h.weight"].t()).to(torch.bfloat16)
+    for persistent in (False, True):
+        ops.set_decode_persistent(persistent)
+        med, best = timeit(lambda: ops.attn_decode_bf16(enc, proj, pk, steps, None, early_exit=False))
+        print("attn_decode_bf16 B=%d %s: median %.3f ms, best %.3f ms" % (
+            B, "persistent (1 launch)" if persistent else "chain (80 launches)", med, best))
+    ops.set_decode_persistent(True)
+
+# phase trace of the persistent decoder (CTA 0): per step [head work, barrier, attention work, barrier, cell work, barrier]
+import ctypes
+from multimodal_scene_text_recognition_b200 import _cabi
+for B in BATCHES:
+    enc = (torch.randn(B, T, H, device=dev) * 0.5).to(torch.bfloat16)
+    proj = (enc.float() @ sd[p + "i2h.weight"].t()).to(torch.bfloat16)
+    ops.attn_decode_bf16(enc, proj, pk, steps, None, early_exit=False)
+    ops.attn_decode_bf16(enc, proj, pk, steps, None, early_exit=False)
+    torch.cuda.synchronize()
+    n = 1 + 6 * steps
+    buf = (ctypes.c_ulonglong * n)()
+    _cabi.check(_cabi.lib().mstr_debug_decode_trace(ctypes.cast(buf, ctypes.c_void_p), n))
+    t = np.array(list(buf), dtype=np.float64)
+    d = np.diff(t).reshape(steps, 6) / 1e3
+    names = ["head work", "barrier 1", "attention", "barrier 2", "cell work", "barrier 3"]
+    print("persistent decoder phase trace B=%d (us, median over steps): %s | step total %.1f" % (
+        B, ", ".join("%s %.2f" % (nm, v) for nm, v in zip(names, np.median(d, axis=0))), np.median(d.sum(axis=1))))

@@ -262,7 +262,7 @@ def other_config(geom, B, precision, dev, peaks, semantic="overlap", reps=5):
 def run_ours(args):
     import torch.distributed as dist
     from multimodal_scene_text_recognition_b200 import _cabi, config, ops, parallel, synth
-    from multimodal_scene_text_recognition_b200.pipeline import HostBatchPrefetcher
+    from multimodal_scene_text_recognition_b200.pipeline import GraphedRecognizer, HostBatchPrefetcher
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the recognition path has no CPU implementation "
@@ -279,6 +279,18 @@ def run_ours(args):
     peaks = _peaks()
     model = build_model(synth.CFG_A, args.precision, dev)
     steps_out = config.MAX_TEXT_LENGTH + 1
+    # CUDA-graph replay of the forward (pipeline.GraphedRecognizer): one cudaGraphLaunch per step instead of ~50 launches
+    # issued from Python.  "auto": on for N > 1, where the shards are small (512 crops at N = 8: ~5 ms of GPU work against
+    # ~1.3 ms of host enqueue, on a host shared by N ranks); at N = 1 the eager path is used so that the per-launch
+    # CUDA events of the roofline can be recorded inside the timed region (a graph replay has no per-kernel events).
+    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
+    graphed = GraphedRecognizer(model) if use_graph else None
+
+    def recognize(x, sem):
+        if graphed is not None:
+            return graphed(x, *sem)
+        with torch.no_grad():
+            return model.recognize(x, *sem)
 
     def make_workload(global_batch, sharded):
         """This rank's crops: two alternating host sets (pinned) and their device copies.  ``sharded``: every rank
@@ -316,8 +328,7 @@ def run_ours(args):
     def make_steps(wl):
         def step_device(k):
             x, sem = wl["dev"][k % 2]
-            with torch.no_grad():
-                out = model.recognize(x, *sem)
+            out = recognize(x, sem)
             return gather(out["ids"], out["lengths"], wl["global"])
 
         prefetcher = HostBatchPrefetcher(dev, depth=2)
@@ -334,8 +345,7 @@ def run_ours(args):
                 stage(k)
             tensors, ready, sid = staged.pop(k)
             torch.cuda.current_stream().wait_event(ready)
-            with torch.no_grad():
-                out = model.recognize(tensors[0], *tensors[1:])
+            out = recognize(tensors[0], tensors[1:])
             prefetcher.release(sid)
             stage(k + 1)                                    # H2D of the next step's inputs, overlapped
             ids, lengths = gather(out["ids"], out["lengths"], wl["global"])
@@ -375,10 +385,25 @@ def run_ours(args):
         torch.cuda.synchronize()
         gather_events.clear()
         launches0 = _cabi.launch_count()
-        ops.TIMER = ops.KernelTimer() if (with_timer and rank == 0) else None
+        ops.TIMER = ops.KernelTimer() if (with_timer and rank == 0 and graphed is None) else None
         total_ms, per_rank = timed(step_device, args.steps)
         timer, ops.TIMER = ops.TIMER, None
         launches = _cabi.launch_count() - launches0
+        timer_where = "inside the timed region"
+        if graphed is not None:
+            # the kernels of a replayed step were launched (and counted) once, at capture
+            launches = graphed.launches_per_replay(wl["dev"][0][0], *wl["dev"][0][1]) * args.steps
+            if with_timer and rank == 0:
+                # per-launch CUDA events cannot be recorded inside a graph replay: the same kernels, launched eagerly
+                # for the same number of steps right after the timed region (steady state, same clocks)
+                x, sem = wl["dev"][0]
+                ops.TIMER = ops.KernelTimer()
+                with torch.no_grad():
+                    for _ in range(args.steps):
+                        model.recognize(x, *sem)
+                torch.cuda.synchronize()
+                timer, ops.TIMER = ops.TIMER, None
+                timer_where = "eager launches of the same kernels right after the (graph-replayed) timed region"
         gather_ms = sum(s.elapsed_time(e) for s, e in gather_events) / max(args.steps, 1)
         for k in range(2):                     # the host-buffer path has its own allocation pattern: warm it up too
             step_e2e(k)
@@ -389,7 +414,7 @@ def run_ours(args):
         d2h = (wl["ids_host"].numel() + wl["len_host"].numel()) * 4 * world
         return {"global": global_batch, "local": wl["local"], "total_ms": total_ms, "per_rank_ms": per_rank,
                 "gather_ms_per_step": gather_ms, "e2e_ms": e2e_ms, "launches": launches, "timer": timer,
-                "h2d": h2d, "d2h": d2h}
+                "timer_where": timer_where, "h2d": h2d, "d2h": d2h}
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     strong = args.scaling == "strong"
@@ -444,6 +469,7 @@ def run_ours(args):
         "config": {
             "workload": WORKLOAD, "global_batch": main["global"], "batch_per_gpu": main["local"],
             "precision": args.precision,
+            "launch": "CUDA graph replay (1 cudaGraphLaunch per step)" if use_graph else "eager (one launch per kernel)",
             "parallelism": ("one global batch sharded %d crops per rank, 1 process/GPU, allgather(ids) only" % main["local"]
                             if strong else "%d crops per rank, 1 process/GPU, allgather(ids) only" % main["local"])
             if world > 1 else "single GPU",
@@ -463,7 +489,7 @@ def run_ours(args):
                           conv["ms"] / max(conv["launches"], 1)),
             "achieved": round(conv_tflops, 1), "peak": peak, "unit": "TFLOP/s",
             "frac": round(conv_tflops / peak, 4) if peak else None, "traffic": traffic,
-            "peak_source": peaks["source"] + ", sustained cuBLAS bf16",
+            "peak_source": peaks["source"] + ", sustained cuBLAS bf16", "timed": main["timer_where"],
             "whole_step_frac": round(value / world * CONV_FLOP_PER_CROP / 1e12 / peak, 4),
             "all_conv_gemm_tflops": round(gemm_work / max(gemm_ms, 1e-9) / 1e9, 1),
         },
@@ -497,6 +523,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="crops of the global batch (strong) / per GPU (weak)")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
     ap.add_argument("--precision", choices=["bf16", "tf32", "fp32"], default="bf16")
+    ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto", help="CUDA-graph replay of the forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip other_configs / gpu_eager_baseline / the other scaling mode")
     ap.add_argument("--kernel-table", default=None, help="write the per-call-site kernel table (JSON) to this path")

@@ -72,7 +72,9 @@ int mstr_tps_rectify(const float* img, const float* c_prime, const float* basis,
  * (modules/feature_extraction.py:58-60,111-113 conv0_1/bn0_1; modules/transformation.py:49-51
  * conv.0/conv.1/ReLU/MaxPool).  SIMT: K = 9*C_in is too small for tensor cores.
  *   x [B][C_in][H][W] f32 NCHW;  w [C_out][C_in][3][3] f32;  scale/shift [C_out] f32 (folded BN)
- *   out NHWC [B][H'][W'][C_out] of out_dtype, H' = H/2 if pool else H.
+ *   pool = 0: out NHWC [B][H][W][C_out] of out_dtype;  pool = 1: fused 2x2 max-pool, out [B][H/2][W/2][C_out];
+ *   pool = 2: bf16 only, out is the padded-flat activation [B][H+2][W+2][C_out] with a ZERO one-pixel ring that
+ *             mstr_conv3x3_flat_bf16 consumes.
  */
 int mstr_conv3x3_first(const float* x, const float* w, const float* scale, const float* shift,
                        void* out, int out_dtype, int B, int C_in, int H, int W, int C_out,
@@ -133,6 +135,23 @@ int mstr_conv_gemm_tf32(const float* x, const float* w_hi, const float* w_lo, co
  */
 int mstr_maxpool_nhwc(const void* x, void* out, int dtype, int B, int H, int W, int C, int kh,
                       int kw, int sh, int sw, int ph, int pw, mstr_stream_t stream);
+/* 2x2 / stride 2 max-pool whose INPUT is a padded-flat bf16 activation [B][H+2][W+2][C] (one-pixel ring, skipped), the
+ * layout mstr_conv3x3_flat_bf16 writes; out [B][H/2][W/2][C] bf16 (modules/feature_extraction.py:66,116). */
+int mstr_maxpool2x2_ring_bf16(const void* x_ring, void* out, int B, int H, int W, int C, mstr_stream_t stream);
+
+/* 3x3 / stride 1 / pad 1 convolution + folded BatchNorm + ReLU over a PADDED-FLAT activation (csrc/conv_flat.cu):
+ * replaces conv0_2 + bn0_2 + ReLU (modules/feature_extraction.py:61-63,113-115) in the bf16 mode.
+ *   x   [B][H+2][W+2][C_in] bf16 whose one-pixel ring is zero (mstr_conv3x3_first with pool = 2 writes it)
+ *   w   [C_out][3][3][C_in] bf16; scale, shift [C_out] f32 (NULL = 1 / 0)
+ *   out [B][H+2][W+2][C_out] bf16, ring written as zeros
+ * Every activation row is loaded once per tile of 256 positions; the nine taps are shared-memory descriptor offsets.
+ * C_in = 32 and C_out = 64 only. */
+int mstr_conv3x3_flat_bf16(const void* x, const void* w, const float* scale, const float* shift, void* out, int B,
+                           int H, int W, int C_in, int C_out, int relu, mstr_stream_t stream);
+/* Test hook of mstr_conv3x3_flat_bf16: 0 (default) leaves the "matrix base offset" field of the row-shifted A
+ * descriptors zero - correct on B200, the swizzle is applied to absolute address bits; 1 sets it to the phase of the
+ * start address (wrong result; kept as the experiment that pins the rule, tests/test_gpu_kernels.py). */
+int mstr_debug_flat_desc_mode(int mode);
 int mstr_mean_hw(const void* x, float* out, int dtype, int B, int H, int W, int C,
                  mstr_stream_t stream);
 int mstr_mean_h(const void* x, void* out, float* out_f32, int dtype, int B, int H, int W, int C,
@@ -209,7 +228,8 @@ int mstr_attn_decode(const float* enc, const float* proj, const float* w_h2h, co
  *   w_head [384][Hd] bf16: rows 0..255 = h2h.weight, rows 256..256+C-1 = generator.weight, rest zero
  *   w_cat  [4*Hd][2*Hd] bf16: [rnn.weight_ih[:, :Hd] | rnn.weight_hh] with rows re-ordered like
  *          mstr_bilstm_recurrent_bf16's w_hh_packed (chunk*128 + g*32 + j <- g*Hd + chunk*32 + j)
- *   w_tok  [C][4*Hd] f32 = rnn.weight_ih[:, Hd:]^T (original gate-major columns); bias [4*Hd] f32
+ *   w_tok  [C][4*Hd] f32 = rnn.weight_ih[:, Hd:]^T (original gate-major columns); bias [4*Hd] f32, or NULL when
+ *          the caller has already added it to every row of w_tok (one load less per gate and unit)
  *   workspace: mstr_attn_decode_bf16_workspace_bytes(B, Hd) bytes of device memory (16-byte aligned)
  *   logits must be zero-initialised by the caller; ids / lengths / alpha_out as in mstr_attn_decode.
  */
@@ -220,13 +240,15 @@ int mstr_attn_decode_bf16(const void* enc_bf16, const void* proj_bf16, const voi
                           int32_t* lengths, float* alpha_out, int B, int T, int Hd, int C, int steps,
                           int early_exit, mstr_stream_t stream);
 
-/* mstr_attn_decode_bf16 runs as one persistent launch (on = 1, the default).  on = 0 selects the same phases as a
- * chain of three launches per step (programmatic dependent launch); both give bit-identical results - the chain is
- * kept as the cross-check of the persistent kernel's barriers (tests/test_gpu_kernels.py). */
+/* Driver of mstr_attn_decode_bf16: on = -1 (default) picks by batch size - the persistent launch up to 2048 crops,
+ * where a step is latency bound, the chain of three launches per step (programmatic dependent launch) beyond, where the
+ * attention phase is bandwidth bound; 1 / 0 force one.  Both give bit-identical results (tests/test_gpu_kernels.py). */
 int mstr_set_decode_persistent(int on);
 /* Diagnostic: %globaltimer (ns) of CTA 0 at the start of the last persistent decode on the current device and at
- * every grid-barrier entry and exit (two values per barrier, three barriers per step); synchronises the device. */
-int mstr_debug_decode_trace(unsigned long long* out_host, int n);
+ * every grid-barrier entry and exit (two values per barrier, three barriers per step) -> out_host[n]; optionally the
+ * barrier-entry time of every CTA at the first 48 barriers -> per_cta_host[48 * 160] (barrier-major).  Synchronises
+ * the device. */
+int mstr_debug_decode_trace(unsigned long long* out_host, int n, unsigned long long* per_cta_host, int n_cta);
 
 /* Input side of the path: the loader's transforms.Resize((32,100)) + ToTensor()
  * (coco_dataset.py:27,40-41) on a ragged batch of grayscale uint8 crops, bit-exact with Pillow's antialiased

@@ -31,6 +31,9 @@ SIGNATURES = {
     "mstr_conv_gemm_bf16_dual": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 13 + [_P]),
     "mstr_conv_gemm_tf32": (c_int, [_P, _P, _P, _P, _P, _P, _P] + [_I] * 12 + [_P]),
     "mstr_maxpool_nhwc": (c_int, [_P, _P] + [_I] * 11 + [_P]),
+    "mstr_maxpool2x2_ring_bf16": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "mstr_conv3x3_flat_bf16": (c_int, [_P, _P, _P, _P, _P] + [_I] * 6 + [_P]),
+    "mstr_debug_flat_desc_mode": (c_int, [_I]),
     "mstr_mean_hw": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mstr_mean_h": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mstr_cast": (c_int, [_P, _P, _I, _I, c_int64, _P]),
@@ -42,7 +45,7 @@ SIGNATURES = {
     "mstr_attn_decode_bf16_workspace_bytes": (c_int64, [_I, _I]),
     "mstr_attn_decode_bf16": (c_int, [_P] * 15 + [_I] * 6 + [_P]),
     "mstr_set_decode_persistent": (c_int, [_I]),
-    "mstr_debug_decode_trace": (c_int, [_P, _I]),
+    "mstr_debug_decode_trace": (c_int, [_P, _I, _P, _I]),
     "mstr_resize_to_tensor_u8": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

@@ -67,6 +67,11 @@ RNN_TENSOR_CORES = True
 # bf16 mode only: run the 32-channel 3x3 convolution (conv0_2) over horizontal pixel pairs
 # (_pack.pack_conv_pixel_pairs): identical results, better tensor-core tile shapes.
 CONV_PIXEL_PAIRS = True
+# bf16 mode only: conv0_1 writes a padded-flat activation (one-pixel zero ring) and conv0_2 runs as ONE slab load per
+# output tile with the nine taps formed as shared-memory descriptor offsets (csrc/conv_flat.cu); maxpool1 skips the ring.
+# Applies when conv0_1 reads the image (C_in <= 4) and conv0_2 is 32 -> 64, 3x3 / 1 / 1; otherwise (and when False)
+# conv0_2 takes the pixel-pair path above.
+CONV0_FLAT = True
 # bf16 mode only: compute a BasicBlock's conv2/bn2, its 1x1 downsample conv/bn, the residual add and the ReLU as
 # one GEMM (weights concatenated along K, BatchNorm scales folded into the bf16 weights).
 FUSE_DOWNSAMPLE = True

@@ -1,24 +1,36 @@
-// Attention decoder for the bf16 throughput mode: the three GEMMs of every decode step run on the
-// tensor cores, the Bahdanau attention on all SMs, and the whole greedy loop is enqueued by ONE
-// C-ABI call (mstr_attn_decode_bf16) as three launches per step:
+// Attention decoder for the bf16 throughput mode: the three GEMMs of every decode step run on the tensor cores, the
+// Bahdanau attention on all SMs, and the whole greedy (or teacher-forced) loop is ONE C-ABI call
+// (mstr_attn_decode_bf16).  A step has three phases:
 //
 //   head_i   [hp_i | logits_{i-1}] = h_i [W_h2h ; W_gen]^T      tcgen05 GEMM, N = 384 (3 tiles of 128)
-//            epilogue: hp_i += b_h2h (f32, for the attention kernel); logits_{i-1} += b_gen -> stored,
-//            thread-local argmax over the 97 classes (TMEM lane = crop) -> id, next token, [s] bookkeeping
+//            hp tiles: += b_h2h, fp32, out through swizzled shared-memory slabs and TMA stores;
+//            logits tile: transposed through shared memory, then one warp per crop row adds b_gen, stores the row with
+//            coalesced stores and finds the argmax with shuffles -> id, next token, [s] bookkeeping
 //   ctx_i    e_t = w_score . tanh(proj[b,t,:] + hp_i[b,:]), alpha = softmax_T(e), ctx = sum_t alpha_t enc[b,t,:]
-//            one warp per crop, 16-byte bf16 loads, shuffle reductions, tanh.approx; writes ctx (bf16) into
-//            the left half of the [ctx | h] operand buffer
+//            the time steps of a crop are split into FOUR interleaved subsets, each reduced with its own online
+//            softmax (16-byte bf16 loads one iteration ahead, lane = 8 channels, shuffle reductions, tanh.approx) and
+//            combined in a fixed order; 1, 2 or 4 warps share the four subsets of a crop, so the arithmetic - and the
+//            result, bit for bit - does not depend on how many warps a batch size gets; writes ctx (bf16) into the left
+//            half of the [ctx | h] operand buffer
 //   cell_i   gates = [ctx_i | h_i] [W_ctx | W_hh]^T + W_tok[token_i] + bias -> (h_{i+1}, c_{i+1})
-//            tcgen05 GEMM, N = 1024 with rows packed (chunk of 32 units, gate, unit) so that one
-//            128-column tile carries i,f,g,o of the same units and the LSTM cell is thread-local in the
-//            epilogue; c stays f32 in global memory (L2 resident), h_{i+1} is written as bf16 into the
-//            right half of the other [ctx | h] buffer
+//            tcgen05 GEMM, N = 1024 with rows packed (chunk of 32 units, gate, unit) so that one 128-column tile
+//            carries i,f,g,o of the same units and the LSTM cell is thread-local in the epilogue; c stays f32 in global
+//            memory (L2 resident, transposed [H][B]), h_{i+1} is written as bf16 into the right half of the other
+//            [ctx | h] buffer
+// Every GEMM epilogue runs on EIGHT warps (two per TMEM lane quarter, each half of the tile's columns).
 //
-// Replaces modules/decoders.py:26-64 (Attention.forward greedy :52-62 and teacher-forced :41-50
-// branches), :79-101 (AttentionCell.forward), :17/:59 (generator), :19-24 (_char_to_onehot: a one-hot
-// times W_ih is a row gather of W_tok).  proj = i2h(enc) is loop invariant (:81) and computed once by
-// the caller.  Differences to the fp32 SIMT kernel (attn_decode.cu): proj / enc / h / ctx are bf16
-// operands (fp32 accumulation everywhere), tanh.approx in the attention scores.
+// Two drivers run the same phase bodies (same tiles, MMA order and epilogue arithmetic: bit-identical results):
+//   * attn_decode_persistent_kernel (default): ONE cooperative launch, one CTA per SM, resident for all steps; the
+//     phases are distributed over the grid and separated by grid-wide barriers; TMEM, mbarriers and tensor maps are
+//     set up once;
+//   * the launch chain (mstr_set_decode_persistent(0)): three launches per step with programmatic dependent launch -
+//     the cross-check of the persistent kernel's barriers and proxy fences (tests/test_gpu_kernels.py).
+//
+// Replaces modules/decoders.py:26-64 (Attention.forward greedy :52-62 and teacher-forced :41-50 branches), :79-101
+// (AttentionCell.forward), :17/:59 (generator), :19-24 (_char_to_onehot: a one-hot times W_ih is a row gather of
+// W_tok).  proj = i2h(enc) is loop invariant (:81) and computed once by the caller.  Differences to the fp32 SIMT
+// kernel (attn_decode.cu): proj / enc / h / ctx are bf16 operands (fp32 accumulation everywhere), tanh.approx in the
+// attention scores.
 #include <atomic>
 
 #include "tc_common.cuh"
@@ -29,8 +41,14 @@ constexpr int AT_H = 256;
 constexpr int AT_BLOCK = 128;      // BLOCK_M = BLOCK_N
 constexpr int AT_STAGES = 3;
 constexpr int AT_TILE_BYTES = 128 * 128;   // [128 rows][64 k] bf16, 128B swizzle
-constexpr int AT_THREADS = 192;
-constexpr int AT_SMEM_BYTES = 1024 + AT_STAGES * 2 * AT_TILE_BYTES + 256;
+constexpr int AT_EPI_WARPS = 8;            // two per TMEM lane quarter
+constexpr int AT_EPI_THREADS = 32 * AT_EPI_WARPS;
+constexpr int AT_THREADS = 64 + AT_EPI_THREADS;   // launch chain: producer, MMA issuer, 8 epilogue warps
+constexpr int AT_STG_LD = AT_BLOCK + 1;    // odd row stride of the transposing stage (conflict-free row-wise writes)
+constexpr int AT_STG_BYTES = AT_BLOCK * AT_STG_LD * 4 + 512;   // 66560: stage, or 4 f32 output slabs + 128 bias values
+constexpr int AT_SMEM_BYTES = 1024 + AT_STAGES * 2 * AT_TILE_BYTES + 256 + 512;
+static_assert(4 * EPI_SLAB_BYTES + 512 <= AT_STG_BYTES, "hp slabs + bias fit in the stage");
+static_assert(AT_STG_BYTES <= AT_STAGES * 2 * AT_TILE_BYTES, "the launch chain reuses its operand stages as the stage");
 
 struct DecodeState {
   // operand / state buffers (device)
@@ -39,7 +57,7 @@ struct DecodeState {
   float* cst;             // [256][B] (transposed: the cell epilogue's lane = crop accesses are coalesced)
   int32_t* tok;           // [B] token fed to the current step
   int32_t* done;          // [B] crop has emitted [s]
-  int32_t* live;          // [1] number of crops still decoding (early exit)
+  int32_t* live;          // [1] number of crops still decoding (early exit); live[1] = grid-barrier arrival counter
   // parameters
   const float* b_h2h; const float* b_gen; const float* w_score; const float* w_tok; const float* bias;
   const int64_t* text;    // optional teacher forcing [B][steps]
@@ -48,21 +66,372 @@ struct DecodeState {
   int B, T, C, steps, early_exit;
 };
 
-// Programmatic dependent launch: every kernel of the decode chain is launched with
+// Programmatic dependent launch (launch chain): every kernel of the chain is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may be scheduled (and run their prologue:
 // barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel drains; griddep_wait() blocks
 // until the previous grid has completed and its writes are visible, and must precede every dependent access.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 __device__ __forceinline__ float at_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float at_tanh(float x) { return fmaf(2.f, at_sigmoid(2.f * x), -1.f); }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+
+// One of the eight epilogue warps: TMEM lane quarter (= warp index mod 4, a hardware rule), column half, lane.
+struct EpiWho {
+  int quarter, half, lane;
+  __device__ __forceinline__ int row() const { return quarter * 32 + lane; }       // crop row of the tile
+  __device__ __forceinline__ int tid() const { return half * 128 + quarter * 32 + lane; }   // 0..255
+};
+
+// ======================================================================================================
+// phase bodies shared by the persistent kernel and the launch chain
+// ======================================================================================================
+
+// ---- head epilogue, column tiles 0 and 1: hp_i = h_i W_h2h^T + b_h2h -----------------------------------
+// The accumulator layout gives every thread one crop ROW, and rows are 1 KB apart in global memory: direct stores cost
+// 32 L1 wavefronts per instruction, and a transposing stage with per-row copy loops was measured at 3.3 us per tile.
+// Each column half goes through its own pair of swizzled [128 x 32] f32 slabs and leaves by TMA store
+// (tc_common.cuh: epi_stage_store); the issuing threads wait for their stores before the phase ends, because the
+// attention phase of OTHER CTAs reads hp.  `stage_prologue` (bias -> shared memory) runs before the accumulator is
+// awaited.  Called by all 256 epilogue threads.
+template <typename WaitAcc, typename Release>
+__device__ __forceinline__ void at_head_hp_epilogue(const DecodeState& s, const CUtensorMap* tmHp, uint8_t* stg,
+                                                    const uint32_t taddr, const EpiWho& w, const int m0, const int n_tile,
+                                                    WaitAcc wait_acc, Release release) {
+  float* sBias = reinterpret_cast<float*>(stg + 4 * EPI_SLAB_BYTES);
+  if (w.tid() < AT_BLOCK) sBias[w.tid()] = __ldg(s.b_h2h + n_tile * AT_BLOCK + w.tid());
+  wait_acc();                                            // also orders the bias staging before its use (bar.sync inside)
+  EpiStage est{stg + w.half * 2 * EPI_SLAB_BYTES, EPI_SLAB_BYTES, 2, 0, 2 + 2 * w.half};
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    const int c0 = w.half * 64 + c * 32;
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+    tmem_ld_wait();
+    if (c == 1) {
+      tc_fence_before();
+      release();
+    }
+    float y[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]) + sBias[c0 + j];
+    epi_stage_store<true>(est, tmHp, y, w.row(), n_tile * AT_BLOCK + c0, m0, w.quarter * 32 + w.lane);
+  }
+  if (w.quarter == 0 && w.lane == 0) {                   // the thread that issued this half's stores
+    bulk_wait_all();
+    fence_proxy_async_global();
+  }
+}
+
+// ---- head epilogue, column tile 2: logits of decode step (step-1) = h_step W_gen^T + b_gen ---------------
+// Phase 1: the raw accumulator is transposed into the stage (lane = row writes with an odd stride).  Phase 2: one warp
+// per crop row, lanes = classes: + b_gen, coalesced stores of the row, argmax by shuffles (the lowest index wins ties,
+// like torch.max), then the lanes do the per-crop bookkeeping of their rows.  (The first version kept the argmax
+// thread-local in phase 1: 97 dependent load-add-compare-store rounds per thread, 6 us per tile.)
+template <typename WaitAcc, typename Release>
+__device__ __forceinline__ void at_head_logits_epilogue(const DecodeState& s, float* stg, const uint32_t taddr, const EpiWho& w,
+                                                        const int m0, const int step, WaitAcc wait_acc, Release release) {
+  constexpr int LD = AT_STG_LD;
+  constexpr int ROWS = AT_BLOCK / AT_EPI_WARPS;          // 16 rows per warp in phase 2
+  const int ls = step - 1;
+  const int w8 = w.half * 4 + w.quarter;                 // 0..7
+  const int r0 = w8 * ROWS;
+  // per-row state of phase 2, lane L < ROWS <-> row r0 + L: loaded before the accumulator is awaited
+  const int my_crop = m0 + r0 + w.lane;
+  const bool my_valid = w.lane < ROWS && my_crop < s.B;
+  const int my_done = my_valid ? __ldcg(s.done + my_crop) : 0;
+  float bg[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) bg[q] = (q * 32 + w.lane < s.C) ? __ldg(s.b_gen + q * 32 + w.lane) : 0.f;
+  wait_acc();
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    const int c0 = w.half * 64 + c * 32;
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stg[w.row() * LD + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  release();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  int my_best = 0;
+#pragma unroll 4
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int crop = m0 + r0 + rr;
+    if (crop >= s.B) break;                              // uniform over the warp
+    const int row_done = __shfl_sync(0xffffffffu, my_done, rr);
+    float y[4];
+    float best = -INFINITY;
+    int besti = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int cls = q * 32 + w.lane;
+      y[q] = stg[(r0 + rr) * LD + cls] + bg[q];
+      if (cls < s.C && y[q] > best) { best = y[q]; besti = cls; }     // ascending classes: the lowest index wins ties
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    if (!(s.early_exit && row_done)) {
+      float* lrow = s.logits + ((size_t)crop * s.steps + ls) * s.C;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q * 32 + w.lane < s.C) lrow[q * 32 + w.lane] = y[q];
+    }
+    if (w.lane == rr) my_best = besti;
+  }
+  if (my_valid) {
+    const bool was_done = s.early_exit && my_done != 0;
+    if (was_done) {
+      s.ids[(size_t)my_crop * s.steps + ls] = 0;         // argmax of the zero-initialised logits row
+    } else {
+      s.ids[(size_t)my_crop * s.steps + ls] = my_best;
+      if (my_best == 1 && my_done == 0) {
+        if (s.lengths && __ldcg(s.lengths + my_crop) == s.steps) s.lengths[my_crop] = ls;
+        if (s.early_exit) {
+          s.done[my_crop] = 1;
+          atomicSub(s.live, 1);
+        }
+      }
+    }
+    if (step < s.steps) s.tok[my_crop] = s.text ? (int)s.text[(size_t)my_crop * s.steps + step] : my_best;
+  }
+}
+
+// ---- cell epilogue: this tile = 32 hidden units x 4 gates of 128 crops; this warp: 16 of the units -------
+// Everything the LSTM cell needs besides the accumulator - the token's row of W_tok (+ bias) and the previous cell
+// state - is loaded one group of 4 units AHEAD (the first group before the accumulator is even complete: `wait_acc`
+// blocks on the MMAs), so the L2 round trips overlap the MMAs and the gate math.
+template <typename WaitAcc, typename Release>
+__device__ __forceinline__ void at_cell_epilogue(const DecodeState& s, const uint32_t taddr, const EpiWho& w, const int m0,
+                                                 const int n_tile, const int step, WaitAcc wait_acc, Release release) {
+  const int crop = m0 + w.row();
+  const bool valid = crop < s.B;
+  const int ubase = w.half * 16;                         // first of this warp's 16 units within the tile's 32
+  const int unit0 = n_tile * 32 + ubase;
+  const int tok = valid ? __ldcg(s.tok + crop) : 0;
+  const float* wt = s.w_tok + (size_t)tok * (4 * AT_H);
+  float* ccol = s.cst + (size_t)unit0 * s.B + (valid ? crop : 0);   // cell state is kept [H][B]: lane = crop is coalesced
+  __nv_bfloat16* hrow = s.xh[(step + 1) & 1] + (size_t)(valid ? crop : 0) * (2 * AT_H) + AT_H + unit0;
+  float4 addn[4];
+  float cpn[4];
+  auto load_group = [&](const int sub) {                  // 4 units: W_tok[tok] (+ bias) of the four gates, c_{t-1}
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = g * AT_H + unit0 + sub * 4;
+      float4 t = __ldg(reinterpret_cast<const float4*>(wt + col));
+      if (s.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(s.bias + col));
+        t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+      }
+      addn[g] = t;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cpn[j] = __ldcg(ccol + (size_t)(sub * 4 + j) * s.B);
+  };
+  if (valid) load_group(0);
+  wait_acc();
+  uint32_t hpk[4];
+#pragma unroll
+  for (int sub = 0; sub < 4; ++sub) {
+    float add[4][4], cp[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { add[g][0] = addn[g].x; add[g][1] = addn[g].y; add[g][2] = addn[g].z; add[g][3] = addn[g].w; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cp[j] = cpn[j];
+    if (valid && sub < 3) load_group(sub + 1);
+    uint32_t a[4][4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) tmem_ld4(taddr + (uint32_t)(g * 32 + ubase + sub * 4), a[g]);
+    tmem_ld_wait();
+    if (sub == 3) {                                    // the accumulator is in registers: hand it back
+      tc_fence_before();
+      release();
+    }
+    float hv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gi = __uint_as_float(a[0][j]) + add[0][j];
+      const float gf = __uint_as_float(a[1][j]) + add[1][j];
+      const float gg = __uint_as_float(a[2][j]) + add[2][j];
+      const float go = __uint_as_float(a[3][j]) + add[3][j];
+      const float cn = fmaf(at_sigmoid(gf), cp[j], at_sigmoid(gi) * at_tanh(gg));
+      cp[j] = cn;
+      hv[j] = at_sigmoid(go) * at_tanh(cn);
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ccol[(size_t)(sub * 4 + j) * s.B] = cp[j];
+    }
+    hpk[(sub & 1) * 2] = pack_bf16x2(hv[0], hv[1]);
+    hpk[(sub & 1) * 2 + 1] = pack_bf16x2(hv[2], hv[3]);
+    if ((sub & 1) && valid) *reinterpret_cast<uint4*>(hrow + (sub - 1) * 4) = make_uint4(hpk[0], hpk[1], hpk[2], hpk[3]);
+  }
+}
+
+// ---- Bahdanau attention of one crop ----------------------------------------------------------------
+// The time steps are split into AT_VSUB = 4 interleaved subsets (t = v, v + 4, ...).  Each subset is reduced in a single
+// pass with an online softmax: every iteration scores four time steps of proj and folds them into a running (max,
+// denominator, context) while the eight 16-byte loads of the NEXT iteration are already in flight.  The partial
+// results go to shared memory and are combined in the fixed order v = 0..3.  W = 1, 2 or 4 warps share the four subsets
+// of a crop (warp `sub` takes v = sub, sub + W, ...): the arithmetic is the same for every W, so a crop's result does not
+// depend on the batch it arrived in.  The dependent chain per crop is 2 * 4 / W memory round trips - with few crops
+// per SM that chain IS the phase time (one warp walking all 26 steps: 7 round trips, 9 us).
+// `part`: [AT_VSUB][AT_PART] floats of this crop group (and round parity); `bar_id`: named barrier of the group (W > 1).
+constexpr int AT_VSUB = 4;
+constexpr int AT_PART = 4 + AT_H;
+template <int W>
+__device__ __forceinline__ void at_attention_crop(const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ proj,
+                                                  const DecodeState& s, const int step, const int crop, const int lane,
+                                                  const int sub, float* part, const int bar_id) {
+  const int T = s.T;
+  float hp[8], ws[8];
+  {
+    const float4* hp4 = reinterpret_cast<const float4*>(s.hp + (size_t)crop * AT_H + lane * 8);
+    const float4* ws4 = reinterpret_cast<const float4*>(s.w_score + lane * 8);
+    const float4 a = __ldcg(hp4), b = __ldcg(hp4 + 1), c = __ldg(ws4), d = __ldg(ws4 + 1);
+    hp[0] = a.x; hp[1] = a.y; hp[2] = a.z; hp[3] = a.w; hp[4] = b.x; hp[5] = b.y; hp[6] = b.z; hp[7] = b.w;
+    ws[0] = c.x; ws[1] = c.y; ws[2] = c.z; ws[3] = c.w; ws[4] = d.x; ws[5] = d.y; ws[6] = d.z; ws[7] = d.w;
+  }
+  const uint4* pj = reinterpret_cast<const uint4*>(proj + (size_t)crop * T * AT_H) + lane;   // 32 uint4 per time step
+  const uint4* en = reinterpret_cast<const uint4*>(enc + (size_t)crop * T * AT_H) + lane;
+  constexpr int MAX_SLOTS = 3;   // T <= 96
+  float e_slot[MAX_SLOTS];       // score of time step t lives in lane t % 32, slot t / 32 (for alpha_out)
+#pragma unroll
+  for (int k = 0; k < MAX_SLOTS; ++k) e_slot[k] = -INFINITY;
+#pragma unroll 1
+  for (int v = sub; v < AT_VSUB; v += W) {
+    const int nj = v < T ? (T - v + AT_VSUB - 1) / AT_VSUB : 0;      // time steps of this subset: t = v + 4 j
+    float mx = -INFINITY, den = 0.f;
+    float cx[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cx[q] = 0.f;
+    uint4 np[4], ne[4];
+    auto load_iter = [&](const int j0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool in = j0 + u < nj;
+        const size_t t = (size_t)(v + AT_VSUB * (j0 + u));
+        np[u] = in ? __ldg(pj + t * 32) : make_uint4(0u, 0u, 0u, 0u);
+        ne[u] = in ? __ldg(en + t * 32) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    if (nj > 0) load_iter(0);
+    for (int j0 = 0; j0 < nj; j0 += 4) {
+      uint4 vp[4], ve[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { vp[u] = np[u]; ve[u] = ne[u]; }
+      if (j0 + 4 < nj) load_iter(j0 + 4);
+      float e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w4[4] = {vp[u].x, vp[u].y, vp[u].z, vp[u].w};
+        float p = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16x2(w4[q]);
+          p = fmaf(ws[2 * q], tanh_approx(f.x + hp[2 * q]), p);
+          p = fmaf(ws[2 * q + 1], tanh_approx(f.y + hp[2 * q + 1]), p);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        const bool in = j0 + u < nj;
+        const int t = v + AT_VSUB * (j0 + u);
+        e[u] = in ? p : -INFINITY;
+        if (in && (t & 31) == lane) {
+#pragma unroll
+          for (int k = 0; k < MAX_SLOTS; ++k)
+            if ((t >> 5) == k) e_slot[k] = p;
+        }
+      }
+      // online softmax update with the four new scores (all lanes hold the same e[], mx, den)
+      const float m_new = fmaxf(fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])), mx);
+      const float rescale = __expf(mx - m_new);          // 0 on the first iteration (mx = -inf)
+      den *= rescale;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cx[q] *= rescale;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float a = __expf(e[u] - m_new);            // 0 for padded time steps (e = -inf)
+        den += a;
+        const uint32_t w4[4] = {ve[u].x, ve[u].y, ve[u].z, ve[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16x2(w4[q]);
+          cx[2 * q] = fmaf(a, f.x, cx[2 * q]);
+          cx[2 * q + 1] = fmaf(a, f.y, cx[2 * q + 1]);
+        }
+      }
+      mx = m_new;
+    }
+    float* mine = part + v * AT_PART;
+    if (lane == 0) { mine[0] = mx; mine[1] = den; }
+    *reinterpret_cast<float4*>(mine + 4 + lane * 8) = make_float4(cx[0], cx[1], cx[2], cx[3]);
+    *reinterpret_cast<float4*>(mine + 8 + lane * 8) = make_float4(cx[4], cx[5], cx[6], cx[7]);
+  }
+  // combine the four partial results (every warp of the group reads all of them)
+  if constexpr (W > 1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * W) : "memory");
+  else __syncwarp();
+  float m = -INFINITY;
+#pragma unroll
+  for (int v = 0; v < AT_VSUB; ++v) m = fmaxf(m, part[v * AT_PART]);
+  float den = 0.f;
+  float cx[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) cx[q] = 0.f;
+#pragma unroll
+  for (int v = 0; v < AT_VSUB; ++v) {
+    const float sc = __expf(part[v * AT_PART] - m);      // 0 for a subset without time steps (max = -inf)
+    den = fmaf(part[v * AT_PART + 1], sc, den);
+    const float4 c0 = *reinterpret_cast<const float4*>(part + v * AT_PART + 4 + lane * 8);
+    const float4 c1 = *reinterpret_cast<const float4*>(part + v * AT_PART + 8 + lane * 8);
+    cx[0] = fmaf(c0.x, sc, cx[0]); cx[1] = fmaf(c0.y, sc, cx[1]); cx[2] = fmaf(c0.z, sc, cx[2]); cx[3] = fmaf(c0.w, sc, cx[3]);
+    cx[4] = fmaf(c1.x, sc, cx[4]); cx[5] = fmaf(c1.y, sc, cx[5]); cx[6] = fmaf(c1.z, sc, cx[6]); cx[7] = fmaf(c1.w, sc, cx[7]);
+  }
+  const float inv = 1.f / den;
+  if (s.alpha_out) {
+#pragma unroll
+    for (int k = 0; k < MAX_SLOTS; ++k) {
+      const int t = k * 32 + lane;
+      if (t < T && ((t % AT_VSUB) % W) == sub) s.alpha_out[((size_t)crop * s.steps + step) * T + t] = __expf(e_slot[k] - m) * inv;
+    }
+  }
+  if (sub == 0) {
+    __nv_bfloat16* dst = s.xh[step & 1] + (size_t)crop * (2 * AT_H) + lane * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(cx[0] * inv, cx[1] * inv), pack_bf16x2(cx[2] * inv, cx[3] * inv),
+                                                pack_bf16x2(cx[4] * inv, cx[5] * inv), pack_bf16x2(cx[6] * inv, cx[7] * inv));
+  }
+  if constexpr (W == 1) __syncwarp();                    // the partials are rewritten by this warp's next crop
+}
+
+// Warps per crop in the attention phase: as many as keep every SM's warps busy in one round (the result does not
+// depend on it).
+static inline int attention_warps_per_crop(int B, int sms) {
+  const int warps = sms * 16;
+  return 4 * B <= warps ? 4 : (2 * B <= warps ? 2 : 1);
+}
+
+// ======================================================================================================
+// launch chain
+// ======================================================================================================
 // EPI 0: head (hp + logits/argmax), EPI 1: LSTM cell.  One 128x128 output tile per CTA; K = num_k * 64.
 template <int EPI>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(AT_THREADS, 1)
 rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const DecodeState s, const int step, const int num_k) {
+                const __grid_constant__ CUtensorMap tmHp, const DecodeState s, const int step, const int num_k) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -78,6 +447,7 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
+    if (EPI == 0) prefetch_tensormap(&tmHp);
     for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
@@ -123,138 +493,22 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue: TMEM lane = crop row =====================
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const int crop = m0 + row;
-    const bool valid = crop < s.B;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    mbar_wait(tfull_bar, 0);
-    tc_fence_after();
+    // ===================== epilogue: TMEM lane = crop row; warps 2..9 =====================
+    const EpiWho w{warp & 3, (warp - 2) >> 2, lane};
+    const uint32_t taddr = tmem_base + ((uint32_t)(w.quarter * 32) << 16);
+    auto nothing = [] {};
     if constexpr (EPI == 0) {
-      // The accumulator layout gives every thread one crop ROW, and rows are 1 KB (hp) / 10 KB (logits) apart in
-      // global memory: a direct store costs 32 L1 wavefronts per instruction (an elimination run priced these
-      // stores at 0.35 of the decoder's 1.9 ms).  The tile is therefore transposed through the (now idle)
-      // operand stages: row-wise writes with an odd stride (conflict free), then each warp copies whole rows
-      // with 128-byte coalesced stores.
-      float* stg = reinterpret_cast<float*>(smem);
-      const int ew = warp - 2;               // 0..3
+      // the operand stages are idle once the accumulator is complete: they double as the stage - so nothing may be
+      // written there before the MMAs have finished (the bias staging of the hp tiles comes after the wait)
+      auto wait_first = [&] { mbar_wait(tfull_bar, 0); tc_fence_after(); };
       if (n_tile < 2) {
-        // hp_i = h_i W_h2h^T + b_h2h  (consumed by attn_context_kernel of this step)
-        constexpr int LD = AT_BLOCK + 1;
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT_BLOCK; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[row * LD + c0 + j] = __uint_as_float(v[j]);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        float bias4[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) bias4[q] = __ldg(s.b_h2h + n_tile * AT_BLOCK + q * 32 + lane);
-#pragma unroll 4
-        for (int r = ew * 32; r < ew * 32 + 32; ++r) {
-          if (m0 + r >= s.B) break;
-          float* dst = s.hp + (size_t)(m0 + r) * AT_H + n_tile * AT_BLOCK;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q * 32 + lane] = stg[r * LD + q * 32 + lane] + bias4[q];
-        }
+        wait_first();
+        at_head_hp_epilogue(s, &tmHp, smem, taddr, w, m0, n_tile, [&] { asm volatile("bar.sync 1, 256;" ::: "memory"); }, nothing);
       } else if (step > 0) {
-        // logits of decode step (step-1) = h_step W_gen^T + b_gen; argmax feeds the token of `step`
-        constexpr int LD = 101;              // >= num_classes rounded up to odd; C <= 128 is checked by the host
-        const int ld = (s.C | 1) > LD ? (s.C | 1) : LD;
-        int* skip = reinterpret_cast<int*>(stg + AT_BLOCK * 129);   // per row: do not store (crop finished / out of range)
-        const int ls = step - 1;
-        const bool was_done = valid && s.early_exit && s.done[crop];
-        float best = -INFINITY;
-        int besti = 0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT_BLOCK; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int cls = c0 + j;
-            if (cls < s.C) {
-              const float y = __uint_as_float(v[j]) + __ldg(s.b_gen + cls);
-              stg[row * ld + cls] = y;
-              if (y > best) { best = y; besti = cls; }      // ascending: the lowest index wins ties
-            }
-          }
-        }
-        skip[row] = (!valid || was_done) ? 1 : 0;
-        if (valid) {
-          if (was_done) {
-            s.ids[(size_t)crop * s.steps + ls] = 0;          // argmax of the zero-initialised logits row
-          } else {
-            s.ids[(size_t)crop * s.steps + ls] = besti;
-            if (besti == 1 && !s.done[crop]) {
-              if (s.lengths && s.lengths[crop] == s.steps) s.lengths[crop] = ls;
-              if (s.early_exit) {
-                s.done[crop] = 1;
-                atomicSub(s.live, 1);
-              }
-            }
-          }
-          if (step < s.steps) s.tok[crop] = s.text ? (int)s.text[(size_t)crop * s.steps + step] : besti;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll 2
-        for (int r = ew * 32; r < ew * 32 + 32; ++r) {
-          if (skip[r]) continue;
-          float* lrow = s.logits + ((size_t)(m0 + r) * s.steps + ls) * s.C;
-          for (int cls = lane; cls < s.C; cls += 32) lrow[cls] = stg[r * ld + cls];
-        }
+        at_head_logits_epilogue(s, reinterpret_cast<float*>(smem), taddr, w, m0, step, wait_first, nothing);
       }
     } else {
-      // LSTM cell: this tile = 32 hidden units x 4 gates of 128 crops
-      const int unit0 = n_tile * 32;
-      const int tok = valid ? s.tok[crop] : 0;
-      const float* wt = s.w_tok + (size_t)tok * (4 * AT_H);
-      float* ccol = s.cst + (size_t)unit0 * s.B + (valid ? crop : 0);   // cell state is kept [H][B]: lane = crop is coalesced
-      __nv_bfloat16* hrow = s.xh[(step + 1) & 1] + (size_t)(valid ? crop : 0) * (2 * AT_H) + AT_H + unit0;
-#pragma unroll 1
-      for (int sub = 0; sub < 4; ++sub) {            // 8 units at a time
-        uint32_t a[4][8];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld8(taddr + (uint32_t)(g * 32 + sub * 8), a[g]);
-        tmem_ld_wait();
-        if (valid) {
-          float add[4][8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = g * AT_H + unit0 + sub * 8;
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(wt + col));
-            const float4 t1 = __ldg(reinterpret_cast<const float4*>(wt + col) + 1);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(s.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(s.bias + col) + 1);
-            add[g][0] = t0.x + b0.x; add[g][1] = t0.y + b0.y; add[g][2] = t0.z + b0.z; add[g][3] = t0.w + b0.w;
-            add[g][4] = t1.x + b1.x; add[g][5] = t1.y + b1.y; add[g][6] = t1.z + b1.z; add[g][7] = t1.w + b1.w;
-          }
-          float cp[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cp[j] = ccol[(size_t)(sub * 8 + j) * s.B];
-          float hv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float gi = __uint_as_float(a[0][j]) + add[0][j];
-            const float gf = __uint_as_float(a[1][j]) + add[1][j];
-            const float gg = __uint_as_float(a[2][j]) + add[2][j];
-            const float go = __uint_as_float(a[3][j]) + add[3][j];
-            const float cn = fmaf(at_sigmoid(gf), cp[j], at_sigmoid(gi) * at_tanh(gg));
-            cp[j] = cn;
-            hv[j] = at_sigmoid(go) * at_tanh(cn);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ccol[(size_t)(sub * 8 + j) * s.B] = cp[j];
-          *reinterpret_cast<uint4*>(hrow + sub * 8) =
-              make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]),
-                         pack_bf16x2(hv[6], hv[7]));
-        }
-      }
+      at_cell_epilogue(s, taddr, w, m0, n_tile, step, [&] { mbar_wait(tfull_bar, 0); tc_fence_after(); }, nothing);
     }
   }
 
@@ -266,511 +520,20 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-// Bahdanau attention of one decode step: one warp per crop, lane = 8 channels.
-// Single pass with an online softmax: every iteration loads four time steps of BOTH proj and enc (eight 16-byte
-// loads in flight per lane), scores them and folds them into a running (max, denominator, context).  The earlier
-// two-pass version (scores over all of proj, softmax, then enc) was a chain of 14 dependent memory round trips per
-// warp; with all 4096 warps resident at once that chain IS the kernel time (26 us at 52 % of the HBM peak).
-// 4 warps per block, 7 blocks per SM (72 registers): 28 warps x 148 SMs hold all 4096 crops of the bench batch at once.
+// Attention phase of the launch chain: 4 warps per block = 4 / W crops.
 constexpr int AT_CTX_WARPS = 4;
-__global__ void __launch_bounds__(32 * AT_CTX_WARPS, 7)
+template <int W>
+__global__ void __launch_bounds__(32 * AT_CTX_WARPS, 4)
 attn_context_kernel(const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ proj,
                     const DecodeState s, const int step) {
+  __shared__ __align__(16) float part[(AT_CTX_WARPS / W) * AT_VSUB * AT_PART];
   griddep_wait();
   griddep_launch();
   if (s.early_exit && *s.live == 0) return;
-  const int lane = threadIdx.x & 31;
-  const int crop = blockIdx.x * AT_CTX_WARPS + (threadIdx.x >> 5);
-  if (crop >= s.B) return;
-  const int T = s.T;
-  float hp[8], ws[8];
-  {
-    const float4* hp4 = reinterpret_cast<const float4*>(s.hp + (size_t)crop * AT_H + lane * 8);
-    const float4* ws4 = reinterpret_cast<const float4*>(s.w_score + lane * 8);
-    const float4 a = hp4[0], b = hp4[1], c = __ldg(ws4), d = __ldg(ws4 + 1);
-    hp[0] = a.x; hp[1] = a.y; hp[2] = a.z; hp[3] = a.w; hp[4] = b.x; hp[5] = b.y; hp[6] = b.z; hp[7] = b.w;
-    ws[0] = c.x; ws[1] = c.y; ws[2] = c.z; ws[3] = c.w; ws[4] = d.x; ws[5] = d.y; ws[6] = d.z; ws[7] = d.w;
-  }
-  const uint4* pj = reinterpret_cast<const uint4*>(proj + (size_t)crop * T * AT_H) + lane;   // 32 uint4 per time step
-  const uint4* en = reinterpret_cast<const uint4*>(enc + (size_t)crop * T * AT_H) + lane;
-  constexpr int MAX_SLOTS = 3;   // T <= 96
-  float e_slot[MAX_SLOTS];       // score of time step t lives in lane t % 32, slot t / 32 (for alpha_out)
-#pragma unroll
-  for (int k = 0; k < MAX_SLOTS; ++k) e_slot[k] = -INFINITY;
-  float mx = -INFINITY, den = 0.f;
-  float cx[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) cx[q] = 0.f;
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    uint4 vp[4], ve[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool in = t0 + u < T;
-      vp[u] = in ? __ldg(pj + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
-      ve[u] = in ? __ldg(en + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    float e[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t w4[4] = {vp[u].x, vp[u].y, vp[u].z, vp[u].w};
-      float part = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f = unpack_bf16x2(w4[q]);
-        part = fmaf(ws[2 * q], tanh_approx(f.x + hp[2 * q]), part);
-        part = fmaf(ws[2 * q + 1], tanh_approx(f.y + hp[2 * q + 1]), part);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      const int t = t0 + u;
-      e[u] = t < T ? part : -INFINITY;
-      if (t < T && (t & 31) == lane) {
-#pragma unroll
-        for (int k = 0; k < MAX_SLOTS; ++k)
-          if ((t >> 5) == k) e_slot[k] = part;
-      }
-    }
-    // online softmax update with the four new scores (all lanes hold the same e[], mx, den)
-    const float m_new = fmaxf(fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])), mx);
-    const float rescale = __expf(mx - m_new);          // 0 on the first iteration (mx = -inf)
-    den *= rescale;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) cx[q] *= rescale;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float a = __expf(e[u] - m_new);            // 0 for padded time steps (e = -inf)
-      den += a;
-      const uint32_t w4[4] = {ve[u].x, ve[u].y, ve[u].z, ve[u].w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f = unpack_bf16x2(w4[q]);
-        cx[2 * q] = fmaf(a, f.x, cx[2 * q]);
-        cx[2 * q + 1] = fmaf(a, f.y, cx[2 * q + 1]);
-      }
-    }
-    mx = m_new;
-  }
-  const float inv = 1.f / den;
-  if (s.alpha_out) {
-#pragma unroll
-    for (int k = 0; k < MAX_SLOTS; ++k) {
-      const int t = k * 32 + lane;
-      if (t < T) s.alpha_out[((size_t)crop * s.steps + step) * T + t] = __expf(e_slot[k] - mx) * inv;
-    }
-  }
-  __nv_bfloat16* dst = s.xh[step & 1] + (size_t)crop * (2 * AT_H) + lane * 8;
-  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(cx[0] * inv, cx[1] * inv), pack_bf16x2(cx[2] * inv, cx[3] * inv),
-                                              pack_bf16x2(cx[4] * inv, cx[5] * inv), pack_bf16x2(cx[6] * inv, cx[7] * inv));
-}
-
-// =====================================================================================================
-// PERSISTENT decoder: ONE cooperative launch runs all steps.
-//
-// The launch chain above pays, per step, three launch latencies, three prologues (barrier init, TMEM allocation,
-// tensor-map prefetch) and three pipeline drains: at 256 crops the decoder took 0.83 ms for ~0.1 ms of work.  Here one
-// CTA per SM stays resident for the whole decode; the three phases of a step - head GEMM tiles, attention over crops,
-// cell GEMM tiles - are distributed over the grid and separated by a grid-wide barrier (one atomic per CTA on an L2
-// word, ~1 us).  TMEM, the mbarriers and the tensor maps are set up once.  The phase bodies are the ones of the chain
-// kernels (same tiles, same MMA order, same epilogue arithmetic), so the results are bit-identical to the chain.
-//
-// What changes with the persistence:
-//  * buffers that one CTA writes and another reads in a later phase (hp, [ctx|h], c, tok, done, live, lengths) are
-//    read with ld.global.cg (L2; the L1 of the reading SM may still hold the line of the previous step);
-//  * the [ctx|h] operand is written with ordinary stores and read by TMA (async proxy) in the next phase: writers
-//    execute fence.proxy.async.global before the barrier, the TMA-issuing thread after it;
-//  * the attention phase walks its crops in alternating direction (even steps ascending, odd steps descending): every
-//    step touches all of proj+enc (109 MB at 4096 crops, about the L2 capacity), and with a fixed direction an LRU
-//    cache holds exactly the lines that are needed LAST; zig-zag reuse starts with the most recently used lines.
-// =====================================================================================================
-constexpr int PD_WARPS = 16;
-constexpr int PD_THREADS = 32 * PD_WARPS;
-constexpr int PD_STG_BYTES = AT_BLOCK * (AT_BLOCK + 1) * 4 + 512;      // transposing stage of the head epilogue + skip flags
-constexpr int PD_SMEM_BYTES = 1024 + AT_STAGES * 2 * AT_TILE_BYTES + PD_STG_BYTES + 256;
-
-__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Phase trace of CTA 0 (diagnostic, mstr_debug_decode_trace): %globaltimer at every barrier entry (this CTA's phase
-// work is done) and exit (every CTA's is), so phase work, barrier wait and barrier latency can be told apart.
-constexpr int PD_TRACE_MAX = 512;
-__device__ unsigned long long g_pd_trace[PD_TRACE_MAX];
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// Grid-wide barrier (all CTAs are co-resident: cooperative launch).  `target` is this CTA's running arrival target.
-__device__ __forceinline__ void pd_grid_barrier(unsigned int* counter, unsigned int& target, int& trace_n) {
-  fence_proxy_async_global();              // this thread's global stores -> later async-proxy (TMA) reads of any CTA
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (blockIdx.x == 0 && trace_n < PD_TRACE_MAX) g_pd_trace[trace_n++] = globaltimer_ns();
-    target += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    const long long t0 = clock64();
-    while (ld_acquire_gpu(counter) < target) {
-      if (clock64() - t0 > 4000000000ll) {
-        printf("mstr: grid barrier timed out (block %d)\n", blockIdx.x);
-        __trap();
-      }
-    }
-    __threadfence();
-    fence_proxy_async_global();
-    if (blockIdx.x == 0 && trace_n < PD_TRACE_MAX) g_pd_trace[trace_n++] = globaltimer_ns();
-  }
-  __syncthreads();
-}
-
-struct PdPipe {            // running ring / accumulator state of one role, carried across tiles, phases and steps
-  int stage = 0;
-  uint32_t phase = 0;
-  uint32_t acc_phase = 0;
-};
-
-// One GEMM phase over this CTA's tiles.  EPI 0: head, n_tiles_n column tiles starting at n_first; EPI 1: cell.
-template <int EPI>
-__device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUtensorMap* tmB, const DecodeState& s,
-                                              const int step, const int num_k, const int n_first, const int n_count,
-                                              const int m_tiles, uint8_t* sA, uint8_t* sB, float* stg, uint64_t* full_bar,
-                                              uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                              const uint32_t tmem_base, PdPipe& pipe) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = n_count * m_tiles;
-  if (warp == 0) {
-    if (lane == 0) {
-      fence_proxy_async_global();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = n_first + tile % n_count, m0 = (tile / n_count) * AT_BLOCK;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[pipe.stage], pipe.phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[pipe.stage], 2 * AT_TILE_BYTES);
-          tma_load_2d(sA + pipe.stage * AT_TILE_BYTES, tmA, &full_bar[pipe.stage], kb * 64, m0);
-          tma_load_2d(sB + pipe.stage * AT_TILE_BYTES, tmB, &full_bar[pipe.stage], kb * 64, n_tile * AT_BLOCK);
-          if (++pipe.stage == AT_STAGES) { pipe.stage = 0; pipe.phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(AT_BLOCK, AT_BLOCK);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar, pipe.acc_phase ^ 1);       // the epilogue of the previous tile has drained the accumulator
-        tc_fence_after();
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&full_bar[pipe.stage], pipe.phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + pipe.stage * AT_TILE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + pipe.stage * AT_TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, make_smem_desc<128>(a_addr + k * 32), make_smem_desc<128>(b_addr + k * 32), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[pipe.stage]);
-          if (kb == num_k - 1) umma_commit(tfull_bar);
-          if (++pipe.stage == AT_STAGES) { pipe.stage = 0; pipe.phase ^= 1; }
-        }
-        pipe.acc_phase ^= 1;
-      }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue: TMEM lane = crop row (warps 4..7 = lane quarters 0..3) =====================
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = n_first + tile % n_count, m0 = (tile / n_count) * AT_BLOCK;
-      const int crop = m0 + row;
-      const bool valid = crop < s.B;
-      mbar_wait(tfull_bar, pipe.acc_phase);
-      tc_fence_after();
-      if constexpr (EPI == 0) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // the previous tile's rows have left the stage
-        if (n_tile < 2) {
-          constexpr int LD = AT_BLOCK + 1;
-#pragma unroll 1
-          for (int c0 = 0; c0 < AT_BLOCK; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) stg[row * LD + c0 + j] = __uint_as_float(v[j]);
-          }
-          tc_fence_before();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (lane == 0) mbar_arrive(tempty_bar);
-          float bias4[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) bias4[q] = __ldg(s.b_h2h + n_tile * AT_BLOCK + q * 32 + lane);
-#pragma unroll 4
-          for (int r = quarter * 32; r < quarter * 32 + 32; ++r) {
-            if (m0 + r >= s.B) break;
-            float* dst = s.hp + (size_t)(m0 + r) * AT_H + n_tile * AT_BLOCK;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q * 32 + lane] = stg[r * LD + q * 32 + lane] + bias4[q];
-          }
-        } else {
-          constexpr int LD = 101;
-          const int ld = (s.C | 1) > LD ? (s.C | 1) : LD;
-          int* skip = reinterpret_cast<int*>(stg + AT_BLOCK * 129);
-          const int ls = step - 1;
-          const bool is_done = valid && __ldcg(s.done + crop) != 0;
-          const bool was_done = s.early_exit && is_done;
-          float best = -INFINITY;
-          int besti = 0;
-#pragma unroll 1
-          for (int c0 = 0; c0 < AT_BLOCK; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int cls = c0 + j;
-              if (cls < s.C) {
-                const float y = __uint_as_float(v[j]) + __ldg(s.b_gen + cls);
-                stg[row * ld + cls] = y;
-                if (y > best) { best = y; besti = cls; }      // ascending: the lowest index wins ties
-              }
-            }
-          }
-          tc_fence_before();
-          skip[row] = (!valid || was_done) ? 1 : 0;
-          if (valid) {
-            if (was_done) {
-              s.ids[(size_t)crop * s.steps + ls] = 0;
-            } else {
-              s.ids[(size_t)crop * s.steps + ls] = besti;
-              if (besti == 1 && !is_done) {
-                if (s.lengths && __ldcg(s.lengths + crop) == s.steps) s.lengths[crop] = ls;
-                if (s.early_exit) {
-                  s.done[crop] = 1;
-                  atomicSub(s.live, 1);
-                }
-              }
-            }
-            if (step < s.steps) s.tok[crop] = s.text ? (int)s.text[(size_t)crop * s.steps + step] : besti;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (lane == 0) mbar_arrive(tempty_bar);
-#pragma unroll 2
-          for (int r = quarter * 32; r < quarter * 32 + 32; ++r) {
-            if (skip[r]) continue;
-            float* lrow = s.logits + ((size_t)(m0 + r) * s.steps + ls) * s.C;
-            for (int cls = lane; cls < s.C; cls += 32) lrow[cls] = stg[r * ld + cls];
-          }
-        }
-      } else {
-        const int unit0 = n_tile * 32;
-        const int tok = valid ? __ldcg(s.tok + crop) : 0;
-        const float* wt = s.w_tok + (size_t)tok * (4 * AT_H);
-        float* ccol = s.cst + (size_t)unit0 * s.B + (valid ? crop : 0);
-        __nv_bfloat16* hrow = s.xh[(step + 1) & 1] + (size_t)(valid ? crop : 0) * (2 * AT_H) + AT_H + unit0;
-#pragma unroll 1
-        for (int sub = 0; sub < 4; ++sub) {
-          uint32_t a[4][8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld8(taddr + (uint32_t)(g * 32 + sub * 8), a[g]);
-          tmem_ld_wait();
-          if (sub == 3) {                                   // the accumulator is in registers: hand it back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar);
-          }
-          if (valid) {
-            float add[4][8];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = g * AT_H + unit0 + sub * 8;
-              const float4 t0 = __ldg(reinterpret_cast<const float4*>(wt + col));
-              const float4 t1 = __ldg(reinterpret_cast<const float4*>(wt + col) + 1);
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(s.bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(s.bias + col) + 1);
-              add[g][0] = t0.x + b0.x; add[g][1] = t0.y + b0.y; add[g][2] = t0.z + b0.z; add[g][3] = t0.w + b0.w;
-              add[g][4] = t1.x + b1.x; add[g][5] = t1.y + b1.y; add[g][6] = t1.z + b1.z; add[g][7] = t1.w + b1.w;
-            }
-            float cp[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cp[j] = __ldcg(ccol + (size_t)(sub * 8 + j) * s.B);
-            float hv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float gi = __uint_as_float(a[0][j]) + add[0][j];
-              const float gf = __uint_as_float(a[1][j]) + add[1][j];
-              const float gg = __uint_as_float(a[2][j]) + add[2][j];
-              const float go = __uint_as_float(a[3][j]) + add[3][j];
-              const float cn = fmaf(at_sigmoid(gf), cp[j], at_sigmoid(gi) * at_tanh(gg));
-              cp[j] = cn;
-              hv[j] = at_sigmoid(go) * at_tanh(cn);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ccol[(size_t)(sub * 8 + j) * s.B] = cp[j];
-            *reinterpret_cast<uint4*>(hrow + sub * 8) =
-                make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]),
-                           pack_bf16x2(hv[6], hv[7]));
-          }
-        }
-      }
-      pipe.acc_phase ^= 1;
-    }
-  }
-  __syncwarp();
-}
-
-// Attention of one crop by one warp (lane = 8 channels): the body of attn_context_kernel.
-__device__ __forceinline__ void pd_attention_crop(const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ proj,
-                                                  const DecodeState& s, const int step, const int crop, const int lane) {
-  const int T = s.T;
-  float hp[8], ws[8];
-  {
-    const float4* hp4 = reinterpret_cast<const float4*>(s.hp + (size_t)crop * AT_H + lane * 8);
-    const float4* ws4 = reinterpret_cast<const float4*>(s.w_score + lane * 8);
-    const float4 a = __ldcg(hp4), b = __ldcg(hp4 + 1), c = __ldg(ws4), d = __ldg(ws4 + 1);
-    hp[0] = a.x; hp[1] = a.y; hp[2] = a.z; hp[3] = a.w; hp[4] = b.x; hp[5] = b.y; hp[6] = b.z; hp[7] = b.w;
-    ws[0] = c.x; ws[1] = c.y; ws[2] = c.z; ws[3] = c.w; ws[4] = d.x; ws[5] = d.y; ws[6] = d.z; ws[7] = d.w;
-  }
-  const uint4* pj = reinterpret_cast<const uint4*>(proj + (size_t)crop * T * AT_H) + lane;
-  const uint4* en = reinterpret_cast<const uint4*>(enc + (size_t)crop * T * AT_H) + lane;
-  constexpr int MAX_SLOTS = 3;   // T <= 96
-  float e_slot[MAX_SLOTS];
-#pragma unroll
-  for (int k = 0; k < MAX_SLOTS; ++k) e_slot[k] = -INFINITY;
-  float mx = -INFINITY, den = 0.f;
-  float cx[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) cx[q] = 0.f;
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    uint4 vp[4], ve[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool in = t0 + u < T;
-      vp[u] = in ? __ldg(pj + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
-      ve[u] = in ? __ldg(en + (size_t)(t0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    float e[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t w4[4] = {vp[u].x, vp[u].y, vp[u].z, vp[u].w};
-      float part = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f = unpack_bf16x2(w4[q]);
-        part = fmaf(ws[2 * q], tanh_approx(f.x + hp[2 * q]), part);
-        part = fmaf(ws[2 * q + 1], tanh_approx(f.y + hp[2 * q + 1]), part);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      const int t = t0 + u;
-      e[u] = t < T ? part : -INFINITY;
-      if (t < T && (t & 31) == lane) {
-#pragma unroll
-        for (int k = 0; k < MAX_SLOTS; ++k)
-          if ((t >> 5) == k) e_slot[k] = part;
-      }
-    }
-    const float m_new = fmaxf(fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])), mx);
-    const float rescale = __expf(mx - m_new);
-    den *= rescale;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) cx[q] *= rescale;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float a = __expf(e[u] - m_new);
-      den += a;
-      const uint32_t w4[4] = {ve[u].x, ve[u].y, ve[u].z, ve[u].w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f = unpack_bf16x2(w4[q]);
-        cx[2 * q] = fmaf(a, f.x, cx[2 * q]);
-        cx[2 * q + 1] = fmaf(a, f.y, cx[2 * q + 1]);
-      }
-    }
-    mx = m_new;
-  }
-  const float inv = 1.f / den;
-  if (s.alpha_out) {
-#pragma unroll
-    for (int k = 0; k < MAX_SLOTS; ++k) {
-      const int t = k * 32 + lane;
-      if (t < T) s.alpha_out[((size_t)crop * s.steps + step) * T + t] = __expf(e_slot[k] - mx) * inv;
-    }
-  }
-  __nv_bfloat16* dst = s.xh[step & 1] + (size_t)crop * (2 * AT_H) + lane * 8;
-  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(cx[0] * inv, cx[1] * inv), pack_bf16x2(cx[2] * inv, cx[3] * inv),
-                                              pack_bf16x2(cx[4] * inv, cx[5] * inv), pack_bf16x2(cx[6] * inv, cx[7] * inv));
-}
-
-struct PdMaps {
-  CUtensorMap h[2], xh[2], head, cat;
-};
-
-__global__ void __launch_bounds__(PD_THREADS, 1)
-attn_decode_persistent_kernel(const __grid_constant__ PdMaps maps, const __nv_bfloat16* __restrict__ enc,
-                              const __nv_bfloat16* __restrict__ proj, const DecodeState s, unsigned int* gbar) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + AT_STAGES * AT_TILE_BYTES;
-  float* stg = reinterpret_cast<float*>(smem + 2 * AT_STAGES * AT_TILE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * AT_STAGES * AT_TILE_BYTES + PD_STG_BYTES);
-  uint64_t* empty_bar = full_bar + AT_STAGES;
-  uint64_t* tfull_bar = empty_bar + AT_STAGES;
-  uint64_t* tempty_bar = tfull_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&maps.h[0]); prefetch_tensormap(&maps.h[1]);
-    prefetch_tensormap(&maps.xh[0]); prefetch_tensormap(&maps.xh[1]);
-    prefetch_tensormap(&maps.head); prefetch_tensormap(&maps.cat);
-    for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 4);                              // one arrival per epilogue warp
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int m_tiles = (s.B + AT_BLOCK - 1) / AT_BLOCK;
-  const int gw = blockIdx.x * PD_WARPS + warp, GW = gridDim.x * PD_WARPS;
-  const int my_crops = gw < s.B ? (s.B - gw + GW - 1) / GW : 0;
-  unsigned int target = 0;
-  int trace_n = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) g_pd_trace[trace_n++] = globaltimer_ns();
-  PdPipe pipe;
-  for (int i = 0; i <= s.steps; ++i) {
-    // ---- head_i: hp_i (column tiles 0,1) and logits_{i-1} (tile 2; nothing to store at i = 0, only tile 2 at i = steps)
-    const int n_first = (i == s.steps) ? 2 : 0;
-    const int n_count = (i == s.steps) ? 1 : (i == 0 ? 2 : 3);
-    pd_gemm_phase<0>(&maps.h[i & 1], &maps.head, s, i, AT_H / 64, n_first, n_count, m_tiles, sA, sB, stg, full_bar,
-                     empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
-    if (i == s.steps) break;
-    pd_grid_barrier(gbar, target, trace_n);
-    if (s.early_exit && __ldcg(s.live) == 0) break;        // every crop has emitted [s]: the remaining logits stay zero
-    // ---- attention_i over this warp's crops, zig-zag over the steps
-    for (int kk = 0; kk < my_crops; ++kk) {
-      const int k = (i & 1) ? (my_crops - 1 - kk) : kk;
-      pd_attention_crop(enc, proj, s, i, gw + k * GW, lane);
-    }
-    pd_grid_barrier(gbar, target, trace_n);
-    // ---- cell_i
-    pd_gemm_phase<1>(&maps.xh[i & 1], &maps.cat, s, i, 2 * AT_H / 64, 0, 4 * AT_H / AT_BLOCK, m_tiles, sA, sB, stg, full_bar,
-                     empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
-    pd_grid_barrier(gbar, target, trace_n);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
-  }
+  const int crop = blockIdx.x * (AT_CTX_WARPS / W) + warp / W;
+  if (crop >= s.B) return;                               // uniform over the W warps of a group
+  at_attention_crop<W>(enc, proj, s, step, crop, lane, warp % W, part + (warp / W) * AT_VSUB * AT_PART, 2 + warp / W);
 }
 
 // token_0 = [GO] (0) or text[:, 0]; lengths = steps; done = 0; live = B; ids zero-filled.
@@ -788,10 +551,252 @@ __global__ void decode_init_kernel(const DecodeState s) {
   for (int j = i; j < s.B * s.steps; j += gridDim.x * blockDim.x) s.ids[j] = 0;
 }
 
+// ======================================================================================================
+// PERSISTENT decoder: ONE cooperative launch runs all steps.
+//
+// The launch chain pays, per step, three launch latencies, three prologues (barrier init, TMEM allocation,
+// tensor-map prefetch) and three pipeline drains.  Here one CTA per SM stays resident for the whole decode; the
+// three phases of a step are distributed over the grid and separated by a grid-wide barrier (one atomic per CTA on an
+// L2 word).  What changes with the persistence:
+//  * buffers that one CTA writes and another reads in a later phase (hp, [ctx|h], c, tok, done, live, lengths) are
+//    read with ld.global.cg (L2; the L1 of the reading SM may still hold the line of the previous step);
+//  * the [ctx|h] operand is written with ordinary stores and read by TMA (async proxy) in the next phase: writers
+//    execute fence.proxy.async.global before the barrier, the TMA-issuing thread after it; hp goes the other way
+//    (TMA stores, read with ordinary loads): the storing thread waits for its bulk group and fences;
+//  * the attention phase walks its crops in alternating direction (even steps ascending, odd steps descending): every
+//    step touches all of proj+enc (109 MB at 4096 crops, about the L2 capacity), and with a fixed direction an LRU
+//    cache holds exactly the lines that are needed LAST; zig-zag reuse starts with the most recently used lines.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 8..15 = GEMM epilogues; all 16 warps run the attention phase.
+// ======================================================================================================
+constexpr int PD_WARPS = 16;
+constexpr int PD_THREADS = 32 * PD_WARPS;
+constexpr int PD_SMEM_BYTES = 1024 + AT_STAGES * 2 * AT_TILE_BYTES + AT_STG_BYTES + 256;
+static_assert(PD_WARPS * AT_VSUB * AT_PART * 4 <= AT_STG_BYTES, "attention partials of all warps (W = 1) live in the stage");
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Phase trace (diagnostic, mstr_debug_decode_trace): %globaltimer of CTA 0 at every barrier entry (this CTA's phase
+// work is done) and exit (every CTA's is), the entry time of EVERY CTA at the first PD_TRACE_BARRIERS barriers, and a
+// fine trace of the GEMM tiles of CTAs 0..3 in step PD_FINE_STEP - phase work, barrier wait, barrier latency,
+// stragglers and the stages of a tile can be told apart (tools/tune_seq.py prints them).
+constexpr int PD_TRACE_MAX = 512;
+constexpr int PD_TRACE_BARRIERS = 48;
+constexpr int PD_TRACE_CTAS = 160;
+constexpr int PD_FINE_STEP = 6;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ unsigned long long g_pd_trace[PD_TRACE_MAX];
+__device__ unsigned long long g_pd_trace_cta[PD_TRACE_BARRIERS * PD_TRACE_CTAS];
+// [phase (0 head, 1 cell)][CTA 0..3][16 slots]: 0 phase entry, 1 first TMA issued, 2 first operand stage arrived,
+// 3 last MMA committed, 4 accumulator complete (epilogue woke), 6 accumulator released, 7 epilogue done
+__device__ unsigned long long g_pd_fine[2 * 4 * 16];
+#define PD_FINE(phase_id, slot)                                                                         \
+  do {                                                                                                  \
+    if (step == PD_FINE_STEP && blockIdx.x < 4) g_pd_fine[((phase_id) * 4 + blockIdx.x) * 16 + (slot)] = globaltimer_ns(); \
+  } while (0)
+
+// Grid-wide barrier (all CTAs are co-resident: cooperative launch).  `target` is this CTA's running arrival target.
+__device__ __forceinline__ void pd_grid_barrier(unsigned int* counter, unsigned int& target, int& trace_n) {
+  fence_proxy_async_global();              // this thread's global stores -> later async-proxy (TMA) reads of any CTA
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t_in = globaltimer_ns();
+    const int nb = (int)(target / gridDim.x);
+    if (nb < PD_TRACE_BARRIERS && blockIdx.x < PD_TRACE_CTAS) g_pd_trace_cta[nb * PD_TRACE_CTAS + blockIdx.x] = t_in;
+    if (blockIdx.x == 0 && trace_n < PD_TRACE_MAX) g_pd_trace[trace_n++] = t_in;
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(counter) < target) {
+      if (clock64() - t0 > 4000000000ll) {
+        printf("mstr: grid barrier timed out (block %d)\n", blockIdx.x);
+        __trap();
+      }
+    }
+    fence_proxy_async_global();
+    if (blockIdx.x == 0 && trace_n < PD_TRACE_MAX) g_pd_trace[trace_n++] = globaltimer_ns();
+  }
+  __syncthreads();
+}
+
+struct PdPipe {            // running ring / accumulator state of one role, carried across tiles, phases and steps
+  int stage = 0;
+  uint32_t phase = 0;
+  uint32_t acc_phase = 0;
+};
+
+struct PdMaps {
+  CUtensorMap h[2], xh[2], head, cat, hp;
+};
+
+// One GEMM phase over this CTA's tiles.  EPI 0: head, n_count column tiles starting at n_first; EPI 1: cell.
+template <int EPI>
+__device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmHp,
+                                              const DecodeState& s, const int step, const int num_k, const int n_first,
+                                              const int n_count, const int m_tiles, uint8_t* sA, uint8_t* sB, uint8_t* stg,
+                                              uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, const uint32_t tmem_base, PdPipe& pipe) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = n_count * m_tiles;
+  if (warp == 0) {
+    if (lane == 0) {
+      PD_FINE(EPI, 0);
+      fence_proxy_async_global();
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = n_first + tile % n_count, m0 = (tile / n_count) * AT_BLOCK;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[pipe.stage], pipe.phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[pipe.stage], 2 * AT_TILE_BYTES);
+          tma_load_2d(sA + pipe.stage * AT_TILE_BYTES, tmA, &full_bar[pipe.stage], kb * 64, m0);
+          tma_load_2d(sB + pipe.stage * AT_TILE_BYTES, tmB, &full_bar[pipe.stage], kb * 64, n_tile * AT_BLOCK);
+          if (kb == 0) PD_FINE(EPI, 1);
+          if (++pipe.stage == AT_STAGES) { pipe.stage = 0; pipe.phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(AT_BLOCK, AT_BLOCK);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar, pipe.acc_phase ^ 1);       // the epilogue of the previous tile has drained the accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[pipe.stage], pipe.phase);
+          if (kb == 0) PD_FINE(EPI, 2);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + pipe.stage * AT_TILE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + pipe.stage * AT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, make_smem_desc<128>(a_addr + k * 32), make_smem_desc<128>(b_addr + k * 32), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[pipe.stage]);
+          if (kb == num_k - 1) { umma_commit(tfull_bar); PD_FINE(EPI, 3); }
+          if (++pipe.stage == AT_STAGES) { pipe.stage = 0; pipe.phase ^= 1; }
+        }
+        pipe.acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: TMEM lane = crop row; warps 8..15 =====================
+    const EpiWho w{warp & 3, (warp - 8) >> 2, lane};
+    const uint32_t taddr = tmem_base + ((uint32_t)(w.quarter * 32) << 16);
+    const bool tr = warp == 8 && lane == 0;
+    auto release = [&] {                                 // one arrival per epilogue warp hands the accumulator back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+      if (tr) PD_FINE(EPI, 6);
+    };
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = n_first + tile % n_count, m0 = (tile / n_count) * AT_BLOCK;
+      auto wait_acc = [&] {
+        mbar_wait(tfull_bar, pipe.acc_phase);
+        if (tr) PD_FINE(EPI, 4);
+        tc_fence_after();
+      };
+      if constexpr (EPI == 0) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // the previous tile's rows / bias have left the stage
+        if (n_tile < 2) {
+          at_head_hp_epilogue(s, tmHp, stg, taddr, w, m0, n_tile,
+                              [&] { wait_acc(); asm volatile("bar.sync 1, 256;" ::: "memory"); }, release);
+        } else {
+          at_head_logits_epilogue(s, reinterpret_cast<float*>(stg), taddr, w, m0, step, wait_acc, release);
+        }
+      } else {
+        at_cell_epilogue(s, taddr, w, m0, n_tile, step, wait_acc, release);
+      }
+      if (tr) PD_FINE(EPI, 7);
+      pipe.acc_phase ^= 1;
+    }
+  }
+  __syncwarp();
+}
+
+template <int W>
+__global__ void __launch_bounds__(PD_THREADS, 1)
+attn_decode_persistent_kernel(const __grid_constant__ PdMaps maps, const __nv_bfloat16* __restrict__ enc,
+                              const __nv_bfloat16* __restrict__ proj, const DecodeState s, unsigned int* gbar) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + AT_STAGES * AT_TILE_BYTES;
+  uint8_t* stg = smem + 2 * AT_STAGES * AT_TILE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + AT_STG_BYTES);
+  uint64_t* empty_bar = full_bar + AT_STAGES;
+  uint64_t* tfull_bar = empty_bar + AT_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&maps.h[0]); prefetch_tensormap(&maps.h[1]);
+    prefetch_tensormap(&maps.xh[0]); prefetch_tensormap(&maps.xh[1]);
+    prefetch_tensormap(&maps.head); prefetch_tensormap(&maps.cat); prefetch_tensormap(&maps.hp);
+    for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, AT_EPI_WARPS);                   // one arrival per epilogue warp
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (s.B + AT_BLOCK - 1) / AT_BLOCK;
+  // attention: groups of W adjacent warps, one crop per group and round
+  constexpr int GROUPS = PD_WARPS / W;
+  const int group = warp / W, sub = warp % W;
+  const int gg = blockIdx.x * GROUPS + group, GG = gridDim.x * GROUPS;
+  const int my_crops = gg < s.B ? (s.B - gg + GG - 1) / GG : 0;
+  float* part_base = reinterpret_cast<float*>(stg);
+  unsigned int target = 0;
+  int trace_n = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_pd_trace[trace_n++] = globaltimer_ns();
+  PdPipe pipe;
+  for (int i = 0; i <= s.steps; ++i) {
+    const int step = i;
+    // ---- head_i: hp_i (column tiles 0,1) and logits_{i-1} (tile 2; nothing to store at i = 0, only tile 2 at i = steps)
+    const int n_first = (i == s.steps) ? 2 : 0;
+    const int n_count = (i == s.steps) ? 1 : (i == 0 ? 2 : 3);
+    pd_gemm_phase<0>(&maps.h[i & 1], &maps.head, &maps.hp, s, step, AT_H / 64, n_first, n_count, m_tiles, sA, sB, stg, full_bar,
+                     empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
+    if (i == s.steps) break;
+    pd_grid_barrier(gbar, target, trace_n);
+    if (s.early_exit && __ldcg(s.live) == 0) break;        // every crop has emitted [s]: the remaining logits stay zero
+    // ---- attention_i over this group's crops, zig-zag over the steps.  Partials: W = 1: a private block per warp;
+    // W > 1: a block per group and round parity (the next round may start before a slow warp has read this one)
+    for (int kk = 0; kk < my_crops; ++kk) {
+      const int k = (i & 1) ? (my_crops - 1 - kk) : kk;
+      float* part = part_base + (size_t)((W == 1 ? warp : (kk & 1) * GROUPS + group)) * AT_VSUB * AT_PART;
+      at_attention_crop<W>(enc, proj, s, step, gg + k * GG, lane, sub, part, 2 + group);
+    }
+    pd_grid_barrier(gbar, target, trace_n);
+    // ---- cell_i
+    pd_gemm_phase<1>(&maps.xh[i & 1], &maps.cat, &maps.hp, s, step, 2 * AT_H / 64, 0, 4 * AT_H / AT_BLOCK, m_tiles, sA, sB, stg,
+                     full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
+    pd_grid_barrier(gbar, target, trace_n);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 static TmaEncoders g_attn_enc;
 
-static inline size_t group_ws_bytes(int Bg) {
-  // xh[2][Bg][2H] bf16 | hp [Bg][H] f32 | c [Bg][H] f32 | tok [Bg] | done [Bg] | live, rounded to 256 bytes
+static inline size_t decode_ws_bytes(int Bg) {
+  // xh[2][Bg][2H] bf16 | hp [Bg][H] f32 | c [Bg][H] f32 | tok [Bg] | done [Bg] | live, barrier counter; rounded to 256 bytes
   size_t b = (size_t)Bg * AT_H * (2 * 2 * 2 + 4 + 4) + (size_t)Bg * 8 + 16;
   return (b + 255) & ~(size_t)255;
 }
@@ -803,36 +808,62 @@ struct DecodeArgs {
   int T, C, steps, early_exit;
 };
 
-static std::atomic<int> g_persistent{1};    // 1 = one cooperative launch for all steps (default); 0 = launch chain
+// Driver selection: -1 = by batch size (default), 1 = persistent, 0 = launch chain.  Measured (B200, 26 steps): the
+// persistent kernel wins while a step is latency bound (256 crops 0.64 vs 0.83 ms for the original chain, 512 crops
+// 0.65 vs 0.94 ms); at 4096 crops the attention phase is bandwidth bound and the chain's 28 resident warps per SM cover
+// the memory latency better than the persistent kernel's 16 (1.38 vs 1.52 ms).  Results are bit-identical either way.
+static std::atomic<int> g_persistent{-1};
+constexpr int PD_MAX_BATCH = 2048;
 
-// One crop group [g0, g0 + Bg): its own state block and either the persistent launch or the chain of launches on `st`.
-static int decode_group(const DecodeArgs& a, uint8_t* ws, int g0, int Bg, cudaStream_t st, bool persistent) {
+template <int W>
+static int launch_persistent(const PdMaps& maps, const __nv_bfloat16* enc, const __nv_bfloat16* proj, const DecodeState& s,
+                             cudaStream_t st) {
+  static unsigned long long smem_set_pd = 0;
+  int rc = ensure_dynamic_smem((const void*)attn_decode_persistent_kernel<W>, PD_SMEM_BYTES, &smem_set_pd);
+  if (rc != MSTR_OK) return rc;
+  int per_sm = 0;
+  MSTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_decode_persistent_kernel<W>, PD_THREADS, PD_SMEM_BYTES));
+  MSTR_REQUIRE(per_sm >= 1, MSTR_ERR_UNSUPPORTED, "attn_decode_persistent_kernel does not fit on an SM");
+  cudaLaunchAttribute coop[1];
+  coop[0].id = cudaLaunchAttributeCooperative;
+  coop[0].val.cooperative = 1;
+  cudaLaunchConfig_t c = {};
+  c.gridDim = dim3(sm_count()); c.blockDim = dim3(PD_THREADS); c.dynamicSmemBytes = PD_SMEM_BYTES; c.stream = st;
+  c.attrs = coop; c.numAttrs = 1;
+  MSTR_CUDA(cudaLaunchKernelEx(&c, attn_decode_persistent_kernel<W>, maps, enc, proj, s,
+                               reinterpret_cast<unsigned int*>(s.live + 1)));
+  MSTR_LAUNCH_CHECK("attn_decode_persistent_kernel");
+  return MSTR_OK;
+}
+
+// State block in the workspace, then either the persistent launch or the chain of launches on `st`.
+static int decode_run(const DecodeArgs& a, uint8_t* ws, int B, cudaStream_t st, bool persistent) {
   DecodeState s;
-  const size_t xh_bytes = (size_t)Bg * 2 * AT_H * 2;
+  const size_t xh_bytes = (size_t)B * 2 * AT_H * 2;
   s.xh[0] = reinterpret_cast<__nv_bfloat16*>(ws);
   s.xh[1] = reinterpret_cast<__nv_bfloat16*>(ws + xh_bytes);
   s.hp = reinterpret_cast<float*>(ws + 2 * xh_bytes);
-  s.cst = s.hp + (size_t)Bg * AT_H;
-  s.tok = reinterpret_cast<int32_t*>(s.cst + (size_t)Bg * AT_H);
-  s.done = s.tok + Bg;
-  s.live = s.done + Bg;
+  s.cst = s.hp + (size_t)B * AT_H;
+  s.tok = reinterpret_cast<int32_t*>(s.cst + (size_t)B * AT_H);
+  s.done = s.tok + B;
+  s.live = s.done + B;
   s.b_h2h = a.b_h2h; s.b_gen = a.b_gen; s.w_score = a.w_score; s.w_tok = a.w_tok; s.bias = a.bias;
-  s.text = a.text ? a.text + (size_t)g0 * a.steps : nullptr;
-  s.logits = a.logits + (size_t)g0 * a.steps * a.C;
-  s.ids = a.ids + (size_t)g0 * a.steps;
-  s.lengths = a.lengths ? a.lengths + g0 : nullptr;
-  s.alpha_out = a.alpha_out ? a.alpha_out + (size_t)g0 * a.steps * a.T : nullptr;
-  s.B = Bg; s.T = a.T; s.C = a.C; s.steps = a.steps; s.early_exit = a.early_exit;
+  s.text = a.text;
+  s.logits = a.logits;
+  s.ids = a.ids;
+  s.lengths = a.lengths;
+  s.alpha_out = a.alpha_out;
+  s.B = B; s.T = a.T; s.C = a.C; s.steps = a.steps; s.early_exit = a.early_exit;
   // h_0 = c_0 = 0 (decoders.py:36-38); ctx halves are overwritten before use
-  MSTR_CUDA(cudaMemsetAsync(ws, 0, 2 * xh_bytes + (size_t)Bg * AT_H * 8, st));
-  decode_init_kernel<<<ceil_div(Bg, 256), 256, 0, st>>>(s);
+  MSTR_CUDA(cudaMemsetAsync(ws, 0, 2 * xh_bytes + (size_t)B * AT_H * 8, st));
+  decode_init_kernel<<<ceil_div(B, 256), 256, 0, st>>>(s);
   MSTR_LAUNCH_CHECK("decode_init_kernel");
 
-  // tensor maps: h view [Bg][256] with row stride 512 elements; [ctx|h] view [Bg][512]; weights
-  alignas(64) CUtensorMap tmH[2], tmXH[2], tmHead, tmCat;
+  // tensor maps: h view [B][256] with row stride 512 elements; [ctx|h] view [B][512]; weights; hp as a TMA-store target
+  alignas(64) CUtensorMap tmH[2], tmXH[2], tmHead, tmCat, tmHp;
   int rc;
   for (int p = 0; p < 2; ++p) {
-    cuuint64_t dims[2] = {(cuuint64_t)AT_H, (cuuint64_t)Bg};
+    cuuint64_t dims[2] = {(cuuint64_t)AT_H, (cuuint64_t)B};
     cuuint64_t strides[1] = {(cuuint64_t)(2 * AT_H * 2)};
     cuuint32_t box[2] = {64, AT_BLOCK};
     cuuint32_t estr[2] = {1, 1};
@@ -840,36 +871,25 @@ static int decode_group(const DecodeArgs& a, uint8_t* ws, int g0, int Bg, cudaSt
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled(h) failed with CUresult %d", (int)r);
-    rc = encode_tiled_2d_bf16(g_attn_enc, &tmXH[p], s.xh[p], 2 * AT_H, Bg, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_tiled_2d_bf16(g_attn_enc, &tmXH[p], s.xh[p], 2 * AT_H, B, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != MSTR_OK) return rc;
   }
   rc = encode_tiled_2d_bf16(g_attn_enc, &tmHead, a.w_head, AT_H, 3 * AT_BLOCK, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != MSTR_OK) return rc;
   rc = encode_tiled_2d_bf16(g_attn_enc, &tmCat, a.w_cat, 2 * AT_H, 4 * AT_H, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != MSTR_OK) return rc;
+  rc = encode_output_2d(g_attn_enc, &tmHp, s.hp, true, (uint64_t)AT_H, (uint64_t)B);
+  if (rc != MSTR_OK) return rc;
 
-  const int m_tiles = ceil_div(Bg, AT_BLOCK);
-  const __nv_bfloat16* enc = a.enc + (size_t)g0 * a.T * AT_H;
-  const __nv_bfloat16* proj = a.proj + (size_t)g0 * a.T * AT_H;
+  const int m_tiles = ceil_div(B, AT_BLOCK);
+  const int W = attention_warps_per_crop(B, sm_count());
   if (persistent) {
-    static unsigned long long smem_set_pd = 0;
-    rc = ensure_dynamic_smem((const void*)attn_decode_persistent_kernel, PD_SMEM_BYTES, &smem_set_pd);
-    if (rc != MSTR_OK) return rc;
-    int per_sm = 0;
-    MSTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_decode_persistent_kernel, PD_THREADS, PD_SMEM_BYTES));
-    MSTR_REQUIRE(per_sm >= 1, MSTR_ERR_UNSUPPORTED, "attn_decode_persistent_kernel does not fit on an SM");
     PdMaps maps;
     maps.h[0] = tmH[0]; maps.h[1] = tmH[1]; maps.xh[0] = tmXH[0]; maps.xh[1] = tmXH[1]; maps.head = tmHead; maps.cat = tmCat;
-    cudaLaunchAttribute coop[1];
-    coop[0].id = cudaLaunchAttributeCooperative;
-    coop[0].val.cooperative = 1;
-    cudaLaunchConfig_t c = {};
-    c.gridDim = dim3(sm_count()); c.blockDim = dim3(PD_THREADS); c.dynamicSmemBytes = PD_SMEM_BYTES; c.stream = st;
-    c.attrs = coop; c.numAttrs = 1;
-    MSTR_CUDA(cudaLaunchKernelEx(&c, attn_decode_persistent_kernel, maps, enc, proj, s,
-                                 reinterpret_cast<unsigned int*>(s.live + 1)));
-    MSTR_LAUNCH_CHECK("attn_decode_persistent_kernel");
-    return MSTR_OK;
+    maps.hp = tmHp;
+    if (W == 4) return launch_persistent<4>(maps, a.enc, a.proj, s, st);
+    if (W == 2) return launch_persistent<2>(maps, a.enc, a.proj, s, st);
+    return launch_persistent<1>(maps, a.enc, a.proj, s, st);
   }
   cudaLaunchAttribute pdl[1];
   pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -884,18 +904,20 @@ static int decode_group(const DecodeArgs& a, uint8_t* ws, int g0, int Bg, cudaSt
     // head_i: hp_i (tiles 0,1) and logits_{i-1} (tile 2); the last iteration only needs the logits tile
     {
       cudaLaunchConfig_t c = config(dim3(3, m_tiles), AT_THREADS, AT_SMEM_BYTES);
-      MSTR_CUDA(cudaLaunchKernelEx(&c, rnn_gemm_kernel<0>, tmH[i & 1], tmHead, s, i, AT_H / 64));
+      MSTR_CUDA(cudaLaunchKernelEx(&c, rnn_gemm_kernel<0>, tmH[i & 1], tmHead, tmHp, s, i, AT_H / 64));
       MSTR_LAUNCH_CHECK("rnn_gemm_kernel<head>");
     }
     if (i == a.steps) break;
     {
-      cudaLaunchConfig_t c = config(dim3(ceil_div(Bg, AT_CTX_WARPS)), 32 * AT_CTX_WARPS, 0);
-      MSTR_CUDA(cudaLaunchKernelEx(&c, attn_context_kernel, enc, proj, s, i));
+      cudaLaunchConfig_t c = config(dim3(ceil_div(B, AT_CTX_WARPS / W)), 32 * AT_CTX_WARPS, 0);
+      if (W == 4) MSTR_CUDA(cudaLaunchKernelEx(&c, attn_context_kernel<4>, a.enc, a.proj, s, i));
+      else if (W == 2) MSTR_CUDA(cudaLaunchKernelEx(&c, attn_context_kernel<2>, a.enc, a.proj, s, i));
+      else MSTR_CUDA(cudaLaunchKernelEx(&c, attn_context_kernel<1>, a.enc, a.proj, s, i));
       MSTR_LAUNCH_CHECK("attn_context_kernel");
     }
     {
       cudaLaunchConfig_t c = config(dim3(4 * AT_H / AT_BLOCK, m_tiles), AT_THREADS, AT_SMEM_BYTES);
-      MSTR_CUDA(cudaLaunchKernelEx(&c, rnn_gemm_kernel<1>, tmXH[i & 1], tmCat, s, i, 2 * AT_H / 64));
+      MSTR_CUDA(cudaLaunchKernelEx(&c, rnn_gemm_kernel<1>, tmXH[i & 1], tmCat, tmHp, s, i, 2 * AT_H / 64));
       MSTR_LAUNCH_CHECK("rnn_gemm_kernel<cell>");
     }
   }
@@ -904,22 +926,30 @@ static int decode_group(const DecodeArgs& a, uint8_t* ws, int g0, int Bg, cudaSt
 
 }  // namespace mstr
 
-extern "C" __attribute__((visibility("default"))) int mstr_debug_decode_trace(unsigned long long* out_host, int n) {
+extern "C" __attribute__((visibility("default"))) int mstr_debug_decode_trace(unsigned long long* out_host, int n,
+                                                                              unsigned long long* per_cta_host, int n_cta) {
   using namespace mstr;
   MSTR_REQUIRE(out_host && n > 0 && n <= PD_TRACE_MAX, MSTR_ERR_BAD_ARG, "mstr_debug_decode_trace: bad argument");
   MSTR_CUDA(cudaMemcpyFromSymbol(out_host, g_pd_trace, sizeof(unsigned long long) * (size_t)n));
+  if (per_cta_host && n_cta == 2 * 4 * 16) {
+    MSTR_CUDA(cudaMemcpyFromSymbol(per_cta_host, g_pd_fine, sizeof(unsigned long long) * (size_t)n_cta));
+  } else if (per_cta_host) {
+    MSTR_REQUIRE(n_cta == PD_TRACE_BARRIERS * PD_TRACE_CTAS, MSTR_ERR_BAD_ARG, "mstr_debug_decode_trace: per-CTA buffer must hold %d values",
+                 PD_TRACE_BARRIERS * PD_TRACE_CTAS);
+    MSTR_CUDA(cudaMemcpyFromSymbol(per_cta_host, g_pd_trace_cta, sizeof(unsigned long long) * (size_t)n_cta));
+  }
   return MSTR_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int mstr_set_decode_persistent(int on) {
-  mstr::g_persistent.store(on ? 1 : 0);
+  mstr::g_persistent.store(on < 0 ? -1 : (on ? 1 : 0));
   return MSTR_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t mstr_attn_decode_bf16_workspace_bytes(int B, int Hd) {
   (void)Hd;
   using namespace mstr;
-  return (int64_t)group_ws_bytes((B + AT_BLOCK - 1) / AT_BLOCK * AT_BLOCK);
+  return (int64_t)decode_ws_bytes((B + AT_BLOCK - 1) / AT_BLOCK * AT_BLOCK);
 }
 
 extern "C" __attribute__((visibility("default"))) int mstr_attn_decode_bf16(
@@ -928,8 +958,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_attn_decode_bf16(
     void* workspace, float* logits, int32_t* ids, int32_t* lengths, float* alpha_out, int B, int T, int Hd, int C,
     int steps, int early_exit, mstr_stream_t stream) {
   using namespace mstr;
-  MSTR_REQUIRE(enc_bf16 && proj_bf16 && w_head && b_h2h && b_gen && w_score && w_cat && w_tok && bias && workspace &&
-                   logits && ids,
+  MSTR_REQUIRE(enc_bf16 && proj_bf16 && w_head && b_h2h && b_gen && w_score && w_cat && w_tok && workspace && logits && ids,
                MSTR_ERR_BAD_ARG, "mstr_attn_decode_bf16: null pointer");
   MSTR_REQUIRE(B > 0 && T > 0 && steps > 0 && C > 0, MSTR_ERR_BAD_ARG, "mstr_attn_decode_bf16: bad size");
   MSTR_REQUIRE(Hd == AT_H, MSTR_ERR_UNSUPPORTED, "mstr_attn_decode_bf16: hidden size %d != %d", Hd, AT_H);
@@ -950,5 +979,6 @@ extern "C" __attribute__((visibility("default"))) int mstr_attn_decode_bf16(
 
   DecodeArgs a{static_cast<const __nv_bfloat16*>(enc_bf16), static_cast<const __nv_bfloat16*>(proj_bf16), w_head, w_cat,
                b_h2h, b_gen, w_score, w_tok, bias, text, logits, ids, lengths, alpha_out, T, C, steps, early_exit};
-  return decode_group(a, static_cast<uint8_t*>(workspace), 0, B, st, g_persistent.load(std::memory_order_relaxed) != 0);
+  const int mode = g_persistent.load(std::memory_order_relaxed);
+  return decode_run(a, static_cast<uint8_t*>(workspace), B, st, mode < 0 ? B <= PD_MAX_BATCH : mode != 0);
 }

@@ -18,7 +18,10 @@ constexpr int kFirstMaxCin = 4;
 constexpr int kFirstMaxCout = 64;
 constexpr int kImagesPerBlock = 8;
 
-template <typename T, bool POOL, int CIN>
+// PADOUT (not pooled): the output is written as a padded-flat activation [B][H+2][W+2][Cout] whose one-pixel ring is
+// ZERO (the layout conv_flat.cu consumes): every thread stores its four pixels one row down / one column right, and the
+// threads on the image border also store the ring pixels next to their strip.
+template <typename T, bool POOL, int CIN, bool PADOUT = false>
 __global__ void __launch_bounds__(256, (CIN == 1 && !POOL) ? 3 : 2)
 conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -151,6 +154,35 @@ conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
       }
       store8(dst + (size_t)q * Cout, v);
     }
+  } else if constexpr (PADOUT) {
+    const int Wp = W + 2;
+    T* dst = out + (((size_t)b * (H + 2) + ry + 1) * Wp + sx * 4 + 1) * Cout + g * 8;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(acc[0][p][j], sc[j], sf[j]), 0.f);
+      store8(dst + (size_t)p * Cout, v);
+    }
+    // the zero ring: left / right column of this row, and the row above / below (with its corners)
+    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool first_col = sx == 0, last_col = sx == strips - 1;
+    if (first_col) store8(dst - Cout, zero);
+    if (last_col) store8(dst + (size_t)4 * Cout, zero);
+    if (ry == 0 || ry == H - 1) {
+      T* edge = (ry == 0) ? dst - (size_t)Wp * Cout : dst + (size_t)Wp * Cout;
+      if (ry == 0 && ry == H - 1) {   // H == 1: both rows
+        T* below = dst + (size_t)Wp * Cout;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) store8(below + (size_t)p * Cout, zero);
+        if (first_col) store8(below - Cout, zero);
+        if (last_col) store8(below + (size_t)4 * Cout, zero);
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) store8(edge + (size_t)p * Cout, zero);
+      if (first_col) store8(edge - Cout, zero);
+      if (last_col) store8(edge + (size_t)4 * Cout, zero);
+    }
   } else {
     T* dst = out + (((size_t)b * H + ry) * W + sx * 4) * Cout + g * 8;
 #pragma unroll
@@ -164,14 +196,14 @@ conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
   }   // images
 }
 
-template <typename T, bool POOL>
+template <typename T, bool POOL, bool PADOUT = false>
 static void launch_first(int cin, dim3 grid, cudaStream_t st, const float* x, const float* w, const float* scale,
                          const float* shift, T* out, int B, int H, int W, int Cout) {
   switch (cin) {
-    case 1: conv3x3_first_kernel<T, POOL, 1><<<grid, 256, 0, st>>>(x, w, scale, shift, out, B, H, W, Cout); break;
-    case 2: conv3x3_first_kernel<T, POOL, 2><<<grid, 256, 0, st>>>(x, w, scale, shift, out, B, H, W, Cout); break;
-    case 3: conv3x3_first_kernel<T, POOL, 3><<<grid, 256, 0, st>>>(x, w, scale, shift, out, B, H, W, Cout); break;
-    default: conv3x3_first_kernel<T, POOL, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, out, B, H, W, Cout); break;
+    case 1: conv3x3_first_kernel<T, POOL, 1, PADOUT><<<grid, 256, 0, st>>>(x, w, scale, shift, out, B, H, W, Cout); break;
+    case 2: conv3x3_first_kernel<T, POOL, 2, PADOUT><<<grid, 256, 0, st>>>(x, w, scale, shift, out, B, H, W, Cout); break;
+    case 3: conv3x3_first_kernel<T, POOL, 3, PADOUT><<<grid, 256, 0, st>>>(x, w, scale, shift, out, B, H, W, Cout); break;
+    default: conv3x3_first_kernel<T, POOL, 4, PADOUT><<<grid, 256, 0, st>>>(x, w, scale, shift, out, B, H, W, Cout); break;
   }
 }
 
@@ -181,6 +213,9 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv3x3_first(const f
                                   const float* shift, void* out, int out_dtype, int B, int C_in,
                                   int H, int W, int C_out, int pool, mstr_stream_t stream) {
   using namespace mstr;
+  const bool pad_out = pool == 2;          // pool: 0 = plain, 1 = fused 2x2 max-pool, 2 = padded-flat bf16 output with a zero ring
+  if (pad_out) pool = 0;
+  MSTR_REQUIRE(!pad_out || out_dtype == MSTR_BF16, MSTR_ERR_UNSUPPORTED, "mstr_conv3x3_first: the padded-flat output is bf16 only");
   MSTR_REQUIRE(x && w && scale && shift && out, MSTR_ERR_BAD_ARG, "mstr_conv3x3_first: null pointer");
   MSTR_REQUIRE(B > 0 && H > 0 && W > 0, MSTR_ERR_BAD_ARG, "mstr_conv3x3_first: bad size");
   MSTR_REQUIRE(C_in >= 1 && C_in <= kFirstMaxCin, MSTR_ERR_UNSUPPORTED,
@@ -196,6 +231,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv3x3_first(const f
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == MSTR_BF16) {
     if (pool) launch_first<__nv_bfloat16, true>(C_in, grid, st, x, w, scale, shift, (__nv_bfloat16*)out, B, H, W, C_out);
+    else if (pad_out) launch_first<__nv_bfloat16, false, true>(C_in, grid, st, x, w, scale, shift, (__nv_bfloat16*)out, B, H, W, C_out);
     else      launch_first<__nv_bfloat16, false>(C_in, grid, st, x, w, scale, shift, (__nv_bfloat16*)out, B, H, W, C_out);
   } else if (out_dtype == MSTR_F32) {
     if (pool) launch_first<float, true>(C_in, grid, st, x, w, scale, shift, (float*)out, B, H, W, C_out);

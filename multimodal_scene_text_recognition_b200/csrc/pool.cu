@@ -54,9 +54,10 @@ maxpool_nhwc_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, 
 // 8 channels; the four 16-byte taps are ALL issued before the first max (the generic kernel's runtime loops
 // serialise load -> max -> load, four DRAM latencies per item: 4.2 TB/s), out-of-range taps read as -inf.
 // bf16 max is exact, so the packed HMNMX2 path gives the same bits as the fp32 path.
+// `ring`: the input is a padded-flat activation [B][H + 2 ring][W + 2 ring][C] (conv_flat.cu); its ring is skipped.
 __global__ void __launch_bounds__(256)
 maxpool2x2_bf16_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H, int W, int cv, int P, int Q,
-                       int sh, int sw, int ph, int pw, int total) {
+                       int sh, int sw, int ph, int pw, int total, int ring) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= total) return;
   const int c = i % cv;
@@ -71,7 +72,7 @@ maxpool2x2_bf16_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int
   for (int t = 0; t < 4; ++t) {
     const int y = y0 + (t >> 1), xx = x0 + (t & 1);
     const bool ok = (y >= 0) && (y < H) && (xx >= 0) && (xx < W);
-    v[t] = ok ? __ldg(x + ((size_t)(b * H + y) * W + xx) * cv + c) : ninf;
+    v[t] = ok ? __ldg(x + ((size_t)(b * (H + 2 * ring) + y + ring) * (W + 2 * ring) + xx + ring) * cv + c) : ninf;
   }
   auto mx = [](uint32_t a, uint32_t bb) {
     __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&bb));
@@ -147,7 +148,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_maxpool_nhwc(const vo
     if (kh == 2 && kw == 2 && ph <= 1 && pw <= 1 && items < (int64_t)1 << 31 && (int64_t)B * H * W * (C / 8) < (int64_t)1 << 31) {
       // every window has at least one in-range tap when the padding is smaller than the window
       maxpool2x2_bf16_kernel<<<(int)ceil_div64(items, 256), 256, 0, st>>>(
-          (const uint4*)x, (uint4*)out, H, W, C / 8, P, Q, sh, sw, ph, pw, (int)items);
+          (const uint4*)x, (uint4*)out, H, W, C / 8, P, Q, sh, sw, ph, pw, (int)items, 0);
     } else {
       maxpool_nhwc_kernel<__nv_bfloat16, 8><<<grid_for(items, 256), 256, 0, st>>>(
           (const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, P, Q, kh, kw, sh, sw, ph, pw);
@@ -161,6 +162,22 @@ extern "C" __attribute__((visibility("default"))) int mstr_maxpool_nhwc(const vo
     MSTR_REQUIRE(false, MSTR_ERR_BAD_ARG, "mstr_maxpool_nhwc: unknown dtype %d", dtype);
   }
   MSTR_LAUNCH_CHECK("maxpool_nhwc_kernel");
+  return MSTR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mstr_maxpool2x2_ring_bf16(const void* x_ring, void* out, int B, int H, int W,
+                                                                                 int C, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x_ring && out, MSTR_ERR_BAD_ARG, "mstr_maxpool2x2_ring_bf16: null pointer");
+  MSTR_REQUIRE(B > 0 && H > 1 && W > 1 && C > 0 && C % 8 == 0, MSTR_ERR_BAD_ARG, "mstr_maxpool2x2_ring_bf16: bad size");
+  MSTR_REQUIRE(aligned16(x_ring) && aligned16(out), MSTR_ERR_BAD_ARG, "mstr_maxpool2x2_ring_bf16: pointers must be 16-byte aligned");
+  const int P = H / 2, Q = W / 2;
+  const int64_t items = (int64_t)B * P * Q * (C / 8);
+  MSTR_REQUIRE(items < (int64_t)1 << 31 && (int64_t)B * (H + 2) * (W + 2) * (C / 8) < (int64_t)1 << 31, MSTR_ERR_UNSUPPORTED,
+               "mstr_maxpool2x2_ring_bf16: tensor too large");
+  maxpool2x2_bf16_kernel<<<(int)ceil_div64(items, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x_ring, (uint4*)out, H, W, C / 8, P, Q, 2, 2, 0, 0, (int)items, 1);
+  MSTR_LAUNCH_CHECK("maxpool2x2_bf16_kernel");
   return MSTR_OK;
 }
 

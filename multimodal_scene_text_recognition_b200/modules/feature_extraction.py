@@ -158,13 +158,26 @@ class ResNet(nn.Module):
         require_eval(self)
         precision = config.PRECISION
         x = x.contiguous()
-        if x.shape[1] <= 4:
+        c2, mp = self.conv0_2, self.maxpool1
+        flat = (precision == 'bf16' and config.CONV0_FLAT and x.shape[1] <= 4 and x.shape[2] % 2 == 0 and x.shape[3] % 4 == 0
+                and (c2.in_channels, c2.out_channels) == (32, 64) and tuple(c2.kernel_size) == (3, 3)
+                and tuple(c2.stride) == (1, 1) and tuple(c2.padding) == (1, 1) and x.shape[3] + 2 <= 1000
+                and mp.kernel_size in (2, (2, 2)) and mp.stride in (2, (2, 2)) and mp.padding in (0, (0, 0)))
+        if flat:
+            # conv0_1 -> padded-flat activation -> conv0_2 with one slab load per tile -> maxpool1 skipping the ring
             w, scale, shift = pack_first_conv(self.conv0_1, self.bn0_1)
-            h = ops.conv3x3_first(x, w, scale, shift, act_dtype(precision), pool=False)
+            h = ops.conv3x3_first(x, w, scale, shift, torch.bfloat16, pool=False, ring=True)
+            w, scale, shift = pack_conv(c2, self.bn0_2, precision)
+            h = ops.conv3x3_flat(h, w, scale, shift, relu=True)
+            h = ops.maxpool2x2_ring(h)
         else:
-            h = _conv_bn(_to_nhwc(x, precision), self.conv0_1, self.bn0_1, precision, relu=True)
-        h = _conv_bn(h, self.conv0_2, self.bn0_2, precision, relu=True)
-        h = self._pool(h, self.maxpool1)
+            if x.shape[1] <= 4:
+                w, scale, shift = pack_first_conv(self.conv0_1, self.bn0_1)
+                h = ops.conv3x3_first(x, w, scale, shift, act_dtype(precision), pool=False)
+            else:
+                h = _conv_bn(_to_nhwc(x, precision), self.conv0_1, self.bn0_1, precision, relu=True)
+            h = _conv_bn(h, self.conv0_2, self.bn0_2, precision, relu=True)
+            h = self._pool(h, self.maxpool1)
         for blk in self.layer1:
             h = blk.forward_nhwc(h, precision)
         h = _conv_bn(h, self.conv1, self.bn1, precision, relu=True)

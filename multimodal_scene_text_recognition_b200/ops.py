@@ -168,19 +168,58 @@ def tps_rectify(img: Optional[torch.Tensor], c_prime: torch.Tensor, basis: torch
 
 
 def conv3x3_first(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
-                  out_dtype: torch.dtype, pool: bool) -> torch.Tensor:
-    """x [B,Cin,H,W] f32 NCHW -> NHWC [B,H',W',Cout] (conv3x3 pad1 + folded BN + ReLU [+ maxpool 2x2])."""
+                  out_dtype: torch.dtype, pool: bool, ring: bool = False) -> torch.Tensor:
+    """x [B,Cin,H,W] f32 NCHW -> NHWC [B,H',W',Cout] (conv3x3 pad1 + folded BN + ReLU [+ maxpool 2x2]).
+    ``ring=True`` (bf16, not pooled): the padded-flat activation [B,H+2,W+2,Cout] with a zero one-pixel ring that
+    conv3x3_flat consumes."""
     _req(x, "x", torch.float32); _req(w, "w", torch.float32)
     _req(scale, "scale", torch.float32); _req(shift, "shift", torch.float32)
     B, Cin, H, W = x.shape
     Cout = w.shape[0]
-    assert w.shape == (Cout, Cin, 3, 3)
-    P, Q = (H // 2, W // 2) if pool else (H, W)
+    assert w.shape == (Cout, Cin, 3, 3) and not (pool and ring)
+    P, Q = (H // 2, W // 2) if pool else ((H + 2, W + 2) if ring else (H, W))
     out = torch.empty((B, P, Q, Cout), device=x.device, dtype=out_dtype)
     with _timed("conv3x3_first", float(out.numel() * out.element_size() + x.numel() * 4), "byte",
-                "B%d %dx%d %d->%d%s: NHWC out + image in" % (B, H, W, Cin, Cout, " +pool" if pool else "")), _on(x, w, scale, shift) as st:
+                "B%d %dx%d %d->%d%s: NHWC out + image in" % (B, H, W, Cin, Cout, " +pool" if pool else (" +ring" if ring else ""))), \
+            _on(x, w, scale, shift) as st:
         check(lib().mstr_conv3x3_first(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(out), _dt(out), B, Cin, H, W,
-                                       Cout, int(pool), st), "mstr_conv3x3_first")
+                                       Cout, 2 if ring else int(pool), st), "mstr_conv3x3_first")
+    return out
+
+
+def conv3x3_flat(x_ring: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+                 relu: bool = True) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution + folded BN + ReLU over a padded-flat bf16 activation.
+    x_ring [B,H+2,W+2,Cin] with a zero ring, w [Cout,3,3,Cin] bf16 -> [B,H+2,W+2,Cout] bf16, ring zero."""
+    _req(x_ring, "x_ring", torch.bfloat16); _req(w, "w", torch.bfloat16)
+    _req(scale, "scale", torch.float32); _req(shift, "shift", torch.float32)
+    B, Hp, Wp, Cin = x_ring.shape
+    Cout = w.shape[0]
+    assert w.shape == (Cout, 3, 3, Cin) and Hp > 2 and Wp > 2
+    H, W = Hp - 2, Wp - 2
+    out = torch.empty((B, Hp, Wp, Cout), device=x_ring.device, dtype=torch.bfloat16)
+    with _timed("conv3x3_flat", 2.0 * B * H * W * Cout * 9 * Cin, "flop",
+                "M=%d (B%d %dx%d) %d->%d 3x3, padded-flat" % (B * H * W, B, H, W, Cin, Cout)), _on(x_ring, w, scale, shift) as st:
+        check(lib().mstr_conv3x3_flat_bf16(ptr(x_ring), ptr(w), ptr(scale), ptr(shift), ptr(out), B, H, W, Cin, Cout,
+                                           int(relu), st), "mstr_conv3x3_flat_bf16")
+    return out
+
+
+def flat_desc_mode(mode: int) -> None:
+    """Test hook of conv3x3_flat (mstr_debug_flat_desc_mode): 0 = base-offset field left zero (default, correct on
+    B200), 1 = set to the phase of the start address (wrong: kept as the experiment that pins the hardware rule)."""
+    check(lib().mstr_debug_flat_desc_mode(int(mode)), "mstr_debug_flat_desc_mode")
+
+
+def maxpool2x2_ring(x_ring: torch.Tensor) -> torch.Tensor:
+    """2x2 / stride 2 max-pool of a padded-flat bf16 activation [B,H+2,W+2,C] -> [B,H/2,W/2,C] (ring skipped)."""
+    _req(x_ring, "x_ring", torch.bfloat16)
+    B, Hp, Wp, C = x_ring.shape
+    H, W = Hp - 2, Wp - 2
+    out = torch.empty((B, H // 2, W // 2, C), device=x_ring.device, dtype=torch.bfloat16)
+    with _timed("maxpool_nhwc", float(B * H * W * C + out.numel()) * 2, "byte",
+                "B%d %dx%dx%d (ring) -> %dx%d in + out" % (B, H, W, C, H // 2, W // 2)), _on(x_ring) as st:
+        check(lib().mstr_maxpool2x2_ring_bf16(ptr(x_ring), ptr(out), B, H, W, C, st), "mstr_maxpool2x2_ring_bf16")
     return out
 
 
@@ -436,10 +475,10 @@ def resize_to_tensor_u8(pixels: torch.Tensor, offsets: torch.Tensor, sizes_hw: t
     return out
 
 
-def set_decode_persistent(on: bool = True) -> None:
-    """Tensor-core decoder as ONE persistent cooperative launch (default) or as the chain of three launches per step
-    (bit-identical results; the chain is the cross-check of the persistent kernel)."""
-    check(lib().mstr_set_decode_persistent(int(bool(on))), "mstr_set_decode_persistent")
+def set_decode_persistent(on=None) -> None:
+    """Driver of the tensor-core decoder: None = by batch size (default: ONE persistent cooperative launch up to 2048
+    crops, the chain of three launches per step beyond), True / False force one.  Bit-identical results."""
+    check(lib().mstr_set_decode_persistent(-1 if on is None else int(bool(on))), "mstr_set_decode_persistent")
 
 
 def attn_decode_bf16(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int, text: Optional[torch.Tensor],
@@ -459,12 +498,15 @@ def attn_decode_bf16(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps:
         assert text.shape[0] == B and text.shape[1] >= steps
         if text.shape[1] != steps:
             text = text[:, :steps].contiguous()
+    # the token rows of W_ih with the LSTMCell bias folded in (fp32 add, the same one the kernel would do per element)
+    if "w_tokb" not in packed:
+        packed["w_tokb"] = (packed["w_tok"] + packed["bias"][None, :]).contiguous()
     macs = Hd * Hd + 2 * T * Hd + 4 * Hd * 2 * Hd + C * Hd
     with _timed("attn_decode_bf16", 2.0 * B * steps * macs, "flop",
-                "B%d T%d %d steps (tcgen05, 1 persistent launch)" % (B, T, steps)), _on(enc, proj, text, *[v for v in packed.values() if isinstance(v, torch.Tensor)]) as st:
+                "B%d T%d %d steps (tcgen05, %s)" % (B, T, steps, "1 persistent launch" if B <= 2048 else "launch chain")), _on(enc, proj, text, *[v for v in packed.values() if isinstance(v, torch.Tensor)]) as st:
         check(lib().mstr_attn_decode_bf16(ptr(enc), ptr(proj), ptr(packed["w_head"]), ptr(packed["b_h2h"]),
                                           ptr(packed["b_gen"]), ptr(packed["w_score"]), ptr(packed["w_cat"]),
-                                          ptr(packed["w_tok"]), ptr(packed["bias"]), ptr(text), ptr(ws), ptr(logits),
+                                          ptr(packed["w_tokb"]), 0, ptr(text), ptr(ws), ptr(logits),
                                           ptr(ids), ptr(lengths), ptr(alpha), B, T, Hd, C, steps, int(early_exit),
                                           st), "mstr_attn_decode_bf16")
     return {"logits": logits, "ids": ids, "lengths": lengths, "alpha": alpha, "h": None, "c": None}

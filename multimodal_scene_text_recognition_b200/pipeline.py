@@ -169,10 +169,12 @@ class GraphedRecognizer:
                 self.model.recognize(*static_in)
         torch.cuda.current_stream(dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
+        launches0 = _cabi.launch_count()
         with torch.cuda.graph(graph), torch.no_grad():
             out = self.model.recognize(*static_in)
+        launches = _cabi.launch_count() - launches0
         static_out = {k: out[k] for k in ("logits", "ids", "lengths")}
-        return graph, static_in, static_out
+        return graph, static_in, static_out, launches
 
     def __call__(self, image, overlap, scene, ious):
         tensors = [image, overlap, scene, ious]
@@ -182,12 +184,19 @@ class GraphedRecognizer:
         entry = self._graphs.get(key)
         if entry is None:
             entry = self._graphs[key] = self._capture(tensors)
-        graph, static_in, static_out = entry
+        graph, static_in, static_out, _launches = entry
         for d, s in zip(static_in, tensors):
             if d.data_ptr() != s.data_ptr():
                 d.copy_(s, non_blocking=True)
         graph.replay()
         return static_out
+
+    def launches_per_replay(self, image, overlap, scene, ious) -> int:
+        """Kernel launches of this library recorded in the graph of this geometry (what one replay executes)."""
+        key = self._key([image, overlap, scene, ious])
+        if key not in self._graphs:
+            self._graphs[key] = self._capture([image, overlap, scene, ious])
+        return int(self._graphs[key][3])
 
     def static_inputs(self, image, overlap, scene, ious):
         """The graph's own input tensors for this geometry (capturing it if needed): a producer (e.g. the host

@@ -37,6 +37,13 @@ def _t(a):   # NHWC numpy -> NCHW float64
     return nchw(a).astype(F64)
 
 
+def _ring_of(a):
+    """The one-pixel ring of a padded-flat [B, H+2, W+2, C] array (interior zeroed)."""
+    r = np.array(a, copy=True)
+    r[:, 1:-1, 1:-1] = 0
+    return r
+
+
 def _replay(name, args, kw, out):
     """(what, got, exact_reference_before_rounding) of one recorded launch, or None if it is not a bf16 launch."""
     if name == "conv3x3_first":
@@ -46,7 +53,26 @@ def _replay(name, args, kw, out):
         y = orc.relu(y * host(scale).astype(F64)[None, :, None, None] + host(shift).astype(F64)[None, :, None, None])
         if pool:
             y = orc.maxpool2d(y)
-        return "first %s%s" % (tuple(w.shape), "+pool" if pool else ""), host(out), nhwc(y)
+        got = host(out)
+        if kw.get("ring"):
+            assert not _ring_of(got).any(), "conv0_1: the ring of the padded-flat output must be zero"
+            got = got[:, 1:-1, 1:-1]
+        return "first %s%s" % (tuple(w.shape), "+pool" if pool else (" +ring" if kw.get("ring") else "")), got, nhwc(y)
+    if name == "conv3x3_flat":
+        x, w, scale, shift = args[:4]
+        xin = host(x)
+        assert not _ring_of(xin).any(), "conv3x3_flat: the input ring must be zero"
+        y = orc.conv2d(_t(xin[:, 1:-1, 1:-1]), host(w).astype(F64).transpose(0, 3, 1, 2), (1, 1), (1, 1))
+        y = y * host(scale).astype(F64)[None, :, None, None] + host(shift).astype(F64)[None, :, None, None]
+        if kw.get("relu", True):
+            y = orc.relu(y)
+        got = host(out)
+        assert not _ring_of(got).any(), "conv3x3_flat: the output ring must be zero"
+        return "flat conv %s on %s" % (tuple(w.shape), tuple(x.shape)), got[:, 1:-1, 1:-1], nhwc(y)
+    if name == "maxpool2x2_ring":
+        x = args[0]
+        y = orc.maxpool2d(_t(host(x)[:, 1:-1, 1:-1]))
+        return "maxpool (ring) %s" % (tuple(x.shape),), host(out), nhwc(y)
     if name == "maxpool_nhwc":
         x = args[0]
         rest = list(args[1:]) + [None] * 3
@@ -104,13 +130,13 @@ def bf16_run(sd_cfg_a):
 def test_every_conv_launch_matches_rounding_matched_function_of_its_inputs(bf16_run):
     rows, checked = [], 0
     for name, args, kw, out in bf16_run["calls"]:
-        if name not in ("conv3x3_first", "maxpool_nhwc", "conv_gemm", "conv_gemm_dual"):
+        if name not in ("conv3x3_first", "conv3x3_flat", "maxpool_nhwc", "maxpool2x2_ring", "conv_gemm", "conv_gemm_dual"):
             continue
         r = _replay(name, args, kw, out)
         if r is None:
             continue
         what, got, ref = r
-        if name == "maxpool_nhwc":
+        if name in ("maxpool_nhwc", "maxpool2x2_ring"):
             assert np.array_equal(got.astype(F64), ref), "%s: max-pool must be exact" % what
             continue
         exact, within, rel = bf16_agreement(got, ref)
@@ -150,16 +176,33 @@ def test_packed_operands_are_what_the_oracle_states(bf16_run, sd_cfg_a):
         # torch and numpy form w * scale with the same single fp32 multiply; the bf16 rounding of it is unique
         assert (got == want).mean() >= 0.9999 and np.abs(got - want).max() <= np.abs(want).max() * 2.0 ** -7, blk
         np.testing.assert_allclose(host(shift), b2 + bd, rtol=1e-6, atol=1e-7)
-    # conv0_2 over pixel pairs is the same sum of the same products: compare with the direct conv on one batch
-    st = bf16_run["stages"]
-    call = [c for c in bf16_run["calls"] if c[0] == "conv_gemm" and tuple(c[1][1].shape) == (128, 3, 3, 64)
-            and c[1][0].shape[1] == 32][0]
-    xin = host(call[1][0]).reshape(bf16_run["B"], 32, 100, 32)
+    # conv0_2 (padded-flat kernel): the packed weight is the bf16 rounding of the reference weight, and the launch
+    # equals the direct convolution of its interior
+    call = [c for c in bf16_run["calls"] if c[0] == "conv3x3_flat"][0]
+    assert np.array_equal(host(call[1][1]), orc.round_bf16(sd_cfg_a[n + "conv0_2.weight"]).transpose(0, 2, 3, 1))
+    xin = host(call[1][0])[:, 1:-1, 1:-1]
     s, b = fold("bn0_2")
     y = orc.conv2d(_t(xin), orc.round_bf16(sd_cfg_a[n + "conv0_2.weight"]).astype(F64), (1, 1), (1, 1))
     y = nhwc(orc.relu(y * s.astype(F64)[None, :, None, None] + b.astype(F64)[None, :, None, None]))
-    exact, within, rel = bf16_agreement(host(call[3]).reshape(y.shape), y)
-    assert exact >= 0.99 and within == 1.0, "conv0_2 (pixel pairs) vs direct conv: %.5f %.5f %.1e" % (exact, within, rel)
+    exact, within, rel = bf16_agreement(host(call[3])[:, 1:-1, 1:-1], y)
+    assert exact >= 0.99 and within == 1.0, "conv0_2 (padded-flat) vs direct conv: %.5f %.5f %.1e" % (exact, within, rel)
+
+
+def test_conv0_2_pixel_pair_fallback_matches_flat_path(sd_cfg_a):
+    """config.CONV0_FLAT = False takes conv0_2 over horizontal pixel pairs (the fallback for geometries the flat kernel
+    does not cover): the same sums of the same products - equal to the flat path up to accumulation order."""
+    x = synth.make_crops(779, 4)
+    outs = {}
+    try:
+        for flat in (True, False):
+            m = load_model(sd_cfg_a, precision="bf16", CONV0_FLAT=flat)
+            with torch.no_grad():
+                outs[flat] = host(m.FeatureExtraction.forward_nhwc(m.Transformation(dev(x))))
+            torch.cuda.synchronize()
+    finally:
+        config.CONV0_FLAT = True
+    assert err(outs[False], outs[True])[1] <= 4e-2
+    assert (outs[False] == outs[True]).mean() > 0.3
 
 
 def test_sequence_model_from_gpu_features_matches_matched_oracle(bf16_run, sd_cfg_a):
@@ -198,13 +241,16 @@ def test_free_running_divergence_curve(bf16_run, sd_cfg_a):
     trace = []
     orc.resnet_forward(rect, sd_cfg_a, np.dtype(np.float32), "bf16", trace=trace)
     m = bf16_run["model"]
-    with OpRecorder(("conv3x3_first", "conv_gemm", "conv_gemm_dual", "maxpool_nhwc")) as rec, torch.no_grad():
+    with OpRecorder(("conv3x3_first", "conv3x3_flat", "conv_gemm", "conv_gemm_dual", "maxpool_nhwc", "maxpool2x2_ring")) as rec, \
+            torch.no_grad():
         m.FeatureExtraction.forward_nhwc(st["rectified"])
     torch.cuda.synchronize()
     assert len(rec.calls) == len(trace), (len(rec.calls), len(trace))
     lines = []
     for (name, ref), (_n, _a, _k, out) in zip(trace, rec.calls):
         o = out[0] if isinstance(out, tuple) else out
+        if _n in ("conv3x3_flat",) or (_n == "conv3x3_first" and _k.get("ring")):
+            o = o[:, 1:-1, 1:-1]                               # padded-flat launches: compare the interior
         got = nchw(host(o).reshape((ref.shape[0], ref.shape[2], ref.shape[3], ref.shape[1])))
         differ = float((got != ref).mean())
         rel = err(got, ref)[1]

@@ -258,6 +258,84 @@ def test_small_im2col_tensor_map():
 
 
 # ------------------------------------------------------------------------------------------------
+# padded-flat path: conv0_1 (ring output) -> conv3x3_flat -> maxpool over the ring
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,cin,H,W", [(5, 1, 32, 100), (9, 3, 8, 12), (2, 3, 64, 256)])
+def test_padded_flat_conv_path(B, cin, H, W):
+    """mstr_conv3x3_first(pool=2) writes [B,H+2,W+2,32] with a zero ring; mstr_conv3x3_flat_bf16 (one slab load per
+    256-position tile, nine taps as row-shifted shared-memory descriptors) must equal the
+    convolution of the interior evaluated exactly, rounded to bf16, and write a zero ring; mstr_maxpool2x2_ring_bf16
+    pools the interior.  Tiles straddle image rows and images; the first / last tiles read rows outside the tensor."""
+    r = rng(51)
+    x = r.uniform(0, 1, (B, cin, H, W)).astype(np.float32)
+    w1 = (r.standard_normal((32, cin, 3, 3)) / np.sqrt(9 * cin)).astype(np.float32)
+    s1, b1 = r.uniform(0.5, 1.5, 32).astype(np.float32), r.normal(0, 0.2, 32).astype(np.float32)
+    w2 = orc.round_bf16((r.standard_normal((64, 3, 3, 32)) / np.sqrt(9 * 32)).astype(np.float32))
+    s2, b2 = r.uniform(0.5, 1.5, 64).astype(np.float32), r.normal(0, 0.2, 64).astype(np.float32)
+    bf = torch.bfloat16
+    plain = ops.conv3x3_first(dev(x), dev(w1), dev(s1), dev(b1), bf, pool=False)
+    ring = ops.conv3x3_first(dev(x), dev(w1), dev(s1), dev(b1), bf, pool=False, ring=True)
+    torch.cuda.synchronize()
+    assert tuple(ring.shape) == (B, H + 2, W + 2, 32)
+    assert torch.equal(ring[:, 1:-1, 1:-1], plain), "interior of the ring output differs from the plain output"
+    edge = ring.clone(); edge[:, 1:-1, 1:-1] = 0
+    assert not edge.any(), "the ring must be zero"
+    # flat convolution vs float64 on the same bf16 activations
+    act = host(plain).astype(np.float64)                                     # [B,H,W,32]
+    ref = orc.conv2d(nchw(act), w2.transpose(0, 3, 1, 2).astype(np.float64), (1, 1), (1, 1))
+    ref = nhwc(orc.relu(ref * s2.astype(np.float64)[None, :, None, None] + b2.astype(np.float64)[None, :, None, None]))
+    out = ops.conv3x3_flat(ring, dev(w2, bf), dev(s2), dev(b2), relu=True)
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (B, H + 2, W + 2, 64)
+    got = host(out[:, 1:-1, 1:-1]).astype(np.float64)
+    tol = np.abs(ref) * 2.0 ** -7 + 2e-5 * np.abs(ref).max()
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), "%d of %d outputs off by more than a bf16 ulp (max err %.3e of max %.3e)" % (
+        bad.sum(), bad.size, np.abs(got - ref).max(), np.abs(ref).max())
+    exact = (got == orc.round_bf16(ref.astype(np.float32)).astype(np.float64)).mean()
+    assert exact > 0.99, "only %.4f of the outputs are the bf16 rounding of the exact result" % exact
+    edge = out.clone(); edge[:, 1:-1, 1:-1] = 0
+    assert not edge.any(), "the output ring must be zero"
+    # equals the im2col kernel on the same operands up to accumulation order
+    same = ops.conv_gemm(plain, dev(w2, bf), dev(s2), dev(b2), None, stride=(1, 1), pad=(1, 1), relu=True)
+    torch.cuda.synchronize()
+    assert (host(same) == host(out[:, 1:-1, 1:-1])).mean() > 0.995
+    # pool over the ring == pool of the interior
+    pooled = ops.maxpool2x2_ring(out)
+    ref_pool = ops.maxpool_nhwc(out[:, 1:-1, 1:-1].contiguous(), (2, 2), (2, 2), (0, 0))
+    torch.cuda.synchronize()
+    assert torch.equal(pooled, ref_pool)
+
+
+def test_padded_flat_conv_descriptor_base_offset():
+    """Pins the hardware rule conv_flat.cu relies on: the tensor core applies the operand swizzle to the bits of the
+    final shared-memory address, so an A descriptor that starts inside a swizzle atom (a row-shifted view of the slab)
+    is correct with the "matrix base offset" field left at ZERO; setting the field to the phase of the start address
+    (debug mode 1) gives a wrong result (measured: 0.58 of the output range).  If mode 1 ever becomes the correct one,
+    the descriptor semantics have changed and the kernel needs a second look."""
+    r = rng(52)
+    B, H, W = 3, 8, 12
+    bf = torch.bfloat16
+    act = orc.round_bf16(r.uniform(0, 1, (B, H, W, 32)).astype(np.float32))
+    ring = np.zeros((B, H + 2, W + 2, 32), np.float32); ring[:, 1:-1, 1:-1] = act
+    w2 = orc.round_bf16((r.standard_normal((64, 3, 3, 32)) / np.sqrt(288)).astype(np.float32))
+    outs = {}
+    try:
+        for mode in (0, 1):
+            ops.flat_desc_mode(mode)
+            outs[mode] = host(ops.conv3x3_flat(dev(ring, bf), dev(w2, bf), None, None, relu=False)[:, 1:-1, 1:-1])
+            torch.cuda.synchronize()
+    finally:
+        ops.flat_desc_mode(0)
+    ref = nhwc(orc.conv2d(nchw(act.astype(np.float64)), w2.transpose(0, 3, 1, 2).astype(np.float64), (1, 1), (1, 1)))
+    e0 = np.abs(outs[0] - ref).max() / np.abs(ref).max()
+    e1 = np.abs(outs[1] - ref).max() / np.abs(ref).max()
+    print("\nflat conv: max error without the base offset %.2e, with it %.2e" % (e0, e1))
+    assert e0 < 1e-2, "plain row-shifted descriptors must be right (%.3e)" % e0
+    assert e1 > 1e-1, "with the base-offset field the result was expected to be wrong (%.3e)" % e1
+
+
+# ------------------------------------------------------------------------------------------------
 # pooling / reductions / cast / embedding
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -488,7 +566,7 @@ def test_attn_decode_bf16_persistent_kernel_matches_launch_chain(sd_cfg_a, B, T,
         persistent = run()
         again = run()
     finally:
-        ops.set_decode_persistent(True)
+        ops.set_decode_persistent(None)
     for other in (persistent, again):
         for a, b in zip(chain, other):
             for x, y in zip(a, b):

@@ -46,7 +46,7 @@ for B in BATCHES:
         med, best = timeit(lambda: ops.attn_decode_bf16(enc, proj, pk, steps, None, early_exit=False))
         print("attn_decode_bf16 B=%d %s: median %.3f ms, best %.3f ms" % (
             B, "persistent (1 launch)" if persistent else "chain (80 launches)", med, best))
-    ops.set_decode_persistent(True)
+    ops.set_decode_persistent(None)
 
 # phase trace of the persistent decoder (CTA 0): per step [head work, barrier, attention work, barrier, cell work, barrier]
 import ctypes
@@ -54,14 +54,38 @@ from multimodal_scene_text_recognition_b200 import _cabi
 for B in BATCHES:
     enc = (torch.randn(B, T, H, device=dev) * 0.5).to(torch.bfloat16)
     proj = (enc.float() @ sd[p + "i2h.weight"].t()).to(torch.bfloat16)
+    ops.set_decode_persistent(True)
     ops.attn_decode_bf16(enc, proj, pk, steps, None, early_exit=False)
     ops.attn_decode_bf16(enc, proj, pk, steps, None, early_exit=False)
     torch.cuda.synchronize()
+    ops.set_decode_persistent(None)
     n = 1 + 6 * steps
     buf = (ctypes.c_ulonglong * n)()
-    _cabi.check(_cabi.lib().mstr_debug_decode_trace(ctypes.cast(buf, ctypes.c_void_p), n))
+    NB, NC = 48, 160
+    per = (ctypes.c_ulonglong * (NB * NC))()
+    _cabi.check(_cabi.lib().mstr_debug_decode_trace(ctypes.cast(buf, ctypes.c_void_p), n, ctypes.cast(per, ctypes.c_void_p), NB * NC))
     t = np.array(list(buf), dtype=np.float64)
     d = np.diff(t).reshape(steps, 6) / 1e3
     names = ["head work", "barrier 1", "attention", "barrier 2", "cell work", "barrier 3"]
     print("persistent decoder phase trace B=%d (us, median over steps): %s | step total %.1f" % (
         B, ", ".join("%s %.2f" % (nm, v) for nm, v in zip(names, np.median(d, axis=0))), np.median(d.sum(axis=1))))
+    # arrival of every CTA at the barriers of steps 3..14, relative to the barrier's first arrival
+    arr = np.array(list(per), dtype=np.float64).reshape(NB, NC)[:, :148]
+    rel = (arr - arr.min(axis=1, keepdims=True)) / 1e3
+    for ph, nm in enumerate(["after head", "after attention", "after cell"]):
+        r = rel[9 + ph:45:3]
+        late = np.median(r, axis=0)
+        order = np.argsort(-late)[:6]
+        print("  arrival spread %s: median last-first %.2f us; latest CTAs %s" % (
+            nm, np.median(r.max(axis=1)), ", ".join("%d(+%.1f)" % (c, late[c]) for c in order)))
+    fine = (ctypes.c_ulonglong * 128)()
+    _cabi.check(_cabi.lib().mstr_debug_decode_trace(ctypes.cast(buf, ctypes.c_void_p), n, ctypes.cast(fine, ctypes.c_void_p), 128))
+    f = np.array(list(fine), dtype=np.float64).reshape(2, 4, 16)
+    slots = ["entry", "tma issued", "stage arrived", "mma committed", "acc complete", "-", "acc released", "epilogue done"]
+    for ph, nm in enumerate(["head", "cell"]):
+        for cta in range(4):
+            row = f[ph, cta]
+            if row[0] == 0:
+                continue
+            print("  fine %s CTA %d (us since phase entry): %s" % (nm, cta, ", ".join(
+                "%s %.2f" % (slots[k], (row[k] - row[0]) / 1e3) for k in (1, 2, 3, 4, 6, 7) if row[k] > 0)))

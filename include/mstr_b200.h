@@ -142,12 +142,14 @@ int mstr_maxpool2x2_ring_bf16(const void* x_ring, void* out, int B, int H, int W
 /* 3x3 / stride 1 / pad 1 convolution + folded BatchNorm + ReLU over a PADDED-FLAT activation (csrc/conv_flat.cu):
  * replaces conv0_2 + bn0_2 + ReLU (modules/feature_extraction.py:61-63,113-115) in the bf16 mode.
  *   x   [B][H+2][W+2][C_in] bf16 whose one-pixel ring is zero (mstr_conv3x3_first with pool = 2 writes it)
- *   w   [C_out][3][3][C_in] bf16; scale, shift [C_out] f32 (NULL = 1 / 0)
+ *   w   [C_out][3][3][C_in] bf16 (device)
+ *   scale_host, shift_host [C_out] f32 in HOST memory (NULL = 1 / 0): the folded BatchNorm is passed to the kernel by
+ *        value (kernel parameters are constant-bank operands of the epilogue's FMAs), read during this call
  *   out [B][H+2][W+2][C_out] bf16, ring written as zeros
  * Every activation row is loaded once per tile of 256 positions; the nine taps are shared-memory descriptor offsets.
  * C_in = 32 and C_out = 64 only. */
-int mstr_conv3x3_flat_bf16(const void* x, const void* w, const float* scale, const float* shift, void* out, int B,
-                           int H, int W, int C_in, int C_out, int relu, mstr_stream_t stream);
+int mstr_conv3x3_flat_bf16(const void* x, const void* w, const float* scale_host, const float* shift_host, void* out,
+                           int B, int H, int W, int C_in, int C_out, int relu, mstr_stream_t stream);
 /* Test hook of mstr_conv3x3_flat_bf16: 0 (default) leaves the "matrix base offset" field of the row-shifted A
  * descriptors zero - correct on B200, the swizzle is applied to absolute address bits; 1 sets it to the phase of the
  * start address (wrong result; kept as the experiment that pins the rule, tests/test_gpu_kernels.py). */

@@ -66,6 +66,16 @@ def pack_conv(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, precision: str):
     return cached(conv, ('conv', precision), [conv.weight] + bn_sources(bn), build)
 
 
+def pack_conv_flat(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d):
+    """Padded-flat kernel (ops.conv3x3_flat): (w [Cout,R,S,Cin] bf16 on the device, scale, shift as HOST f32 tensors -
+    the kernel takes the folded BatchNorm by value)."""
+    def build():
+        scale, shift = fold_bn(bn)
+        w = conv.weight.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+        return w, scale.cpu().contiguous(), shift.cpu().contiguous()
+    return cached(conv, ('flat',), [conv.weight] + bn_sources(bn), build)
+
+
 def pack_first_conv(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d):
     """Image-reading conv: fp32 [Cout,Cin,3,3] weights (SIMT kernel) + folded BN."""
     def build():

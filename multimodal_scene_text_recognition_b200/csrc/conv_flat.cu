@@ -44,7 +44,7 @@ constexpr int CF_EPI_WARPS = 8;
 constexpr int CF_THREADS = 64 + 32 * CF_EPI_WARPS;
 constexpr int CF_OUT_SLAB = 128 * CF_COUT * 2;   // [128 positions][64 channels] bf16: 128-byte rows, 128B swizzle = 16 KB
 constexpr int CF_EPI_BYTES = 2 * 2 * CF_OUT_SLAB;             // two groups x two slabs
-constexpr int CF_TAIL_BYTES = 2 * CF_COUT * 4 + 16 * 8 + 16;
+constexpr int CF_TAIL_BYTES = 16 * 8 + 16;
 constexpr int CF_MAX_STAGES = 4;
 
 struct CfParams {
@@ -53,8 +53,14 @@ struct CfParams {
   int box_rows, nload, slab_bytes, stages;
   int relu;
   int desc_mode;                                 // 0: plain shifted start address (correct, default); 1: + base offset (experiment)
-  const float* scale;
-  const float* shift;
+};
+// Folded BatchNorm travels as a KERNEL PARAMETER: parameters live in the constant bank, and with the channel loop
+// unrolled every scale / shift is a constant-bank operand of its FFMA - no load instruction.  (Staged in shared memory
+// they cost 128 broadcast LDS per thread and tile: ncu showed the LSU shared-load pipe 24 % busy and the epilogue, at
+// ~500 issued instructions per warp and tile, slower than the tile's MMAs.)
+struct CfAffine {
+  float scale[CF_COUT];
+  float shift[CF_COUT];
 };
 
 __device__ __forceinline__ uint64_t cf_desc_a(uint32_t addr, int mode) {
@@ -65,15 +71,13 @@ __device__ __forceinline__ uint64_t cf_desc_a(uint32_t addr, int mode) {
 
 __global__ void __launch_bounds__(CF_THREADS, 1)
 conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmO, const CfParams p) {
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CfAffine bn, const CfParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;                                          // [9][64 rows][64 B], 64B swizzle
   uint8_t* sSlab = sW + CF_W_BYTES;                            // [stages][slab_bytes]
   uint8_t* sEpi = sSlab + p.stages * p.slab_bytes;             // 1024-aligned: slab_bytes is a multiple of 1024
-  float* sScale = reinterpret_cast<float*>(sEpi + CF_EPI_BYTES);
-  float* sShift = sScale + CF_COUT;
-  uint64_t* wfull_bar = reinterpret_cast<uint64_t*>(sShift + CF_COUT);
+  uint64_t* wfull_bar = reinterpret_cast<uint64_t*>(sEpi + CF_EPI_BYTES);
   uint64_t* sfull_bar = wfull_bar + 1;                         // [CF_MAX_STAGES]
   uint64_t* sempty_bar = sfull_bar + CF_MAX_STAGES;            // [CF_MAX_STAGES]
   uint64_t* tfull_bar = sempty_bar + CF_MAX_STAGES;            // [2]
@@ -81,10 +85,6 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < CF_COUT; i += CF_THREADS) {
-    sScale[i] = p.scale ? __ldg(p.scale + i) : 1.f;
-    sShift[i] = p.shift ? __ldg(p.shift + i) : 0.f;
-  }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmX);
     prefetch_tensormap(&tmW);
@@ -185,16 +185,21 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
       uint32_t packed[32];
+      if (interior) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float r0 = fmaf(__uint_as_float(v0[2 * j]), sScale[2 * j], sShift[2 * j]);
-        float r1 = fmaf(__uint_as_float(v0[2 * j + 1]), sScale[2 * j + 1], sShift[2 * j + 1]);
-        float r2 = fmaf(__uint_as_float(v1[2 * j]), sScale[32 + 2 * j], sShift[32 + 2 * j]);
-        float r3 = fmaf(__uint_as_float(v1[2 * j + 1]), sScale[32 + 2 * j + 1], sShift[32 + 2 * j + 1]);
-        if (p.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
+        for (int j = 0; j < 16; ++j) {
+          float r0 = fmaf(__uint_as_float(v0[2 * j]), bn.scale[2 * j], bn.shift[2 * j]);
+          float r1 = fmaf(__uint_as_float(v0[2 * j + 1]), bn.scale[2 * j + 1], bn.shift[2 * j + 1]);
+          float r2 = fmaf(__uint_as_float(v1[2 * j]), bn.scale[32 + 2 * j], bn.shift[32 + 2 * j]);
+          float r3 = fmaf(__uint_as_float(v1[2 * j + 1]), bn.scale[32 + 2 * j + 1], bn.shift[32 + 2 * j + 1]);
+          if (p.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
+          packed[j] = pack_bf16x2(r0, r1);
+          packed[16 + j] = pack_bf16x2(r2, r3);
+        }
+      } else {
         // the ring is written as zeros: it is the next layer's padding
-        packed[j] = interior ? pack_bf16x2(r0, r1) : 0u;
-        packed[16 + j] = interior ? pack_bf16x2(r2, r3) : 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) packed[j] = 0u;
       }
       uint8_t* slab = slabs + turn * CF_OUT_SLAB;
       asm volatile("bar.sync %0, 128;" ::"r"(bar_a) : "memory");   // the store that last read this slab has drained it
@@ -237,8 +242,8 @@ extern "C" __attribute__((visibility("default"))) int mstr_debug_flat_desc_mode(
 }
 
 extern "C" __attribute__((visibility("default"))) int mstr_conv3x3_flat_bf16(
-    const void* x, const void* w, const float* scale, const float* shift, void* out, int B, int H, int W, int C_in,
-    int C_out, int relu, mstr_stream_t stream) {
+    const void* x, const void* w, const float* scale_host, const float* shift_host, void* out, int B, int H, int W,
+    int C_in, int C_out, int relu, mstr_stream_t stream) {
   using namespace mstr;
   MSTR_REQUIRE(x && w && out, MSTR_ERR_BAD_ARG, "mstr_conv3x3_flat_bf16: null pointer");
   MSTR_REQUIRE(B > 0 && H > 0 && W > 0, MSTR_ERR_BAD_ARG, "mstr_conv3x3_flat_bf16: bad size");
@@ -264,7 +269,6 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv3x3_flat_bf16(
   MSTR_REQUIRE(p.stages >= 2, MSTR_ERR_UNSUPPORTED, "mstr_conv3x3_flat_bf16: W=%d needs a slab of %d bytes", W, p.slab_bytes);
   p.relu = relu;
   p.desc_mode = g_flat_desc_mode.load(std::memory_order_relaxed);
-  p.scale = scale; p.shift = shift;
   alignas(64) CUtensorMap tmX, tmW, tmO;
   rc = encode_tiled_2d_bf16(g_flat_enc, &tmX, x, CF_CIN, (uint64_t)p.NP, CF_CIN, (uint32_t)p.box_rows, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != MSTR_OK) return rc;
@@ -272,12 +276,17 @@ extern "C" __attribute__((visibility("default"))) int mstr_conv3x3_flat_bf16(
   if (rc != MSTR_OK) return rc;
   rc = encode_tiled_2d_bf16(g_flat_enc, &tmO, out, CF_COUT, (uint64_t)p.NP, CF_COUT, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != MSTR_OK) return rc;
+  CfAffine bn;
+  for (int i = 0; i < CF_COUT; ++i) {
+    bn.scale[i] = scale_host ? scale_host[i] : 1.f;
+    bn.shift[i] = shift_host ? shift_host[i] : 0.f;
+  }
   const int smem_bytes = 1024 + CF_W_BYTES + p.stages * p.slab_bytes + CF_EPI_BYTES + CF_TAIL_BYTES;
   static unsigned long long smem_set = 0;
   rc = ensure_dynamic_smem((const void*)conv3x3_flat_kernel, 227 * 1024, &smem_set);
   if (rc != MSTR_OK) return rc;
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv3x3_flat_kernel<<<grid, CF_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, p);
+  conv3x3_flat_kernel<<<grid, CF_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, bn, p);
   MSTR_LAUNCH_CHECK("conv3x3_flat_kernel");
   return MSTR_OK;
 }

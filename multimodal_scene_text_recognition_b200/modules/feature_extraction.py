@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import config, ops
-from .._pack import (act_dtype, pack_block_tail, pack_conv, pack_conv_pixel_pairs, pack_first_conv,
+from .._pack import (act_dtype, pack_block_tail, pack_conv, pack_conv_flat, pack_conv_pixel_pairs, pack_first_conv,
                      require_eval, require_inference)
 
 
@@ -167,7 +167,7 @@ class ResNet(nn.Module):
             # conv0_1 -> padded-flat activation -> conv0_2 with one slab load per tile -> maxpool1 skipping the ring
             w, scale, shift = pack_first_conv(self.conv0_1, self.bn0_1)
             h = ops.conv3x3_first(x, w, scale, shift, torch.bfloat16, pool=False, ring=True)
-            w, scale, shift = pack_conv(c2, self.bn0_2, precision)
+            w, scale, shift = pack_conv_flat(c2, self.bn0_2)
             h = ops.conv3x3_flat(h, w, scale, shift, relu=True)
             h = ops.maxpool2x2_ring(h)
         else:

@@ -190,16 +190,20 @@ def conv3x3_first(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: 
 def conv3x3_flat(x_ring: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
                  relu: bool = True) -> torch.Tensor:
     """3x3 / stride 1 / pad 1 convolution + folded BN + ReLU over a padded-flat bf16 activation.
-    x_ring [B,H+2,W+2,Cin] with a zero ring, w [Cout,3,3,Cin] bf16 -> [B,H+2,W+2,Cout] bf16, ring zero."""
+    x_ring [B,H+2,W+2,Cin] with a zero ring, w [Cout,3,3,Cin] bf16 -> [B,H+2,W+2,Cout] bf16, ring zero.
+    scale / shift: HOST f32 tensors [Cout] (they are passed to the kernel by value; _pack.pack_conv_flat caches host
+    copies so that no device->host copy happens per call) or None."""
     _req(x_ring, "x_ring", torch.bfloat16); _req(w, "w", torch.bfloat16)
-    _req(scale, "scale", torch.float32); _req(shift, "shift", torch.float32)
     B, Hp, Wp, Cin = x_ring.shape
     Cout = w.shape[0]
     assert w.shape == (Cout, 3, 3, Cin) and Hp > 2 and Wp > 2
+    for name, t in (("scale", scale), ("shift", shift)):
+        if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != Cout):
+            raise TypeError("conv3x3_flat: %s must be a contiguous host f32 tensor of %d values" % (name, Cout))
     H, W = Hp - 2, Wp - 2
     out = torch.empty((B, Hp, Wp, Cout), device=x_ring.device, dtype=torch.bfloat16)
     with _timed("conv3x3_flat", 2.0 * B * H * W * Cout * 9 * Cin, "flop",
-                "M=%d (B%d %dx%d) %d->%d 3x3, padded-flat" % (B * H * W, B, H, W, Cin, Cout)), _on(x_ring, w, scale, shift) as st:
+                "M=%d (B%d %dx%d) %d->%d 3x3, padded-flat" % (B * H * W, B, H, W, Cin, Cout)), _on(x_ring, w) as st:
         check(lib().mstr_conv3x3_flat_bf16(ptr(x_ring), ptr(w), ptr(scale), ptr(shift), ptr(out), B, H, W, Cin, Cout,
                                            int(relu), st), "mstr_conv3x3_flat_bf16")
     return out

@@ -63,7 +63,7 @@ def _replay(name, args, kw, out):
         xin = host(x)
         assert not _ring_of(xin).any(), "conv3x3_flat: the input ring must be zero"
         y = orc.conv2d(_t(xin[:, 1:-1, 1:-1]), host(w).astype(F64).transpose(0, 3, 1, 2), (1, 1), (1, 1))
-        y = y * host(scale).astype(F64)[None, :, None, None] + host(shift).astype(F64)[None, :, None, None]
+        y = y * scale.numpy().astype(F64)[None, :, None, None] + shift.numpy().astype(F64)[None, :, None, None]
         if kw.get("relu", True):
             y = orc.relu(y)
         got = host(out)
@@ -180,6 +180,9 @@ def test_packed_operands_are_what_the_oracle_states(bf16_run, sd_cfg_a):
     # equals the direct convolution of its interior
     call = [c for c in bf16_run["calls"] if c[0] == "conv3x3_flat"][0]
     assert np.array_equal(host(call[1][1]), orc.round_bf16(sd_cfg_a[n + "conv0_2.weight"]).transpose(0, 2, 3, 1))
+    s_f, b_f = fold("bn0_2")
+    np.testing.assert_allclose(call[1][2].numpy(), s_f, rtol=2e-7, atol=0)
+    np.testing.assert_allclose(call[1][3].numpy(), b_f, rtol=1e-6, atol=1e-7)
     xin = host(call[1][0])[:, 1:-1, 1:-1]
     s, b = fold("bn0_2")
     y = orc.conv2d(_t(xin), orc.round_bf16(sd_cfg_a[n + "conv0_2.weight"]).astype(F64), (1, 1), (1, 1))

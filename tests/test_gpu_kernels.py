@@ -284,7 +284,7 @@ def test_padded_flat_conv_path(B, cin, H, W):
     act = host(plain).astype(np.float64)                                     # [B,H,W,32]
     ref = orc.conv2d(nchw(act), w2.transpose(0, 3, 1, 2).astype(np.float64), (1, 1), (1, 1))
     ref = nhwc(orc.relu(ref * s2.astype(np.float64)[None, :, None, None] + b2.astype(np.float64)[None, :, None, None]))
-    out = ops.conv3x3_flat(ring, dev(w2, bf), dev(s2), dev(b2), relu=True)
+    out = ops.conv3x3_flat(ring, dev(w2, bf), torch.from_numpy(s2), torch.from_numpy(b2), relu=True)
     torch.cuda.synchronize()
     assert tuple(out.shape) == (B, H + 2, W + 2, 64)
     got = host(out[:, 1:-1, 1:-1]).astype(np.float64)

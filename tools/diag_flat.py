@@ -14,8 +14,8 @@ w1 = torch.randn(32, 1, 3, 3, device=dev, generator=g) / 3
 s1 = torch.rand(32, device=dev, generator=g) + 0.5
 b1 = torch.randn(32, device=dev, generator=g) * 0.1
 w2 = (torch.randn(64, 3, 3, 32, device=dev, generator=g) / 17).to(torch.bfloat16)
-s2 = torch.rand(64, device=dev, generator=g) + 0.5
-b2 = torch.randn(64, device=dev, generator=g) * 0.1
+s2 = torch.rand(64) + 0.5
+b2 = torch.randn(64) * 0.1
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 

@@ -213,8 +213,10 @@ __device__ __forceinline__ void at_head_logits_epilogue(const DecodeState& s, fl
 
 // ---- cell epilogue: this tile = 32 hidden units x 4 gates of 128 crops; this warp: 16 of the units -------
 // Everything the LSTM cell needs besides the accumulator - the token's row of W_tok (+ bias) and the previous cell
-// state - is loaded one group of 4 units AHEAD (the first group before the accumulator is even complete: `wait_acc`
-// blocks on the MMAs), so the L2 round trips overlap the MMAs and the gate math.
+// state - does not depend on this phase's GEMM, and the per-lane (row = crop, rows 4 KB apart) gathers cost 32 L1
+// wavefronts per instruction: ALL of them are issued before the accumulator is awaited (`wait_acc` blocks on the TMA
+// loads and the MMAs, which do not use the load/store path), so that what follows the wait is only TMEM loads, the
+// gate math and the stores.  (Loading one group of 4 units ahead left ~3 of the 5 us of this epilogue exposed.)
 template <typename WaitAcc, typename Release>
 __device__ __forceinline__ void at_cell_epilogue(const DecodeState& s, const uint32_t taddr, const EpiWho& w, const int m0,
                                                  const int n_tile, const int step, WaitAcc wait_acc, Release release) {
@@ -226,33 +228,27 @@ __device__ __forceinline__ void at_cell_epilogue(const DecodeState& s, const uin
   const float* wt = s.w_tok + (size_t)tok * (4 * AT_H);
   float* ccol = s.cst + (size_t)unit0 * s.B + (valid ? crop : 0);   // cell state is kept [H][B]: lane = crop is coalesced
   __nv_bfloat16* hrow = s.xh[(step + 1) & 1] + (size_t)(valid ? crop : 0) * (2 * AT_H) + AT_H + unit0;
-  float4 addn[4];
-  float cpn[4];
-  auto load_group = [&](const int sub) {                  // 4 units: W_tok[tok] (+ bias) of the four gates, c_{t-1}
+  float4 add4[4][4];                                     // [group of 4 units][gate]
+  float cprev[16];
+#pragma unroll
+  for (int sub = 0; sub < 4; ++sub) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int col = g * AT_H + unit0 + sub * 4;
-      float4 t = __ldg(reinterpret_cast<const float4*>(wt + col));
+      float4 t = valid ? __ldg(reinterpret_cast<const float4*>(wt + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (s.bias) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(s.bias + col));
         t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
       }
-      addn[g] = t;
+      add4[sub][g] = t;
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cpn[j] = __ldcg(ccol + (size_t)(sub * 4 + j) * s.B);
-  };
-  if (valid) load_group(0);
+  for (int j = 0; j < 16; ++j) cprev[j] = valid ? __ldcg(ccol + (size_t)j * s.B) : 0.f;
   wait_acc();
   uint32_t hpk[4];
 #pragma unroll
   for (int sub = 0; sub < 4; ++sub) {
-    float add[4][4], cp[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) { add[g][0] = addn[g].x; add[g][1] = addn[g].y; add[g][2] = addn[g].z; add[g][3] = addn[g].w; }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) cp[j] = cpn[j];
-    if (valid && sub < 3) load_group(sub + 1);
     uint32_t a[4][4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) tmem_ld4(taddr + (uint32_t)(g * 32 + ubase + sub * 4), a[g]);
@@ -261,20 +257,24 @@ __device__ __forceinline__ void at_cell_epilogue(const DecodeState& s, const uin
       tc_fence_before();
       release();
     }
-    float hv[4];
+    const float add[4][4] = {{add4[sub][0].x, add4[sub][0].y, add4[sub][0].z, add4[sub][0].w},
+                             {add4[sub][1].x, add4[sub][1].y, add4[sub][1].z, add4[sub][1].w},
+                             {add4[sub][2].x, add4[sub][2].y, add4[sub][2].z, add4[sub][2].w},
+                             {add4[sub][3].x, add4[sub][3].y, add4[sub][3].z, add4[sub][3].w}};
+    float hv[4], cn4[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float gi = __uint_as_float(a[0][j]) + add[0][j];
       const float gf = __uint_as_float(a[1][j]) + add[1][j];
       const float gg = __uint_as_float(a[2][j]) + add[2][j];
       const float go = __uint_as_float(a[3][j]) + add[3][j];
-      const float cn = fmaf(at_sigmoid(gf), cp[j], at_sigmoid(gi) * at_tanh(gg));
-      cp[j] = cn;
+      const float cn = fmaf(at_sigmoid(gf), cprev[sub * 4 + j], at_sigmoid(gi) * at_tanh(gg));
+      cn4[j] = cn;
       hv[j] = at_sigmoid(go) * at_tanh(cn);
     }
     if (valid) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ccol[(size_t)(sub * 4 + j) * s.B] = cp[j];
+      for (int j = 0; j < 4; ++j) ccol[(size_t)(sub * 4 + j) * s.B] = cn4[j];
     }
     hpk[(sub & 1) * 2] = pack_bf16x2(hv[0], hv[1]);
     hpk[(sub & 1) * 2 + 1] = pack_bf16x2(hv[2], hv[3]);
@@ -543,6 +543,7 @@ __global__ void decode_init_kernel(const DecodeState s) {
     *s.live = s.B;
     s.live[1] = 0;          // arrival counter of the persistent kernel's grid barrier
   }
+  if (i < 256) s.live[2 + i] = 0;   // PD_DYN_STEPS crop counters of the persistent kernel's attention phase
   if (i < s.B) {
     s.tok[i] = s.text ? (int)s.text[(size_t)i * s.steps] : 0;
     s.done[i] = 0;
@@ -569,6 +570,7 @@ __global__ void decode_init_kernel(const DecodeState s) {
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 8..15 = GEMM epilogues; all 16 warps run the attention phase.
 // ======================================================================================================
 constexpr int PD_WARPS = 16;
+constexpr int PD_DYN_STEPS = 256;   // per-step crop counters of the attention phase in the workspace (live[2 .. 2+256))
 constexpr int PD_THREADS = 32 * PD_WARPS;
 constexpr int PD_SMEM_BYTES = 1024 + AT_STAGES * 2 * AT_TILE_BYTES + AT_STG_BYTES + 256;
 static_assert(PD_WARPS * AT_VSUB * AT_PART * 4 <= AT_STG_BYTES, "attention partials of all warps (W = 1) live in the stage");
@@ -594,16 +596,19 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 __device__ unsigned long long g_pd_trace[PD_TRACE_MAX];
 __device__ unsigned long long g_pd_trace_cta[PD_TRACE_BARRIERS * PD_TRACE_CTAS];
-// [phase (0 head, 1 cell)][CTA 0..3][16 slots]: 0 phase entry, 1 first TMA issued, 2 first operand stage arrived,
-// 3 last MMA committed, 4 accumulator complete (epilogue woke), 6 accumulator released, 7 epilogue done
-__device__ unsigned long long g_pd_fine[2 * 4 * 16];
+// [phase (0 hp tiles, 1 cell, 2 logits tiles)][owner of tile 0..3][16 slots]: 0 phase entry, 1 first TMA issued,
+// 2 first operand stage arrived, 3 last MMA committed, 4 accumulator complete (epilogue woke), 6 accumulator released,
+// 7 epilogue done
+__device__ unsigned long long g_pd_fine[3 * 4 * 16];
 #define PD_FINE(phase_id, slot)                                                                         \
   do {                                                                                                  \
-    if (step == PD_FINE_STEP && blockIdx.x < 4) g_pd_fine[((phase_id) * 4 + blockIdx.x) * 16 + (slot)] = globaltimer_ns(); \
+    if (step == PD_FINE_STEP && first < 4) g_pd_fine[((phase_id) * 4 + first) * 16 + (slot)] = globaltimer_ns(); \
   } while (0)
 
-// Grid-wide barrier (all CTAs are co-resident: cooperative launch).  `target` is this CTA's running arrival target.
-__device__ __forceinline__ void pd_grid_barrier(unsigned int* counter, unsigned int& target, int& trace_n) {
+// Grid-wide barrier (all CTAs are co-resident: cooperative launch), split into ARRIVE (this CTA's work of the phase is
+// done and visible) and WAIT (every CTA has arrived).  `target` is this CTA's running arrival target.  Work a CTA does
+// between its arrive and its wait is work nobody waits for at THIS barrier (the logits tiles, see the kernel).
+__device__ __forceinline__ void pd_barrier_arrive(unsigned int* counter, unsigned int& target, int& trace_n) {
   fence_proxy_async_global();              // this thread's global stores -> later async-proxy (TMA) reads of any CTA
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -614,6 +619,10 @@ __device__ __forceinline__ void pd_grid_barrier(unsigned int* counter, unsigned 
     target += gridDim.x;
     __threadfence();
     atomicAdd(counter, 1u);
+  }
+}
+__device__ __forceinline__ void pd_barrier_wait(unsigned int* counter, const unsigned int target, int& trace_n) {
+  if (threadIdx.x == 0) {
     const long long t0 = clock64();
     while (ld_acquire_gpu(counter) < target) {
       if (clock64() - t0 > 4000000000ll) {
@@ -626,6 +635,10 @@ __device__ __forceinline__ void pd_grid_barrier(unsigned int* counter, unsigned 
   }
   __syncthreads();
 }
+__device__ __forceinline__ void pd_grid_barrier(unsigned int* counter, unsigned int& target, int& trace_n) {
+  pd_barrier_arrive(counter, target, trace_n);
+  pd_barrier_wait(counter, target, trace_n);
+}
 
 struct PdPipe {            // running ring / accumulator state of one role, carried across tiles, phases and steps
   int stage = 0;
@@ -637,27 +650,29 @@ struct PdMaps {
   CUtensorMap h[2], xh[2], head, cat, hp;
 };
 
-// One GEMM phase over this CTA's tiles.  EPI 0: head, n_count column tiles starting at n_first; EPI 1: cell.
+// One GEMM phase over this CTA's tiles: first, first + gridDim.x, ... of the n_count x m_tiles tiles (column tile
+// fastest).  EPI 0: head, n_count column tiles starting at n_first; EPI 1: cell.
 template <int EPI>
 __device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmHp,
-                                              const DecodeState& s, const int step, const int num_k, const int n_first,
+                                              const DecodeState& s, const int step, const int num_k, const int first,
+                                              const int n_first,
                                               const int n_count, const int m_tiles, uint8_t* sA, uint8_t* sB, uint8_t* stg,
                                               uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, const uint32_t tmem_base, PdPipe& pipe) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = n_count * m_tiles;
+  const int FINE_ID = EPI == 1 ? 1 : (n_first == 2 ? 2 : 0);
   if (warp == 0) {
     if (lane == 0) {
-      PD_FINE(EPI, 0);
-      fence_proxy_async_global();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      PD_FINE(FINE_ID, 0);       // (thread 0 executed fence.proxy.async.global when it left the last grid barrier)
+      for (int tile = first; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = n_first + tile % n_count, m0 = (tile / n_count) * AT_BLOCK;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[pipe.stage], pipe.phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[pipe.stage], 2 * AT_TILE_BYTES);
           tma_load_2d(sA + pipe.stage * AT_TILE_BYTES, tmA, &full_bar[pipe.stage], kb * 64, m0);
           tma_load_2d(sB + pipe.stage * AT_TILE_BYTES, tmB, &full_bar[pipe.stage], kb * 64, n_tile * AT_BLOCK);
-          if (kb == 0) PD_FINE(EPI, 1);
+          if (kb == 0) PD_FINE(FINE_ID, 1);
           if (++pipe.stage == AT_STAGES) { pipe.stage = 0; pipe.phase ^= 1; }
         }
       }
@@ -665,12 +680,12 @@ __device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUte
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(AT_BLOCK, AT_BLOCK);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar, pipe.acc_phase ^ 1);       // the epilogue of the previous tile has drained the accumulator
         tc_fence_after();
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[pipe.stage], pipe.phase);
-          if (kb == 0) PD_FINE(EPI, 2);
+          if (kb == 0) PD_FINE(FINE_ID, 2);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + pipe.stage * AT_TILE_BYTES);
           const uint32_t b_addr = smem_u32(sB + pipe.stage * AT_TILE_BYTES);
@@ -679,7 +694,7 @@ __device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUte
             umma_bf16(tmem_base, make_smem_desc<128>(a_addr + k * 32), make_smem_desc<128>(b_addr + k * 32), idesc,
                       (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[pipe.stage]);
-          if (kb == num_k - 1) { umma_commit(tfull_bar); PD_FINE(EPI, 3); }
+          if (kb == num_k - 1) { umma_commit(tfull_bar); PD_FINE(FINE_ID, 3); }
           if (++pipe.stage == AT_STAGES) { pipe.stage = 0; pipe.phase ^= 1; }
         }
         pipe.acc_phase ^= 1;
@@ -693,13 +708,13 @@ __device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUte
     auto release = [&] {                                 // one arrival per epilogue warp hands the accumulator back
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);
-      if (tr) PD_FINE(EPI, 6);
+      if (tr) PD_FINE(FINE_ID, 6);
     };
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = n_first + tile % n_count, m0 = (tile / n_count) * AT_BLOCK;
       auto wait_acc = [&] {
         mbar_wait(tfull_bar, pipe.acc_phase);
-        if (tr) PD_FINE(EPI, 4);
+        if (tr) PD_FINE(FINE_ID, 4);
         tc_fence_after();
       };
       if constexpr (EPI == 0) {
@@ -713,7 +728,7 @@ __device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUte
       } else {
         at_cell_epilogue(s, taddr, w, m0, n_tile, step, wait_acc, release);
       }
-      if (tr) PD_FINE(EPI, 7);
+      if (tr) PD_FINE(FINE_ID, 7);
       pipe.acc_phase ^= 1;
     }
   }
@@ -762,27 +777,63 @@ attn_decode_persistent_kernel(const __grid_constant__ PdMaps maps, const __nv_bf
   int trace_n = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) g_pd_trace[trace_n++] = globaltimer_ns();
   PdPipe pipe;
+  // Tile ownership.  Cell tiles go to CTAs 0, 1, ...; head tiles to CTAs G-1, G-2, ... (the logits tiles first, then
+  // the hp tiles): the attention phase hands out crops from CTA 0 upwards, so the top CTAs have the fewest (at batches
+  // up to 2048 none), and a CTA never holds a head and a cell tile while 11 m_tiles <= G.
+  const int G = (int)gridDim.x;
+  const int from_top = G - 1 - (int)blockIdx.x;
+  const int first_logits = from_top;
+  const int first_hp = (from_top - m_tiles % G + G) % G;
+  // The attention phase needs hp_i (head column tiles 0, 1) but not the logits / argmax of step i-1 (tile 2: the
+  // slowest tile of the phase, 6.9 us against 3.3 us) - only the cell phase needs the token.  So a CTA ARRIVES at the
+  // barrier behind the head phase once its hp tiles are done, works on its logits tiles, and only then waits: nobody
+  // waits for a logits tile before the barrier that follows the attention phase.  With early exit the all-crops-done
+  // test therefore moves behind that second barrier (the attention phase of the step has then run once more, which
+  // only shows in alpha_out: with early exit AND alpha_out the barrier is not split).
+  const bool split = !(s.early_exit && s.alpha_out != nullptr);
   for (int i = 0; i <= s.steps; ++i) {
     const int step = i;
-    // ---- head_i: hp_i (column tiles 0,1) and logits_{i-1} (tile 2; nothing to store at i = 0, only tile 2 at i = steps)
-    const int n_first = (i == s.steps) ? 2 : 0;
-    const int n_count = (i == s.steps) ? 1 : (i == 0 ? 2 : 3);
-    pd_gemm_phase<0>(&maps.h[i & 1], &maps.head, &maps.hp, s, step, AT_H / 64, n_first, n_count, m_tiles, sA, sB, stg, full_bar,
-                     empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
+    // ---- head_i: hp_i (column tiles 0,1; not at i = steps) and logits_{i-1} (tile 2; nothing to store at i = 0)
+    if (i < s.steps)
+      pd_gemm_phase<0>(&maps.h[i & 1], &maps.head, &maps.hp, s, step, AT_H / 64, first_hp, 0, 2, m_tiles, sA, sB, stg, full_bar,
+                       empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
+    if (split && i < s.steps) pd_barrier_arrive(gbar, target, trace_n);
+    if (i > 0)
+      pd_gemm_phase<0>(&maps.h[i & 1], &maps.head, &maps.hp, s, step, AT_H / 64, first_logits, 2, 1, m_tiles, sA, sB, stg, full_bar,
+                       empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
     if (i == s.steps) break;
-    pd_grid_barrier(gbar, target, trace_n);
-    if (s.early_exit && __ldcg(s.live) == 0) break;        // every crop has emitted [s]: the remaining logits stay zero
+    if (split) pd_barrier_wait(gbar, target, trace_n);
+    else pd_grid_barrier(gbar, target, trace_n);
+    if (!split && s.early_exit && __ldcg(s.live) == 0) break;   // every crop has emitted [s]: the remaining logits stay zero
     // ---- attention_i over this group's crops, zig-zag over the steps.  Partials: W = 1: a private block per warp;
     // W > 1: a block per group and round parity (the next round may start before a slow warp has read this one)
-    for (int kk = 0; kk < my_crops; ++kk) {
-      const int k = (i & 1) ? (my_crops - 1 - kk) : kk;
-      float* part = part_base + (size_t)((W == 1 ? warp : (kk & 1) * GROUPS + group)) * AT_VSUB * AT_PART;
-      at_attention_crop<W>(enc, proj, s, step, gg + k * GG, lane, sub, part, 2 + group);
+    if (W == 1 && s.B > GG && i < PD_DYN_STEPS) {
+      // more crops than warps: the first round is static (logical index gg), the rest is handed out through a per-step
+      // counter, fetched while the current crop is being worked on, so the phase ends within one crop time (~12 us at
+      // 4096 crops) of the first idle warp whatever B is.  Logical index l <-> crop l (even steps) / B-1-l (odd steps):
+      // the zig-zag described above.  Tried on top of this and measured slower at 4096 crops (25.3 us per step): L2
+      // evict-first / no-L1-allocate loads (25.9), one bulk L2 prefetch of the crop's proj + enc block per crop (29.2).
+      int* counter = s.live + 2 + i;
+      float* part = part_base + (size_t)warp * AT_VSUB * AT_PART;
+      int l = gg;
+      while (l < s.B) {
+        const int fetched = lane == 0 ? atomicAdd(counter, 1) : 0;
+        at_attention_crop<W>(enc, proj, s, step, (i & 1) ? s.B - 1 - l : l, lane, sub, part, 2 + group);
+        l = GG + __shfl_sync(0xffffffffu, fetched, 0);
+      }
+    } else {
+      for (int kk = 0; kk < my_crops; ++kk) {
+        const int k = (i & 1) ? (my_crops - 1 - kk) : kk;
+        float* part = part_base + (size_t)((W == 1 ? warp : (kk & 1) * GROUPS + group)) * AT_VSUB * AT_PART;
+        at_attention_crop<W>(enc, proj, s, step, gg + k * GG, lane, sub, part, 2 + group);
+      }
     }
+    if (threadIdx.x == 0) { prefetch_tensormap(&maps.xh[i & 1]); prefetch_tensormap(&maps.cat); }
     pd_grid_barrier(gbar, target, trace_n);
+    if (split && s.early_exit && __ldcg(s.live) == 0) break;
     // ---- cell_i
-    pd_gemm_phase<1>(&maps.xh[i & 1], &maps.cat, &maps.hp, s, step, 2 * AT_H / 64, 0, 4 * AT_H / AT_BLOCK, m_tiles, sA, sB, stg,
-                     full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
+    pd_gemm_phase<1>(&maps.xh[i & 1], &maps.cat, &maps.hp, s, step, 2 * AT_H / 64, (int)blockIdx.x, 0, 4 * AT_H / AT_BLOCK, m_tiles,
+                     sA, sB, stg, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
     pd_grid_barrier(gbar, target, trace_n);
   }
   tc_fence_before();
@@ -796,8 +847,9 @@ attn_decode_persistent_kernel(const __grid_constant__ PdMaps maps, const __nv_bf
 static TmaEncoders g_attn_enc;
 
 static inline size_t decode_ws_bytes(int Bg) {
-  // xh[2][Bg][2H] bf16 | hp [Bg][H] f32 | c [Bg][H] f32 | tok [Bg] | done [Bg] | live, barrier counter; rounded to 256 bytes
-  size_t b = (size_t)Bg * AT_H * (2 * 2 * 2 + 4 + 4) + (size_t)Bg * 8 + 16;
+  // xh[2][Bg][2H] bf16 | hp [Bg][H] f32 | c [Bg][H] f32 | tok [Bg] | done [Bg] | live, barrier counter, 256 per-step crop
+  // counters; rounded to 256 bytes
+  size_t b = (size_t)Bg * AT_H * (2 * 2 * 2 + 4 + 4) + (size_t)Bg * 8 + 16 + 4 * 256;
   return (b + 255) & ~(size_t)255;
 }
 
@@ -808,12 +860,12 @@ struct DecodeArgs {
   int T, C, steps, early_exit;
 };
 
-// Driver selection: -1 = by batch size (default), 1 = persistent, 0 = launch chain.  Measured (B200, 26 steps): the
-// persistent kernel wins while a step is latency bound (256 crops 0.64 vs 0.83 ms for the original chain, 512 crops
-// 0.65 vs 0.94 ms); at 4096 crops the attention phase is bandwidth bound and the chain's 28 resident warps per SM cover
-// the memory latency better than the persistent kernel's 16 (1.38 vs 1.52 ms).  Results are bit-identical either way.
+// Driver selection: -1 = default (persistent), 1 = persistent, 0 = launch chain.  Measured (B200, 26 steps, persistent /
+// chain): 256 crops 0.49 / 0.51 ms, 512 crops 0.50 / 0.55, 2048 crops 0.78 / 0.83, 4096 crops 1.28 / 1.40 - the
+// persistent kernel wins at every batch size since the logits tiles left the critical path (split barrier) and the
+// attention phase hands out crops dynamically; the chain stays as the cross-check.  Results are bit-identical.
 static std::atomic<int> g_persistent{-1};
-constexpr int PD_MAX_BATCH = 2048;
+constexpr int PD_MAX_BATCH = 1 << 20;
 
 template <int W>
 static int launch_persistent(const PdMaps& maps, const __nv_bfloat16* enc, const __nv_bfloat16* proj, const DecodeState& s,
@@ -931,7 +983,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_debug_decode_trace(un
   using namespace mstr;
   MSTR_REQUIRE(out_host && n > 0 && n <= PD_TRACE_MAX, MSTR_ERR_BAD_ARG, "mstr_debug_decode_trace: bad argument");
   MSTR_CUDA(cudaMemcpyFromSymbol(out_host, g_pd_trace, sizeof(unsigned long long) * (size_t)n));
-  if (per_cta_host && n_cta == 2 * 4 * 16) {
+  if (per_cta_host && n_cta == 3 * 4 * 16) {
     MSTR_CUDA(cudaMemcpyFromSymbol(per_cta_host, g_pd_fine, sizeof(unsigned long long) * (size_t)n_cta));
   } else if (per_cta_host) {
     MSTR_REQUIRE(n_cta == PD_TRACE_BARRIERS * PD_TRACE_CTAS, MSTR_ERR_BAD_ARG, "mstr_debug_decode_trace: per-CTA buffer must hold %d values",

@@ -507,7 +507,7 @@ def attn_decode_bf16(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps:
         packed["w_tokb"] = (packed["w_tok"] + packed["bias"][None, :]).contiguous()
     macs = Hd * Hd + 2 * T * Hd + 4 * Hd * 2 * Hd + C * Hd
     with _timed("attn_decode_bf16", 2.0 * B * steps * macs, "flop",
-                "B%d T%d %d steps (tcgen05, %s)" % (B, T, steps, "1 persistent launch" if B <= 2048 else "launch chain")), _on(enc, proj, text, *[v for v in packed.values() if isinstance(v, torch.Tensor)]) as st:
+                "B%d T%d %d steps (tcgen05, 1 persistent launch)" % (B, T, steps)), _on(enc, proj, text, *[v for v in packed.values() if isinstance(v, torch.Tensor)]) as st:
         check(lib().mstr_attn_decode_bf16(ptr(enc), ptr(proj), ptr(packed["w_head"]), ptr(packed["b_h2h"]),
                                           ptr(packed["b_gen"]), ptr(packed["w_score"]), ptr(packed["w_cat"]),
                                           ptr(packed["w_tokb"]), 0, ptr(text), ptr(ws), ptr(logits),

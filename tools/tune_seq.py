@@ -78,14 +78,14 @@ for B in BATCHES:
         order = np.argsort(-late)[:6]
         print("  arrival spread %s: median last-first %.2f us; latest CTAs %s" % (
             nm, np.median(r.max(axis=1)), ", ".join("%d(+%.1f)" % (c, late[c]) for c in order)))
-    fine = (ctypes.c_ulonglong * 128)()
-    _cabi.check(_cabi.lib().mstr_debug_decode_trace(ctypes.cast(buf, ctypes.c_void_p), n, ctypes.cast(fine, ctypes.c_void_p), 128))
-    f = np.array(list(fine), dtype=np.float64).reshape(2, 4, 16)
+    fine = (ctypes.c_ulonglong * 192)()
+    _cabi.check(_cabi.lib().mstr_debug_decode_trace(ctypes.cast(buf, ctypes.c_void_p), n, ctypes.cast(fine, ctypes.c_void_p), 192))
+    f = np.array(list(fine), dtype=np.float64).reshape(3, 4, 16)
     slots = ["entry", "tma issued", "stage arrived", "mma committed", "acc complete", "-", "acc released", "epilogue done"]
-    for ph, nm in enumerate(["head", "cell"]):
+    for ph, nm in enumerate(["hp", "cell", "logits"]):
         for cta in range(4):
             row = f[ph, cta]
             if row[0] == 0:
                 continue
-            print("  fine %s CTA %d (us since phase entry): %s" % (nm, cta, ", ".join(
+            print("  fine %s tile %d (us since phase entry): %s" % (nm, cta, ", ".join(
                 "%s %.2f" % (slots[k], (row[k] - row[0]) / 1e3) for k in (1, 2, 3, 4, 6, 7) if row[k] > 0)))

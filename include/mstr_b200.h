@@ -242,13 +242,14 @@ int mstr_attn_decode_bf16(const void* enc_bf16, const void* proj_bf16, const voi
                           int32_t* lengths, float* alpha_out, int B, int T, int Hd, int C, int steps,
                           int early_exit, mstr_stream_t stream);
 
-/* Driver of mstr_attn_decode_bf16: on = -1 (default) picks by batch size - the persistent launch up to 2048 crops,
- * where a step is latency bound, the chain of three launches per step (programmatic dependent launch) beyond, where the
- * attention phase is bandwidth bound; 1 / 0 force one.  Both give bit-identical results (tests/test_gpu_kernels.py). */
+/* Driver of mstr_attn_decode_bf16: on = -1 (default) or 1: ONE persistent cooperative launch for all steps (faster at
+ * every batch size measured, 256 .. 4096 crops); 0: the chain of three launches per step (programmatic dependent
+ * launch), kept as the cross-check.  Both give bit-identical results (tests/test_gpu_kernels.py). */
 int mstr_set_decode_persistent(int on);
 /* Diagnostic: %globaltimer (ns) of CTA 0 at the start of the last persistent decode on the current device and at
  * every grid-barrier entry and exit (two values per barrier, three barriers per step) -> out_host[n]; optionally the
- * barrier-entry time of every CTA at the first 48 barriers -> per_cta_host[48 * 160] (barrier-major).  Synchronises
+ * barrier-entry time of every CTA at the first 48 barriers -> per_cta_host[48 * 160] (barrier-major), or, with
+ * n_cta = 192, the tile-level trace [hp, cell, logits][tile 0..3][16 slots] of step 6.  Synchronises
  * the device. */
 int mstr_debug_decode_trace(unsigned long long* out_host, int n, unsigned long long* per_cta_host, int n_cta);
 
@@ -264,6 +265,44 @@ int mstr_debug_decode_trace(unsigned long long* out_host, int n, unsigned long l
 int mstr_resize_to_tensor_u8(const void* pixels, const int64_t* offsets, const int32_t* sizes_hw, float* out,
                              int* status, int B, int out_h, int out_w, int max_in_h, int max_in_w,
                              mstr_stream_t stream);
+
+/* ---- transformer encoder / decoder family ------------------------------------------
+ * The reference's TF_Encoder (modules/encoders.py:68-143: PositionalEncoding, 6 custom post-norm layers, LayerNorm),
+ * TF_Decoder (modules/decoders.py:103-275: nn.Embedding + PositionalEncoding, 6 decoder layers, greedy loop) and
+ * Linear_Decoder (:278-296) are GEMMs (mstr_conv_gemm_* with 1x1 kernels: bias, ReLU and residual in the epilogue)
+ * plus the kernels below.  dtype = MSTR_F32 or MSTR_BF16 is the storage type of the activations; all arithmetic is
+ * fp32. */
+/* nn.LayerNorm over the last dimension: out[r] = (x[r] - mean) / sqrt(var + eps) * gamma + beta (biased variance).
+ * x, out [rows][D] of `dtype`; D % 32 == 0, D <= 1024. */
+int mstr_layer_norm(const void* x, const float* gamma, const float* beta, void* out, int64_t rows, int D, float eps,
+                    int dtype, mstr_stream_t stream);
+/* PositionalEncoding.forward in eval mode (encoders.py:162-165): out[b][t][:] = x[b][t][:] + pe[t][:];
+ * x [B][T][D] (f32 or bf16), pe [>=T][D] f32, out f32 or bf16 (f32 -> f32, f32 -> bf16, bf16 -> bf16). */
+int mstr_add_pos_encoding(const void* x, int x_dtype, const float* pe, void* out, int out_dtype, int B, int T, int D,
+                          mstr_stream_t stream);
+/* nn.Embedding + PositionalEncoding of the decoder targets (decoders.py:117,256-262):
+ * out[b][t][:] = emb[tokens[b][t]][:] + pe[t0 + t][:];  tokens [B][T] int32, emb [C][D] f32, out [B][T][D]. */
+int mstr_embed_tokens(const int32_t* tokens, const float* emb, const float* pe, void* out, int out_dtype, int B, int T,
+                      int D, int C, int t0, mstr_stream_t stream);
+/* Core of nn.MultiheadAttention for whole sequences (encoders.py:186-187 self attention; decoders.py:441-442 with
+ * the square subsequent mask when causal != 0; :450-451 attention over the memory): query i of crop b at
+ * q + (b*Lq + i)*ldq, key j at k + (b*Lk + j)*ldkv, likewise v (elements; head h at column h*dh) - for a packed in_proj
+ * output [B][L][3E] that is q = qkv, k = qkv + E, v = qkv + 2E, ldq = ldkv = 3E.
+ * out [B][Lq][heads*dh] = softmax(q k^T / sqrt(dh)) v per head, before out_proj.  Lq, Lk <= 32, dh = 32 or 64. */
+int mstr_mha(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int B, int Lq, int Lk,
+             int heads, int dh, int causal, int dtype, mstr_stream_t stream);
+/* The same for ONE query per crop against Lk keys / values (greedy decode with a K/V cache, and the memory attention
+ * decoders.py:450-451): q [B][ldq]; key j of crop b, head h at k_cache + b*kv_batch_stride + j*ldkv + h*dh (elements),
+ * likewise v_cache; when k_new / v_new ([B][ld_new], head h at h*dh) are given they are first stored as row Lk-1 of
+ * the caches.  out [B][heads*dh].  Lk <= 32, dh = 32 or 64. */
+int mstr_mha_step(const void* q, int ldq, void* k_cache, void* v_cache, int ldkv, int64_t kv_batch_stride,
+                  const void* k_new, const void* v_new, int ld_new, void* out, int B, int Lk, int heads, int dh,
+                  int dtype, mstr_stream_t stream);
+/* t_output[-1].max(1) of the greedy loop (decoders.py:276-279): logits [B][ld] f32 (ld >= C; columns >= C ignored);
+ * copies the C logits of crop b to logits_out + b*out_row_stride (optional), stores the argmax (lowest index on ties)
+ * to ids[b*ids_row_stride] and next_tok[b*next_stride] (both optional). */
+int mstr_argmax_tokens(const float* logits, int ld, float* logits_out, int64_t out_row_stride, int32_t* ids,
+                       int ids_row_stride, int32_t* next_tok, int next_stride, int B, int C, mstr_stream_t stream);
 
 #ifdef __cplusplus
 }

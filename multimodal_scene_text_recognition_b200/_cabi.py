@@ -47,6 +47,12 @@ SIGNATURES = {
     "mstr_set_decode_persistent": (c_int, [_I]),
     "mstr_debug_decode_trace": (c_int, [_P, _I, _P, _I]),
     "mstr_resize_to_tensor_u8": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mstr_layer_norm": (c_int, [_P, _P, _P, _P, c_int64, _I, ctypes.c_float, _I, _P]),
+    "mstr_add_pos_encoding": (c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "mstr_embed_tokens": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "mstr_mha": (c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "mstr_mha_step": (c_int, [_P, _I, _P, _P, _I, c_int64, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "mstr_argmax_tokens": (c_int, [_P, _I, _P, c_int64, _P, _I, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

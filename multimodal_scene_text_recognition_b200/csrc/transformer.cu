@@ -1,0 +1,342 @@
+// Small kernels of the transformer encoder / decoder family: everything between the GEMMs.
+// The GEMMs themselves (in_proj, out_proj, linear1/2, hid_to_emb, emb_to_classes) run on the conv-GEMM kernels
+// (1x1 "convolutions": conv_tc2.cu / conv_tc.cu on tcgen05 in bf16 mode, conv_tf32.cu / conv_simt.cu in the parity
+// modes) with the bias, the ReLU and the residual in their epilogues.
+//
+//   layer_norm_kernel      nn.LayerNorm over the last dimension (encoders.py:78,166-167; decoders.py:112,364-366)
+//   add_pos_kernel         PositionalEncoding.forward: x + pe[:T] (encoders.py:162-165), eval mode (dropout = identity)
+//   embed_tokens_kernel    nn.Embedding + PositionalEncoding of the decoder's targets (decoders.py:117,256-262)
+//   mha_full_kernel        softmax(q k^T / sqrt(dh) [+ causal mask]) v for whole sequences, nn.MultiheadAttention's core
+//                          (encoders.py:186-187; decoders.py:441-442 with tgt_mask, :450-451 over the memory), one warp
+//                          per (crop, head), lane = query position
+//   mha_step_kernel        the same for ONE query per crop against Lk cached keys: the greedy loop with a K/V cache
+//                          (decoders.py:250-279 recomputes every earlier position at every step; with the causal
+//                          mask those rows do not change, so the cache gives the same numbers) and the
+//                          memory attention (decoders.py:450-451); lane = key, then lane = channel
+//   argmax_tokens_kernel   t_output[-1].max(1), targets[t+1] = char_index, output[t] = t_output[t] (decoders.py:276-279)
+//
+// All arithmetic is fp32; T = float (parity modes) or __nv_bfloat16 (throughput mode) is the storage type.
+#include "common.cuh"
+
+namespace mstr {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layer_norm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  T* __restrict__ out, int64_t rows, int D, float eps) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* xr = x + row * D;
+  float v[32];                                            // D <= 1024
+  const int n = D >> 5;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < n) { v[i] = Elem<T>::load(xr + i * 32 + lane); s += v[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < n) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)D + eps);         // biased variance, like torch
+  T* orow = out + row * D;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < n) {
+      const int c = i * 32 + lane;
+      Elem<T>::store(orow + c, fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c)));
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+add_pos_kernel(const TI* __restrict__ x, const float* __restrict__ pe, TO* __restrict__ out, int64_t total, int T, int D) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int d = (int)(i % D);
+  const int t = (int)((i / D) % T);
+  Elem<TO>::store(out + i, Elem<TI>::load(x + i) + __ldg(pe + (int64_t)t * D + d));
+}
+
+// tokens [B*T] (row-major [B][T]); out[b][t][:] = emb[token] + pe[t0 + t]
+template <typename TO>
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const int32_t* __restrict__ tokens, const float* __restrict__ emb, const float* __restrict__ pe,
+                    TO* __restrict__ out, int64_t total, int T, int D, int C, int t0) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int d = (int)(i % D);
+  const int64_t bt = i / D;
+  const int t = (int)(bt % T);
+  int tok = tokens[bt];
+  if (tok < 0 || tok >= C) tok = 0;                       // the reference's nn.Embedding would raise
+  Elem<TO>::store(out + i, __ldg(emb + (int64_t)tok * D + d) + __ldg(pe + (int64_t)(t0 + t) * D + d));
+}
+
+// One warp per (crop, head); lane = query position (Lq, Lk <= 32).  K and V of the head are staged in shared memory as
+// f32.  q row i of crop b at q + (b*Lq + i)*ldq, key j at k + (b*Lk + j)*ldkv (likewise v); head h at column h*DH.
+template <typename T, int DH>
+__global__ void __launch_bounds__(128)
+mha_full_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, const T* __restrict__ v, int ldkv,
+                T* __restrict__ out, int B, int Lq, int Lk, int heads, int causal, float scale) {
+  extern __shared__ float smem[];
+  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  if (item >= (int64_t)B * heads) return;                 // whole warps leave together
+  const int b = (int)(item / heads), h = (int)(item % heads);
+  float* sk = smem + (size_t)warp_in_block * 2 * 32 * DH;
+  float* sv = sk + 32 * DH;
+  const T* kb = k + (int64_t)b * Lk * ldkv + h * DH;
+  const T* vb = v + (int64_t)b * Lk * ldkv + h * DH;
+  for (int i = lane; i < Lk * DH; i += 32) {
+    const int j = i / DH, d = i % DH;
+    sk[i] = Elem<T>::load(kb + (int64_t)j * ldkv + d);
+    sv[i] = Elem<T>::load(vb + (int64_t)j * ldkv + d);
+  }
+  __syncwarp();
+  if (lane >= Lq) return;
+  const T* qr = q + ((int64_t)b * Lq + lane) * ldq + h * DH;
+  float acc[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = Elem<T>::load(qr + d) * scale;   // q is scaled first, like torch
+  float s[32];
+  float mx = -INFINITY;
+  const int last = causal ? lane : Lk - 1;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    s[j] = -INFINITY;
+    if (j < Lk && j <= last) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) a = fmaf(acc[d], sk[j * DH + d], a);
+      s[j] = a;
+      mx = fmaxf(mx, a);
+    }
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    s[j] = (j < Lk && j <= last) ? expf(s[j] - mx) : 0.f;
+    den += s[j];
+  }
+  const float inv = 1.f / den;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = 0.f;             // the query is no longer needed: reuse as the output accumulator
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < Lk && j <= last) {
+      const float p = s[j] * inv;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, sv[j * DH + d], acc[d]);
+    }
+  }
+  T* orow = out + ((int64_t)b * Lq + lane) * heads * DH + h * DH;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) Elem<T>::store(orow + d, acc[d]);
+}
+
+// One warp per (crop, head), ONE query: lane = key for the scores and the softmax, lane = channel (DH / 32 each) for the
+// weighted sum.  Optionally appends this step's k / v rows (k_new, v_new: [B][ld_new], head h at h*DH) to the cache at
+// position Lk - 1 first.
+template <typename T, int DH>
+__global__ void __launch_bounds__(128)
+mha_step_kernel(const T* __restrict__ q, int ldq, T* __restrict__ kc, T* __restrict__ vc, int ldkv, int64_t kv_batch_stride,
+                const T* __restrict__ k_new, const T* __restrict__ v_new, int ld_new, T* __restrict__ out, int B, int Lk,
+                int heads, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= (int64_t)B * heads) return;
+  const int b = (int)(item / heads), h = (int)(item % heads);
+  T* kb = kc + (int64_t)b * kv_batch_stride + h * DH;
+  T* vb = vc + (int64_t)b * kv_batch_stride + h * DH;
+  if (k_new) {
+    for (int d = lane; d < DH; d += 32) {
+      kb[(int64_t)(Lk - 1) * ldkv + d] = k_new[(int64_t)b * ld_new + h * DH + d];
+      vb[(int64_t)(Lk - 1) * ldkv + d] = v_new[(int64_t)b * ld_new + h * DH + d];
+    }
+    __syncwarp();
+  }
+  const T* qr = q + (int64_t)b * ldq + h * DH;
+  float sc = -INFINITY;
+  if (lane < Lk) {
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) a = fmaf(Elem<T>::load(qr + d) * scale, Elem<T>::load(kb + (int64_t)lane * ldkv + d), a);
+    sc = a;
+  }
+  float mx = sc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float e = lane < Lk ? expf(sc - mx) : 0.f;
+  float den = e;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  const float p = e / den;
+  float acc[DH / 32];
+#pragma unroll
+  for (int u = 0; u < DH / 32; ++u) acc[u] = 0.f;
+  for (int j = 0; j < Lk; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, p, j);
+#pragma unroll
+    for (int u = 0; u < DH / 32; ++u) acc[u] = fmaf(pj, Elem<T>::load(vb + (int64_t)j * ldkv + u * 32 + lane), acc[u]);
+  }
+  T* orow = out + (int64_t)b * heads * DH + h * DH;
+#pragma unroll
+  for (int u = 0; u < DH / 32; ++u) Elem<T>::store(orow + u * 32 + lane, acc[u]);
+}
+
+// One warp per crop: logits row (f32, ld >= C) -> output row, argmax (the lowest index wins ties, like torch.max).
+__global__ void __launch_bounds__(256)
+argmax_tokens_kernel(const float* __restrict__ logits, int ld, float* __restrict__ logits_out, int64_t out_row_stride,
+                     int32_t* __restrict__ ids, int ids_row_stride, int32_t* __restrict__ next_tok, int next_stride,
+                     int B, int C) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float best = -INFINITY;
+  int besti = 0;
+  for (int c = lane; c < C; c += 32) {
+    const float y = logits[b * ld + c];
+    if (logits_out) logits_out[b * out_row_stride + c] = y;
+    if (y > best) { best = y; besti = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  if (lane == 0) {
+    if (ids) ids[b * ids_row_stride] = besti;
+    if (next_tok) next_tok[b * next_stride] = besti;
+  }
+}
+
+}  // namespace mstr
+
+#define MSTR_EXPORT extern "C" __attribute__((visibility("default")))
+
+MSTR_EXPORT int mstr_layer_norm(const void* x, const float* gamma, const float* beta, void* out, int64_t rows, int D,
+                                float eps, int dtype, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x && gamma && beta && out, MSTR_ERR_BAD_ARG, "mstr_layer_norm: null pointer");
+  MSTR_REQUIRE(rows > 0 && D > 0, MSTR_ERR_BAD_ARG, "mstr_layer_norm: bad size");
+  MSTR_REQUIRE(D % 32 == 0 && D <= 1024, MSTR_ERR_UNSUPPORTED, "mstr_layer_norm: D=%d must be a multiple of 32, <= 1024", D);
+  const int blocks = (int)ceil_div64(rows * 32, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MSTR_BF16)
+    layer_norm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta,
+                                                             static_cast<__nv_bfloat16*>(out), rows, D, eps);
+  else
+    layer_norm_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, static_cast<float*>(out), rows, D, eps);
+  MSTR_LAUNCH_CHECK("layer_norm_kernel");
+  return MSTR_OK;
+}
+
+MSTR_EXPORT int mstr_add_pos_encoding(const void* x, int x_dtype, const float* pe, void* out, int out_dtype, int B, int T, int D,
+                                      mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x && pe && out, MSTR_ERR_BAD_ARG, "mstr_add_pos_encoding: null pointer");
+  MSTR_REQUIRE(B > 0 && T > 0 && D > 0, MSTR_ERR_BAD_ARG, "mstr_add_pos_encoding: bad size");
+  const int64_t total = (int64_t)B * T * D;
+  const int blocks = (int)ceil_div64(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef __nv_bfloat16 bf;
+  if (x_dtype == MSTR_BF16 && out_dtype == MSTR_BF16)
+    add_pos_kernel<bf, bf><<<blocks, 256, 0, st>>>(static_cast<const bf*>(x), pe, static_cast<bf*>(out), total, T, D);
+  else if (x_dtype == MSTR_F32 && out_dtype == MSTR_BF16)
+    add_pos_kernel<float, bf><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), pe, static_cast<bf*>(out), total, T, D);
+  else if (x_dtype == MSTR_F32 && out_dtype == MSTR_F32)
+    add_pos_kernel<float, float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), pe, static_cast<float*>(out), total, T, D);
+  else
+    MSTR_REQUIRE(false, MSTR_ERR_UNSUPPORTED, "mstr_add_pos_encoding: unsupported dtype pair %d -> %d", x_dtype, out_dtype);
+  MSTR_LAUNCH_CHECK("add_pos_kernel");
+  return MSTR_OK;
+}
+
+MSTR_EXPORT int mstr_embed_tokens(const int32_t* tokens, const float* emb, const float* pe, void* out, int out_dtype, int B, int T,
+                                  int D, int C, int t0, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(tokens && emb && pe && out, MSTR_ERR_BAD_ARG, "mstr_embed_tokens: null pointer");
+  MSTR_REQUIRE(B > 0 && T > 0 && D > 0 && C > 0 && t0 >= 0, MSTR_ERR_BAD_ARG, "mstr_embed_tokens: bad size");
+  const int64_t total = (int64_t)B * T * D;
+  const int blocks = (int)ceil_div64(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == MSTR_BF16)
+    embed_tokens_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(tokens, emb, pe, static_cast<__nv_bfloat16*>(out), total, T, D, C, t0);
+  else
+    embed_tokens_kernel<float><<<blocks, 256, 0, st>>>(tokens, emb, pe, static_cast<float*>(out), total, T, D, C, t0);
+  MSTR_LAUNCH_CHECK("embed_tokens_kernel");
+  return MSTR_OK;
+}
+
+MSTR_EXPORT int mstr_mha(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int B, int Lq, int Lk,
+                         int heads, int dh, int causal, int dtype, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(q && k && v && out, MSTR_ERR_BAD_ARG, "mstr_mha: null pointer");
+  MSTR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, MSTR_ERR_BAD_ARG, "mstr_mha: bad size");
+  MSTR_REQUIRE(Lq <= 32 && Lk <= 32 && (dh == 32 || dh == 64), MSTR_ERR_UNSUPPORTED,
+               "mstr_mha: Lq=%d, Lk=%d (<= 32), head dim %d (32 or 64)", Lq, Lk, dh);
+  MSTR_REQUIRE(!causal || Lq == Lk, MSTR_ERR_BAD_ARG, "mstr_mha: the causal mask needs Lq == Lk");
+  const float scale = 1.0f / sqrtf((float)dh);
+  const int warps = 4;
+  const int blocks = (int)ceil_div64((int64_t)B * heads, warps);
+  const size_t smem = (size_t)warps * 2 * 32 * dh * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef __nv_bfloat16 bf;
+#define MSTR_MHA_FULL(T, DH)                                                                                      \
+  do {                                                                                                            \
+    static unsigned long long done = 0;                                                                           \
+    int rc = ensure_dynamic_smem((const void*)mha_full_kernel<T, DH>, (int)smem, &done);                          \
+    if (rc != MSTR_OK) return rc;                                                                                 \
+    mha_full_kernel<T, DH><<<blocks, 32 * warps, smem, st>>>(static_cast<const T*>(q), ldq, static_cast<const T*>(k), \
+                                                            static_cast<const T*>(v), ldkv, static_cast<T*>(out), B, Lq, \
+                                                            Lk, heads, causal, scale);                            \
+  } while (0)
+  if (dtype == MSTR_BF16) { if (dh == 64) MSTR_MHA_FULL(bf, 64); else MSTR_MHA_FULL(bf, 32); }
+  else { if (dh == 64) MSTR_MHA_FULL(float, 64); else MSTR_MHA_FULL(float, 32); }
+#undef MSTR_MHA_FULL
+  MSTR_LAUNCH_CHECK("mha_full_kernel");
+  return MSTR_OK;
+}
+
+MSTR_EXPORT int mstr_mha_step(const void* q, int ldq, void* k_cache, void* v_cache, int ldkv, int64_t kv_batch_stride,
+                              const void* k_new, const void* v_new, int ld_new, void* out, int B, int Lk, int heads, int dh,
+                              int dtype, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(q && k_cache && v_cache && out, MSTR_ERR_BAD_ARG, "mstr_mha_step: null pointer");
+  MSTR_REQUIRE((k_new == nullptr) == (v_new == nullptr), MSTR_ERR_BAD_ARG, "mstr_mha_step: k_new and v_new go together");
+  MSTR_REQUIRE(B > 0 && Lk > 0 && heads > 0, MSTR_ERR_BAD_ARG, "mstr_mha_step: bad size");
+  MSTR_REQUIRE(Lk <= 32 && (dh == 32 || dh == 64), MSTR_ERR_UNSUPPORTED, "mstr_mha_step: Lk=%d (<= 32), head dim %d (32 or 64)", Lk, dh);
+  const float scale = 1.0f / sqrtf((float)dh);
+  const int blocks = (int)ceil_div64((int64_t)B * heads, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef __nv_bfloat16 bf;
+#define MSTR_MHA_STEP(T, DH)                                                                                          \
+  mha_step_kernel<T, DH><<<blocks, 128, 0, st>>>(static_cast<const T*>(q), ldq, static_cast<T*>(k_cache),             \
+                                                 static_cast<T*>(v_cache), ldkv, kv_batch_stride,                     \
+                                                 static_cast<const T*>(k_new), static_cast<const T*>(v_new), ld_new,  \
+                                                 static_cast<T*>(out), B, Lk, heads, scale)
+  if (dtype == MSTR_BF16) { if (dh == 64) MSTR_MHA_STEP(bf, 64); else MSTR_MHA_STEP(bf, 32); }
+  else { if (dh == 64) MSTR_MHA_STEP(float, 64); else MSTR_MHA_STEP(float, 32); }
+#undef MSTR_MHA_STEP
+  MSTR_LAUNCH_CHECK("mha_step_kernel");
+  return MSTR_OK;
+}
+
+MSTR_EXPORT int mstr_argmax_tokens(const float* logits, int ld, float* logits_out, int64_t out_row_stride, int32_t* ids,
+                                   int ids_row_stride, int32_t* next_tok, int next_stride, int B, int C, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(logits, MSTR_ERR_BAD_ARG, "mstr_argmax_tokens: null pointer");
+  MSTR_REQUIRE(B > 0 && C > 0 && ld >= C, MSTR_ERR_BAD_ARG, "mstr_argmax_tokens: bad size");
+  const int blocks = (int)ceil_div64((int64_t)B * 32, 256);
+  argmax_tokens_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(logits, ld, logits_out, out_row_stride, ids, ids_row_stride,
+                                                                 next_tok, next_stride, B, C);
+  MSTR_LAUNCH_CHECK("argmax_tokens_kernel");
+  return MSTR_OK;
+}

@@ -3,7 +3,8 @@
 ``Model()`` builds the same sub-modules under the same attribute names (``Transformation``,
 ``FeatureExtraction``, ``AdaptiveAvgPool``, ``get_semantic_vectors``, ``encoder``, ``decoder``),
 so a reference checkpoint (253 tensors in the LSTM/LSTM configuration) loads with
-``load_state_dict``.  ``Model.forward(input, text, overlap, scene, ious, is_train=True)`` returns
+``load_state_dict``.  ``config.ENCODER`` / ``config.DECODER`` select the LSTM path (the north-star hot path) or
+the reference's default Transformer / Transformer and Transformer / Linear configurations (modules/transformer.py).  ``Model.forward(input, text, overlap, scene, ious, is_train=True)`` returns
 the ``[B, MAX_TEXT_LENGTH + 1, num_classes]`` logits like the reference; ``recognize`` is the same
 pass returning the decoded ids and lengths the fused decoder already produced.
 
@@ -81,14 +82,13 @@ class Model(nn.Module):
 
     # ---------------------------------------------------------------------------------------
     def _run(self, input, text, overlap, scene, ious, is_train, stages=None):
-        if config.ENCODER != 'LSTM':
-            raise NotImplementedError("only config.ENCODER == 'LSTM' is implemented (model.py:99)")
+        lstm_encoder = isinstance(self.encoder, nn.Sequential)
         if input.shape[0] == 0:
             # empty batch (e.g. the last, empty shard of a rank): the reference returns an empty
             # [0, steps, classes] tensor from Attention.forward; nothing is launched here
             if not input.is_cuda:
                 raise _cabi.MstrError("the recognition path has no CPU implementation: move the inputs to a CUDA device")
-            steps = config.MAX_TEXT_LENGTH + 1
+            steps = config.MAX_TEXT_LENGTH + (0 if isinstance(self.decoder, TF_Decoder) and not is_train else 1)
             dev = input.device
             return {"logits": torch.zeros((0, steps, self.decoder.num_classes), device=dev),
                     "ids": torch.zeros((0, steps), device=dev, dtype=torch.int32),
@@ -103,6 +103,13 @@ class Model(nn.Module):
         # Semantic vectors (model.py:96); computed because the reference computes them - the LSTM
         # encoder / attention decoder never read them (decoders.py:79-101)
         semantics = self.get_semantic_vectors(overlap, scene, ious)
+        if not lstm_encoder:
+            # transformer family (model.py:101-105): the encoder output stays in the activation dtype
+            enc = self.encoder.forward_features(visual)
+            out = self.decoder.decode(enc, text, is_train, enc_act=enc)
+            if stages is not None:
+                stages.update(rectified=rect, features=feat, visual=visual, semantics=semantics, enc1=ops.cast(enc, torch.float32))
+            return out
         # Encode (model.py:100)
         bf16 = config.PRECISION == 'bf16'
         enc0 = self.encoder[0].forward_features(visual, want_f32=not bf16, want_act=bf16)

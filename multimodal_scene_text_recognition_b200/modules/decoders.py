@@ -10,8 +10,8 @@ with optional early exit on ``[s]``.
 ``semantics`` is accepted and ignored, as in the reference (AttentionCell.forward never reads
 it, decoders.py:79-101).
 
-The transformer / linear decoders (decoders.py:103-516) are out of scope; the names resolve
-and raise.
+The transformer / linear decoders (decoders.py:103-516) are mirrored in modules/transformer.py and re-exported
+here.
 """
 from __future__ import annotations
 
@@ -138,20 +138,6 @@ class AttentionCell(nn.Module):
         return (res["h"], res["c"]), res["alpha"].permute(0, 2, 1)
 
 
-class _OutOfScope(nn.Module):
-    _what = ""
-
-    def __init__(self, *args, **kwargs):
-        super().__init__()
-        raise NotImplementedError(
-            "%s belongs to the reference's transformer / fusion experiments (%s); this repository "
-            "implements only the LSTM/LSTM recognition path (config.ENCODER = config.DECODER = 'LSTM')"
-            % (type(self).__name__, self._what))
-
-
-class TF_Decoder(_OutOfScope):
-    _what = "modules/decoders.py:103-275"
-
-
-class Linear_Decoder(_OutOfScope):
-    _what = "modules/decoders.py:278-296"
+# the transformer / linear decoders live in modules/transformer.py; the reference defines these names in this module
+from .transformer import (TF_Decoder, Linear_Decoder, TransformerDecoder, TransformerDecoderLayer,  # noqa: E402,F401
+                          PositionalEncoding, MLP)

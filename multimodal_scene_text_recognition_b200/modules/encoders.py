@@ -11,8 +11,8 @@ reference's; neither container's own forward is ever called.  The work is three 
    directions;
 3. Linear(2H -> out) + bias - GEMM.
 
-The transformer / Oscar encoders of the reference (encoders.py:32-243) are a different model
-family and out of this repository's scope; the names resolve and raise.
+The transformer encoder of the reference (encoders.py:68-243) is mirrored in modules/transformer.py and re-exported
+here; ``Oscar_Bert`` (encoders.py:34-66, a BERT-base encoder) resolves and raises.
 """
 from __future__ import annotations
 
@@ -82,14 +82,13 @@ class _OutOfScope(nn.Module):
     def __init__(self, *args, **kwargs):
         super().__init__()
         raise NotImplementedError(
-            "%s belongs to the reference's transformer / fusion experiments (%s); this repository "
-            "implements only the LSTM/LSTM recognition path (config.ENCODER = config.DECODER = 'LSTM')"
-            % (type(self).__name__, self._what))
-
-
-class TF_Encoder(_OutOfScope):
-    _what = "modules/encoders.py:69-143"
+            "%s belongs to the reference's Oscar / BERT experiment (%s, 'No pretrained models yet' in its config.py:46); "
+            "this repository implements the LSTM and the transformer encoders" % (type(self).__name__, self._what))
 
 
 class Oscar_Bert(_OutOfScope):
     _what = "modules/encoders.py:34-66"
+
+
+# the transformer encoder family lives in modules/transformer.py; the reference defines these names in this module
+from .transformer import TF_Encoder, PositionalEncoding, TransformerEncoderLayer, MLP  # noqa: E402,F401

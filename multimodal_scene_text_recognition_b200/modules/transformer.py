@@ -1,0 +1,413 @@
+"""Transformer encoder / decoder family behind the reference's module interface.
+
+Mirrors ``TF_Encoder`` (modules/encoders.py:68-143), ``TF_Decoder`` (modules/decoders.py:103-275) and
+``Linear_Decoder`` (:278-296) with every fusion switch of ``config`` at its default (False): the reference's own
+default configuration, ``ENCODER = DECODER = 'Transformer'`` (config.py:27-28).  The helper classes keep the
+reference's names, constructor arguments, attribute names and construction order, so the state-dict keys
+(``encoder.encoder_layer.*``, ``encoder.encoder.layers.{i}.*``, ``decoder.decoder.layers.{i}.self_attn.in_proj_weight``
+...) and the weights a given seed produces are the reference's.  ``nn.MultiheadAttention`` / ``nn.Linear`` /
+``nn.LayerNorm`` / ``nn.Embedding`` are parameter containers only: their own forward is never called.
+
+Work per layer: the GEMMs (in_proj, out_proj, linear1 + ReLU, linear2) run on the conv-GEMM kernels with bias, ReLU
+and the residual in the epilogue (``ops.linear``); between them ``ops.mha`` / ``ops.mha_step`` (attention core),
+``ops.layer_norm``, ``ops.add_pos_encoding`` / ``ops.embed_tokens`` and ``ops.argmax_tokens`` (csrc/transformer.cu).
+
+Two things differ from the reference's code, neither in the numbers it defines:
+* the greedy loop keeps a K/V cache.  The reference re-runs the decoder over positions 0..t at every step
+  (decoders.py:250-279); under its causal mask the rows of earlier positions do not change, so the cache yields the
+  same ``t_output[t]``;
+* ``nn.TransformerEncoder.forward`` of the installed torch (2.11) passes ``is_causal=`` to the layer, which the
+  reference's own ``TransformerEncoderLayer.forward`` (encoders.py:185) does not accept: the reference's encoder
+  raises TypeError here.  What it computes under the torch it was written for is layers in order, then ``norm`` -
+  that is what ``TF_Encoder`` does (and what the golden fixtures drive the reference's layer objects with).
+
+Eval mode only (dropout is the identity); the fusion experiments (PRE_ENCODER_MLP, OSCAR_ENCODER, PRE_DECODER_MLP,
+CLS_DECODER_INIT, MULTIHEAD_*, POST_DECODER_MLP) raise NotImplementedError at construction.
+"""
+from __future__ import annotations
+
+import copy
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import config, ops
+from .._pack import act_dtype, cached, require_inference, wrap_weight
+
+
+def _no_fusion(*flags):
+    on = [f for f in flags if getattr(config, f, False)]
+    if on:
+        raise NotImplementedError("config.%s: the semantic-fusion experiments of the reference are not implemented "
+                                  "(SURVEY.md 8 f4 covers the default configuration)" % ", config.".join(on))
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+class PositionalEncoding(nn.Module):
+    """encoders.py:146-165 / decoders.py:300-317: sinusoidal table registered as the buffer ``pe`` [max_len, 1, d]."""
+
+    def __init__(self, d_model, dropout=0.1, max_len=26):
+        super(PositionalEncoding, self).__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(max_len, d_model)
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer('pe', pe.unsqueeze(0).transpose(0, 1))
+
+    def table(self) -> torch.Tensor:
+        """[max_len, d] f32 view of the buffer."""
+        return self.pe.detach().float().view(self.pe.shape[0], self.pe.shape[2])
+
+    def forward(self, x):
+        """x [T, B, d] (the reference's layout) -> x + pe[:T]."""
+        require_inference(x)
+        xb = x.permute(1, 0, 2).contiguous()
+        return ops.add_pos_encoding(xb, self.table().contiguous(), xb.dtype).permute(1, 0, 2)
+
+
+class MLP(nn.Module):
+    """encoders.py:200-243 / decoders.py:473-516.  Only the fusion experiments build it; kept so the name resolves."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        raise NotImplementedError("MLP is used by the reference's semantic-fusion experiments only, which are not implemented")
+
+
+def _mha_pack(attn: nn.MultiheadAttention, precision: str):
+    E = attn.embed_dim
+    w, b = _f(attn.in_proj_weight), _f(attn.in_proj_bias)
+    return {"w_in": wrap_weight(w, precision), "b_in": b,
+            "w_q": wrap_weight(w[:E].contiguous(), precision), "b_q": b[:E].contiguous(),
+            "w_kv": wrap_weight(w[E:].contiguous(), precision), "b_kv": b[E:].contiguous(),
+            "w_out": wrap_weight(_f(attn.out_proj.weight), precision), "b_out": _f(attn.out_proj.bias)}
+
+
+def _mha_sources(attn: nn.MultiheadAttention):
+    return [attn.in_proj_weight, attn.in_proj_bias, attn.out_proj.weight, attn.out_proj.bias]
+
+
+def _ffn_pack(layer, precision: str):
+    return {"w1": wrap_weight(_f(layer.linear1.weight), precision), "b1": _f(layer.linear1.bias),
+            "w2": wrap_weight(_f(layer.linear2.weight), precision), "b2": _f(layer.linear2.bias)}
+
+
+def _ln(norm: nn.LayerNorm):
+    return (_f(norm.weight), _f(norm.bias), float(norm.eps))
+
+
+class TransformerEncoderLayer(nn.Module):
+    """encoders.py:167-197.  NOT the textbook post-norm layer: the residual stream itself is normalised and the
+    sub-layer output is added AFTER the norm (``src = norm1(src); src = src + src2``, :188-189, :191-192)."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu"):
+        super(TransformerEncoderLayer, self).__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.activation = torch.nn.functional.relu
+
+    def _packed(self, precision: str):
+        src = _mha_sources(self.self_attn) + [self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                                              self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias]
+
+        def build():
+            pk = {"sa": _mha_pack(self.self_attn, precision), "n1": _ln(self.norm1), "n2": _ln(self.norm2)}
+            pk.update(_ffn_pack(self, precision))
+            return pk
+        return cached(self, ("tf_enc_layer", precision), src, build)
+
+    def forward_btd(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B, T, d] in the activation dtype -> same."""
+        pk = self._packed(config.PRECISION)
+        sa = pk["sa"]
+        E = x.shape[-1]
+        qkv = ops.linear(x, sa["w_in"], sa["b_in"])                                   # [B,T,3E]
+        att = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], self.self_attn.num_heads)
+        n = ops.layer_norm(x, *pk["n1"])                                              # src = norm1(src)
+        x = ops.linear(att, sa["w_out"], sa["b_out"], residual=n)                     # src = src + src2
+        h = ops.linear(x, pk["w1"], pk["b1"], relu=True)
+        n = ops.layer_norm(x, *pk["n2"])
+        return ops.linear(h, pk["w2"], pk["b2"], residual=n)
+
+    def forward(self, src, src_mask=None, src_key_padding_mask=None):
+        """src [T, B, d] like the reference (masks are not supported: the reference never passes one)."""
+        if src_mask is not None or src_key_padding_mask is not None:
+            raise NotImplementedError("attention masks are not used by the reference's encoder")
+        require_inference(src)
+        x = ops.cast(src.permute(1, 0, 2).contiguous(), act_dtype(config.PRECISION))
+        return self.forward_btd(x).permute(1, 0, 2)
+
+
+class _LayerStack(nn.Module):
+    """Container with the attribute names of nn.TransformerEncoder / the reference's TransformerDecoder
+    (decoders.py:321-346): ``layers`` (deep copies of one initialised layer, so all start equal) and ``norm``."""
+
+    def __init__(self, layer, num_layers, norm=None):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = norm
+
+
+class TF_Encoder(nn.Module):
+    """Transformer encoder: col feats [B, T, HIDDEN_DIM] -> [B, T, HIDDEN_DIM] (encoders.py:68-143)."""
+
+    def __init__(self):
+        super(TF_Encoder, self).__init__()
+        _no_fusion('PRE_ENCODER_MLP')
+        self.pos_encoder = PositionalEncoding(config.HIDDEN_DIM)
+        self.encoder_layer = TransformerEncoderLayer(d_model=config.HIDDEN_DIM, nhead=8, dim_feedforward=2048, dropout=0.1)
+        self.layer_norm = nn.LayerNorm(config.HIDDEN_DIM)
+        self.encoder = _LayerStack(self.encoder_layer, num_layers=6, norm=self.layer_norm)
+
+    def forward_features(self, col_feats: torch.Tensor) -> torch.Tensor:
+        """[B, T, d] (f32 or activation dtype) -> [B, T, d] in the activation dtype."""
+        require_inference(col_feats)
+        if self.training:
+            raise RuntimeError("TF_Encoder is in train mode: dropout is not implemented - call model.eval()")
+        dt = act_dtype(config.PRECISION)
+        x = ops.add_pos_encoding(col_feats.contiguous(), self.pos_encoder.table().contiguous(), dt)
+        for layer in self.encoder.layers:
+            x = layer.forward_btd(x)
+        return ops.layer_norm(x, *_ln(self.encoder.norm))
+
+    def forward(self, col_feats, semantics, is_train=False):
+        return ops.cast(self.forward_features(col_feats), torch.float32)
+
+
+class TransformerDecoderLayer(nn.Module):
+    """decoders.py:348-466 with the MULTIHEAD_* switches off: the textbook post-norm decoder layer.  ``semantic_to_emb``
+    is created (and saved in checkpoints) by the reference but never used."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1):
+        super(TransformerDecoderLayer, self).__init__()
+        _no_fusion('MULTIHEAD_PRE_TARGET', 'MULTIHEAD_PRE_MEMORY', 'MULTIHEAD_POST_MEMORY')
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.multihead_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.semantic_to_emb = nn.Linear(config.HIDDEN_DIM, config.EMBED_DIM)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.activation = torch.nn.functional.relu
+
+    def _packed(self, precision: str):
+        src = (_mha_sources(self.self_attn) + _mha_sources(self.multihead_attn) +
+               [self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias] +
+               [p for n in (self.norm1, self.norm2, self.norm3) for p in (n.weight, n.bias)])
+
+        def build():
+            pk = {"sa": _mha_pack(self.self_attn, precision), "ca": _mha_pack(self.multihead_attn, precision),
+                  "n1": _ln(self.norm1), "n2": _ln(self.norm2), "n3": _ln(self.norm3)}
+            pk.update(_ffn_pack(self, precision))
+            return pk
+        return cached(self, ("tf_dec_layer", precision), src, build)
+
+    def memory_kv(self, memory: torch.Tensor) -> torch.Tensor:
+        """k | v projections of the memory for this layer's multihead_attn: [B, T, 2E] (computed once per forward)."""
+        ca = self._packed(config.PRECISION)["ca"]
+        return ops.linear(memory, ca["w_kv"], ca["b_kv"])
+
+    def _tail(self, x, att, pk, mem_att):
+        """From the self-attention core's output to the layer's output; ``mem_att(q)`` is the memory attention core."""
+        sa, ca = pk["sa"], pk["ca"]
+        x = ops.layer_norm(ops.linear(att, sa["w_out"], sa["b_out"], residual=x), *pk["n1"])      # :441-444
+        q = ops.linear(x, ca["w_q"], ca["b_q"])
+        x = ops.layer_norm(ops.linear(mem_att(q), ca["w_out"], ca["b_out"], residual=x), *pk["n2"])   # :450-453
+        h = ops.linear(x, pk["w1"], pk["b1"], relu=True)
+        return ops.layer_norm(ops.linear(h, pk["w2"], pk["b2"], residual=x), *pk["n3"])           # :461-463
+
+    def forward_sequence(self, x: torch.Tensor, mem_kv: torch.Tensor) -> torch.Tensor:
+        """Whole target sequence under the causal mask (teacher forcing): x [B, L, E] -> [B, L, E]."""
+        pk = self._packed(config.PRECISION)
+        E, H = x.shape[-1], self.self_attn.num_heads
+        qkv = ops.linear(x, pk["sa"]["w_in"], pk["sa"]["b_in"])
+        att = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], H, causal=True)
+        return self._tail(x, att, pk, lambda q: ops.mha(q, mem_kv[..., :E], mem_kv[..., E:], H))
+
+    def forward_step(self, x: torch.Tensor, pos: int, k_cache: torch.Tensor, v_cache: torch.Tensor,
+                     mem_kv: torch.Tensor) -> torch.Tensor:
+        """One target position: x [B, E]; this position's k / v rows are appended to the caches [B, Lmax, E]."""
+        pk = self._packed(config.PRECISION)
+        E, H = x.shape[-1], self.self_attn.num_heads
+        qkv = ops.linear(x, pk["sa"]["w_in"], pk["sa"]["b_in"])                      # [B, 3E]
+        att = ops.mha_step(qkv[:, :E], k_cache, v_cache, pos + 1, H, k_new=qkv[:, E:2 * E], v_new=qkv[:, 2 * E:])
+        return self._tail(x, att, pk,
+                          lambda q: ops.mha_step(q, mem_kv[..., :E], mem_kv[..., E:], mem_kv.shape[1], H))
+
+    def forward(self, tgt, memory, semantics, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None, is_train=False):
+        """tgt [L, B, E], memory [T, B, E] like the reference; ``tgt_mask`` given means the causal mask (the only
+        mask the reference builds, decoders.py:142-145)."""
+        require_inference(tgt, memory)
+        dt = act_dtype(config.PRECISION)
+        x = ops.cast(tgt.permute(1, 0, 2).contiguous(), dt)
+        mem_kv = self.memory_kv(ops.cast(memory.permute(1, 0, 2).contiguous(), dt))
+        if tgt_mask is None:
+            raise NotImplementedError("the reference always passes the square subsequent mask")
+        return self.forward_sequence(x, mem_kv).permute(1, 0, 2)
+
+
+class TransformerDecoder(_LayerStack):
+    """decoders.py:321-346."""
+
+
+class TF_Decoder(nn.Module):
+    """Transformer decoder: encoder output [B, T, HIDDEN_DIM] -> logits [B, steps, num_classes] (decoders.py:103-275):
+    greedy over MAX_TEXT_LENGTH steps at inference, teacher-forced over MAX_TEXT_LENGTH + 1 positions in training
+    mode."""
+
+    def __init__(self, num_classes):
+        super(TF_Decoder, self).__init__()
+        self.decoder_layer = TransformerDecoderLayer(d_model=config.EMBED_DIM, nhead=8, dim_feedforward=2048, dropout=0.1)
+        self.layer_norm = nn.LayerNorm(config.EMBED_DIM)
+        self.decoder = TransformerDecoder(self.decoder_layer, num_layers=6, norm=self.layer_norm)
+        self.pos_encoder = PositionalEncoding(config.EMBED_DIM)
+        self.hid_to_emb = nn.Linear(config.HIDDEN_DIM, config.EMBED_DIM)
+        self.emb = nn.Embedding(num_classes, config.EMBED_DIM)
+        self.emb_to_classes = nn.Linear(config.EMBED_DIM, num_classes)
+        self.num_classes = num_classes
+        _no_fusion('PRE_DECODER_MLP', 'CLS_DECODER_INIT', 'POST_DECODER_MLP')
+        self.sem_cls = False
+
+    def _generate_square_subsequent_mask(self, sz):
+        mask = (torch.triu(torch.ones(sz, sz)) == 1).transpose(0, 1)
+        return mask.float().masked_fill(mask == 0, float('-inf')).masked_fill(mask == 1, float(0.0))
+
+    def _packed(self, precision: str):
+        src = [self.hid_to_emb.weight, self.hid_to_emb.bias, self.emb.weight, self.emb_to_classes.weight,
+               self.emb_to_classes.bias]
+
+        def build():
+            C, E = self.emb_to_classes.weight.shape
+            Cp = (C + 127) // 128 * 128                   # GEMM tiles want a multiple of 128 output columns
+            w = torch.zeros((Cp, E), device=self.emb.weight.device, dtype=torch.float32)
+            b = torch.zeros((Cp,), device=self.emb.weight.device, dtype=torch.float32)
+            w[:C] = self.emb_to_classes.weight.detach().float()
+            b[:C] = self.emb_to_classes.bias.detach().float()
+            return {"w_mem": wrap_weight(_f(self.hid_to_emb.weight), precision), "b_mem": _f(self.hid_to_emb.bias),
+                    "emb": _f(self.emb.weight), "w_cls": wrap_weight(w, precision), "b_cls": b}
+        return cached(self, ("tf_dec", precision), src, build)
+
+    def _classes(self, x, pk):
+        """emb_to_classes on the normalised decoder output: f32 [..., Cpad]."""
+        if config.PRECISION == 'bf16':
+            return ops.linear(x, pk["w_cls"], pk["b_cls"], want_f32=True, want_bf16=False)
+        return ops.linear(x, pk["w_cls"], pk["b_cls"])
+
+    def decode(self, encoder_output, text, is_train, enc_act=None):
+        """dict(logits [B, steps, C] f32, ids [B, steps] i32, lengths [B] i32)."""
+        require_inference(encoder_output)
+        if self.training:
+            raise RuntimeError("TF_Decoder is in train mode: dropout is not implemented - call model.eval()")
+        precision = config.PRECISION
+        dt = act_dtype(precision)
+        pk = self._packed(precision)
+        enc = enc_act if (enc_act is not None and enc_act.dtype == dt) else ops.cast(encoder_output.contiguous(), dt)
+        B, T, _ = enc.shape
+        dev = enc.device
+        C, E = self.num_classes, self.emb.weight.shape[1]
+        pe = self.pos_encoder.table().contiguous()
+        memory = ops.linear(enc, pk["w_mem"], pk["b_mem"])                            # hid_to_emb: [B, T, E]
+        layers = list(self.decoder.layers)
+        mem_kv = [layer.memory_kv(memory) for layer in layers]
+        final = _ln(self.decoder.norm)
+        if is_train:
+            # teacher forcing (decoders.py:228-248): all MAX_TEXT_LENGTH + 1 target positions under the causal mask
+            if text is None:
+                raise ValueError("is_train=True needs the teacher-forcing text (decoders.py:230-233)")
+            L = config.MAX_TEXT_LENGTH + 1
+            tokens = text.to(device=dev)[:, :L].to(torch.int32).contiguous()
+            if tokens.shape[1] != L:
+                raise ValueError("text must hold MAX_TEXT_LENGTH + 1 = %d target positions" % L)
+            x = ops.embed_tokens(tokens, pk["emb"], pe, 0, dt)
+            for layer, kv in zip(layers, mem_kv):
+                x = layer.forward_sequence(x, kv)
+            cls = self._classes(ops.layer_norm(x, *final), pk)                        # [B, L, Cpad] f32
+            logits = torch.empty((B, L, C), device=dev, dtype=torch.float32)
+            ids = torch.empty((B, L), device=dev, dtype=torch.int32)
+            ops.argmax_tokens(cls.view(B * L, -1), C, logits.view(B * L, C), ids.view(B * L), None)
+            return {"logits": logits, "ids": ids, "lengths": _lengths(ids)}
+        # greedy (decoders.py:250-279): position t reads targets[t] (targets[0] = 0 = [GO]) and yields targets[t+1]
+        steps = config.MAX_TEXT_LENGTH
+        logits = torch.empty((B, steps, C), device=dev, dtype=torch.float32)
+        ids = torch.empty((B, steps), device=dev, dtype=torch.int32)
+        tok = torch.zeros((B, 1), device=dev, dtype=torch.int32)
+        k_cache = [torch.empty((B, steps, E), device=dev, dtype=dt) for _ in layers]
+        v_cache = [torch.empty((B, steps, E), device=dev, dtype=dt) for _ in layers]
+        for t in range(steps):
+            x = ops.embed_tokens(tok, pk["emb"], pe, t, dt).view(B, E)
+            for i, layer in enumerate(layers):
+                x = layer.forward_step(x, t, k_cache[i], v_cache[i], mem_kv[i])
+            cls = self._classes(ops.layer_norm(x, *final), pk)                        # [B, Cpad] f32
+            ops.argmax_tokens(cls, C, logits[:, t], ids[:, t], tok.view(B))
+        return {"logits": logits, "ids": ids, "lengths": _lengths(ids)}
+
+    def forward(self, encoder_output, text, semantics, is_train):
+        return self.decode(encoder_output, text, is_train)["logits"]
+
+
+class Linear_Decoder(nn.Module):
+    """One nn.Linear over the encoder output (decoders.py:278-296): [B, T, HIDDEN_DIM] -> [B, T, num_classes]."""
+
+    def __init__(self, num_classes):
+        super(Linear_Decoder, self).__init__()
+        self.linear_decoder = nn.Linear(config.HIDDEN_DIM, num_classes)
+        self.num_classes = num_classes
+        self.init_weights()
+
+    def init_weights(self):
+        initrange = 0.1
+        self.linear_decoder.bias.data.zero_()
+        self.linear_decoder.weight.data.uniform_(-initrange, initrange)
+
+    def decode(self, encoder_output, text, is_train, enc_act=None):
+        require_inference(encoder_output)
+        precision = config.PRECISION
+        dt = act_dtype(precision)
+        lin = self.linear_decoder
+
+        def build():
+            C, K = lin.weight.shape
+            Cp = (C + 127) // 128 * 128
+            w = torch.zeros((Cp, K), device=lin.weight.device, dtype=torch.float32)
+            b = torch.zeros((Cp,), device=lin.weight.device, dtype=torch.float32)
+            w[:C] = lin.weight.detach().float()
+            b[:C] = lin.bias.detach().float()
+            return {"w": wrap_weight(w, precision), "b": b}
+        pk = cached(self, ("linear_dec", precision), [lin.weight, lin.bias], build)
+        enc = enc_act if (enc_act is not None and enc_act.dtype == dt) else ops.cast(encoder_output.contiguous(), dt)
+        B, T, _ = enc.shape
+        C = self.num_classes
+        cls = ops.linear(enc, pk["w"], pk["b"], want_f32=True, want_bf16=False) if precision == 'bf16' \
+            else ops.linear(enc, pk["w"], pk["b"])
+        logits = torch.empty((B, T, C), device=enc.device, dtype=torch.float32)
+        ids = torch.empty((B, T), device=enc.device, dtype=torch.int32)
+        ops.argmax_tokens(cls.view(B * T, -1), C, logits.view(B * T, C), ids.view(B * T), None)
+        return {"logits": logits, "ids": ids, "lengths": _lengths(ids)}
+
+    def forward(self, encoder_output, text, semantics, is_train):
+        return self.decode(encoder_output, text, is_train)["logits"]
+
+
+def _lengths(ids: torch.Tensor) -> torch.Tensor:
+    """Index of the first [s] (id 1) per crop, or the number of steps (what training_functions.py:188-189 cuts at)."""
+    stop = ids == 1
+    first = torch.argmax(stop.to(torch.int32), dim=1)
+    return torch.where(stop.any(dim=1), first, torch.full_like(first, ids.shape[1])).to(torch.int32)

@@ -304,8 +304,9 @@ def conv_gemm_dual(x: torch.Tensor, x2: torch.Tensor, w_cat: torch.Tensor, shift
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
-           want_f32: bool = False, want_bf16: bool = True):
-    """nn.Linear on the last dimension through the same GEMM kernels (x [..., K], w [N, K])."""
+           want_f32: bool = False, want_bf16: bool = True, residual: Optional[torch.Tensor] = None):
+    """nn.Linear on the last dimension through the same GEMM kernels (x [..., K], w [N, K]); ``residual`` [..., N] of
+    x's dtype is added in the epilogue (before the ReLU)."""
     lead = x.shape[:-1]
     K = x.shape[-1]
     M = 1
@@ -313,7 +314,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu:
         M *= d
     x4 = x.reshape(M, 1, 1, K)
     w4 = w.reshape(w.shape[0], 1, 1, K)
-    res = conv_gemm(x4, w4, None, bias, relu=relu, want_f32=want_f32, want_bf16=want_bf16)
+    r4 = None if residual is None else residual.reshape(M, 1, 1, w.shape[0])
+    res = conv_gemm(x4, w4, None, bias, r4, relu=relu, want_f32=want_f32, want_bf16=want_bf16)
     shape = tuple(lead) + (w.shape[0],)
     if isinstance(res, tuple):
         return tuple(r.reshape(shape) for r in res)
@@ -362,6 +364,88 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     with _on(x) as st:
         check(lib().mstr_cast(ptr(x), ptr(out), _dt(x), _dt(out), x.numel(), st), "mstr_cast")
     return out
+
+
+# ---- transformer family: everything between the GEMMs --------------------------------------------
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """nn.LayerNorm over the last dimension, x [..., D] f32 or bf16 -> same dtype."""
+    _req(x, "x"); _req(gamma, "gamma", torch.float32); _req(beta, "beta", torch.float32)
+    D = x.shape[-1]
+    out = torch.empty_like(x)
+    with _timed("layer_norm", 2.0 * x.numel() * x.element_size(), "byte", "%d rows x %d" % (x.numel() // D, D)), \
+            _on(x, gamma, beta) as st:
+        check(lib().mstr_layer_norm(ptr(x), ptr(gamma), ptr(beta), ptr(out), x.numel() // D, D, float(eps), _dt(x), st),
+              "mstr_layer_norm")
+    return out
+
+
+def add_pos_encoding(x: torch.Tensor, pe: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """x [B,T,D] + pe[:T] -> [B,T,D] of ``dtype`` (PositionalEncoding.forward, eval mode)."""
+    _req(x, "x"); _req(pe, "pe", torch.float32)
+    B, T, D = x.shape
+    assert pe.shape[0] >= T and pe.shape[1] == D
+    out = torch.empty((B, T, D), device=x.device, dtype=dtype)
+    with _on(x, pe) as st:
+        check(lib().mstr_add_pos_encoding(ptr(x), _dt(x), ptr(pe), ptr(out), _dt(out), B, T, D, st), "mstr_add_pos_encoding")
+    return out
+
+
+def embed_tokens(tokens: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor, t0: int, dtype: torch.dtype) -> torch.Tensor:
+    """tokens [B,T] int32 -> emb[tokens] + pe[t0:t0+T]  [B,T,D] of ``dtype``."""
+    _req(tokens, "tokens", torch.int32); _req(emb, "emb", torch.float32); _req(pe, "pe", torch.float32)
+    B, T = tokens.shape
+    C, D = emb.shape
+    assert pe.shape[0] >= t0 + T and pe.shape[1] == D
+    out = torch.empty((B, T, D), device=tokens.device, dtype=dtype)
+    with _on(tokens, emb, pe) as st:
+        check(lib().mstr_embed_tokens(ptr(tokens), ptr(emb), ptr(pe), ptr(out), _dt(out), B, T, D, C, t0, st), "mstr_embed_tokens")
+    return out
+
+
+def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, causal: bool = False) -> torch.Tensor:
+    """softmax(q k^T / sqrt(dh) [+ causal mask]) v per head, before out_proj.  q [B,Lq,E], k / v [B,Lk,E]: views with
+    unit stride along E and dense batches (stride(0) == L * stride(1)), e.g. the thirds of an in_proj output."""
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    for t, L in ((q, Lq), (k, Lk), (v, Lk)):
+        assert t.is_cuda and t.dtype == q.dtype and t.stride(2) == 1 and t.stride(0) == L * t.stride(1), "mha: unsupported view"
+    assert k.stride() == v.stride() and k.shape == v.shape
+    out = torch.empty((B, Lq, E), device=q.device, dtype=q.dtype)
+    with _timed("mha", 4.0 * B * Lq * Lk * E, "flop", "B%d Lq%d Lk%d %d heads x %d" % (B, Lq, Lk, heads, E // heads)), \
+            _on(q, k, v) as st:
+        check(lib().mstr_mha(ptr(q), q.stride(1), ptr(k), ptr(v), k.stride(1), ptr(out), B, Lq, Lk, heads, E // heads,
+                             int(causal), _dt(q), st), "mstr_mha")
+    return out
+
+
+def mha_step(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, Lk: int, heads: int,
+             k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One query per crop: q [B,E] (a view with row stride q.stride(0)), k_cache / v_cache views [B,>=Lk,E] (any row /
+    batch strides, unit stride along E); k_new / v_new [B,E] views are first stored as row Lk-1 of the caches."""
+    B, E = q.shape
+    for t in (q, k_cache, v_cache, k_new, v_new):
+        if t is not None:
+            assert t.is_cuda and t.stride(-1) == 1 and t.dtype == q.dtype
+    assert k_cache.stride() == v_cache.stride() and k_cache.shape[1] >= Lk
+    if k_new is not None:
+        assert v_new is not None and k_new.stride(0) == v_new.stride(0)
+    out = torch.empty((B, E), device=q.device, dtype=q.dtype)
+    with _on(q, k_cache, v_cache, k_new, v_new) as st:
+        check(lib().mstr_mha_step(ptr(q), q.stride(0), ptr(k_cache), ptr(v_cache), k_cache.stride(1), k_cache.stride(0),
+                                  ptr(k_new), ptr(v_new), 0 if k_new is None else k_new.stride(0), ptr(out), B, Lk, heads,
+                                  E // heads, _dt(q), st), "mstr_mha_step")
+    return out
+
+
+def argmax_tokens(logits: torch.Tensor, C: int, logits_out: Optional[torch.Tensor], ids: Optional[torch.Tensor],
+                  next_tok: Optional[torch.Tensor]) -> None:
+    """logits [B,ld] f32; logits_out / ids / next_tok are (strided) views with one row / element per crop."""
+    _req(logits, "logits", torch.float32)
+    B, ld = logits.shape
+    with _on(logits, logits_out, ids, next_tok) as st:
+        check(lib().mstr_argmax_tokens(ptr(logits), ld, ptr(logits_out), 0 if logits_out is None else logits_out.stride(0),
+                                       ptr(ids), 0 if ids is None else ids.stride(0), ptr(next_tok),
+                                       0 if next_tok is None else next_tok.stride(0), B, C, st), "mstr_argmax_tokens")
 
 
 def embed_semantics(ids: torch.Tensor, table: torch.Tensor, ious: Optional[torch.Tensor], mode: int) -> torch.Tensor:

@@ -334,3 +334,113 @@ def make_semantics(seed: int, batch: int, n_overlap: int = 15, n_scene: int = 52
         scene[b, :k] = rng.choice(n_classes, size=k, replace=False) + 1
     ious = np.full((batch, n_scene), -1000.0, np.float32)
     return overlap, scene, ious
+
+
+# ---- transformer family (reference config.py:27-31 defaults) ---------------------------------------
+def positional_table(d_model: int, max_len: int = 26) -> np.ndarray:
+    """PositionalEncoding's buffer ``pe`` [max_len, 1, d_model] (encoders.py:151-159), computed in fp32 like torch."""
+    position = np.arange(max_len, dtype=np.float32)[:, None]
+    div_term = np.exp(np.arange(0, d_model, 2).astype(np.float32) * np.float32(-np.log(10000.0) / d_model)).astype(np.float32)
+    pe = np.zeros((max_len, d_model), np.float32)
+    pe[:, 0::2] = np.sin(position * div_term)
+    pe[:, 1::2] = np.cos(position * div_term)
+    return pe[:, None, :]
+
+
+def transformer_spec(decoder: str = "Transformer", hidden_dim: int = 512, embed_dim: int = 256, ff: int = 2048,
+                     num_classes: int = 97, layers: int = 6) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(name, shape, kind) of the encoder / decoder tensors of the Transformer configurations (TF_Encoder with
+    TF_Decoder: 462 tensors with the rest of the model, with Linear_Decoder: 314)."""
+    spec: List[Tuple[str, Tuple[int, ...], str]] = []
+
+    def mha(p: str, d: int) -> None:
+        spec.extend([(p + "in_proj_weight", (3 * d, d), "xavier"), (p + "in_proj_bias", (3 * d,), "bias"),
+                     (p + "out_proj.weight", (d, d), "lin"), (p + "out_proj.bias", (d,), "bias")])
+
+    def norm(p: str, d: int) -> None:
+        spec.extend([(p + "weight", (d,), "ln_w"), (p + "bias", (d,), "ln_b")])
+
+    def enc_layer(p: str) -> None:
+        mha(p + "self_attn.", hidden_dim)
+        spec.extend([(p + "linear1.weight", (ff, hidden_dim), "lin"), (p + "linear1.bias", (ff,), "bias"),
+                     (p + "linear2.weight", (hidden_dim, ff), "lin"), (p + "linear2.bias", (hidden_dim,), "bias")])
+        norm(p + "norm1.", hidden_dim); norm(p + "norm2.", hidden_dim)
+
+    def dec_layer(p: str) -> None:
+        mha(p + "self_attn.", embed_dim); mha(p + "multihead_attn.", embed_dim)
+        spec.extend([(p + "linear1.weight", (ff, embed_dim), "lin"), (p + "linear1.bias", (ff,), "bias"),
+                     (p + "linear2.weight", (embed_dim, ff), "lin"), (p + "linear2.bias", (embed_dim,), "bias"),
+                     (p + "semantic_to_emb.weight", (embed_dim, hidden_dim), "lin"), (p + "semantic_to_emb.bias", (embed_dim,), "bias")])
+        norm(p + "norm1.", embed_dim); norm(p + "norm2.", embed_dim); norm(p + "norm3.", embed_dim)
+
+    spec.append(("encoder.pos_encoder.pe", (26, 1, hidden_dim), "pe"))
+    enc_layer("encoder.encoder_layer.")
+    norm("encoder.layer_norm.", hidden_dim)
+    for i in range(layers):
+        enc_layer("encoder.encoder.layers.%d." % i)
+    spec.extend([("encoder.encoder.norm.weight", (hidden_dim,), "alias:encoder.layer_norm.weight"),
+                 ("encoder.encoder.norm.bias", (hidden_dim,), "alias:encoder.layer_norm.bias")])
+    if decoder == "Linear":
+        spec.extend([("decoder.linear_decoder.weight", (num_classes, hidden_dim), "classes"),
+                     ("decoder.linear_decoder.bias", (num_classes,), "bias")])
+        return spec
+    dec_layer("decoder.decoder_layer.")
+    norm("decoder.layer_norm.", embed_dim)
+    for i in range(layers):
+        dec_layer("decoder.decoder.layers.%d." % i)
+    spec.extend([("decoder.decoder.norm.weight", (embed_dim,), "alias:decoder.layer_norm.weight"),
+                 ("decoder.decoder.norm.bias", (embed_dim,), "alias:decoder.layer_norm.bias"),
+                 ("decoder.pos_encoder.pe", (26, 1, embed_dim), "pe"),
+                 ("decoder.hid_to_emb.weight", (embed_dim, hidden_dim), "lin"), ("decoder.hid_to_emb.bias", (embed_dim,), "bias"),
+                 ("decoder.emb.weight", (num_classes, embed_dim), "embedding"),
+                 ("decoder.emb_to_classes.weight", (num_classes, embed_dim), "classes"),
+                 ("decoder.emb_to_classes.bias", (num_classes,), "bias")])
+    return spec
+
+
+# Gains over the default scales, tuned once against the reference's modules (B=32, seeds 999/123): sharper attention
+# (q and k rows of every in_proj), a stronger encoder feed-forward branch and memory attention, a weaker token
+# embedding - the decode then depends on the crop (32/32 distinct strings, 11 distinct characters, median top-1/top-2
+# margin 0.19 x logit std) instead of on the token feedback alone (4 distinct strings with every gain at 1).
+TRANSFORMER_GAINS = {"classes": 4.0, "embedding": 0.5, "qk": 4.0, "enc_linear2": 4.0, "dec_memory_out": 2.0}
+
+
+def make_state_dict_transformer(seed: int = 999, decoder: str = "Transformer", geom: Geometry = CFG_A) -> Dict[str, np.ndarray]:
+    """Seeded synthetic weights of the Transformer / Transformer (or Transformer / Linear) configuration: the rectifier,
+    ResNet and embedding table of ``make_state_dict`` plus independent random weights for every encoder / decoder layer
+    (the reference's default init makes the six layers equal copies, encoders.py:80, and decodes every crop to one
+    repeated character).  ``*.norm`` aliases ``layer_norm`` like in the reference's modules."""
+    base = make_state_dict(seed, geom)
+    out = {k: v for k, v in base.items() if not (k.startswith("encoder.") or k.startswith("decoder."))}
+    rng = np.random.Generator(np.random.PCG64(seed + 7))
+    for name, shape, kind in transformer_spec(decoder, num_classes=geom.num_classes):
+        if kind == "pe":
+            v = positional_table(shape[2], shape[0])
+        elif kind == "xavier":
+            a = np.sqrt(6.0 / (shape[0] + shape[1]))
+            v = rng.uniform(-a, a, shape)
+            v[:2 * shape[1]] *= TRANSFORMER_GAINS["qk"]
+        elif kind == "lin":
+            k = 1.0 / np.sqrt(shape[1])
+            v = rng.uniform(-k, k, shape)
+            if name.startswith("encoder.") and name.endswith("linear2.weight"):
+                v = v * TRANSFORMER_GAINS["enc_linear2"]
+            if name.endswith("multihead_attn.out_proj.weight"):
+                v = v * TRANSFORMER_GAINS["dec_memory_out"]
+        elif kind == "classes":
+            k = TRANSFORMER_GAINS["classes"] / np.sqrt(shape[1])
+            v = rng.uniform(-k, k, shape)
+        elif kind == "bias":
+            v = rng.uniform(-0.05, 0.05, shape)
+        elif kind == "ln_w":
+            v = rng.uniform(0.8, 1.2, shape)
+        elif kind == "ln_b":
+            v = rng.standard_normal(shape) * 0.1
+        elif kind == "embedding":
+            v = rng.standard_normal(shape) * TRANSFORMER_GAINS["embedding"]
+        elif kind.startswith("alias:"):
+            v = out[kind[6:]]
+        else:  # pragma: no cover
+            raise KeyError(kind)
+        out[name] = np.ascontiguousarray(v, dtype=np.float32)
+    return out

@@ -1,0 +1,147 @@
+"""CPU ORACLE (test infrastructure, NOT a product path) for the transformer encoder / decoder family.
+
+A numpy restatement of the reference's ``TF_Encoder`` (modules/encoders.py:68-197), ``TF_Decoder``
+(modules/decoders.py:103-275, :321-466) and ``Linear_Decoder`` (:278-296) with every fusion switch of config.py:40-53
+at its default (False), in eval mode (dropout = identity).  The arithmetic lives in PyTorch ATen (nn.MultiheadAttention,
+nn.LayerNorm, nn.Linear, nn.Embedding; third-party, un-vendored; the image has torch 2.11.0), so the operator semantics
+restated here are ATen's: q is scaled by 1/sqrt(head dim) before q k^T, softmax over the keys, LayerNorm with the biased
+variance and eps 1e-5.
+
+The greedy loop is restated the way the reference runs it - the whole target prefix 0..t goes through the decoder at
+every step under the square subsequent mask (decoders.py:250-279), no K/V cache - so that the CUDA path's cache is
+checked against the recomputation, not against itself.
+
+PINNING: ``tests/golden/make_golden_tf.py`` (build container) runs the reference's OWN module objects on the seeded
+synthetic weights of ``synth.make_state_dict_transformer`` and stores their outputs in ``tests/golden/cfg_tf.npz``;
+``tests/test_oracle_golden.py`` checks this file against them.  One caveat, stated there too: the reference's
+``TF_Encoder.forward`` itself raises TypeError under torch 2.11 (``nn.TransformerEncoder.forward`` passes
+``is_causal=`` to the reference's layer class, which does not take it), so the fixture drives the reference's
+``pos_encoder``, its six ``TransformerEncoderLayer`` objects and its ``norm`` from a three-line loop - what
+``nn.TransformerEncoder.forward`` did in the torch the reference was written for.  ``TF_Decoder.forward`` and
+``Linear_Decoder.forward`` run unmodified.
+
+Only ``tests/`` may import this module.  The product path (the CUDA extension) never does.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+LN_EPS = 1e-5  # nn.LayerNorm default (encoders.py:78,176-177; decoders.py:112,364-366)
+
+
+def linear(x, w, b=None):
+    y = x @ w.T
+    return y if b is None else y + b
+
+
+def layer_norm(x, w, b):
+    mu = x.mean(axis=-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(axis=-1, keepdims=True)
+    return (x - mu) / np.sqrt(var + x.dtype.type(LN_EPS)) * w + b
+
+
+def softmax(x, axis):
+    e = np.exp(x - x.max(axis=axis, keepdims=True))
+    return e / e.sum(axis=axis, keepdims=True)
+
+
+def multihead_attention(q_in, k_in, v_in, sd, prefix, heads, mask=None):
+    """nn.MultiheadAttention.forward(query, key, value, attn_mask)[0] in eval mode, batch-first here:
+    q_in [B, Lq, E], k_in / v_in [B, Lk, E]; ``mask`` [Lq, Lk] additive (0 / -inf)."""
+    dt = q_in.dtype
+    w, b = sd[prefix + "in_proj_weight"].astype(dt), sd[prefix + "in_proj_bias"].astype(dt)
+    E = q_in.shape[-1]
+    dh = E // heads
+    q = linear(q_in, w[:E], b[:E]) * dt.type(1.0 / np.sqrt(dh))
+    k = linear(k_in, w[E:2 * E], b[E:2 * E])
+    v = linear(v_in, w[2 * E:], b[2 * E:])
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    q = q.reshape(B, Lq, heads, dh).transpose(0, 2, 1, 3)
+    k = k.reshape(B, Lk, heads, dh).transpose(0, 2, 1, 3)
+    v = v.reshape(B, Lk, heads, dh).transpose(0, 2, 1, 3)
+    s = q @ k.transpose(0, 1, 3, 2)                         # [B, heads, Lq, Lk]
+    if mask is not None:
+        s = s + mask.astype(dt)
+    o = (softmax(s, axis=-1) @ v).transpose(0, 2, 1, 3).reshape(B, Lq, E)
+    return linear(o, sd[prefix + "out_proj.weight"].astype(dt), sd[prefix + "out_proj.bias"].astype(dt))
+
+
+def _ln(x, sd, prefix):
+    return layer_norm(x, sd[prefix + "weight"].astype(x.dtype), sd[prefix + "bias"].astype(x.dtype))
+
+
+def _ffn(x, sd, prefix):
+    dt = x.dtype
+    h = np.maximum(linear(x, sd[prefix + "linear1.weight"].astype(dt), sd[prefix + "linear1.bias"].astype(dt)), 0)
+    return linear(h, sd[prefix + "linear2.weight"].astype(dt), sd[prefix + "linear2.bias"].astype(dt))
+
+
+def encoder_layer(src, sd, prefix, heads=8):
+    """TransformerEncoderLayer.forward (encoders.py:185-193): the sub-layer output is added AFTER the norm of the
+    residual stream - ``src = norm1(src); src = src + src2``."""
+    src2 = multihead_attention(src, src, src, sd, prefix + "self_attn.", heads)
+    src = _ln(src, sd, prefix + "norm1.") + src2
+    src2 = _ffn(src, sd, prefix)
+    return _ln(src, sd, prefix + "norm2.") + src2
+
+
+def tf_encoder(col_feats, sd, dt=np.float32, layers=6, prefix="encoder."):
+    """TF_Encoder.forward (encoders.py:127-143) with PRE_ENCODER_MLP off: positional encoding, the layers, the norm."""
+    x = col_feats.astype(dt)
+    pe = sd[prefix + "pos_encoder.pe"].astype(dt)[:, 0, :]
+    x = x + pe[None, :x.shape[1], :]
+    for i in range(layers):
+        x = encoder_layer(x, sd, "%sencoder.layers.%d." % (prefix, i))
+    return _ln(x, sd, prefix + "encoder.norm.")
+
+
+def decoder_layer(tgt, memory, sd, prefix, mask, heads=8):
+    """TransformerDecoderLayer.forward (decoders.py:433-466) with the MULTIHEAD_* switches off."""
+    tgt = _ln(tgt + multihead_attention(tgt, tgt, tgt, sd, prefix + "self_attn.", heads, mask), sd, prefix + "norm1.")
+    tgt = _ln(tgt + multihead_attention(tgt, memory, memory, sd, prefix + "multihead_attn.", heads), sd, prefix + "norm2.")
+    return _ln(tgt + _ffn(tgt, sd, prefix), sd, prefix + "norm3.")
+
+
+def _causal_mask(n):
+    """_generate_square_subsequent_mask (decoders.py:142-145)."""
+    m = np.zeros((n, n), np.float64)
+    m[np.triu_indices(n, 1)] = -np.inf
+    return m
+
+
+def _decoder_stack(x, memory, sd, prefix, layers):
+    mask = _causal_mask(x.shape[1])
+    for i in range(layers):
+        x = decoder_layer(x, memory, sd, "%sdecoder.layers.%d." % (prefix, i), mask)
+    return _ln(x, sd, prefix + "decoder.norm.")
+
+
+def tf_decoder(enc, sd, max_len=25, text: Optional[np.ndarray] = None, dt=np.float32, layers=6, prefix="decoder."):
+    """TF_Decoder.forward (decoders.py:213-296 of the class body, :228-279 the two branches).
+    text None: greedy, logits [B, max_len, C]; text [B, >= max_len + 1]: teacher forcing, logits [B, max_len + 1, C]."""
+    enc = enc.astype(dt)
+    memory = linear(enc, sd[prefix + "hid_to_emb.weight"].astype(dt), sd[prefix + "hid_to_emb.bias"].astype(dt))
+    emb = sd[prefix + "emb.weight"].astype(dt)
+    pe = sd[prefix + "pos_encoder.pe"].astype(dt)[:, 0, :]
+    w_c, b_c = sd[prefix + "emb_to_classes.weight"].astype(dt), sd[prefix + "emb_to_classes.bias"].astype(dt)
+    B = enc.shape[0]
+    if text is not None:
+        L = max_len + 1
+        x = emb[text[:, :L]] + pe[None, :L]
+        return linear(_decoder_stack(x, memory, sd, prefix, layers), w_c, b_c)
+    targets = np.zeros((B, max_len + 1), np.int64)
+    out = np.zeros((B, max_len, w_c.shape[0]), dt)
+    for t in range(max_len):
+        x = emb[targets[:, :t + 1]] + pe[None, :t + 1]        # the reference embeds all positions and slices [:t+1]
+        y = linear(_decoder_stack(x, memory, sd, prefix, layers), w_c, b_c)
+        targets[:, t + 1] = y[:, -1].argmax(axis=1)
+        out[:, t] = y[:, t]
+    return out
+
+
+def linear_decoder(enc, sd, dt=np.float32, prefix="decoder."):
+    """Linear_Decoder.forward (decoders.py:293-295)."""
+    return linear(enc.astype(dt), sd[prefix + "linear_decoder.weight"].astype(dt), sd[prefix + "linear_decoder.bias"].astype(dt))

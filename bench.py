@@ -21,7 +21,8 @@ One JSON line on stdout (rank 0):
                 against the measured cuBLAS bf16 peak of MEASURED_PEAKS.json
   ranks         per-rank device time of the timed steps (min / max over ranks) and the allgather's own CUDA-event time
   other_configs the other BASELINE.json configurations under the same clock sampler (N = 1): batch 256 in bf16 and
-                3xTF32, scene-mode semantic vectors, the 3x64x256 / 51-step stress geometry
+                3xTF32, scene-mode semantic vectors, the 3x64x256 / 51-step stress geometry; and the reference's default
+                model family (Transformer encoder with the Transformer / Linear decoder)
   cpu_baseline  the UNMODIFIED reference (baseline/_ref: its own Model.forward, fp32, all host threads; kind
                 "reference") on a bounded sample of the same workload - or the CPU port (oracle/torch_port.py, kind
                 "port") where baseline/_ref is absent
@@ -259,6 +260,37 @@ def other_config(geom, B, precision, dev, peaks, semantic="overlap", reps=5):
             "whole_step_frac": round(B / (ms * 1e-3) * flop / 1e12 / peak, 4)}
 
 
+def transformer_config(decoder, B, dev, peaks, reps=3):
+    """The reference's default model family (config.py:27-28): Transformer encoder with the Transformer
+    (greedy, 25 steps, K/V cache) or the Linear decoder, bf16, the whole forward replayed as one CUDA graph."""
+    from multimodal_scene_text_recognition_b200 import config, model as M, synth
+    from multimodal_scene_text_recognition_b200.pipeline import GraphedRecognizer
+    saved = (config.ENCODER, config.DECODER)
+    try:
+        config.ENCODER, config.DECODER, config.PRECISION, config.MAX_TEXT_LENGTH = "Transformer", decoder, "bf16", 25
+        model = M.load_numpy_state_dict(M.Model().eval(), synth.make_state_dict_transformer(WEIGHT_SEED, decoder=decoder)).to(dev)
+        x = torch.from_numpy(synth.make_crops(DATA_SEED, B)).to(dev)
+        sem = [torch.from_numpy(a).to(dev) for a in synth.make_semantics(DATA_SEED + 1, B)]
+        graphed = GraphedRecognizer(model)
+        launches = graphed.launches_per_replay(x, *sem)
+        ts = []
+        for _ in range(2):
+            graphed(x, *sem)
+        torch.cuda.synchronize()
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); graphed(x, *sem); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ms = float(np.median(ts))
+    finally:
+        config.ENCODER, config.DECODER = saved
+    return {"geometry": "1x32x100, Transformer encoder + %s decoder (%s)" % (
+                decoder, "25 greedy steps" if decoder == "Transformer" else "26 columns"),
+            "batch": B, "precision": "bf16", "launch": "CUDA graph replay, %d kernels" % launches, "ms": round(ms, 3),
+            "crops_per_s": round(B / ms * 1e3, 1),
+            "whole_step_frac": round(B / (ms * 1e-3) * CONV_FLOP_PER_CROP / 1e12 / peaks["bf16_sustained"], 4)}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from multimodal_scene_text_recognition_b200 import _cabi, config, ops, parallel, synth
@@ -430,6 +462,8 @@ def run_ours(args):
             other_config(synth.CFG_A, 256, "tf32", dev, peaks, reps=3),
             other_config(synth.CFG_A, 4096, "bf16", dev, peaks, semantic="scene", reps=3),
             other_config(synth.CFG_S, 1024, "bf16", dev, peaks, reps=3),
+            transformer_config("Transformer", 4096, dev, peaks),
+            transformer_config("Linear", 4096, dev, peaks),
         ]
     clocks = sampler.stop() if sampler else None
     if world == 1 and rank == 0 and not args.no_extras:

@@ -12,7 +12,7 @@
 //   mha_step_kernel        the same for ONE query per crop against Lk cached keys: the greedy loop with a K/V cache
 //                          (decoders.py:250-279 recomputes every earlier position at every step; with the causal
 //                          mask those rows do not change, so the cache gives the same numbers) and the
-//                          memory attention (decoders.py:450-451); lane = key, then lane = channel
+//                          memory attention (decoders.py:450-451); one warp per crop, every row one coalesced request
 //   argmax_tokens_kernel   t_output[-1].max(1), targets[t+1] = char_index, output[t] = t_output[t] (decoders.py:276-279)
 //
 // All arithmetic is fp32; T = float (parity modes) or __nv_bfloat16 (throughput mode) is the storage type.
@@ -20,20 +20,61 @@
 
 namespace mstr {
 
-template <typename T>
+// 16-byte chunk helpers: N consecutive elements of T as f32
+template <typename T> struct Chunk;
+template <> struct Chunk<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Chunk<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(w[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                              pack_bf16x2(v[6], v[7]));
+  }
+};
+
+// One warp per row.  VEC: every lane owns D / 32 CONSECUTIVE channels and moves them in 16-byte chunks (D a multiple of
+// 32 chunks); otherwise lane-strided scalar accesses.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                   T* __restrict__ out, int64_t rows, int D, float eps) {
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  constexpr int N = Chunk<T>::N;
   const T* xr = x + row * D;
   float v[32];                                            // D <= 1024
-  const int n = D >> 5;
+  const int n = D >> 5;                                   // channels per lane
+  auto channel = [&](int i) { return VEC ? lane * n + i : i * 32 + lane; };
   float s = 0.f;
+  if (VEC) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (i < n) { v[i] = Elem<T>::load(xr + i * 32 + lane); s += v[i]; }
+    for (int c = 0; c < 32 / N; ++c)
+      if (c * N < n) {
+        float t[N];
+        Chunk<T>::load(xr + lane * n + c * N, t);
+#pragma unroll
+        for (int u = 0; u < N; ++u) { v[c * N + u] = t[u]; s += t[u]; }
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < n) { v[i] = Elem<T>::load(xr + i * 32 + lane); s += v[i]; }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / (float)D;
@@ -48,9 +89,23 @@ layer_norm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, cons
 #pragma unroll
   for (int i = 0; i < 32; ++i)
     if (i < n) {
-      const int c = i * 32 + lane;
-      Elem<T>::store(orow + c, fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c)));
+      const int c = channel(i);
+      v[i] = fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c));
     }
+  if (VEC) {
+#pragma unroll
+    for (int c = 0; c < 32 / N; ++c)
+      if (c * N < n) {
+        float t[N];
+#pragma unroll
+        for (int u = 0; u < N; ++u) t[u] = v[c * N + u];
+        Chunk<T>::store(orow + lane * n + c * N, t);
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < n) Elem<T>::store(orow + i * 32 + lane, v[i]);
+  }
 }
 
 template <typename TI, typename TO>
@@ -93,10 +148,18 @@ mha_full_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, const
   float* sv = sk + 32 * DH;
   const T* kb = k + (int64_t)b * Lk * ldkv + h * DH;
   const T* vb = v + (int64_t)b * Lk * ldkv + h * DH;
-  for (int i = lane; i < Lk * DH; i += 32) {
-    const int j = i / DH, d = i % DH;
-    sk[i] = Elem<T>::load(kb + (int64_t)j * ldkv + d);
-    sv[i] = Elem<T>::load(vb + (int64_t)j * ldkv + d);
+  {
+    constexpr int N = Chunk<T>::N, PER_ROW = DH / N;    // 16-byte chunks
+    for (int i = lane; i < Lk * PER_ROW; i += 32) {
+      const int j = i / PER_ROW, d = (i % PER_ROW) * N;
+      float t[N];
+      Chunk<T>::load(kb + (int64_t)j * ldkv + d, t);
+#pragma unroll
+      for (int u = 0; u < N; ++u) sk[j * DH + d + u] = t[u];
+      Chunk<T>::load(vb + (int64_t)j * ldkv + d, t);
+#pragma unroll
+      for (int u = 0; u < N; ++u) sv[j * DH + d + u] = t[u];
+    }
   }
   __syncwarp();
   if (lane >= Lq) return;
@@ -140,54 +203,93 @@ mha_full_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, const
   for (int d = 0; d < DH; ++d) Elem<T>::store(orow + d, acc[d]);
 }
 
-// One warp per (crop, head), ONE query: lane = key for the scores and the softmax, lane = channel (DH / 32 each) for the
-// weighted sum.  Optionally appends this step's k / v rows (k_new, v_new: [B][ld_new], head h at h*DH) to the cache at
-// position Lk - 1 first.
-template <typename T, int DH>
+// ONE query per crop.  One warp per crop covers all heads: the E = heads * DH channels of a row are split over the 32
+// lanes in contiguous pieces of E / 32 channels (32 / heads lanes per head), so every key / value row is ONE coalesced
+// request of the warp (16-byte loads).  Per key: a partial dot product per lane, reduced over the lanes of the head
+// with log2(32 / heads) shuffles; the scores of all keys stay in registers (softmax without further shuffles); then the
+// weighted sum of the value rows, each lane for its own channels.  (A first version - one warp per (crop, head), lane =
+// key, 2-byte loads with a row stride between lanes - took 90 us per launch at 4096 crops; this one a few.)
+// Optionally appends this step's k / v rows (k_new, v_new: [B][ld_new]) to the caches as row Lk - 1 first.
+template <typename T, int DH, int HEADS>
 __global__ void __launch_bounds__(128)
 mha_step_kernel(const T* __restrict__ q, int ldq, T* __restrict__ kc, T* __restrict__ vc, int ldkv, int64_t kv_batch_stride,
                 const T* __restrict__ k_new, const T* __restrict__ v_new, int ld_new, T* __restrict__ out, int B, int Lk,
-                int heads, float scale) {
+                float scale) {
+  constexpr int E = DH * HEADS, PER_LANE = E / 32, N = Chunk<T>::N, CH = PER_LANE / N, LPH = 32 / HEADS;
+  static_assert(PER_LANE % N == 0 && CH >= 1 && (32 % HEADS) == 0, "E / 32 channels per lane in 16-byte chunks");
   const int lane = threadIdx.x & 31;
-  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (item >= (int64_t)B * heads) return;
-  const int b = (int)(item / heads), h = (int)(item % heads);
-  T* kb = kc + (int64_t)b * kv_batch_stride + h * DH;
-  T* vb = vc + (int64_t)b * kv_batch_stride + h * DH;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int c0 = lane * PER_LANE;                       // this lane's channels: c0 .. c0 + PER_LANE - 1 (one head)
+  T* kb = kc + b * kv_batch_stride + c0;
+  T* vb = vc + b * kv_batch_stride + c0;
+  float qv[PER_LANE];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    float t[N];
+    Chunk<T>::load(q + b * ldq + c0 + c * N, t);
+#pragma unroll
+    for (int i = 0; i < N; ++i) qv[c * N + i] = t[i] * scale;     // q is scaled first, like torch
+  }
   if (k_new) {
-    for (int d = lane; d < DH; d += 32) {
-      kb[(int64_t)(Lk - 1) * ldkv + d] = k_new[(int64_t)b * ld_new + h * DH + d];
-      vb[(int64_t)(Lk - 1) * ldkv + d] = v_new[(int64_t)b * ld_new + h * DH + d];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float t[N];
+      Chunk<T>::load(k_new + b * ld_new + c0 + c * N, t);
+      Chunk<T>::store(kb + (int64_t)(Lk - 1) * ldkv + c * N, t);
+      Chunk<T>::load(v_new + b * ld_new + c0 + c * N, t);
+      Chunk<T>::store(vb + (int64_t)(Lk - 1) * ldkv + c * N, t);
     }
-    __syncwarp();
   }
-  const T* qr = q + (int64_t)b * ldq + h * DH;
-  float sc = -INFINITY;
-  if (lane < Lk) {
-    float a = 0.f;
+  float s[32];
+  float mx = -INFINITY;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) a = fmaf(Elem<T>::load(qr + d) * scale, Elem<T>::load(kb + (int64_t)lane * ldkv + d), a);
-    sc = a;
+  for (int j = 0; j < 32; ++j) {
+    s[j] = -INFINITY;
+    if (j < Lk) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float t[N];
+        Chunk<T>::load(kb + (int64_t)j * ldkv + c * N, t);
+#pragma unroll
+        for (int i = 0; i < N; ++i) a = fmaf(qv[c * N + i], t[i], a);
+      }
+#pragma unroll
+      for (int o = LPH / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      s[j] = a;
+      mx = fmaxf(mx, a);
+    }
   }
-  float mx = sc;
+  float den = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float e = lane < Lk ? expf(sc - mx) : 0.f;
-  float den = e;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
-  const float p = e / den;
-  float acc[DH / 32];
-#pragma unroll
-  for (int u = 0; u < DH / 32; ++u) acc[u] = 0.f;
-  for (int j = 0; j < Lk; ++j) {
-    const float pj = __shfl_sync(0xffffffffu, p, j);
-#pragma unroll
-    for (int u = 0; u < DH / 32; ++u) acc[u] = fmaf(pj, Elem<T>::load(vb + (int64_t)j * ldkv + u * 32 + lane), acc[u]);
+  for (int j = 0; j < 32; ++j) {
+    s[j] = j < Lk ? expf(s[j] - mx) : 0.f;
+    den += s[j];
   }
-  T* orow = out + (int64_t)b * heads * DH + h * DH;
+  const float inv = 1.f / den;
 #pragma unroll
-  for (int u = 0; u < DH / 32; ++u) Elem<T>::store(orow + u * 32 + lane, acc[u]);
+  for (int i = 0; i < PER_LANE; ++i) qv[i] = 0.f;       // the query is no longer needed: reuse as the output accumulator
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < Lk) {
+      const float p = s[j] * inv;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float t[N];
+        Chunk<T>::load(vb + (int64_t)j * ldkv + c * N, t);
+#pragma unroll
+        for (int i = 0; i < N; ++i) qv[c * N + i] = fmaf(p, t[i], qv[c * N + i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    float t[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = qv[c * N + i];
+    Chunk<T>::store(out + b * E + c0 + c * N, t);
+  }
 }
 
 // One warp per crop: logits row (f32, ld >= C) -> output row, argmax (the lowest index wins ties, like torch.max).
@@ -229,11 +331,19 @@ MSTR_EXPORT int mstr_layer_norm(const void* x, const float* gamma, const float* 
   MSTR_REQUIRE(D % 32 == 0 && D <= 1024, MSTR_ERR_UNSUPPORTED, "mstr_layer_norm: D=%d must be a multiple of 32, <= 1024", D);
   const int blocks = (int)ceil_div64(rows * 32, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MSTR_BF16)
-    layer_norm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta,
-                                                             static_cast<__nv_bfloat16*>(out), rows, D, eps);
-  else
-    layer_norm_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, static_cast<float*>(out), rows, D, eps);
+  typedef __nv_bfloat16 bf;
+  const bool al = aligned16(x) && aligned16(out);
+  if (dtype == MSTR_BF16) {
+    if (al && D % 256 == 0)
+      layer_norm_kernel<bf, true><<<blocks, 256, 0, st>>>(static_cast<const bf*>(x), gamma, beta, static_cast<bf*>(out), rows, D, eps);
+    else
+      layer_norm_kernel<bf, false><<<blocks, 256, 0, st>>>(static_cast<const bf*>(x), gamma, beta, static_cast<bf*>(out), rows, D, eps);
+  } else {
+    if (al && D % 128 == 0)
+      layer_norm_kernel<float, true><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, static_cast<float*>(out), rows, D, eps);
+    else
+      layer_norm_kernel<float, false><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, static_cast<float*>(out), rows, D, eps);
+  }
   MSTR_LAUNCH_CHECK("layer_norm_kernel");
   return MSTR_OK;
 }
@@ -283,6 +393,8 @@ MSTR_EXPORT int mstr_mha(const void* q, int ldq, const void* k, const void* v, i
   MSTR_REQUIRE(Lq <= 32 && Lk <= 32 && (dh == 32 || dh == 64), MSTR_ERR_UNSUPPORTED,
                "mstr_mha: Lq=%d, Lk=%d (<= 32), head dim %d (32 or 64)", Lq, Lk, dh);
   MSTR_REQUIRE(!causal || Lq == Lk, MSTR_ERR_BAD_ARG, "mstr_mha: the causal mask needs Lq == Lk");
+  MSTR_REQUIRE(aligned16(k) && aligned16(v) && (ldkv * (dtype == MSTR_BF16 ? 2 : 4)) % 16 == 0, MSTR_ERR_BAD_ARG,
+               "mstr_mha: k / v pointers and row stride must be multiples of 16 bytes");
   const float scale = 1.0f / sqrtf((float)dh);
   const int warps = 4;
   const int blocks = (int)ceil_div64((int64_t)B * heads, warps);
@@ -312,16 +424,21 @@ MSTR_EXPORT int mstr_mha_step(const void* q, int ldq, void* k_cache, void* v_cac
   MSTR_REQUIRE(q && k_cache && v_cache && out, MSTR_ERR_BAD_ARG, "mstr_mha_step: null pointer");
   MSTR_REQUIRE((k_new == nullptr) == (v_new == nullptr), MSTR_ERR_BAD_ARG, "mstr_mha_step: k_new and v_new go together");
   MSTR_REQUIRE(B > 0 && Lk > 0 && heads > 0, MSTR_ERR_BAD_ARG, "mstr_mha_step: bad size");
-  MSTR_REQUIRE(Lk <= 32 && (dh == 32 || dh == 64), MSTR_ERR_UNSUPPORTED, "mstr_mha_step: Lk=%d (<= 32), head dim %d (32 or 64)", Lk, dh);
+  MSTR_REQUIRE(Lk <= 32 && heads == 8 && (dh == 32 || dh == 64), MSTR_ERR_UNSUPPORTED,
+               "mstr_mha_step: Lk=%d (<= 32), %d heads (8), head dim %d (32 or 64)", Lk, heads, dh);
+  const int esz = dtype == MSTR_BF16 ? 2 : 4;
+  MSTR_REQUIRE(aligned16(q) && aligned16(k_cache) && aligned16(v_cache) && aligned16(out) && aligned16(k_new) && aligned16(v_new) &&
+                   (ldq * esz) % 16 == 0 && (ldkv * esz) % 16 == 0 && (kv_batch_stride * esz) % 16 == 0 && (ld_new * esz) % 16 == 0,
+               MSTR_ERR_BAD_ARG, "mstr_mha_step: pointers and strides must be multiples of 16 bytes");
   const float scale = 1.0f / sqrtf((float)dh);
-  const int blocks = (int)ceil_div64((int64_t)B * heads, 4);
+  const int blocks = ceil_div(B, 4);
   cudaStream_t st = (cudaStream_t)stream;
   typedef __nv_bfloat16 bf;
 #define MSTR_MHA_STEP(T, DH)                                                                                          \
-  mha_step_kernel<T, DH><<<blocks, 128, 0, st>>>(static_cast<const T*>(q), ldq, static_cast<T*>(k_cache),             \
-                                                 static_cast<T*>(v_cache), ldkv, kv_batch_stride,                     \
-                                                 static_cast<const T*>(k_new), static_cast<const T*>(v_new), ld_new,  \
-                                                 static_cast<T*>(out), B, Lk, heads, scale)
+  mha_step_kernel<T, DH, 8><<<blocks, 128, 0, st>>>(static_cast<const T*>(q), ldq, static_cast<T*>(k_cache),          \
+                                                    static_cast<T*>(v_cache), ldkv, kv_batch_stride,                  \
+                                                    static_cast<const T*>(k_new), static_cast<const T*>(v_new), ld_new, \
+                                                    static_cast<T*>(out), B, Lk, scale)
   if (dtype == MSTR_BF16) { if (dh == 64) MSTR_MHA_STEP(bf, 64); else MSTR_MHA_STEP(bf, 32); }
   else { if (dh == 64) MSTR_MHA_STEP(float, 64); else MSTR_MHA_STEP(float, 32); }
 #undef MSTR_MHA_STEP

@@ -177,17 +177,13 @@ def test_fp32_stress_config(sd_cfg_s, golden_dir):
 # bf16 throughput mode
 # ------------------------------------------------------------------------------------------------
 def test_bf16_matches_quantisation_matched_oracle(sd_cfg_a):
-    """bf16 tensor-core mode vs (a) the oracle with bf16 rounding inserted at the same points and
-    (b) the plain fp32 oracle.
-
-    North-star tolerance for bf16 mode: logits within 2e-2, ids identical on >= 99.9 % of crops.
-    What is reachable on THESE weights is bounded by conditioning, not by the kernels: the synthetic
-    random-init network has top-1/top-2 margins of ~0.36 x logit std and its untrained sequence model
-    amplifies a feature perturbation ~6x (even TF32 rounding of the conv operands
-    alone flips ids on 28 % of crops).  So the gates below are (1) per-stage error against the
-    matched oracle at the level bf16 storage implies (one bf16 ulp = 0.4 %, ~33 layers), (2) the
-    feedback-free teacher-forced logits, and (3) a floor on greedy-id agreement; the measured figures
-    are printed and recorded in DESIGN.md."""
+    """bf16 tensor-core mode, whole model free running from the crops, vs (a) the oracle with bf16 rounding inserted at
+    the same points and (b) the plain fp32 oracle: a RECORD of how far two bf16 evaluations of this untrained network
+    drift apart, with sanity gates only.  The tight bf16 gates live where rounding history cannot blur them:
+    tests/test_gpu_bf16_layers.py - every conv / linear launch against the rounding-matched function of ITS OWN inputs
+    (100 % of the elements within one bf16 ulp, >= 99 % bit-equal), the sequence model from the GPU's own features
+    against the matched oracle (teacher-forced logits <= 3e-2, greedy ids >= 95 % of the steps) - and
+    tests/test_gpu_reference.py (at least as close to the fp32 reference as the reference's own bf16 autocast run)."""
     B = 32
     x, ov, sc, io = _inputs(B, seed=555)
     ref = orc.forward(sd_cfg_a, x, ov, sc, io, quant="bf16", stages=True)
@@ -215,8 +211,8 @@ def test_bf16_matches_quantisation_matched_oracle(sd_cfg_a):
     print("\nbf16 mode, B=%d: features %.2e (matched) %.2e (fp32) | enc1 %.2e | greedy logits %.2e (matched) "
           "%.2e (fp32) | teacher-forced logits vs fp32 %.2e | ids equal %d/%d (matched) %d/%d (fp32)" %
           (B, r_feat, r_feat32, r_enc, r_log, r_log32, r_tf, same.sum(), B, same32.sum(), B))
-    assert r_tf <= 0.5, "teacher-forced bf16 logits rel err %.3e" % r_tf
-    assert same32.mean() >= 0.35, "greedy ids equal to the fp32 oracle on only %d of %d crops" % (same32.sum(), B)
+    steps32 = float((ids == ref32["ids"]).mean())
+    assert steps32 >= 0.8, "greedy ids equal to the fp32 oracle on only %.3f of the steps" % steps32
 
 
 def test_bf16_stress_config_runs_on_tensor_cores(sd_cfg_s, golden_dir):

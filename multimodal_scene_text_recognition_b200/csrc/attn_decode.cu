@@ -21,6 +21,11 @@
 
 namespace mstr {
 
+// A teacher-forcing token outside [0, C) would index past W_tok (the reference's scatter_ raises, decoders.py:23): it is
+// mapped to 0 = [GO]; the host side validates the text under config.CHECK_INPUTS.
+__device__ __forceinline__ int ad_token(const int64_t t, const int C) { return (t < 0 || t >= C) ? 0 : (int)t; }
+
+
 constexpr int AD_H = 256;
 constexpr int AD_CPT = 4;
 constexpr int AD_BT = 8 * AD_CPT;   // 32 crops per CTA
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(256, 1) attn_decode_kernel(const AttnParams p)
   }
   if (tid < AD_BT) {
     const int crop = blockIdx.x * AD_BT + tid;
-    s_tok[tid] = (p.text && crop < p.B) ? (int)p.text[(size_t)crop * p.steps] : 0;  // [GO] = 0
+    s_tok[tid] = (p.text && crop < p.B) ? ad_token(p.text[(size_t)crop * p.steps], p.C) : 0;  // [GO] = 0
     s_done[tid] = (crop < p.B) ? 0 : 1;
   }
 
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(256, 1) attn_decode_kernel(const AttnParams p)
           } else {
             p.ids[(size_t)crop * p.steps + step] = 0;   // argmax of the zero-initialised logits row
           }
-          s_tok[lrow0 + c] = (p.text && step + 1 < p.steps) ? (int)p.text[(size_t)crop * p.steps + step + 1] : besti;
+          s_tok[lrow0 + c] = (p.text && step + 1 < p.steps) ? ad_token(p.text[(size_t)crop * p.steps + step + 1], p.C) : besti;
         }
       }
     }

@@ -74,6 +74,10 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+// A teacher-forcing token outside [0, C) would index past W_tok (the reference's scatter_ raises, decoders.py:23): it is
+// mapped to 0 = [GO]; the host side validates the text under config.CHECK_INPUTS.
+__device__ __forceinline__ int at_token(const int64_t t, const int C) { return (t < 0 || t >= C) ? 0 : (int)t; }
+
 __device__ __forceinline__ float at_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float at_tanh(float x) { return fmaf(2.f, at_sigmoid(2.f * x), -1.f); }
 
@@ -207,7 +211,7 @@ __device__ __forceinline__ void at_head_logits_epilogue(const DecodeState& s, fl
         }
       }
     }
-    if (step < s.steps) s.tok[my_crop] = s.text ? (int)s.text[(size_t)my_crop * s.steps + step] : my_best;
+    if (step < s.steps) s.tok[my_crop] = s.text ? at_token(s.text[(size_t)my_crop * s.steps + step], s.C) : my_best;
   }
 }
 
@@ -545,7 +549,7 @@ __global__ void decode_init_kernel(const DecodeState s) {
   }
   if (i < 256) s.live[2 + i] = 0;   // PD_DYN_STEPS crop counters of the persistent kernel's attention phase
   if (i < s.B) {
-    s.tok[i] = s.text ? (int)s.text[(size_t)i * s.steps] : 0;
+    s.tok[i] = s.text ? at_token(s.text[(size_t)i * s.steps], s.C) : 0;
     s.done[i] = 0;
     if (s.lengths) s.lengths[i] = s.steps;
   }

@@ -84,6 +84,9 @@ class Attention(nn.Module):
             if text is None:
                 raise ValueError("is_train=True needs the teacher-forcing text (decoders.py:41-50)")
             tokens = text.to(device=encoder_output.device, dtype=torch.int64).contiguous()
+            if config.CHECK_INPUTS and tokens.numel() and (int(tokens.min()) < 0 or int(tokens.max()) >= self.num_classes):
+                raise IndexError("teacher-forcing text holds a token outside [0, %d) (decoders.py:23 scatter_ would raise)"
+                                 % self.num_classes)   # costs a device->host sync: off on the hot path (the kernels map it to 0)
         if (precision == 'bf16' and config.RNN_TENSOR_CORES and self.hidden_size == 256
                 and encoder_output.shape[1] <= 96 and self.num_classes <= 128):
             enc_b = enc_act if enc_act is not None else ops.cast(encoder_output.contiguous(), torch.bfloat16)

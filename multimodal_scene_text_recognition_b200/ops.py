@@ -10,7 +10,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _cabi
+from . import _cabi, config
 from ._cabi import MSTR_BF16, MSTR_F32, check, lib, ptr
 
 
@@ -560,12 +560,16 @@ def resize_to_tensor_u8(pixels: torch.Tensor, offsets: torch.Tensor, sizes_hw: t
         check(lib().mstr_resize_to_tensor_u8(ptr(pixels), ptr(offsets), ptr(sizes_hw), ptr(out), ptr(status), B,
                                              int(out_hw[0]), int(out_hw[1]), int(max_in_hw[0]), int(max_in_hw[1]),
                                              st), "mstr_resize_to_tensor_u8")
+    if config.CHECK_INPUTS:      # costs a device->host sync; pipeline.pack_crops validates the sizes on the host anyway
+        bad = int(status.item())
+        if bad:
+            raise ValueError("crop %d is empty or larger than max_in_hw=%s: its output was filled with NaN" % (bad - 1, tuple(max_in_hw)))
     return out
 
 
 def set_decode_persistent(on=None) -> None:
-    """Driver of the tensor-core decoder: None = by batch size (default: ONE persistent cooperative launch up to 2048
-    crops, the chain of three launches per step beyond), True / False force one.  Bit-identical results."""
+    """Driver of the tensor-core decoder: None / True = ONE persistent cooperative launch for all steps (default),
+    False = the chain of three launches per step (the cross-check).  Bit-identical results."""
     check(lib().mstr_set_decode_persistent(-1 if on is None else int(bool(on))), "mstr_set_decode_persistent")
 
 

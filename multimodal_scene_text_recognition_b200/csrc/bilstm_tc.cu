@@ -334,13 +334,14 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   MSTR_REQUIRE(aligned16(gates_x) && aligned16(w_hh_packed) && aligned16(out_bf16), MSTR_ERR_BAD_ARG,
                "mstr_bilstm_recurrent_bf16: pointers must be 16-byte aligned");
   // Two kernels, chosen by occupancy.  The cluster-cooperative kernel (bilstm_cluster.cu: W_hh stationary, 8 CTAs per
-  // crop tile) has a 4.5x shorter step (3.9 us vs 17.7 us) but the device holds only ~13 of its clusters at once, so it
-  // wins while all (crop tile, direction) pairs fit in one wave - batches up to ~800 crops (B=256: 0.101 vs 0.347 ms);
-  // beyond that this kernel's 64+ independent CTAs are level or ahead (B=4096: 0.463 vs 0.482 ms).
+  // crop tile) has a 4.5x shorter step (3.9 us vs 17.7 us) but the device holds only ~13 of its clusters at once: it
+  // runs in ceil(tiles / 13) waves of ~0.1 ms, while this kernel takes ~0.35-0.43 ms whatever the batch (one CTA per
+  // tile, every CTA walks all T steps).  Measured (ms, cluster / this kernel): 512 crops 0.104 / 0.344, 1024 0.194 /
+  // 0.344, 2048 0.289 / 0.351, 3072 0.386 / 0.386, 4096 0.482 / 0.434 - so the cluster kernel up to three waves.
   // mstr_set_bilstm_kernel forces one (the parity tests run both on the same inputs).
   const int forced = g_bilstm_kernel.load(std::memory_order_relaxed);
   const int tiles = ceil_div(B, LT_M) * 2;
-  const bool use_cluster = forced ? forced == 2 : (tiles <= bilstm_cluster_capacity());
+  const bool use_cluster = forced ? forced == 2 : (tiles <= 3 * bilstm_cluster_capacity());
   if (use_cluster) return bilstm_recurrent_bf16_cluster(gates_x, w_hh_packed, out_bf16, B, T, (cudaStream_t)stream);
   int rc = load_tma_encoders(g_lstm_enc);
   if (rc != MSTR_OK) return rc;

@@ -498,8 +498,8 @@ def bilstm_recurrent_bf16(gates_x: torch.Tensor, w_hh_packed: torch.Tensor) -> t
 
 
 def set_bilstm_kernel(which: str = "auto") -> None:
-    """Tensor-core BiLSTM recurrence: "auto" picks by occupancy (the cluster kernel while every crop tile fits in one
-    wave of clusters, the one-CTA-per-tile kernel beyond); "single" / "cluster" force one (parity tests)."""
+    """Tensor-core BiLSTM recurrence: "auto" picks by occupancy (the cluster kernel while the crop tiles fit in three
+    waves of clusters - ~2400 crops -, the one-CTA-per-tile kernel beyond); "single" / "cluster" force one (parity tests)."""
     check(lib().mstr_set_bilstm_kernel({"auto": 0, "single": 1, "cluster": 2}[which]), "mstr_set_bilstm_kernel")
 
 

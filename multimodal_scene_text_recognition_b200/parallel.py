@@ -47,13 +47,36 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, local_rank, world
 
 
-def allgather_ids(ids: torch.Tensor, lengths: torch.Tensor, batch: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Gather per-rank ``ids [b_r, steps]`` / ``lengths [b_r]`` into the global ``[batch, steps]`` /
-    ``[batch]`` on every rank.  Shards are padded to the common ceil size so one fixed-size
-    collective suffices; ids and lengths travel in ONE buffer (lengths as an extra column)."""
+class PendingGather:
+    """Handle of an ids allgather in flight (``allgather_ids_async``).  The collective runs on the backend's own stream
+    behind the work already enqueued on the caller's stream; ``wait()`` makes the caller's CURRENT stream (not the
+    host) wait for it and returns the global ``(ids [batch, steps], lengths [batch])``.  Until then the caller's
+    stream is free: the next step's forward overlaps the exchange."""
+
+    def __init__(self, work, recv, batch, world, steps, ids, lengths):
+        self._work, self._recv, self._batch, self._world, self._steps = work, recv, batch, world, steps
+        self._local = (ids, lengths)
+
+    def wait(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self._work is None:
+            return self._local
+        self._work.wait()
+        recv, batch, world, steps = self._recv, self._batch, self._world, self._steps
+        per = shard_size(batch, world)
+        if world * per != batch:   # drop the padding rows of short / empty trailing shards
+            keep = torch.cat([torch.arange(r * per, r * per + (shard_bounds(batch, r, world)[1] - shard_bounds(batch, r, world)[0]),
+                                           device=recv.device) for r in range(world)])
+            recv = recv.index_select(0, keep)
+        return recv[:, :steps].contiguous(), recv[:, steps].contiguous()
+
+
+def allgather_ids_async(ids: torch.Tensor, lengths: torch.Tensor, batch: int, group=None) -> PendingGather:
+    """Start gathering per-rank ``ids [b_r, steps]`` / ``lengths [b_r]`` into the global ``[batch, steps]`` / ``[batch]``
+    on every rank.  Shards are padded to the common ceil size so one fixed-size collective suffices; ids and lengths
+    travel in ONE buffer (lengths as an extra column)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return ids, lengths
+        return PendingGather(None, None, batch, 1, ids.shape[1], ids, lengths)
     per = shard_size(batch, world)
     steps = ids.shape[1]
     send = torch.zeros((per, steps + 1), dtype=torch.int32, device=ids.device)
@@ -61,12 +84,13 @@ def allgather_ids(ids: torch.Tensor, lengths: torch.Tensor, batch: int, group=No
     send[:n, :steps] = ids
     send[:n, steps] = lengths
     recv = torch.empty((world * per, steps + 1), dtype=torch.int32, device=ids.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    if world * per != batch:   # drop the padding rows of short / empty trailing shards
-        keep = torch.cat([torch.arange(r * per, r * per + (shard_bounds(batch, r, world)[1] - shard_bounds(batch, r, world)[0]),
-                                       device=ids.device) for r in range(world)])
-        recv = recv.index_select(0, keep)
-    return recv[:, :steps].contiguous(), recv[:, steps].contiguous()
+    work = dist.all_gather_into_tensor(recv, send, group=group, async_op=True)
+    return PendingGather(work, recv, batch, world, steps, ids, lengths)
+
+
+def allgather_ids(ids: torch.Tensor, lengths: torch.Tensor, batch: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Blocking form (on the caller's stream) of ``allgather_ids_async``."""
+    return allgather_ids_async(ids, lengths, batch, group).wait()
 
 
 def recognize_sharded(recognize: Callable[..., Dict[str, torch.Tensor]], image: torch.Tensor,

@@ -31,6 +31,12 @@ def _worker(rank, world, port, B, q):
     ok = torch.equal(res["ids"], full["ids"]) and torch.equal(res["lengths"], full["lengths"])
     lo, hi = res["bounds"]
     ok = ok and torch.equal(res["local_ids"], full["ids"][lo:hi])
+    # the overlapped form: two exchanges in flight, waited for in order
+    h1 = parallel.allgather_ids_async(res["local_ids"], res["local_lengths"], B)
+    h2 = parallel.allgather_ids_async(res["local_ids"] + 1, res["local_lengths"], B)
+    i1, l1 = h1.wait()
+    i2, _ = h2.wait()
+    ok = ok and torch.equal(i1, full["ids"]) and torch.equal(l1, full["lengths"]) and torch.equal(i2, full["ids"] + 1)
     q.put((rank, bool(ok), (lo, hi)))
     dist.destroy_process_group()
 

@@ -150,6 +150,11 @@ int mstr_maxpool2x2_ring_bf16(const void* x_ring, void* out, int B, int H, int W
  * C_in = 32 and C_out = 64 only. */
 int mstr_conv3x3_flat_bf16(const void* x, const void* w, const float* scale_host, const float* shift_host, void* out,
                            int B, int H, int W, int C_in, int C_out, int relu, mstr_stream_t stream);
+/* The same with the 2x2 / stride 2 max-pool that follows it (maxpool1, modules/feature_extraction.py:66,116) in the
+ * epilogue: out is the POOLED plain NHWC activation [B][H/2][W/2][C_out] bf16; the pre-pool tensor never reaches HBM.
+ * Bit-identical to mstr_conv3x3_flat_bf16 followed by mstr_maxpool2x2_ring_bf16.  H, W even; W <= 128 or W % 128 == 0. */
+int mstr_conv3x3_flat_pool_bf16(const void* x, const void* w, const float* scale_host, const float* shift_host, void* out,
+                                int B, int H, int W, int C_in, int C_out, int relu, mstr_stream_t stream);
 /* Test hook of mstr_conv3x3_flat_bf16: 0 (default) leaves the "matrix base offset" field of the row-shifted A
  * descriptors zero - correct on B200, the swizzle is applied to absolute address bits; 1 sets it to the phase of the
  * start address (wrong result; kept as the experiment that pins the rule, tests/test_gpu_kernels.py). */

@@ -33,6 +33,7 @@ SIGNATURES = {
     "mstr_maxpool_nhwc": (c_int, [_P, _P] + [_I] * 11 + [_P]),
     "mstr_maxpool2x2_ring_bf16": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "mstr_conv3x3_flat_bf16": (c_int, [_P, _P, _P, _P, _P] + [_I] * 6 + [_P]),
+    "mstr_conv3x3_flat_pool_bf16": (c_int, [_P, _P, _P, _P, _P] + [_I] * 6 + [_P]),
     "mstr_debug_flat_desc_mode": (c_int, [_I]),
     "mstr_mean_hw": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mstr_mean_h": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

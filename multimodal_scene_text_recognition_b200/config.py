@@ -73,6 +73,9 @@ CONV_PIXEL_PAIRS = True
 # Applies when conv0_1 reads the image (C_in <= 4) and conv0_2 is 32 -> 64, 3x3 / 1 / 1; otherwise (and when False)
 # conv0_2 takes the pixel-pair path above.
 CONV0_FLAT = True
+# with CONV0_FLAT: maxpool1 runs in the epilogue of conv0_2 (tiles of two image rows), so the pre-pool activation never
+# reaches HBM; bit-identical to the two separate launches (False).
+CONV0_POOL_FUSED = True
 # bf16 mode only: compute a BasicBlock's conv2/bn2, its 1x1 downsample conv/bn, the residual add and the ReLU as
 # one GEMM (weights concatenated along K, BatchNorm scales folded into the bf16 weights).
 FUSE_DOWNSAMPLE = True

@@ -168,8 +168,12 @@ class ResNet(nn.Module):
             w, scale, shift = pack_first_conv(self.conv0_1, self.bn0_1)
             h = ops.conv3x3_first(x, w, scale, shift, torch.bfloat16, pool=False, ring=True)
             w, scale, shift = pack_conv_flat(c2, self.bn0_2)
-            h = ops.conv3x3_flat(h, w, scale, shift, relu=True)
-            h = ops.maxpool2x2_ring(h)
+            W = x.shape[3]
+            if config.CONV0_POOL_FUSED and (W <= 128 or W % 128 == 0):
+                h = ops.conv3x3_flat_pool(h, w, scale, shift, relu=True)      # maxpool1 in the epilogue
+            else:
+                h = ops.conv3x3_flat(h, w, scale, shift, relu=True)
+                h = ops.maxpool2x2_ring(h)
         else:
             if x.shape[1] <= 4:
                 w, scale, shift = pack_first_conv(self.conv0_1, self.bn0_1)

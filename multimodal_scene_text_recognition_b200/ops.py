@@ -209,6 +209,26 @@ def conv3x3_flat(x_ring: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Te
     return out
 
 
+def conv3x3_flat_pool(x_ring: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+                      relu: bool = True) -> torch.Tensor:
+    """conv3x3_flat followed by the 2x2 / stride 2 max-pool, in one kernel: x_ring [B,H+2,W+2,Cin] (zero ring) ->
+    POOLED plain NHWC [B,H/2,W/2,Cout] bf16.  Bit-identical to maxpool2x2_ring(conv3x3_flat(...))."""
+    _req(x_ring, "x_ring", torch.bfloat16); _req(w, "w", torch.bfloat16)
+    B, Hp, Wp, Cin = x_ring.shape
+    Cout = w.shape[0]
+    assert w.shape == (Cout, 3, 3, Cin) and Hp > 2 and Wp > 2
+    for name, t in (("scale", scale), ("shift", shift)):
+        if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != Cout):
+            raise TypeError("conv3x3_flat_pool: %s must be a contiguous host f32 tensor of %d values" % (name, Cout))
+    H, W = Hp - 2, Wp - 2
+    out = torch.empty((B, H // 2, W // 2, Cout), device=x_ring.device, dtype=torch.bfloat16)
+    with _timed("conv3x3_flat", 2.0 * B * H * W * Cout * 9 * Cin, "flop",
+                "M=%d (B%d %dx%d) %d->%d 3x3, padded-flat, + 2x2 max-pool" % (B * H * W, B, H, W, Cin, Cout)), _on(x_ring, w) as st:
+        check(lib().mstr_conv3x3_flat_pool_bf16(ptr(x_ring), ptr(w), ptr(scale), ptr(shift), ptr(out), B, H, W, Cin, Cout,
+                                                int(relu), st), "mstr_conv3x3_flat_pool_bf16")
+    return out
+
+
 def flat_desc_mode(mode: int) -> None:
     """Test hook of conv3x3_flat (mstr_debug_flat_desc_mode): 0 = base-offset field left zero (default, correct on
     B200), 1 = set to the phase of the start address (wrong: kept as the experiment that pins the hardware rule)."""

@@ -54,7 +54,7 @@ class OpRecorder:
     """Record every call of the listed ``ops`` front ends (positional / keyword arguments and result) while a
     model runs: the per-layer parity tests re-evaluate each recorded launch with the oracle ON THE GPU PATH'S OWN
     INPUTS, so a layer is checked in isolation from the rounding history upstream of it."""
-    NAMES = ("conv3x3_first", "conv3x3_flat", "conv_gemm", "conv_gemm_dual", "maxpool_nhwc", "maxpool2x2_ring",
+    NAMES = ("conv3x3_first", "conv3x3_flat", "conv3x3_flat_pool", "conv_gemm", "conv_gemm_dual", "maxpool_nhwc", "maxpool2x2_ring",
              "bilstm_recurrent_bf16", "attn_decode_bf16", "mean_h")
 
     def __init__(self, names=None):

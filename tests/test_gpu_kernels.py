@@ -305,6 +305,14 @@ def test_padded_flat_conv_path(B, cin, H, W):
     ref_pool = ops.maxpool_nhwc(out[:, 1:-1, 1:-1].contiguous(), (2, 2), (2, 2), (0, 0))
     torch.cuda.synchronize()
     assert torch.equal(pooled, ref_pool)
+    # conv0_2 with maxpool1 in its epilogue (tiles of two image rows): bit-identical to the two launches
+    if W <= 128 or W % 128 == 0:
+        s2h, b2h = torch.from_numpy(s2), torch.from_numpy(b2)
+        two = ops.maxpool2x2_ring(ops.conv3x3_flat(ring, dev(w2, bf), s2h, b2h, relu=True))
+        fused = ops.conv3x3_flat_pool(ring, dev(w2, bf), s2h, b2h, relu=True)
+        torch.cuda.synchronize()
+        assert tuple(fused.shape) == (B, H // 2, W // 2, 64)
+        assert torch.equal(fused, two), "fused conv0_2 + maxpool differs from conv3x3_flat + maxpool2x2_ring"
 
 
 def test_padded_flat_conv_descriptor_base_offset():

@@ -303,6 +303,9 @@ int mstr_mha(const void* q, int ldq, const void* k, const void* v, int ldkv, voi
 int mstr_mha_step(const void* q, int ldq, void* k_cache, void* v_cache, int ldkv, int64_t kv_batch_stride,
                   const void* k_new, const void* v_new, int ld_new, void* out, int B, int Lk, int heads, int dh,
                   int dtype, mstr_stream_t stream);
+/* Exact GELU, 0.5 x (1 + erf(x / sqrt(2))): the activation of BertModel's intermediate layer (the reference's Oscar_Bert,
+ * modules/encoders.py:34-66).  x, out [n] of `dtype` (may alias); n a multiple of 8 (bf16) / 4 (f32). */
+int mstr_gelu(const void* x, void* out, int64_t n, int dtype, mstr_stream_t stream);
 /* t_output[-1].max(1) of the greedy loop (decoders.py:276-279): logits [B][ld] f32 (ld >= C; columns >= C ignored);
  * copies the C logits of crop b to logits_out + b*out_row_stride (optional), stores the argmax (lowest index on ties)
  * to ids[b*ids_row_stride] and next_tok[b*next_stride] (both optional). */

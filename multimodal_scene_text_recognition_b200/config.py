@@ -3,7 +3,7 @@
 The modules read these attributes at call time exactly where the reference does
 (``MAX_TEXT_LENGTH`` in Attention.forward, decoders.py:34; ``SEMANTIC_VECTOR`` in
 Linear_Embedding.forward, semantic_vectors.py:35-47; ``ENCODER`` in Model.forward, model.py:99).
-The LSTM/LSTM recognition path is the hot path (SURVEY.md 8 a-e); 'Transformer' encoder with the 'Transformer' or
+The LSTM/LSTM recognition path is the hot path (SURVEY.md 8 a-e); 'Transformer' (or 'Oscar') encoder with the 'Transformer' or
 'Linear' decoder (the reference's own defaults) is the widening row f4.  The attributes of the fusion experiments
 are kept so that code reading them does not break; turning one on raises NotImplementedError.
 """
@@ -23,7 +23,7 @@ MAX_TEXT_LENGTH = 25
 CHARS = string.printable[:-6]
 MODEL_SAVE_THRESHOLD = 0
 
-ENCODER = 'LSTM'   # LSTM | Transformer   ('Oscar' raises)          - the reference defaults to 'Transformer'
+ENCODER = 'LSTM'   # LSTM | Transformer | Oscar                      - the reference defaults to 'Transformer'
 DECODER = 'LSTM'   # LSTM | Transformer | Linear                     - the reference defaults to 'Transformer'
 
 EMBED_DIM = 256

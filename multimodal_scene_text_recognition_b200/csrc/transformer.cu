@@ -13,6 +13,7 @@
 //                          (decoders.py:250-279 recomputes every earlier position at every step; with the causal
 //                          mask those rows do not change, so the cache gives the same numbers) and the
 //                          memory attention (decoders.py:450-451); one warp per crop, every row one coalesced request
+//   gelu_kernel            exact (erf) GELU of BERT's intermediate layer (encoders.py:34-66 via transformers' BertModel)
 //   argmax_tokens_kernel   t_output[-1].max(1), targets[t+1] = char_index, output[t] = t_output[t] (decoders.py:276-279)
 //
 // All arithmetic is fp32; T = float (parity modes) or __nv_bfloat16 (throughput mode) is the storage type.
@@ -46,8 +47,11 @@ template <> struct Chunk<__nv_bfloat16> {
   }
 };
 
-// One warp per row.  VEC: every lane owns D / 32 CONSECUTIVE channels and moves them in 16-byte chunks (D a multiple of
-// 32 chunks); otherwise lane-strided scalar accesses.
+// One warp per row.  VEC (D a multiple of 32 16-byte chunks): chunk c of lane l is elements (c * 32 + l) * N ..., so every
+// load / store instruction of the warp covers 512 consecutive bytes - of x, of the output AND of gamma / beta (float4).
+// (A first version gave every lane D / 32 consecutive channels and read gamma / beta with scalar loads at a 64-byte
+// lane stride: 32 L1 wavefronts per instruction, 229 us for [106496 x 512] where the traffic needs 30.)  Otherwise
+// lane-strided scalar accesses.
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -59,14 +63,13 @@ layer_norm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, cons
   const T* xr = x + row * D;
   float v[32];                                            // D <= 1024
   const int n = D >> 5;                                   // channels per lane
-  auto channel = [&](int i) { return VEC ? lane * n + i : i * 32 + lane; };
   float s = 0.f;
   if (VEC) {
 #pragma unroll
     for (int c = 0; c < 32 / N; ++c)
       if (c * N < n) {
         float t[N];
-        Chunk<T>::load(xr + lane * n + c * N, t);
+        Chunk<T>::load(xr + (c * 32 + lane) * N, t);
 #pragma unroll
         for (int u = 0; u < N; ++u) { v[c * N + u] = t[u]; s += t[u]; }
       }
@@ -86,25 +89,30 @@ layer_norm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, cons
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)D + eps);         // biased variance, like torch
   T* orow = out + row * D;
-#pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (i < n) {
-      const int c = channel(i);
-      v[i] = fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c));
-    }
   if (VEC) {
 #pragma unroll
     for (int c = 0; c < 32 / N; ++c)
       if (c * N < n) {
+        const int e0 = (c * 32 + lane) * N;
         float t[N];
 #pragma unroll
-        for (int u = 0; u < N; ++u) t[u] = v[c * N + u];
-        Chunk<T>::store(orow + lane * n + c * N, t);
+        for (int u = 0; u < N; u += 4) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + e0 + u));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + e0 + u));
+          t[u] = fmaf((v[c * N + u] - mean) * rstd, g.x, bb.x);
+          t[u + 1] = fmaf((v[c * N + u + 1] - mean) * rstd, g.y, bb.y);
+          t[u + 2] = fmaf((v[c * N + u + 2] - mean) * rstd, g.z, bb.z);
+          t[u + 3] = fmaf((v[c * N + u + 3] - mean) * rstd, g.w, bb.w);
+        }
+        Chunk<T>::store(orow + e0, t);
       }
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (i < n) Elem<T>::store(orow + i * 32 + lane, v[i]);
+      if (i < n) {
+        const int c = i * 32 + lane;
+        Elem<T>::store(orow + c, fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c)));
+      }
   }
 }
 
@@ -165,8 +173,19 @@ mha_full_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, const
   if (lane >= Lq) return;
   const T* qr = q + ((int64_t)b * Lq + lane) * ldq + h * DH;
   float acc[DH];
+  {
+    constexpr int N = Chunk<T>::N;
 #pragma unroll
-  for (int d = 0; d < DH; ++d) acc[d] = Elem<T>::load(qr + d) * scale;   // q is scaled first, like torch
+    for (int c = 0; c < DH / N; ++c) {
+      float t[N];
+      Chunk<T>::load(qr + c * N, t);
+#pragma unroll
+      for (int u = 0; u < N; ++u) acc[c * N + u] = t[u] * scale;         // q is scaled first, like torch
+    }
+  }
+  // K / V rows are read from shared memory as float4 (all lanes the same address: one broadcast wavefront per 16 bytes)
+  const float4* sk4 = reinterpret_cast<const float4*>(sk);
+  const float4* sv4 = reinterpret_cast<const float4*>(sv);
   float s[32];
   float mx = -INFINITY;
   const int last = causal ? lane : Lk - 1;
@@ -174,9 +193,16 @@ mha_full_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, const
   for (int j = 0; j < 32; ++j) {
     s[j] = -INFINITY;
     if (j < Lk && j <= last) {
-      float a = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four partial sums: shorter dependent chains
 #pragma unroll
-      for (int d = 0; d < DH; ++d) a = fmaf(acc[d], sk[j * DH + d], a);
+      for (int d = 0; d < DH / 4; ++d) {
+        const float4 kv = sk4[j * (DH / 4) + d];
+        a0 = fmaf(acc[4 * d], kv.x, a0);
+        a1 = fmaf(acc[4 * d + 1], kv.y, a1);
+        a2 = fmaf(acc[4 * d + 2], kv.z, a2);
+        a3 = fmaf(acc[4 * d + 3], kv.w, a3);
+      }
+      const float a = (a0 + a1) + (a2 + a3);
       s[j] = a;
       mx = fmaxf(mx, a);
     }
@@ -195,12 +221,24 @@ mha_full_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, const
     if (j < Lk && j <= last) {
       const float p = s[j] * inv;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, sv[j * DH + d], acc[d]);
+      for (int d = 0; d < DH / 4; ++d) {
+        const float4 vv = sv4[j * (DH / 4) + d];
+        acc[4 * d] = fmaf(p, vv.x, acc[4 * d]);
+        acc[4 * d + 1] = fmaf(p, vv.y, acc[4 * d + 1]);
+        acc[4 * d + 2] = fmaf(p, vv.z, acc[4 * d + 2]);
+        acc[4 * d + 3] = fmaf(p, vv.w, acc[4 * d + 3]);
+      }
     }
   }
   T* orow = out + ((int64_t)b * Lq + lane) * heads * DH + h * DH;
+  constexpr int N = Chunk<T>::N;
 #pragma unroll
-  for (int d = 0; d < DH; ++d) Elem<T>::store(orow + d, acc[d]);
+  for (int c = 0; c < DH / N; ++c) {
+    float t[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) t[u] = acc[c * N + u];
+    Chunk<T>::store(orow + c * N, t);
+  }
 }
 
 // ONE query per crop.  One warp per crop covers all heads: the E = heads * DH channels of a row are split over the 32
@@ -292,6 +330,20 @@ mha_step_kernel(const T* __restrict__ q, int ldq, T* __restrict__ kc, T* __restr
   }
 }
 
+// y = 0.5 x (1 + erf(x / sqrt(2))), 16 bytes per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+gelu_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t chunks) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= chunks) return;
+  constexpr int N = Chunk<T>::N;
+  float v[N];
+  Chunk<T>::load(x + i * N, v);
+#pragma unroll
+  for (int u = 0; u < N; ++u) v[u] = 0.5f * v[u] * (1.f + erff(v[u] * 0.70710678118654752f));
+  Chunk<T>::store(out + i * N, v);
+}
+
 // One warp per crop: logits row (f32, ld >= C) -> output row, argmax (the lowest index wins ties, like torch.max).
 __global__ void __launch_bounds__(256)
 argmax_tokens_kernel(const float* __restrict__ logits, int ld, float* __restrict__ logits_out, int64_t out_row_stride,
@@ -332,7 +384,7 @@ MSTR_EXPORT int mstr_layer_norm(const void* x, const float* gamma, const float* 
   const int blocks = (int)ceil_div64(rows * 32, 256);
   cudaStream_t st = (cudaStream_t)stream;
   typedef __nv_bfloat16 bf;
-  const bool al = aligned16(x) && aligned16(out);
+  const bool al = aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta);
   if (dtype == MSTR_BF16) {
     if (al && D % 256 == 0)
       layer_norm_kernel<bf, true><<<blocks, 256, 0, st>>>(static_cast<const bf*>(x), gamma, beta, static_cast<bf*>(out), rows, D, eps);
@@ -393,8 +445,9 @@ MSTR_EXPORT int mstr_mha(const void* q, int ldq, const void* k, const void* v, i
   MSTR_REQUIRE(Lq <= 32 && Lk <= 32 && (dh == 32 || dh == 64), MSTR_ERR_UNSUPPORTED,
                "mstr_mha: Lq=%d, Lk=%d (<= 32), head dim %d (32 or 64)", Lq, Lk, dh);
   MSTR_REQUIRE(!causal || Lq == Lk, MSTR_ERR_BAD_ARG, "mstr_mha: the causal mask needs Lq == Lk");
-  MSTR_REQUIRE(aligned16(k) && aligned16(v) && (ldkv * (dtype == MSTR_BF16 ? 2 : 4)) % 16 == 0, MSTR_ERR_BAD_ARG,
-               "mstr_mha: k / v pointers and row stride must be multiples of 16 bytes");
+  MSTR_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out) && (ldkv * (dtype == MSTR_BF16 ? 2 : 4)) % 16 == 0 &&
+                   (ldq * (dtype == MSTR_BF16 ? 2 : 4)) % 16 == 0, MSTR_ERR_BAD_ARG,
+               "mstr_mha: pointers and row strides must be multiples of 16 bytes");
   const float scale = 1.0f / sqrtf((float)dh);
   const int warps = 4;
   const int blocks = (int)ceil_div64((int64_t)B * heads, warps);
@@ -443,6 +496,23 @@ MSTR_EXPORT int mstr_mha_step(const void* q, int ldq, void* k_cache, void* v_cac
   else { if (dh == 64) MSTR_MHA_STEP(float, 64); else MSTR_MHA_STEP(float, 32); }
 #undef MSTR_MHA_STEP
   MSTR_LAUNCH_CHECK("mha_step_kernel");
+  return MSTR_OK;
+}
+
+MSTR_EXPORT int mstr_gelu(const void* x, void* out, int64_t n, int dtype, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(x && out, MSTR_ERR_BAD_ARG, "mstr_gelu: null pointer");
+  const int per = dtype == MSTR_BF16 ? 8 : 4;
+  MSTR_REQUIRE(n > 0 && n % per == 0 && aligned16(x) && aligned16(out), MSTR_ERR_BAD_ARG,
+               "mstr_gelu: n must be a positive multiple of %d, pointers 16-byte aligned", per);
+  const int64_t chunks = n / per;
+  const int blocks = (int)ceil_div64(chunks, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MSTR_BF16)
+    gelu_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), chunks);
+  else
+    gelu_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(out), chunks);
+  MSTR_LAUNCH_CHECK("gelu_kernel");
   return MSTR_OK;
 }
 

@@ -12,7 +12,7 @@ reference's; neither container's own forward is ever called.  The work is three 
 3. Linear(2H -> out) + bias - GEMM.
 
 The transformer encoder of the reference (encoders.py:68-243) is mirrored in modules/transformer.py and re-exported
-here; ``Oscar_Bert`` (encoders.py:34-66, a BERT-base encoder) resolves and raises.
+here, like ``Oscar_Bert`` (encoders.py:34-66, a BERT-base encoder).
 """
 from __future__ import annotations
 
@@ -76,19 +76,5 @@ class BidirectionalLSTM(nn.Module):
         return self.forward_features(col_feats, want_f32=True, want_act=False)
 
 
-class _OutOfScope(nn.Module):
-    _what = ""
-
-    def __init__(self, *args, **kwargs):
-        super().__init__()
-        raise NotImplementedError(
-            "%s belongs to the reference's Oscar / BERT experiment (%s, 'No pretrained models yet' in its config.py:46); "
-            "this repository implements the LSTM and the transformer encoders" % (type(self).__name__, self._what))
-
-
-class Oscar_Bert(_OutOfScope):
-    _what = "modules/encoders.py:34-66"
-
-
-# the transformer encoder family lives in modules/transformer.py; the reference defines these names in this module
-from .transformer import TF_Encoder, PositionalEncoding, TransformerEncoderLayer, MLP  # noqa: E402,F401
+# the transformer / BERT encoder families live in modules/transformer.py; the reference defines these names in this module
+from .transformer import TF_Encoder, Oscar_Bert, PositionalEncoding, TransformerEncoderLayer, MLP  # noqa: E402,F401

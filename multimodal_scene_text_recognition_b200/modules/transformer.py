@@ -21,6 +21,8 @@ Two things differ from the reference's code, neither in the numbers it defines:
   raises TypeError here.  What it computes under the torch it was written for is layers in order, then ``norm`` -
   that is what ``TF_Encoder`` does (and what the golden fixtures drive the reference's layer objects with).
 
+``Oscar_Bert`` (encoders.py:34-66) is mirrored too (BERT-base over the column features).
+
 Eval mode only (dropout is the identity); the fusion experiments (PRE_ENCODER_MLP, OSCAR_ENCODER, PRE_DECODER_MLP,
 CLS_DECODER_INIT, MULTIHEAD_*, POST_DECODER_MLP) raise NotImplementedError at construction.
 """
@@ -404,6 +406,80 @@ class Linear_Decoder(nn.Module):
 
     def forward(self, encoder_output, text, semantics, is_train):
         return self.decode(encoder_output, text, is_train)["logits"]
+
+
+class Oscar_Bert(nn.Module):
+    """BERT-base encoder over the column features (encoders.py:34-66): ``hid_to_bert`` (512 -> 768), a randomly
+    initialised ``transformers.BertModel(BertConfig())`` fed through ``inputs_embeds`` (12 post-norm layers, 12 heads x
+    64, exact-erf GELU feed-forward of 3072, LayerNorm eps 1e-12), ``bert_to_hid`` (768 -> 512).  ``bert_model`` is kept
+    as the parameter container (203 state-dict tensors, the reference's names; its word-embedding table and pooler are
+    never used, as in the reference); its forward is not called.  ``config.OSCAR_ENCODER`` (concatenating the semantic
+    vectors with segment ids, "No pretrained models yet", config.py:46) is one of the fusion switches: it raises."""
+
+    def __init__(self):
+        super(Oscar_Bert, self).__init__()
+        _no_fusion('OSCAR_ENCODER')
+        from transformers import BertConfig, BertModel      # what the reference imports (encoders.py:32)
+        self.bert_config = BertConfig()
+        self.bert_model = BertModel(self.bert_config)
+        self.hid_to_bert = nn.Linear(512, 768)
+        self.bert_to_hid = nn.Linear(768, 512)
+
+    def _packed(self, precision: str):
+        bm = self.bert_model
+        src = [p for p in bm.encoder.parameters()] + [bm.embeddings.position_embeddings.weight,
+                                                      bm.embeddings.token_type_embeddings.weight,
+                                                      bm.embeddings.LayerNorm.weight, bm.embeddings.LayerNorm.bias,
+                                                      self.hid_to_bert.weight, self.hid_to_bert.bias,
+                                                      self.bert_to_hid.weight, self.bert_to_hid.bias]
+
+        def build():
+            emb = bm.embeddings
+            layers = []
+            for lyr in bm.encoder.layer:
+                a = lyr.attention
+                w_qkv = torch.cat([_f(a.self.query.weight), _f(a.self.key.weight), _f(a.self.value.weight)], 0)
+                b_qkv = torch.cat([_f(a.self.query.bias), _f(a.self.key.bias), _f(a.self.value.bias)], 0)
+                layers.append({
+                    "w_qkv": wrap_weight(w_qkv, precision), "b_qkv": b_qkv.contiguous(),
+                    "w_o": wrap_weight(_f(a.output.dense.weight), precision), "b_o": _f(a.output.dense.bias),
+                    "n1": _ln(a.output.LayerNorm),
+                    "w1": wrap_weight(_f(lyr.intermediate.dense.weight), precision), "b1": _f(lyr.intermediate.dense.bias),
+                    "w2": wrap_weight(_f(lyr.output.dense.weight), precision), "b2": _f(lyr.output.dense.bias),
+                    "n2": _ln(lyr.output.LayerNorm)})
+            # inputs_embeds + token_type_embeddings[0] + position_embeddings[t] (BertEmbeddings.forward with
+            # token_type_ids = None -> zeros, position ids 0..T-1): one table, one fp32 add on the host side
+            table = (_f(emb.position_embeddings.weight) + _f(emb.token_type_embeddings.weight)[0][None, :]).contiguous()
+            return {"layers": layers, "table": table, "n0": _ln(emb.LayerNorm),
+                    "w_in": wrap_weight(_f(self.hid_to_bert.weight), precision), "b_in": _f(self.hid_to_bert.bias),
+                    "w_out": wrap_weight(_f(self.bert_to_hid.weight), precision), "b_out": _f(self.bert_to_hid.bias)}
+        return cached(self, ("oscar", precision), src, build)
+
+    def forward_features(self, col_feats: torch.Tensor) -> torch.Tensor:
+        """[B, T, 512] (f32 or activation dtype) -> [B, T, 512] in the activation dtype."""
+        require_inference(col_feats)
+        if self.training:
+            raise RuntimeError("Oscar_Bert is in train mode: dropout is not implemented - call model.eval()")
+        cfg = self.bert_config
+        if cfg.hidden_act != "gelu" or getattr(cfg, "position_embedding_type", "absolute") != "absolute":
+            raise NotImplementedError("only the default BertConfig (gelu, absolute positions) is implemented")
+        precision = config.PRECISION
+        dt = act_dtype(precision)
+        pk = self._packed(precision)
+        heads = cfg.num_attention_heads
+        x = ops.linear(ops.cast(col_feats.contiguous(), dt), pk["w_in"], pk["b_in"])          # hid_to_bert
+        E = x.shape[-1]
+        x = ops.layer_norm(ops.add_pos_encoding(x, pk["table"], dt), *pk["n0"])               # BertEmbeddings
+        for lp in pk["layers"]:
+            qkv = ops.linear(x, lp["w_qkv"], lp["b_qkv"])
+            att = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], heads)
+            x = ops.layer_norm(ops.linear(att, lp["w_o"], lp["b_o"], residual=x), *lp["n1"])  # BertSelfOutput
+            h = ops.gelu_(ops.linear(x, lp["w1"], lp["b1"]))                                  # BertIntermediate
+            x = ops.layer_norm(ops.linear(h, lp["w2"], lp["b2"], residual=x), *lp["n2"])      # BertOutput
+        return ops.linear(x, pk["w_out"], pk["b_out"])                                        # bert_to_hid
+
+    def forward(self, col_feats, semantics, is_train):
+        return ops.cast(self.forward_features(col_feats), torch.float32)
 
 
 def _lengths(ids: torch.Tensor) -> torch.Tensor:

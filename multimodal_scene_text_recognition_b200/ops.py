@@ -457,6 +457,14 @@ def mha_step(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, Lk: 
     return out
 
 
+def gelu_(x: torch.Tensor) -> torch.Tensor:
+    """Exact (erf) GELU in place."""
+    _req(x, "x")
+    with _on(x) as st:
+        check(lib().mstr_gelu(ptr(x), ptr(x), x.numel(), _dt(x), st), "mstr_gelu")
+    return x
+
+
 def argmax_tokens(logits: torch.Tensor, C: int, logits_out: Optional[torch.Tensor], ids: Optional[torch.Tensor],
                   next_tok: Optional[torch.Tensor]) -> None:
     """logits [B,ld] f32; logits_out / ids / next_tok are (strided) views with one row / element per crop."""

@@ -444,3 +444,15 @@ def make_state_dict_transformer(seed: int = 999, decoder: str = "Transformer", g
             raise KeyError(kind)
         out[name] = np.ascontiguousarray(v, dtype=np.float32)
     return out
+
+
+def perturb_parameters_(module, seed: int, scale: float = 0.05) -> None:
+    """In place: add seeded noise (numpy PCG64, ``scale`` x standard normal) to every floating-point parameter of a torch
+    module, in ``named_parameters()`` order.  Used on both sides of the Oscar_Bert parity fixture: BertModel's default
+    init leaves every bias at 0 and every LayerNorm at (1, 0), which would leave those code paths untested."""
+    import torch
+    rng = np.random.Generator(np.random.PCG64(seed))
+    with torch.no_grad():
+        for _name, p in module.named_parameters():
+            if p.is_floating_point():
+                p.add_(torch.from_numpy((rng.standard_normal(tuple(p.shape)) * scale).astype(np.float32)).to(p.device, p.dtype))

@@ -145,3 +145,39 @@ def tf_decoder(enc, sd, max_len=25, text: Optional[np.ndarray] = None, dt=np.flo
 def linear_decoder(enc, sd, dt=np.float32, prefix="decoder."):
     """Linear_Decoder.forward (decoders.py:293-295)."""
     return linear(enc.astype(dt), sd[prefix + "linear_decoder.weight"].astype(dt), sd[prefix + "linear_decoder.bias"].astype(dt))
+
+
+def gelu(x):
+    """transformers' "gelu": x * 0.5 * (1 + erf(x / sqrt(2)))."""
+    from scipy.special import erf
+    return (x * 0.5 * (1.0 + erf(x / np.sqrt(2.0)))).astype(x.dtype)
+
+
+def oscar_bert(col_feats, sd, dt=np.float32, prefix="encoder.", heads=12, layers=12, eps=1e-12):
+    """Oscar_Bert.forward with OSCAR_ENCODER off (encoders.py:47-66): hid_to_bert, BertModel(inputs_embeds=...) -
+    transformers' BertEmbeddings (inputs + token_type_embeddings[0] + position_embeddings[:T], LayerNorm), twelve
+    post-norm BertLayers (separate query / key / value Linears, exact GELU) - and bert_to_hid on the last hidden state."""
+    g = lambda k: sd[prefix + k].astype(dt)
+
+    def ln(x, name):
+        mu = x.mean(-1, keepdims=True)
+        var = ((x - mu) ** 2).mean(-1, keepdims=True)
+        return (x - mu) / np.sqrt(var + dt(eps)) * g(name + ".weight") + g(name + ".bias")
+    dt = np.dtype(dt).type
+    x = linear(col_feats.astype(dt), g("hid_to_bert.weight"), g("hid_to_bert.bias"))
+    B, T, E = x.shape
+    dh = E // heads
+    x = x + g("bert_model.embeddings.token_type_embeddings.weight")[0] + g("bert_model.embeddings.position_embeddings.weight")[None, :T]
+    x = ln(x, "bert_model.embeddings.LayerNorm")
+    for i in range(layers):
+        p = "bert_model.encoder.layer.%d." % i
+        q = linear(x, g(p + "attention.self.query.weight"), g(p + "attention.self.query.bias"))
+        k = linear(x, g(p + "attention.self.key.weight"), g(p + "attention.self.key.bias"))
+        v = linear(x, g(p + "attention.self.value.weight"), g(p + "attention.self.value.bias"))
+        split = lambda t: t.reshape(B, T, heads, dh).transpose(0, 2, 1, 3)
+        s = (split(q) @ split(k).transpose(0, 1, 3, 2)) * dt(1.0 / np.sqrt(dh))
+        ctx = (softmax(s, -1) @ split(v)).transpose(0, 2, 1, 3).reshape(B, T, E)
+        x = ln(linear(ctx, g(p + "attention.output.dense.weight"), g(p + "attention.output.dense.bias")) + x, p + "attention.output.LayerNorm")
+        h = gelu(linear(x, g(p + "intermediate.dense.weight"), g(p + "intermediate.dense.bias")))
+        x = ln(linear(h, g(p + "output.dense.weight"), g(p + "output.dense.bias")) + x, p + "output.LayerNorm")
+    return linear(x, g("bert_to_hid.weight"), g("bert_to_hid.bias"))

@@ -100,9 +100,8 @@ def test_module_interface_matches_reference_contract(sd_cfg_a):
     fresh = transformation.LocalizationNetwork(20, 1)
     assert not fresh.localization_fc2.weight.any()
     assert np.allclose(fresh.localization_fc2.bias.detach().numpy(), synth.rare_fiducial_bias(20))
-    # the Oscar / BERT encoder stays out of scope (the name resolves and raises); the transformer family is built
-    with pytest.raises(NotImplementedError):
-        encoders.Oscar_Bert()
+    # the transformer / BERT families are built (modules/transformer.py); the fusion switches raise
+    assert sig(encoders.Oscar_Bert.forward) == ["self", "col_feats", "semantics", "is_train"]
     assert sig(encoders.TF_Encoder.forward) == ["self", "col_feats", "semantics", "is_train"]
     assert sig(decoders.TF_Decoder.__init__) == ["self", "num_classes"]
     assert sig(decoders.TF_Decoder.forward) == ["self", "encoder_output", "text", "semantics", "is_train"]

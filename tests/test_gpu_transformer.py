@@ -220,3 +220,34 @@ def test_bf16_mode_against_reference(tf_config, sd_tf, g_tf):
           "steps before the first thin margin" % (r_enc, r_tf, (ids == ref).mean(), agree, total))
     assert agree == total
     assert (ids == ref).mean() > 0.5
+
+
+# ------------------------------------------------------------------------------------------------
+# Oscar / BERT encoder
+# ------------------------------------------------------------------------------------------------
+def test_gelu_kernel():
+    r = rng(6)
+    x = (r.standard_normal((1000, 3072)) * 2).astype(np.float32)
+    ref = tfo.gelu(x.astype(np.float64))
+    assert_close(host(ops.gelu_(dev(x))), ref, 2e-6, "gelu f32")
+    xb = orc.round_bf16(x)
+    assert_close(host(ops.gelu_(dev(xb, BF))), tfo.gelu(xb.astype(np.float64)), 5e-3, "gelu bf16")
+
+
+def test_oscar_bert_matches_reference_golden(tf_config, golden_dir):
+    """Oscar_Bert (hid_to_bert -> transformers.BertModel through inputs_embeds -> bert_to_hid) rebuilt from the two
+    seeds of the fixture, against the output of the reference's own class."""
+    from multimodal_scene_text_recognition_b200.modules.encoders import Oscar_Bert
+    g = np.load(os.path.join(golden_dir, "cfg_oscar.npz"))
+    torch.manual_seed(999)
+    m = Oscar_Bert().eval()
+    synth.perturb_parameters_(m, 1234)
+    m = m.to(DEV)
+    for precision, tol in (("fp32", 1e-4), ("tf32", 1e-4), ("bf16", 6e-2)):
+        config.PRECISION = precision
+        with torch.no_grad():
+            y = m.forward_features(dev(g["x"]))
+            y2 = m(dev(g["x"]), None, False)
+        r = assert_close(host(y), g["y"], tol, "Oscar_Bert (%s)" % precision)
+        assert y2.dtype == torch.float32 and torch.equal(y2, y.float())
+        print("\nOscar_Bert %s: output vs reference %.2e" % (precision, r))

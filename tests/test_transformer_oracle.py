@@ -79,3 +79,27 @@ def test_mirror_state_dict_is_the_spec(decoder, count):
     finally:
         config.PRE_ENCODER_MLP = False
         config.ENCODER, config.DECODER = saved
+
+
+def _oscar_mirror():
+    """The mirror built from the two seeds of tests/golden/make_golden_oscar.py."""
+    from multimodal_scene_text_recognition_b200.modules.encoders import Oscar_Bert
+    torch.manual_seed(999)
+    m = Oscar_Bert().eval()
+    synth.perturb_parameters_(m, 1234)
+    return m
+
+
+def test_oscar_bert_mirror_and_oracle_match_reference(golden_dir):
+    """Oscar_Bert: the mirror consumes the RNG like the reference's class (203 tensors, equal checksums), and the numpy
+    restatement of hid_to_bert -> BertModel(inputs_embeds) -> bert_to_hid reproduces the reference's output."""
+    g = np.load(os.path.join(golden_dir, "cfg_oscar.npz"))
+    m = _oscar_mirror()
+    sd = m.state_dict()
+    assert len(sd) == int(g["n_tensors"]) == 203
+    sums = {k: float(v.double().sum()) for k, v in sd.items() if v.is_floating_point()}
+    assert sorted(sums) == list(g["keys"])
+    np.testing.assert_allclose([sums[k] for k in g["keys"]], g["sums"], rtol=1e-9, atol=1e-9)
+    npsd = {"encoder." + k: v.numpy() for k, v in sd.items()}
+    y = tfo.oscar_bert(g["x"], npsd)
+    assert _rel(y, g["y"]) < 5e-5

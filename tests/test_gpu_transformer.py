@@ -251,3 +251,32 @@ def test_oscar_bert_matches_reference_golden(tf_config, golden_dir):
         r = assert_close(host(y), g["y"], tol, "Oscar_Bert (%s)" % precision)
         assert y2.dtype == torch.float32 and torch.equal(y2, y.float())
         print("\nOscar_Bert %s: output vs reference %.2e" % (precision, r))
+
+
+def test_transformer_configuration_edge_cases(tf_config, sd_tf):
+    """Batch sizes around the GEMM tile (1, 129), an empty batch, shard invariance, DataParallel-style prefix loading
+    and the CUDA-graph replay of the whole greedy forward."""
+    from multimodal_scene_text_recognition_b200.pipeline import GraphedRecognizer
+    m = _model(sd_tf, "bf16")
+    x = synth.make_crops(321, 129)
+    ov, sc, io = synth.make_semantics(322, 129)
+    with torch.no_grad():
+        full = m.recognize(dev(x), dev(ov), dev(sc), dev(io))
+        one = m.recognize(dev(x[:1]), dev(ov[:1]), dev(sc[:1]), dev(io[:1]))
+        part = m.recognize(dev(x[64:]), dev(ov[64:]), dev(sc[64:]), dev(io[64:]))
+        empty = m.recognize(dev(x[:0]), dev(ov[:0]), dev(sc[:0]), dev(io[:0]))
+        graphed = GraphedRecognizer(m)
+        g1 = {k: v.clone() for k, v in graphed(dev(x), dev(ov), dev(sc), dev(io)).items()}
+        g2 = graphed(dev(x), dev(ov), dev(sc), dev(io))
+    torch.cuda.synchronize()
+    assert tuple(full["logits"].shape) == (129, 25, 97) and tuple(full["ids"].shape) == (129, 25)
+    assert np.isfinite(host(full["logits"])).all()
+    # a crop's result does not depend on the batch it arrived in (every kernel of the path is row-independent)
+    assert torch.equal(one["ids"], full["ids"][:1]) and torch.equal(one["logits"], full["logits"][:1])
+    assert torch.equal(part["ids"], full["ids"][64:]) and torch.equal(part["logits"], full["logits"][64:])
+    assert tuple(empty["logits"].shape) == (0, 25, 97) and tuple(empty["ids"].shape) == (0, 25)
+    for g in (g1, g2):
+        assert torch.equal(g["ids"], full["ids"]) and torch.equal(g["logits"], full["logits"])
+    # state dict with the DataParallel prefix (get_model, model.py:115) loads into the wrapped model
+    wrapped = torch.nn.DataParallel(M.Model().eval(), device_ids=[0])
+    wrapped.load_state_dict({"module." + k: torch.from_numpy(v) for k, v in sd_tf.items()}, strict=True)

@@ -193,9 +193,11 @@ int mstr_bilstm_recurrent(const float* gates_x, const float* w_hh, float* out_f3
  *               chunk*128 + g*32 + j  holds original row  g*Hd + chunk*32 + j  (chunk = 0..7,
  *               g = gate i,f,g,o, j = 0..31): one 128-column accumulator chunk then carries all four
  *               gates of the same 32 hidden units.
+ *   gates_x     [B][T][2][4*Hd] of gates_dtype: MSTR_F32, or MSTR_BF16 - the input-projection GEMM then writes (and
+ *               this kernel reads) half the bytes; the values are widened to f32 when they enter the accumulators
  *   out_bf16    [B][T][2*Hd] bf16.   Hd must be 256.
  */
-int mstr_bilstm_recurrent_bf16(const float* gates_x, const void* w_hh_packed, void* out_bf16, int B, int T,
+int mstr_bilstm_recurrent_bf16(const void* gates_x, int gates_dtype, const void* w_hh_packed, void* out_bf16, int B, int T,
                                int Hd, mstr_stream_t stream);
 /* Two kernels implement mstr_bilstm_recurrent_bf16 with bit-identical results: one CTA per crop tile streaming W_hh
  * (csrc/bilstm_tc.cu) and a cluster of 8 CTAs per crop tile with stationary W_hh slices (csrc/bilstm_cluster.cu).

@@ -40,7 +40,7 @@ SIGNATURES = {
     "mstr_cast": (c_int, [_P, _P, _I, _I, c_int64, _P]),
     "mstr_embed_semantics": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mstr_bilstm_recurrent": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
-    "mstr_bilstm_recurrent_bf16": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
+    "mstr_bilstm_recurrent_bf16": (c_int, [_P, _I, _P, _P, _I, _I, _I, _P]),
     "mstr_set_bilstm_kernel": (c_int, [_I]),
     "mstr_attn_decode": (c_int, [_P] * 20 + [_I] * 6 + [_P]),
     "mstr_attn_decode_bf16_workspace_bytes": (c_int64, [_I, _I]),

@@ -65,6 +65,10 @@ CHECK_INPUTS = False
 # bf16 mode only: run the recurrent GEMMs of the BiLSTM / attention decoder on the tensor cores (h_t in
 # bf16, fp32 accumulation and cell state, tanh.approx gates).  False keeps the fp32 SIMT recurrences.
 RNN_TENSOR_CORES = True
+# bf16 mode with RNN_TENSOR_CORES: the BiLSTM input projection x W_ih^T + b (gates_x, 872 MB per layer in f32 at 4096
+# crops) is written by its GEMM and read by the recurrence as bf16 - one more bf16 rounding, of the gate
+# pre-activations, on top of the bf16 h_t.  False keeps it in f32.
+GATES_X_BF16 = True
 # bf16 mode only: run the 32-channel 3x3 convolution (conv0_2) over horizontal pixel pairs
 # (_pack.pack_conv_pixel_pairs): identical results, better tensor-core tile shapes.
 CONV_PIXEL_PAIRS = True

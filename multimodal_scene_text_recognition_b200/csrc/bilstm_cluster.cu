@@ -48,9 +48,10 @@ constexpr int LC_THREADS = 32 * (2 + LC_EPI_WARPS + LC_LOAD_WARPS);   // 704
 constexpr int LC_SMEM_BYTES = 1024 + LC_KB * LC_KTILE_BYTES + 2 * LC_H_BUF_BYTES + LC_GX_STAGES * LC_TILE_BYTES + 256;
 
 struct LstmClusterParams {
-  const float* gates_x;         // [B][T][2][4H]
+  const void* gates_x;          // [B][T][2][4H] f32, or bf16 when gx_bf16
   __nv_bfloat16* out;           // [B][T][2H]
   int B, T;
+  int gx_bf16;
 };
 
 __device__ __forceinline__ uint32_t lc_cluster_ctarank() {
@@ -159,7 +160,7 @@ bilstm_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         const int t = dir ? (T - 1 - step) : step;
         for (int g = 0; g < 4; ++g) {
           mbar_wait_quiet(&gempty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&gfull_bar[stage], LC_TILE_BYTES);
+          mbar_arrive_expect_tx(&gfull_bar[stage], p.gx_bf16 ? LC_TILE_BYTES / 2 : LC_TILE_BYTES);
           tma_load_2d(sG + stage * LC_TILE_BYTES, &tmGx, &gfull_bar[stage],
                       (t * 2 + dir) * 4 * LC_H + g * LC_H + (int)rank * 32, crop0);
           if (++stage == LC_GX_STAGES) { stage = 0; phase ^= 1; }
@@ -279,10 +280,14 @@ bilstm_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       for (int g = 0; g < 4; ++g) {
         uint32_t r[32];
         mbar_wait_quiet(&gfull_bar[stage], phase);
-        const uint32_t base = srow + (uint32_t)stage * LC_TILE_BYTES;
+        if (p.gx_bf16) {
+          lds_row32_bf16_as_f32(smem_u32(sG) + (uint32_t)stage * LC_TILE_BYTES, row, r);
+        } else {
+          const uint32_t base = srow + (uint32_t)stage * LC_TILE_BYTES;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          lds_v4(base + (((uint32_t)c ^ sw) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+          for (int c = 0; c < 8; ++c)
+            lds_v4(base + (((uint32_t)c ^ sw) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        }
         tmem_st32(lane_addr + (uint32_t)(acc * 128 + g * 32), r);
         // the store has issued, so the shared-memory reads that feed it have completed: release the stage
         __syncwarp();
@@ -349,7 +354,7 @@ int bilstm_cluster_capacity() {
 }
 
 // Called by mstr_bilstm_recurrent_bf16 (bilstm_tc.cu).
-int bilstm_recurrent_bf16_cluster(const float* gates_x, const void* w_hh_packed, void* out_bf16, int B, int T,
+int bilstm_recurrent_bf16_cluster(const void* gates_x, int gx_bf16, const void* w_hh_packed, void* out_bf16, int B, int T,
                                   cudaStream_t stream) {
   int rc = load_tma_encoders(g_lstm_cluster_enc);
   if (rc != MSTR_OK) return rc;
@@ -359,17 +364,19 @@ int bilstm_recurrent_bf16_cluster(const float* gates_x, const void* w_hh_packed,
   {
     // gates_x viewed as [B rows][T*2*4H f32 columns]; box = 32 columns x 128 crops, rows beyond B are zero filled
     cuuint64_t dims[2] = {(cuuint64_t)T * 2 * 4 * LC_H, (cuuint64_t)B};
-    cuuint64_t strides[1] = {(cuuint64_t)T * 2 * 4 * LC_H * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)T * 2 * 4 * LC_H * (gx_bf16 ? 2 : 4)};
     cuuint32_t box[2] = {32, LC_M};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_lstm_cluster_enc.tiled(&tmGx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(gates_x), dims,
-                                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = g_lstm_cluster_enc.tiled(&tmGx, gx_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                                          const_cast<void*>(gates_x), dims,
+                                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          gx_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled(gates_x) failed with CUresult %d", (int)r);
   }
   rc = lc_prepare();
   if (rc != MSTR_OK) return rc;
-  LstmClusterParams p{gates_x, (__nv_bfloat16*)out_bf16, B, T};
+  LstmClusterParams p{gates_x, (__nv_bfloat16*)out_bf16, B, T, gx_bf16};
   cudaLaunchAttribute attr[1];
   cudaLaunchConfig_t cfg = lc_launch_config(ceil_div(B, LC_M) * 2, stream, attr);
   MSTR_CUDA(cudaLaunchKernelEx(&cfg, bilstm_cluster_kernel, tmW, tmGx, p));

@@ -61,9 +61,10 @@ constexpr int LT_SMEM_BYTES =
 constexpr uint32_t LT_ACC_COL0 = 256;  // TMEM: [0,256) cell state, [256,384) / [384,512) accumulators
 
 struct LstmTcParams {
-  const float* gates_x;         // [B][T][2][4H]
+  const void* gates_x;          // [B][T][2][4H] f32, or bf16 when gx_bf16 (half the HBM round trip of the stage)
   __nv_bfloat16* out;           // [B][T][2H]
   int B, T;
+  int gx_bf16;
 };
 
 __global__ void __launch_bounds__(LT_THREADS, 1)
@@ -240,12 +241,14 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int crop = crop0 + row;
-    const float* gx_crop = p.gates_x + ((size_t)(crop < p.B ? crop : 0) * T * 2 + dir) * (4 * LT_H);
-    const ptrdiff_t t_stride = (ptrdiff_t)(dir ? -1 : 1) * (2 * 4 * LT_H);
-    const float* grow = gx_crop + (size_t)(dir ? T - 1 : 0) * (2 * 4 * LT_H);
-    // L2 prefetch of this crop's 4 KB row, two steps ahead of the TMA loads
-    prefetch_l2_bulk(grow, 4 * LT_H * 4);
-    if (T > 1) prefetch_l2_bulk(grow + t_stride, 4 * LT_H * 4);
+    const uint32_t esz = p.gx_bf16 ? 2u : 4u;
+    const uint32_t row_bytes = 4 * LT_H * esz;
+    const uint8_t* gx_crop = static_cast<const uint8_t*>(p.gates_x) + ((size_t)(crop < p.B ? crop : 0) * T * 2 + dir) * row_bytes;
+    const ptrdiff_t t_stride = (ptrdiff_t)(dir ? -1 : 1) * (ptrdiff_t)(2 * row_bytes);
+    const uint8_t* grow = gx_crop + (size_t)(dir ? T - 1 : 0) * (2 * row_bytes);
+    // L2 prefetch of this crop's 4 KB (2 KB) row, two steps ahead of the TMA loads
+    prefetch_l2_bulk(grow, row_bytes);
+    if (T > 1) prefetch_l2_bulk(grow + t_stride, row_bytes);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + LT_ACC_COL0;
     const uint32_t srow = smem_u32(sG) + (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
@@ -253,7 +256,7 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     uint32_t phase = 0;
     int n = 0;
     for (int step = 0; step < T; ++step, grow += t_stride) {
-      if (step + 2 < T) prefetch_l2_bulk(grow + 2 * t_stride, 4 * LT_H * 4);
+      if (step + 2 < T) prefetch_l2_bulk(grow + 2 * t_stride, row_bytes);
       for (int chunk = 0; chunk < LT_CHUNKS; ++chunk, ++n) {
         const int buf = n & 1;
         const uint32_t acc = lane_addr + (uint32_t)(buf * 128);
@@ -265,10 +268,14 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             tc_fence_after();
           }
           mbar_wait_quiet(&gfull_bar[stage], phase);
-          const uint32_t base = srow + (uint32_t)stage * LT_GX_TILE_BYTES;
+          if (p.gx_bf16) {
+            lds_row32_bf16_as_f32(smem_u32(sG) + (uint32_t)stage * LT_GX_TILE_BYTES, row, r);
+          } else {
+            const uint32_t base = srow + (uint32_t)stage * LT_GX_TILE_BYTES;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            lds_v4(base + (((uint32_t)c ^ sw) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+            for (int c = 0; c < 8; ++c)
+              lds_v4(base + (((uint32_t)c ^ sw) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+          }
           tmem_st32(acc + (uint32_t)(g * 32), r);
           // the store has issued, so the shared-memory reads that feed it have completed: release the stage
           __syncwarp();
@@ -292,7 +299,7 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         for (int chunk = 0; chunk < LT_CHUNKS; ++chunk)
           for (int g = 0; g < 4; ++g) {
             mbar_wait_quiet(&gempty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&gfull_bar[stage], LT_GX_TILE_BYTES);
+            mbar_arrive_expect_tx(&gfull_bar[stage], p.gx_bf16 ? LT_GX_TILE_BYTES / 2 : LT_GX_TILE_BYTES);
             tma_load_2d_hint(sG + stage * LT_GX_TILE_BYTES, &tmGx, &gfull_bar[stage],
                              (t * 2 + dir) * 4 * LT_H + g * LT_H + chunk * LT_CHUNK_UNITS, crop0, stream);
             if (++stage == LT_GX_STAGES) { stage = 0; phase ^= 1; }
@@ -312,7 +319,7 @@ bilstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 static TmaEncoders g_lstm_enc;
 
 // bilstm_cluster.cu: cluster-cooperative variant (W_hh stationary in shared memory, h exchanged through DSMEM)
-int bilstm_recurrent_bf16_cluster(const float* gates_x, const void* w_hh_packed, void* out_bf16, int B, int T,
+int bilstm_recurrent_bf16_cluster(const void* gates_x, int gx_bf16, const void* w_hh_packed, void* out_bf16, int B, int T,
                                   cudaStream_t stream);
 int bilstm_cluster_capacity();
 static std::atomic<int> g_bilstm_kernel{0};   // 0 = by occupancy, 1 = one CTA per tile, 2 = cluster per tile
@@ -326,11 +333,13 @@ extern "C" __attribute__((visibility("default"))) int mstr_set_bilstm_kernel(int
 }
 
 extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16(
-    const float* gates_x, const void* w_hh_packed, void* out_bf16, int B, int T, int Hd, mstr_stream_t stream) {
+    const void* gates_x, int gates_dtype, const void* w_hh_packed, void* out_bf16, int B, int T, int Hd, mstr_stream_t stream) {
   using namespace mstr;
   MSTR_REQUIRE(gates_x && w_hh_packed && out_bf16, MSTR_ERR_BAD_ARG, "mstr_bilstm_recurrent_bf16: null pointer");
   MSTR_REQUIRE(B > 0 && T > 0, MSTR_ERR_BAD_ARG, "mstr_bilstm_recurrent_bf16: bad size");
   MSTR_REQUIRE(Hd == LT_H, MSTR_ERR_UNSUPPORTED, "mstr_bilstm_recurrent_bf16: hidden size %d != %d", Hd, LT_H);
+  MSTR_REQUIRE(gates_dtype == MSTR_F32 || gates_dtype == MSTR_BF16, MSTR_ERR_BAD_ARG, "mstr_bilstm_recurrent_bf16: gates_dtype %d", gates_dtype);
+  const int gx_bf16 = gates_dtype == MSTR_BF16;
   MSTR_REQUIRE(aligned16(gates_x) && aligned16(w_hh_packed) && aligned16(out_bf16), MSTR_ERR_BAD_ARG,
                "mstr_bilstm_recurrent_bf16: pointers must be 16-byte aligned");
   // Two kernels, chosen by occupancy.  The cluster-cooperative kernel (bilstm_cluster.cu: W_hh stationary, 8 CTAs per
@@ -342,7 +351,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   const int forced = g_bilstm_kernel.load(std::memory_order_relaxed);
   const int tiles = ceil_div(B, LT_M) * 2;
   const bool use_cluster = forced ? forced == 2 : (tiles <= 3 * bilstm_cluster_capacity());
-  if (use_cluster) return bilstm_recurrent_bf16_cluster(gates_x, w_hh_packed, out_bf16, B, T, (cudaStream_t)stream);
+  if (use_cluster) return bilstm_recurrent_bf16_cluster(gates_x, gx_bf16, w_hh_packed, out_bf16, B, T, (cudaStream_t)stream);
   int rc = load_tma_encoders(g_lstm_enc);
   if (rc != MSTR_OK) return rc;
   alignas(64) CUtensorMap tmW;
@@ -352,11 +361,13 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   alignas(64) CUtensorMap tmGx;
   {
     cuuint64_t dims[2] = {(cuuint64_t)T * 2 * 4 * LT_H, (cuuint64_t)B};
-    cuuint64_t strides[1] = {(cuuint64_t)T * 2 * 4 * LT_H * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)T * 2 * 4 * LT_H * (gx_bf16 ? 2 : 4)};
     cuuint32_t box[2] = {32, LT_M};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_lstm_enc.tiled(&tmGx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(gates_x), dims, strides,
-                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    // f32: 128-byte rows, 128B swizzle; bf16: 64-byte rows, 64B swizzle (tc_common.cuh: lds_row32_bf16_as_f32)
+    CUresult r = g_lstm_enc.tiled(&tmGx, gx_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                                  const_cast<void*>(gates_x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  gx_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSTR_REQUIRE(r == CUDA_SUCCESS, MSTR_ERR_CUDA, "cuTensorMapEncodeTiled(gates_x) failed with CUresult %d", (int)r);
   }
@@ -368,7 +379,7 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent_bf16
   static unsigned long long smem_set = 0;
   rc = ensure_dynamic_smem((const void*)bilstm_tc_kernel, LT_SMEM_BYTES, &smem_set);
   if (rc != MSTR_OK) return rc;
-  LstmTcParams p{gates_x, (__nv_bfloat16*)out_bf16, B, T};
+  LstmTcParams p{gates_x, (__nv_bfloat16*)out_bf16, B, T, gx_bf16};
   dim3 grid(ceil_div(B, LT_M), 2);
   bilstm_tc_kernel<<<grid, LT_THREADS, LT_SMEM_BYTES, (cudaStream_t)stream>>>(tmW, tmGx, tmOut, p);
   MSTR_LAUNCH_CHECK("bilstm_tc_kernel");

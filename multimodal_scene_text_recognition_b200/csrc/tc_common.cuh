@@ -282,6 +282,22 @@ __device__ __forceinline__ void ldg_nc_32(uint32_t (&r)[32], const float* p) {
 __device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
 }
+// One row of a [rows][32 bf16] shared-memory tile (64-byte rows, 64B swizzle: 16-byte chunk c of row r sits at chunk
+// c ^ ((r >> 1) & 3)) as 32 f32 bit patterns (bf16 -> f32 is a 16-bit shift).
+__device__ __forceinline__ void lds_row32_bf16_as_f32(uint32_t tile_base, int row, uint32_t (&r)[32]) {
+  const uint32_t rb = tile_base + (uint32_t)row * 64u;
+  const uint32_t sw = (uint32_t)((row >> 1) & 3);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t w[4];
+    lds_v4(rb + (((uint32_t)c ^ sw) << 4), w[0], w[1], w[2], w[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      r[8 * c + 2 * k] = w[k] << 16;
+      r[8 * c + 2 * k + 1] = w[k] & 0xffff0000u;
+    }
+  }
+}
 // Whole-segment L2 prefetch (bytes % 16 == 0).  prefetch.global.L2 only brought in half of a 128-byte line
 // (ncu: 50 % L2 sector hits on the demand loads that followed), the bulk form fetches exactly what is asked.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {

@@ -59,7 +59,10 @@ class BidirectionalLSTM(nn.Module):
         B, T, _ = x.shape
         hd = self.rnn.hidden_size
         if precision == 'bf16':
-            gx = ops.linear(x, pk["w_ih"], pk["bias"], want_f32=True, want_bf16=False)    # [B,T,2*4H] f32
+            # the input projection of both directions; with GATES_X_BF16 it is stored (and read back by the recurrence)
+            # as bf16: half the HBM round trip of the stage
+            half = bool(config.RNN_TENSOR_CORES and config.GATES_X_BF16)
+            gx = ops.linear(x, pk["w_ih"], pk["bias"], want_f32=not half, want_bf16=half)    # [B,T,2*4H]
             if config.RNN_TENSOR_CORES:
                 rec = ops.bilstm_recurrent_bf16(gx.view(B, T, 2, 4 * hd), pk["w_hh_tc"])
             else:

@@ -513,14 +513,14 @@ def pack_w_hh_bf16(w_hh: torch.Tensor) -> torch.Tensor:
 
 
 def bilstm_recurrent_bf16(gates_x: torch.Tensor, w_hh_packed: torch.Tensor) -> torch.Tensor:
-    """gates_x [B,T,2,4H] f32, w_hh_packed [2,4H,H] bf16 (pack_w_hh_bf16) -> [B,T,2H] bf16."""
-    _req(gates_x, "gates_x", torch.float32); _req(w_hh_packed, "w_hh_packed", torch.bfloat16)
+    """gates_x [B,T,2,4H] f32 or bf16, w_hh_packed [2,4H,H] bf16 (pack_w_hh_bf16) -> [B,T,2H] bf16."""
+    _req(gates_x, "gates_x"); _req(w_hh_packed, "w_hh_packed", torch.bfloat16)
     B, T = gates_x.shape[:2]
     Hd = w_hh_packed.shape[2]
     assert gates_x.shape == (B, T, 2, 4 * Hd) and w_hh_packed.shape == (2, 4 * Hd, Hd)
     out = torch.empty((B, T, 2 * Hd), device=gates_x.device, dtype=torch.bfloat16)
     with _timed("bilstm_recurrent_bf16", 2.0 * B * T * 2 * 4 * Hd * Hd, "flop", "B%d T%d both directions (tcgen05)" % (B, T)), _on(gates_x, w_hh_packed) as st:
-        check(lib().mstr_bilstm_recurrent_bf16(ptr(gates_x), ptr(w_hh_packed), ptr(out), B, T, Hd, st),
+        check(lib().mstr_bilstm_recurrent_bf16(ptr(gates_x), _dt(gates_x), ptr(w_hh_packed), ptr(out), B, T, Hd, st),
               "mstr_bilstm_recurrent_bf16")
     return out
 

@@ -324,7 +324,7 @@ def _lstm_direction(gx, w_hh, reverse, quant=None):
     return out
 
 
-def bidirectional_lstm(x, sd, prefix, dt=np.float32, quant=None):
+def bidirectional_lstm(x, sd, prefix, dt=np.float32, quant=None, gates_bf16=True):
     """BidirectionalLSTM.forward (encoders.py:17-30): nn.LSTM(bidirectional, batch_first) + Linear."""
     x = x.astype(dt)
     outs = []
@@ -332,6 +332,8 @@ def bidirectional_lstm(x, sd, prefix, dt=np.float32, quant=None):
         w_ih = _q(sd[f"{prefix}.rnn.weight_ih_l0{sfx}"].astype(dt), quant)
         bias = (sd[f"{prefix}.rnn.bias_ih_l0{sfx}"].astype(dt) + sd[f"{prefix}.rnn.bias_hh_l0{sfx}"].astype(dt))
         gx = _q(x, quant) @ w_ih.T + bias
+        if quant and gates_bf16:
+            gx = _q(gx, quant)       # config.GATES_X_BF16: the input projection is stored as bf16
         outs.append(_lstm_direction(gx, sd[f"{prefix}.rnn.weight_hh_l0{sfx}"], rev, quant))
     rec = _q(np.concatenate(outs, axis=2), quant)   # [fwd | bwd], stored bf16 for the Linear GEMM
     w = _q(sd[prefix + ".linear.weight"].astype(dt), quant)

@@ -429,6 +429,25 @@ def test_bilstm_recurrent_bf16_tensor_cores(B, T, kernel):
     assert d.mean() < 2e-3, "mean abs error %.3e" % d.mean()
 
 
+@pytest.mark.parametrize("kernel", ["single", "cluster"])
+def test_bilstm_gates_x_in_bf16_equals_f32_of_the_same_values(kernel):
+    """config.GATES_X_BF16: the recurrence reads the input projection as bf16 (half the traffic) and widens it on the
+    way into the accumulators - so fed with bf16 values it must give, bit for bit, what the f32 path gives on the same
+    values (ragged tiles, both directions, T not a multiple of anything)."""
+    g = torch.Generator(device=DEV).manual_seed(12)
+    for B, T in [(130, 26), (5, 3), (700, 7), (1, 65)]:
+        gx_b = (torch.randn(B, T, 2, 1024, device=DEV, generator=g) * 1.5).to(torch.bfloat16)
+        w = ops.pack_w_hh_bf16(torch.randn(2, 1024, 256, device=DEV, generator=g) / 16)
+        try:
+            ops.set_bilstm_kernel(kernel)
+            a = ops.bilstm_recurrent_bf16(gx_b.float(), w)
+            b = ops.bilstm_recurrent_bf16(gx_b, w)
+            torch.cuda.synchronize()
+        finally:
+            ops.set_bilstm_kernel("auto")
+        assert torch.equal(a, b), "B=%d T=%d %s" % (B, T, kernel)
+
+
 def test_bilstm_cluster_kernel_bit_identical_to_single_cta_kernel():
     """Both tensor-core recurrences feed the same bf16 operands to the MMAs in the same k order, so the cluster
     kernel (DSMEM exchange of h) must reproduce the single-CTA kernel bit for bit: a race detector for the

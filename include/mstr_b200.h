@@ -305,6 +305,18 @@ int mstr_mha(const void* q, int ldq, const void* k, const void* v, int ldkv, voi
 int mstr_mha_step(const void* q, int ldq, void* k_cache, void* v_cache, int ldkv, int64_t kv_batch_stride,
                   const void* k_new, const void* v_new, int ld_new, void* out, int B, int Lk, int heads, int dh,
                   int dtype, mstr_stream_t stream);
+/* get_relevant_semantic of the reference's PRE_ENCODER_MLP / PRE_DECODER_MLP fusion (modules/encoders.py:89-111,
+ * modules/decoders.py:147-170): for every (column t, object o) pair of a crop an MLP on cat(column, object) gives a score,
+ * the scores are soft-maxed over the objects and weight the sum of the object vectors.
+ * mstr_pair_add_relu:    h[b][t][o][:] = relu(a[b][t][:] + s[b][o][:]) - the MLP's first layer from the two halves of its
+ *                        weight applied once per column (a, with the bias) and once per object (s);  a [B][T][C],
+ *                        s [B][O][C], h [B][T][O][C] of `dtype`.
+ * mstr_relevance_reduce: score_o = h2[b][t][o][:] . w3 + b3 (the MLP's last layer), p = softmax over o,
+ *                        out[b][t][:] = sum_o p_o sem[b][o][:];  h2 [B][T][O][C] of `dtype`, w3 [C] f32, sem [B][O][E] f32,
+ *                        out [B][T][E] of `dtype`;  O <= 64, E % 32 == 0, E <= 512. */
+int mstr_pair_add_relu(const void* a, const void* s, void* h, int B, int T, int O, int C, int dtype, mstr_stream_t stream);
+int mstr_relevance_reduce(const void* h2, const float* w3, float b3, const float* sem, void* out, int B, int T, int O, int C,
+                          int E, int dtype, mstr_stream_t stream);
 /* Exact GELU, 0.5 x (1 + erf(x / sqrt(2))): the activation of BertModel's intermediate layer (the reference's Oscar_Bert,
  * modules/encoders.py:34-66).  x, out [n] of `dtype` (may alias); n a multiple of 8 (bf16) / 4 (f32). */
 int mstr_gelu(const void* x, void* out, int64_t n, int dtype, mstr_stream_t stream);

@@ -53,6 +53,8 @@ SIGNATURES = {
     "mstr_embed_tokens": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mstr_mha": (c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "mstr_mha_step": (c_int, [_P, _I, _P, _P, _I, c_int64, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "mstr_pair_add_relu": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mstr_relevance_reduce": (c_int, [_P, _P, ctypes.c_float, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mstr_gelu": (c_int, [_P, _P, c_int64, _I, _P]),
     "mstr_argmax_tokens": (c_int, [_P, _I, _P, c_int64, _P, _I, _P, _I, _I, _I, _P]),
 }

@@ -13,6 +13,9 @@
 //                          (decoders.py:250-279 recomputes every earlier position at every step; with the causal
 //                          mask those rows do not change, so the cache gives the same numbers) and the
 //                          memory attention (decoders.py:450-451); one warp per crop, every row one coalesced request
+//   pair_add_relu_kernel,  get_relevant_semantic of the PRE_ENCODER_MLP / PRE_DECODER_MLP fusion (encoders.py:89-111,
+//   relevance_reduce_kernel  decoders.py:147-170): first MLP layer of every (column, object) pair from the two halves of its
+//                          GEMM, and last MLP layer + softmax over the objects + weighted sum of the object vectors
 //   gelu_kernel            exact (erf) GELU of BERT's intermediate layer (encoders.py:34-66 via transformers' BertModel)
 //   argmax_tokens_kernel   t_output[-1].max(1), targets[t+1] = char_index, output[t] = t_output[t] (decoders.py:276-279)
 //
@@ -330,6 +333,81 @@ mha_step_kernel(const T* __restrict__ q, int ldq, T* __restrict__ kc, T* __restr
   }
 }
 
+// H[b][t][o][:] = relu(A[b][t][:] + S[b][o][:]): the first layer of the relevance MLP on cat(column, object) is linear,
+// so its two halves are computed once per column / per object (two small GEMMs, bias in A) instead of once per pair.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pair_add_relu_kernel(const T* __restrict__ A, const T* __restrict__ S, T* __restrict__ H, int64_t chunks, int Tn, int On,
+                     int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= chunks) return;
+  constexpr int N = Chunk<T>::N;
+  const int cpr = C / N;                                 // chunks per row
+  const int c = (int)(i % cpr);
+  const int64_t row = i / cpr;                           // (b, t, o)
+  const int o = (int)(row % On);
+  const int64_t bt = row / On;
+  const int64_t b = bt / Tn;
+  float a[N], sv[N];
+  Chunk<T>::load(A + bt * C + c * N, a);
+  Chunk<T>::load(S + (b * On + o) * C + c * N, sv);
+#pragma unroll
+  for (int u = 0; u < N; ++u) a[u] = fmaxf(a[u] + sv[u], 0.f);
+  Chunk<T>::store(H + row * C + c * N, a);
+}
+
+// One warp per (crop, column): score_o = H2[b][t][o][:] . w3 + b3, p = softmax over the objects,
+// out[b][t][:] = sum_o p_o sem[b][o][:]  (On <= 64, E % 32 == 0, E <= 512).
+template <typename T>
+__global__ void __launch_bounds__(256)
+relevance_reduce_kernel(const T* __restrict__ H2, const float* __restrict__ w3, float b3, const float* __restrict__ sem,
+                        T* __restrict__ out, int64_t rows, int Tn, int On, int C, int E) {
+  const int64_t bt = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (bt >= rows) return;
+  constexpr int N = Chunk<T>::N;
+  const int64_t b = bt / Tn;
+  float sc[2] = {-INFINITY, -INFINITY};                  // score of object o lives in lane o % 32, slot o / 32
+  for (int o = 0; o < On; ++o) {
+    const T* h = H2 + (bt * On + o) * C;
+    float acc = 0.f;
+    for (int c = lane; c < C / N; c += 32) {
+      float v[N];
+      Chunk<T>::load(h + c * N, v);
+#pragma unroll
+      for (int u = 0; u < N; u += 4) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w3 + c * N + u));
+        acc = fmaf(v[u], w.x, acc); acc = fmaf(v[u + 1], w.y, acc); acc = fmaf(v[u + 2], w.z, acc); acc = fmaf(v[u + 3], w.w, acc);
+      }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if ((o & 31) == lane) sc[o >> 5] = acc + b3;
+  }
+  float mx = fmaxf(sc[0], sc[1]);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  const float e0 = lane < On ? expf(sc[0] - mx) : 0.f;
+  const float e1 = lane + 32 < On ? expf(sc[1] - mx) : 0.f;
+  float den = e0 + e1;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) den += __shfl_xor_sync(0xffffffffu, den, s);
+  const float inv = 1.f / den;
+  float acc[16];                                         // E <= 512: E / 32 channels per lane, lane-strided
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (int o = 0; o < On; ++o) {
+    const float p = __shfl_sync(0xffffffffu, (o < 32 ? e0 : e1), o & 31) * inv;
+    const float* sv = sem + (b * On + o) * E;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k * 32 < E) acc[k] = fmaf(p, __ldg(sv + k * 32 + lane), acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (k * 32 < E) Elem<T>::store(out + bt * E + k * 32 + lane, acc[k]);
+}
+
 // y = 0.5 x (1 + erf(x / sqrt(2))), 16 bytes per thread
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -496,6 +574,46 @@ MSTR_EXPORT int mstr_mha_step(const void* q, int ldq, void* k_cache, void* v_cac
   else { if (dh == 64) MSTR_MHA_STEP(float, 64); else MSTR_MHA_STEP(float, 32); }
 #undef MSTR_MHA_STEP
   MSTR_LAUNCH_CHECK("mha_step_kernel");
+  return MSTR_OK;
+}
+
+MSTR_EXPORT int mstr_pair_add_relu(const void* a, const void* s, void* h, int B, int T, int O, int C, int dtype,
+                                   mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(a && s && h, MSTR_ERR_BAD_ARG, "mstr_pair_add_relu: null pointer");
+  const int per = dtype == MSTR_BF16 ? 8 : 4;
+  MSTR_REQUIRE(B > 0 && T > 0 && O > 0 && C > 0 && C % per == 0 && aligned16(a) && aligned16(s) && aligned16(h), MSTR_ERR_BAD_ARG,
+               "mstr_pair_add_relu: bad size / alignment (C must be a multiple of %d)", per);
+  const int64_t chunks = (int64_t)B * T * O * (C / per);
+  const int blocks = (int)ceil_div64(chunks, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef __nv_bfloat16 bf;
+  if (dtype == MSTR_BF16)
+    pair_add_relu_kernel<bf><<<blocks, 256, 0, st>>>(static_cast<const bf*>(a), static_cast<const bf*>(s), static_cast<bf*>(h), chunks, T, O, C);
+  else
+    pair_add_relu_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(a), static_cast<const float*>(s),
+                                                        static_cast<float*>(h), chunks, T, O, C);
+  MSTR_LAUNCH_CHECK("pair_add_relu_kernel");
+  return MSTR_OK;
+}
+
+MSTR_EXPORT int mstr_relevance_reduce(const void* h2, const float* w3, float b3, const float* sem, void* out, int B, int T, int O,
+                                      int C, int E, int dtype, mstr_stream_t stream) {
+  using namespace mstr;
+  MSTR_REQUIRE(h2 && w3 && sem && out, MSTR_ERR_BAD_ARG, "mstr_relevance_reduce: null pointer");
+  const int per = dtype == MSTR_BF16 ? 8 : 4;
+  MSTR_REQUIRE(B > 0 && T > 0 && O > 0 && C > 0 && C % per == 0 && aligned16(h2) && aligned16(w3), MSTR_ERR_BAD_ARG,
+               "mstr_relevance_reduce: bad size / alignment");
+  MSTR_REQUIRE(O <= 64 && E % 32 == 0 && E <= 512, MSTR_ERR_UNSUPPORTED, "mstr_relevance_reduce: O=%d (<= 64), E=%d (multiple of 32, <= 512)", O, E);
+  const int64_t rows = (int64_t)B * T;
+  const int blocks = (int)ceil_div64(rows * 32, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef __nv_bfloat16 bf;
+  if (dtype == MSTR_BF16)
+    relevance_reduce_kernel<bf><<<blocks, 256, 0, st>>>(static_cast<const bf*>(h2), w3, b3, sem, static_cast<bf*>(out), rows, T, O, C, E);
+  else
+    relevance_reduce_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(h2), w3, b3, sem, static_cast<float*>(out), rows, T, O, C, E);
+  MSTR_LAUNCH_CHECK("relevance_reduce_kernel");
   return MSTR_OK;
 }
 

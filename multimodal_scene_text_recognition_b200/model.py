@@ -105,8 +105,9 @@ class Model(nn.Module):
         semantics = self.get_semantic_vectors(overlap, scene, ious)
         if not lstm_encoder:
             # transformer family (model.py:101-105): the encoder output stays in the activation dtype
-            enc = self.encoder.forward_features(visual)
-            out = self.decoder.decode(enc, text, is_train, enc_act=enc)
+            enc = self.encoder.forward_features(visual, semantics) if isinstance(self.encoder, TF_Encoder) \
+                else self.encoder.forward_features(visual)
+            out = self.decoder.decode(enc, text, is_train, enc_act=enc, semantics=semantics)
             if stages is not None:
                 stages.update(rectified=rect, features=feat, visual=visual, semantics=semantics, enc1=ops.cast(enc, torch.float32))
             return out

@@ -23,13 +23,16 @@ Two things differ from the reference's code, neither in the numbers it defines:
 
 ``Oscar_Bert`` (encoders.py:34-66) is mirrored too (BERT-base over the column features).
 
-Eval mode only (dropout is the identity); the fusion experiments (PRE_ENCODER_MLP, OSCAR_ENCODER, PRE_DECODER_MLP,
-CLS_DECODER_INIT, MULTIHEAD_*, POST_DECODER_MLP) raise NotImplementedError at construction.
+Of the semantic-fusion switches (config.py:40-53) ``PRE_ENCODER_MLP`` and ``PRE_DECODER_MLP`` are built - they are what
+makes the object-tag vectors of ``Linear_Embedding`` reach the prediction (``relevant_semantic`` / ``combine_with_semantic``
+below) -; ``OSCAR_ENCODER``, ``CLS_DECODER_INIT``, ``MULTIHEAD_*`` and ``POST_DECODER_MLP`` raise NotImplementedError at
+construction.  Eval mode only (dropout is the identity).
 """
 from __future__ import annotations
 
 import copy
 import math
+from collections import OrderedDict
 
 import torch
 import torch.nn as nn
@@ -74,11 +77,101 @@ class PositionalEncoding(nn.Module):
 
 
 class MLP(nn.Module):
-    """encoders.py:200-243 / decoders.py:473-516.  Only the fusion experiments build it; kept so the name resolves."""
+    """encoders.py:200-243 / decoders.py:473-516: ``num_layers`` Linear layers (ReLU and a p = 0 dropout between them)
+    registered as ``layers.fc{i}``, weights N(0, sqrt(2 / fan_in)), biases 0.  A parameter container: the fusion code
+    below runs the layers on the GEMM kernels."""
 
-    def __init__(self, *args, **kwargs):
-        super().__init__()
-        raise NotImplementedError("MLP is used by the reference's semantic-fusion experiments only, which are not implemented")
+    def __init__(self, input_size, hidden_size, num_classes, num_layers=1, dropout_p=0.0):
+        super(MLP, self).__init__()
+        self.input_size, self.hidden_size, self.num_classes = input_size, hidden_size, num_classes
+        layers = []
+        for i in range(num_layers):
+            idim = input_size if i == 0 else hidden_size
+            odim = num_classes if i == num_layers - 1 else hidden_size
+            fc = nn.Linear(idim, odim)
+            fc.weight.data.normal_(0.0, math.sqrt(2. / idim))
+            fc.bias.data.fill_(0)
+            layers.append(('fc' + str(i), fc))
+            if i != num_layers - 1:
+                layers.append(('relu' + str(i), nn.ReLU()))
+                layers.append(('dropout' + str(i), nn.Dropout(p=dropout_p)))
+        self.layers = nn.Sequential(OrderedDict(layers))
+
+    def params_to_train(self):
+        return self.layers.parameters()
+
+    def linears(self):
+        return [m for m in self.layers if isinstance(m, nn.Linear)]
+
+    def forward(self, x):
+        """x [..., input_size] -> [..., num_classes] on the GEMM kernels (activation dtype of config.PRECISION)."""
+        require_inference(x)
+        precision = config.PRECISION
+        h = ops.cast(x.contiguous(), act_dtype(precision))
+        lins = self.linears()
+        for i, fc in enumerate(lins):
+            w, b = cached(fc, ("mlp_fc", precision), [fc.weight, fc.bias],
+                          lambda fc=fc: (wrap_weight(_f(fc.weight), precision), _f(fc.bias)))
+            h = ops.linear(h, w, b, relu=i != len(lins) - 1)
+        return h
+
+
+def _relevance_pack(mlp: MLP, feat_dim: int, precision: str):
+    """The 3-layer relevance MLP on cat(column feature [feat_dim], object vector): first layer split into its column
+    and its object half, last layer (-> 1 score) as a vector."""
+    fc0, fc1, fc2 = mlp.linears()
+    if fc2.out_features != 1:
+        raise NotImplementedError("the relevance MLP must end in one score")
+
+    def build():
+        w0 = _f(fc0.weight)
+        return {"w0_feat": wrap_weight(w0[:, :feat_dim].contiguous(), precision), "b0": _f(fc0.bias),
+                "w0_sem": wrap_weight(w0[:, feat_dim:].contiguous(), precision),
+                "w1": wrap_weight(_f(fc1.weight), precision), "b1": _f(fc1.bias),
+                "w2": _f(fc2.weight).view(-1).contiguous(), "b2": float(fc2.bias.detach().float().item())}
+    return cached(mlp, ("relevance", precision, feat_dim), [p for fc in (fc0, fc1, fc2) for p in (fc.weight, fc.bias)], build)
+
+
+def relevant_semantic(feats: torch.Tensor, sem_vec: torch.Tensor, mlp: MLP) -> torch.Tensor:
+    """get_relevant_semantic (encoders.py:89-111, decoders.py:147-170): feats [B, T, F] (activation dtype), sem_vec
+    [B, O, E] f32 -> [B, T, E]: for every (column, object) pair ``mlp(cat(column, object))`` is a score, soft-maxed over
+    the objects, weighting the sum of the object vectors.  The reference materialises cat(...) for all T x O pairs; the
+    first layer is linear, so its column half runs once per column and its object half once per object (two GEMMs) and
+    ``pair_add_relu`` forms the T x O hidden rows; the middle layer is one GEMM over them, the last layer + softmax +
+    weighted sum one kernel."""
+    precision = config.PRECISION
+    dt = act_dtype(precision)
+    pk = _relevance_pack(mlp, feats.shape[-1], precision)
+    sem32 = sem_vec.contiguous().float()
+    a = ops.linear(feats, pk["w0_feat"], pk["b0"])                                  # [B, T, Hd]
+    s_ = ops.linear(ops.cast(sem32, dt), pk["w0_sem"], None)                        # [B, O, Hd]
+    h = ops.pair_add_relu(a, s_)                                                    # [B, T, O, Hd]
+    h = ops.linear(h, pk["w1"], pk["b1"], relu=True)
+    return ops.relevance_reduce(h, pk["w2"], pk["b2"], sem32)                       # [B, T, E]
+
+
+def _combine_pack(mlp: MLP, feat_dim: int, precision: str):
+    lins = mlp.linears()
+
+    def build():
+        w0 = _f(lins[0].weight)
+        rest = [(wrap_weight(_f(fc.weight), precision), _f(fc.bias)) for fc in lins[1:]]
+        return {"w0_feat": wrap_weight(w0[:, :feat_dim].contiguous(), precision), "b0": _f(lins[0].bias),
+                "w0_sem": wrap_weight(w0[:, feat_dim:].contiguous(), precision), "rest": rest}
+    return cached(mlp, ("combine", precision, feat_dim), [p for fc in lins for p in (fc.weight, fc.bias)], build)
+
+
+def combine_with_semantic(feats: torch.Tensor, rel: torch.Tensor, mlp: MLP) -> torch.Tensor:
+    """feats + combine_mlp(cat(feats, rel)) (encoders.py:131-134, decoders.py:220-222) without materialising the
+    concatenation: the first layer as two GEMMs (the second adds the first in its epilogue), the residual ``feats`` in
+    the epilogue of the last."""
+    pk = _combine_pack(mlp, feats.shape[-1], config.PRECISION)
+    h = ops.linear(feats, pk["w0_feat"], pk["b0"])
+    h = ops.linear(rel, pk["w0_sem"], None, residual=h, relu=True)
+    for i, (w, b) in enumerate(pk["rest"]):
+        last = i == len(pk["rest"]) - 1
+        h = ops.linear(h, w, b, relu=not last, residual=feats if last else None)
+    return h
 
 
 def _mha_pack(attn: nn.MultiheadAttention, precision: str):
@@ -167,25 +260,42 @@ class TF_Encoder(nn.Module):
 
     def __init__(self):
         super(TF_Encoder, self).__init__()
-        _no_fusion('PRE_ENCODER_MLP')
         self.pos_encoder = PositionalEncoding(config.HIDDEN_DIM)
         self.encoder_layer = TransformerEncoderLayer(d_model=config.HIDDEN_DIM, nhead=8, dim_feedforward=2048, dropout=0.1)
         self.layer_norm = nn.LayerNorm(config.HIDDEN_DIM)
         self.encoder = _LayerStack(self.encoder_layer, num_layers=6, norm=self.layer_norm)
+        self.pre_encoder_mlp = bool(config.PRE_ENCODER_MLP)
+        if self.pre_encoder_mlp:
+            # encoders.py:83-93: relevance scores of the objects per column, and the map back to the hidden size
+            self.sem_relevence_mlp = MLP(input_size=(config.HIDDEN_DIM + config.EMBED_DIM), hidden_size=config.HIDDEN_DIM,
+                                         num_classes=1, num_layers=3)
+            self.combine_mlp = MLP(input_size=(config.HIDDEN_DIM + config.EMBED_DIM), hidden_size=config.HIDDEN_DIM,
+                                   num_classes=config.HIDDEN_DIM, num_layers=3)
+            self.emb_to_hid = nn.Linear(config.EMBED_DIM, config.HIDDEN_DIM, bias=False)   # never used by the reference either
 
-    def forward_features(self, col_feats: torch.Tensor) -> torch.Tensor:
+    def get_relevant_semantic(self, feats, sem_vec, is_train=False):
+        return relevant_semantic(ops.cast(feats.contiguous(), act_dtype(config.PRECISION)), sem_vec, self.sem_relevence_mlp)
+
+    def forward_features(self, col_feats: torch.Tensor, semantics=None) -> torch.Tensor:
         """[B, T, d] (f32 or activation dtype) -> [B, T, d] in the activation dtype."""
         require_inference(col_feats)
         if self.training:
             raise RuntimeError("TF_Encoder is in train mode: dropout is not implemented - call model.eval()")
         dt = act_dtype(config.PRECISION)
-        x = ops.add_pos_encoding(col_feats.contiguous(), self.pos_encoder.table().contiguous(), dt)
+        col_feats = col_feats.contiguous()
+        if self.pre_encoder_mlp:
+            # encoders.py:128-134: input = col_feats + combine_mlp(cat(col_feats, relevant semantics))
+            if semantics is None:
+                raise ValueError("config.PRE_ENCODER_MLP needs the semantic vectors")
+            feats = ops.cast(col_feats, dt)
+            col_feats = combine_with_semantic(feats, relevant_semantic(feats, semantics, self.sem_relevence_mlp), self.combine_mlp)
+        x = ops.add_pos_encoding(col_feats, self.pos_encoder.table().contiguous(), dt)
         for layer in self.encoder.layers:
             x = layer.forward_btd(x)
         return ops.layer_norm(x, *_ln(self.encoder.norm))
 
     def forward(self, col_feats, semantics, is_train=False):
-        return ops.cast(self.forward_features(col_feats), torch.float32)
+        return ops.cast(self.forward_features(col_feats, semantics), torch.float32)
 
 
 class TransformerDecoderLayer(nn.Module):
@@ -285,7 +395,12 @@ class TF_Decoder(nn.Module):
         self.emb = nn.Embedding(num_classes, config.EMBED_DIM)
         self.emb_to_classes = nn.Linear(config.EMBED_DIM, num_classes)
         self.num_classes = num_classes
-        _no_fusion('PRE_DECODER_MLP', 'CLS_DECODER_INIT', 'POST_DECODER_MLP')
+        self.pre_decoder_mlp = bool(config.PRE_DECODER_MLP)
+        if self.pre_decoder_mlp:      # decoders.py:122-124
+            self.relevant_mlp = MLP(input_size=(config.EMBED_DIM * 2), hidden_size=config.EMBED_DIM, num_classes=1, num_layers=3)
+            self.combine_mlp = MLP(input_size=(config.EMBED_DIM * 2), hidden_size=config.EMBED_DIM, num_classes=config.EMBED_DIM,
+                                   num_layers=2)
+        _no_fusion('CLS_DECODER_INIT', 'POST_DECODER_MLP')
         self.sem_cls = False
 
     def _generate_square_subsequent_mask(self, sz):
@@ -313,7 +428,10 @@ class TF_Decoder(nn.Module):
             return ops.linear(x, pk["w_cls"], pk["b_cls"], want_f32=True, want_bf16=False)
         return ops.linear(x, pk["w_cls"], pk["b_cls"])
 
-    def decode(self, encoder_output, text, is_train, enc_act=None):
+    def get_relevant_semantic(self, feats, sem_vec, mlp, is_train=False):
+        return relevant_semantic(ops.cast(feats.contiguous(), act_dtype(config.PRECISION)), sem_vec, mlp)
+
+    def decode(self, encoder_output, text, is_train, enc_act=None, semantics=None):
         """dict(logits [B, steps, C] f32, ids [B, steps] i32, lengths [B] i32)."""
         require_inference(encoder_output)
         if self.training:
@@ -327,6 +445,11 @@ class TF_Decoder(nn.Module):
         C, E = self.num_classes, self.emb.weight.shape[1]
         pe = self.pos_encoder.table().contiguous()
         memory = ops.linear(enc, pk["w_mem"], pk["b_mem"])                            # hid_to_emb: [B, T, E]
+        if self.pre_decoder_mlp:
+            # decoders.py:218-222: memory = memory + combine_mlp(cat(memory, relevant semantics))
+            if semantics is None:
+                raise ValueError("config.PRE_DECODER_MLP needs the semantic vectors")
+            memory = combine_with_semantic(memory, relevant_semantic(memory, semantics, self.relevant_mlp), self.combine_mlp)
         layers = list(self.decoder.layers)
         mem_kv = [layer.memory_kv(memory) for layer in layers]
         final = _ln(self.decoder.norm)
@@ -362,7 +485,7 @@ class TF_Decoder(nn.Module):
         return {"logits": logits, "ids": ids, "lengths": _lengths(ids)}
 
     def forward(self, encoder_output, text, semantics, is_train):
-        return self.decode(encoder_output, text, is_train)["logits"]
+        return self.decode(encoder_output, text, is_train, semantics=semantics)["logits"]
 
 
 class Linear_Decoder(nn.Module):
@@ -379,7 +502,7 @@ class Linear_Decoder(nn.Module):
         self.linear_decoder.bias.data.zero_()
         self.linear_decoder.weight.data.uniform_(-initrange, initrange)
 
-    def decode(self, encoder_output, text, is_train, enc_act=None):
+    def decode(self, encoder_output, text, is_train, enc_act=None, semantics=None):
         require_inference(encoder_output)
         precision = config.PRECISION
         dt = act_dtype(precision)

@@ -457,6 +457,31 @@ def mha_step(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, Lk: 
     return out
 
 
+def pair_add_relu(a: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """a [B,T,C], s [B,O,C] -> relu(a[:, :, None] + s[:, None]) [B,T,O,C] (same dtype)."""
+    _req(a, "a"); _req(s, "s", a.dtype)
+    B, T, C = a.shape
+    O = s.shape[1]
+    assert s.shape == (B, O, C)
+    h = torch.empty((B, T, O, C), device=a.device, dtype=a.dtype)
+    with _on(a, s) as st:
+        check(lib().mstr_pair_add_relu(ptr(a), ptr(s), ptr(h), B, T, O, C, _dt(a), st), "mstr_pair_add_relu")
+    return h
+
+
+def relevance_reduce(h2: torch.Tensor, w3: torch.Tensor, b3: float, sem: torch.Tensor) -> torch.Tensor:
+    """h2 [B,T,O,C], w3 [C] f32, sem [B,O,E] f32 -> sum_o softmax_o(h2 . w3 + b3) sem[:, o]  [B,T,E] in h2's dtype."""
+    _req(h2, "h2"); _req(w3, "w3", torch.float32); _req(sem, "sem", torch.float32)
+    B, T, O, C = h2.shape
+    E = sem.shape[2]
+    assert sem.shape == (B, O, E) and w3.numel() == C
+    out = torch.empty((B, T, E), device=h2.device, dtype=h2.dtype)
+    with _on(h2, w3, sem) as st:
+        check(lib().mstr_relevance_reduce(ptr(h2), ptr(w3), float(b3), ptr(sem), ptr(out), B, T, O, C, E, _dt(h2), st),
+              "mstr_relevance_reduce")
+    return out
+
+
 def gelu_(x: torch.Tensor) -> torch.Tensor:
     """Exact (erf) GELU in place."""
     _req(x, "x")

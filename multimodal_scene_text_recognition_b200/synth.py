@@ -348,7 +348,8 @@ def positional_table(d_model: int, max_len: int = 26) -> np.ndarray:
 
 
 def transformer_spec(decoder: str = "Transformer", hidden_dim: int = 512, embed_dim: int = 256, ff: int = 2048,
-                     num_classes: int = 97, layers: int = 6) -> List[Tuple[str, Tuple[int, ...], str]]:
+                     num_classes: int = 97, layers: int = 6, pre_encoder_mlp: bool = False,
+                     pre_decoder_mlp: bool = False) -> List[Tuple[str, Tuple[int, ...], str]]:
     """(name, shape, kind) of the encoder / decoder tensors of the Transformer configurations (TF_Encoder with
     TF_Decoder: 462 tensors with the rest of the model, with Linear_Decoder: 314)."""
     spec: List[Tuple[str, Tuple[int, ...], str]] = []
@@ -380,6 +381,15 @@ def transformer_spec(decoder: str = "Transformer", hidden_dim: int = 512, embed_
         enc_layer("encoder.encoder.layers.%d." % i)
     spec.extend([("encoder.encoder.norm.weight", (hidden_dim,), "alias:encoder.layer_norm.weight"),
                  ("encoder.encoder.norm.bias", (hidden_dim,), "alias:encoder.layer_norm.bias")])
+
+    def mlp(p: str, dims) -> None:      # MLP (encoders.py:200-243): layers.fc{i}
+        for i in range(len(dims) - 1):
+            spec.extend([("%slayers.fc%d.weight" % (p, i), (dims[i + 1], dims[i]), "mlp_w"),
+                         ("%slayers.fc%d.bias" % (p, i), (dims[i + 1],), "bias")])
+    if pre_encoder_mlp:                 # encoders.py:83-93
+        mlp("encoder.sem_relevence_mlp.", (hidden_dim + embed_dim, hidden_dim, hidden_dim, 1))
+        mlp("encoder.combine_mlp.", (hidden_dim + embed_dim, hidden_dim, hidden_dim, hidden_dim))
+        spec.append(("encoder.emb_to_hid.weight", (hidden_dim, embed_dim), "lin"))
     if decoder == "Linear":
         spec.extend([("decoder.linear_decoder.weight", (num_classes, hidden_dim), "classes"),
                      ("decoder.linear_decoder.bias", (num_classes,), "bias")])
@@ -395,6 +405,9 @@ def transformer_spec(decoder: str = "Transformer", hidden_dim: int = 512, embed_
                  ("decoder.emb.weight", (num_classes, embed_dim), "embedding"),
                  ("decoder.emb_to_classes.weight", (num_classes, embed_dim), "classes"),
                  ("decoder.emb_to_classes.bias", (num_classes,), "bias")])
+    if pre_decoder_mlp:                 # decoders.py:122-124
+        mlp("decoder.relevant_mlp.", (2 * embed_dim, embed_dim, embed_dim, 1))
+        mlp("decoder.combine_mlp.", (2 * embed_dim, embed_dim, embed_dim))
     return spec
 
 
@@ -405,7 +418,8 @@ def transformer_spec(decoder: str = "Transformer", hidden_dim: int = 512, embed_
 TRANSFORMER_GAINS = {"classes": 4.0, "embedding": 0.5, "qk": 4.0, "enc_linear2": 4.0, "dec_memory_out": 2.0}
 
 
-def make_state_dict_transformer(seed: int = 999, decoder: str = "Transformer", geom: Geometry = CFG_A) -> Dict[str, np.ndarray]:
+def make_state_dict_transformer(seed: int = 999, decoder: str = "Transformer", geom: Geometry = CFG_A,
+                                pre_encoder_mlp: bool = False, pre_decoder_mlp: bool = False) -> Dict[str, np.ndarray]:
     """Seeded synthetic weights of the Transformer / Transformer (or Transformer / Linear) configuration: the rectifier,
     ResNet and embedding table of ``make_state_dict`` plus independent random weights for every encoder / decoder layer
     (the reference's default init makes the six layers equal copies, encoders.py:80, and decodes every crop to one
@@ -413,7 +427,8 @@ def make_state_dict_transformer(seed: int = 999, decoder: str = "Transformer", g
     base = make_state_dict(seed, geom)
     out = {k: v for k, v in base.items() if not (k.startswith("encoder.") or k.startswith("decoder."))}
     rng = np.random.Generator(np.random.PCG64(seed + 7))
-    for name, shape, kind in transformer_spec(decoder, num_classes=geom.num_classes):
+    for name, shape, kind in transformer_spec(decoder, num_classes=geom.num_classes, pre_encoder_mlp=pre_encoder_mlp,
+                                              pre_decoder_mlp=pre_decoder_mlp):
         if kind == "pe":
             v = positional_table(shape[2], shape[0])
         elif kind == "xavier":
@@ -427,6 +442,8 @@ def make_state_dict_transformer(seed: int = 999, decoder: str = "Transformer", g
                 v = v * TRANSFORMER_GAINS["enc_linear2"]
             if name.endswith("multihead_attn.out_proj.weight"):
                 v = v * TRANSFORMER_GAINS["dec_memory_out"]
+        elif kind == "mlp_w":
+            v = rng.standard_normal(shape) * np.sqrt(2.0 / shape[1])     # the MLP's own init (encoders.py:226)
         elif kind == "classes":
             k = TRANSFORMER_GAINS["classes"] / np.sqrt(shape[1])
             v = rng.uniform(-k, k, shape)

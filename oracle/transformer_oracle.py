@@ -88,9 +88,12 @@ def encoder_layer(src, sd, prefix, heads=8):
     return _ln(src, sd, prefix + "norm2.") + src2
 
 
-def tf_encoder(col_feats, sd, dt=np.float32, layers=6, prefix="encoder."):
-    """TF_Encoder.forward (encoders.py:127-143) with PRE_ENCODER_MLP off: positional encoding, the layers, the norm."""
+def tf_encoder(col_feats, sd, dt=np.float32, layers=6, prefix="encoder.", semantics=None):
+    """TF_Encoder.forward (encoders.py:127-143): [PRE_ENCODER_MLP fusion when ``semantics`` is given,] positional
+    encoding, the layers, the norm."""
     x = col_feats.astype(dt)
+    if semantics is not None:
+        x = pre_mlp_fusion(x, semantics, sd, prefix + "sem_relevence_mlp.", prefix + "combine_mlp.")
     pe = sd[prefix + "pos_encoder.pe"].astype(dt)[:, 0, :]
     x = x + pe[None, :x.shape[1], :]
     for i in range(layers):
@@ -119,11 +122,14 @@ def _decoder_stack(x, memory, sd, prefix, layers):
     return _ln(x, sd, prefix + "decoder.norm.")
 
 
-def tf_decoder(enc, sd, max_len=25, text: Optional[np.ndarray] = None, dt=np.float32, layers=6, prefix="decoder."):
+def tf_decoder(enc, sd, max_len=25, text: Optional[np.ndarray] = None, dt=np.float32, layers=6, prefix="decoder.",
+               semantics=None):
     """TF_Decoder.forward (decoders.py:213-296 of the class body, :228-279 the two branches).
     text None: greedy, logits [B, max_len, C]; text [B, >= max_len + 1]: teacher forcing, logits [B, max_len + 1, C]."""
     enc = enc.astype(dt)
     memory = linear(enc, sd[prefix + "hid_to_emb.weight"].astype(dt), sd[prefix + "hid_to_emb.bias"].astype(dt))
+    if semantics is not None:            # PRE_DECODER_MLP (decoders.py:218-222)
+        memory = pre_mlp_fusion(memory, semantics, sd, prefix + "relevant_mlp.", prefix + "combine_mlp.")
     emb = sd[prefix + "emb.weight"].astype(dt)
     pe = sd[prefix + "pos_encoder.pe"].astype(dt)[:, 0, :]
     w_c, b_c = sd[prefix + "emb_to_classes.weight"].astype(dt), sd[prefix + "emb_to_classes.bias"].astype(dt)
@@ -181,3 +187,29 @@ def oscar_bert(col_feats, sd, dt=np.float32, prefix="encoder.", heads=12, layers
         h = gelu(linear(x, g(p + "intermediate.dense.weight"), g(p + "intermediate.dense.bias")))
         x = ln(linear(h, g(p + "output.dense.weight"), g(p + "output.dense.bias")) + x, p + "output.LayerNorm")
     return linear(x, g("bert_to_hid.weight"), g("bert_to_hid.bias"))
+
+
+def mlp(x, sd, prefix):
+    """MLP.forward (encoders.py:238-243): Linear layers ``layers.fc{i}`` with ReLU between them."""
+    i = 0
+    while (prefix + "layers.fc%d.weight" % (i + 1)) in sd:
+        x = np.maximum(linear(x, sd[prefix + "layers.fc%d.weight" % i].astype(x.dtype), sd[prefix + "layers.fc%d.bias" % i].astype(x.dtype)), 0)
+        i += 1
+    return linear(x, sd[prefix + "layers.fc%d.weight" % i].astype(x.dtype), sd[prefix + "layers.fc%d.bias" % i].astype(x.dtype))
+
+
+def get_relevant_semantic(feats, sem_vec, sd, mlp_prefix):
+    """encoders.py:89-111 / decoders.py:147-170: the concatenation of every (column, object) pair through the MLP, softmax
+    over the objects, weighted sum of the object vectors.  feats [B, T, F], sem_vec [B, O, E] -> [B, T, E]."""
+    B, T, _ = feats.shape
+    O = sem_vec.shape[1]
+    sem_seq = np.broadcast_to(sem_vec[:, None], (B, T, O, sem_vec.shape[2]))
+    col_seq = np.broadcast_to(feats[:, :, None], (B, T, O, feats.shape[2]))
+    scores = softmax(mlp(np.concatenate([col_seq, sem_seq], axis=3), sd, mlp_prefix), axis=2)
+    return (sem_seq * scores).sum(axis=2)
+
+
+def pre_mlp_fusion(feats, sem_vec, sd, relevance_prefix, combine_prefix):
+    """feats + combine_mlp(cat(feats, relevant semantics)) (encoders.py:128-134, decoders.py:218-222)."""
+    rel = get_relevant_semantic(feats, sem_vec.astype(feats.dtype), sd, relevance_prefix)
+    return feats + mlp(np.concatenate([feats, rel], axis=2), sd, combine_prefix)

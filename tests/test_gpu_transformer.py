@@ -280,3 +280,62 @@ def test_transformer_configuration_edge_cases(tf_config, sd_tf):
     # state dict with the DataParallel prefix (get_model, model.py:115) loads into the wrapped model
     wrapped = torch.nn.DataParallel(M.Model().eval(), device_ids=[0])
     wrapped.load_state_dict({"module." + k: torch.from_numpy(v) for k, v in sd_tf.items()}, strict=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# semantic fusion: PRE_ENCODER_MLP + PRE_DECODER_MLP
+# ------------------------------------------------------------------------------------------------
+def test_relevant_semantic_kernels():
+    """pair_add_relu + relevance_reduce against the direct evaluation (53 objects: two score slots per lane)."""
+    r = rng(8)
+    B, T, O, C, E = 3, 26, 53, 512, 256
+    a = r.standard_normal((B, T, C)).astype(np.float32)
+    s_ = r.standard_normal((B, O, C)).astype(np.float32)
+    h = ops.pair_add_relu(dev(a), dev(s_))
+    ref_h = np.maximum(a[:, :, None] + s_[:, None], 0)
+    assert np.array_equal(host(h), ref_h)
+    w3 = (r.standard_normal(C) / np.sqrt(C)).astype(np.float32)
+    sem = r.standard_normal((B, O, E)).astype(np.float32)
+    out = ops.relevance_reduce(h, dev(w3), 0.3, dev(sem))
+    sc = ref_h.astype(np.float64) @ w3.astype(np.float64) + 0.3
+    p = tfo.softmax(sc, axis=2)
+    ref = (p[..., None] * sem[:, None].astype(np.float64)).sum(axis=2)
+    assert_close(host(out), ref, 5e-6, "relevance_reduce f32")
+    hb = ops.pair_add_relu(dev(a, BF), dev(s_, BF))
+    outb = ops.relevance_reduce(hb, dev(w3), 0.3, dev(sem))
+    assert_close(host(outb), ref, 3e-2, "relevance_reduce bf16")
+
+
+def test_semantic_fusion_matches_reference_golden(tf_config, golden_dir):
+    """Model with PRE_ENCODER_MLP + PRE_DECODER_MLP: the object-tag vectors reach the prediction.  Fused features, encoder
+    output, greedy ids / logits against the reference's own modules; the whole model from the crops; and the ids must
+    change when the semantic vectors do."""
+    g = np.load(os.path.join(golden_dir, "cfg_tf_fusion.npz"))
+    sd = synth.make_state_dict_transformer(999, pre_encoder_mlp=True, pre_decoder_mlp=True)
+    try:
+        config.PRE_ENCODER_MLP = config.PRE_DECODER_MLP = True
+        for precision, tol in (("fp32", 3e-4), ("tf32", 3e-4)):
+            m = _model(sd, precision)
+            sem = dev(g["semantics"])
+            with torch.no_grad():
+                rel = m.encoder.get_relevant_semantic(dev(g["visual"]), sem)
+                assert_close(host(rel), g["relevant"], 1e-4, "relevant semantics (%s)" % precision)
+                enc = m.encoder.forward_features(dev(g["visual"]), sem)
+                assert_close(host(enc), g["enc"], 2e-4, "encoder output with fusion (%s)" % precision)
+                out = m.decoder.decode(dev(g["enc"]), None, False, semantics=sem)
+                assert np.array_equal(host(out["ids"]), g["ids"])
+                assert_close(host(out["logits"]), g["logits"], tol, "logits with fusion (%s)" % precision)
+        B = g["ids"].shape[0]
+        x = synth.make_crops(123, B)
+        ov, sc, io = synth.make_semantics(124, B)
+        with torch.no_grad():
+            full = m.recognize(dev(x), dev(ov), dev(sc), dev(io))
+            other = m.recognize(dev(x), dev(np.roll(ov, 1, axis=0)), dev(sc), dev(io))
+        assert np.array_equal(host(full["ids"]), g["ids"]), "whole model from the crops"
+        assert (host(other["ids"]) != g["ids"]).mean() > 0.2, "the prediction must depend on the object tags"
+        mb = _model(sd, "bf16")
+        with torch.no_grad():
+            encb = mb.encoder.forward_features(dev(g["visual"]), dev(g["semantics"]))
+        assert_close(host(encb), g["enc"], 8e-2, "encoder output with fusion (bf16)")
+    finally:
+        config.PRE_ENCODER_MLP = config.PRE_DECODER_MLP = False

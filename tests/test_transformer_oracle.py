@@ -103,3 +103,35 @@ def test_oscar_bert_mirror_and_oracle_match_reference(golden_dir):
     npsd = {"encoder." + k: v.numpy() for k, v in sd.items()}
     y = tfo.oscar_bert(g["x"], npsd)
     assert _rel(y, g["y"]) < 5e-5
+
+
+def test_fusion_oracle_matches_reference(golden_dir):
+    """PRE_ENCODER_MLP + PRE_DECODER_MLP: the oracle's get_relevant_semantic / combine restatement, the encoder from the
+    fused features and the greedy decoder with the fused memory against the reference's own modules."""
+    g = np.load(os.path.join(golden_dir, "cfg_tf_fusion.npz"))
+    sd = synth.make_state_dict_transformer(999, pre_encoder_mlp=True, pre_decoder_mlp=True)
+    rel = tfo.get_relevant_semantic(g["visual"], g["semantics"], sd, "encoder.sem_relevence_mlp.")
+    assert _rel(rel, g["relevant"]) < 2e-5
+    fused = tfo.pre_mlp_fusion(g["visual"], g["semantics"], sd, "encoder.sem_relevence_mlp.", "encoder.combine_mlp.")
+    assert _rel(fused, g["fused"]) < 2e-5
+    enc = tfo.tf_encoder(g["visual"], sd, semantics=g["semantics"])
+    assert _rel(enc, g["enc"]) < 1e-4
+    lg = tfo.tf_decoder(g["enc"], sd, semantics=g["semantics"])
+    assert np.array_equal(lg.argmax(2), g["ids"]) and _rel(lg, g["logits"]) < 1e-4
+
+
+def test_fusion_mirror_state_dict():
+    from multimodal_scene_text_recognition_b200 import config, model as M
+    saved = (config.ENCODER, config.DECODER)
+    try:
+        config.ENCODER, config.DECODER, config.PRE_ENCODER_MLP, config.PRE_DECODER_MLP = "Transformer", "Transformer", True, True
+        m = M.Model()
+        sd = synth.make_state_dict_transformer(999, pre_encoder_mlp=True, pre_decoder_mlp=True)
+        assert len(m.state_dict()) == len(sd) == 485          # the reference's count with both switches on
+        M.load_numpy_state_dict(m, sd)
+        with pytest.raises(NotImplementedError):
+            config.POST_DECODER_MLP = True
+            M.Model()
+    finally:
+        config.PRE_ENCODER_MLP = config.PRE_DECODER_MLP = config.POST_DECODER_MLP = False
+        config.ENCODER, config.DECODER = saved

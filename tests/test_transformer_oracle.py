@@ -74,10 +74,10 @@ def test_mirror_state_dict_is_the_spec(decoder, count):
         # the six layers are deep copies of one initialised layer and `norm` IS layer_norm, like in the reference
         assert m.encoder.encoder.norm is m.encoder.layer_norm
         with pytest.raises(NotImplementedError):
-            config.PRE_ENCODER_MLP = True
+            config.MULTIHEAD_PRE_MEMORY = True
             M.Model()
     finally:
-        config.PRE_ENCODER_MLP = False
+        config.MULTIHEAD_PRE_MEMORY = False
         config.ENCODER, config.DECODER = saved
 
 

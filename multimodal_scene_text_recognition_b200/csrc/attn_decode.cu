@@ -27,12 +27,13 @@ __device__ __forceinline__ int ad_token(const int64_t t, const int C) { return (
 
 
 constexpr int AD_H = 256;
-constexpr int AD_CPT = 4;
-constexpr int AD_BT = 8 * AD_CPT;   // 32 crops per CTA
 constexpr int AD_LD = AD_H + 4;
 constexpr int AD_MAXC = 128;        // num_classes <= 128 (one generator pass)
 constexpr int AD_MAX_TSLOTS = 3;    // T <= 96
-constexpr int AD_SMEM_FLOATS = 3 * AD_BT * AD_LD + AD_BT * AD_H + SG_NBUF * SG_WBUF_FLOATS;
+// crops per thread AD_CPT = 4, 2 or 1 (8 AD_CPT crops per CTA): the largest that still gives every SM a CTA.  Every CTA
+// streams all the weights per step whatever its tile, so at small batches small tiles cost L2 traffic, not time (256
+// crops: 32 CTAs of 8 crops instead of 8 of 32); a crop's arithmetic does not depend on the choice.
+template <int CPT> constexpr int ad_smem_floats() { return 3 * 8 * CPT * AD_LD + 8 * CPT * AD_H + SG_NBUF * SG_WBUF_FLOATS; }
 
 struct AttnParams {
   const float* enc; const float* proj;
@@ -60,7 +61,9 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+template <int AD_CPT>
 __global__ void __launch_bounds__(256, 1) attn_decode_kernel(const AttnParams p) {
+  constexpr int AD_BT = 8 * AD_CPT;
   extern __shared__ __align__(16) float smem_f[];
   float* h_cur = smem_f;                       // [BT][LD]
   float* h_nxt = h_cur + AD_BT * AD_LD;        // [BT][LD]
@@ -370,15 +373,21 @@ extern "C" __attribute__((visibility("default"))) int mstr_attn_decode(const flo
   cudaStream_t st = (cudaStream_t)stream;
   attn_decode_init_kernel<<<ceil_div(B, 256), 256, 0, st>>>(lengths, ids, B, steps, early_exit);
   MSTR_LAUNCH_CHECK("attn_decode_init_kernel");
-  static unsigned long long smem_set = 0;
-  const int smem = AD_SMEM_FLOATS * (int)sizeof(float);
-  {
-    const int rc_attr = ensure_dynamic_smem((const void*)attn_decode_kernel, smem, &smem_set);
-    if (rc_attr != MSTR_OK) return rc_attr;
-  }
   AttnParams p{enc, proj, w_h2h, b_h2h, w_score, w_ctx, w_tok, w_hh, bias, w_gen, b_gen, text, h0, c0,
                logits, ids, lengths, alpha_out, h_out, c_out, B, T, C, steps, early_exit};
-  attn_decode_kernel<<<ceil_div(B, AD_BT), 256, smem, st>>>(p);
+#define MSTR_AD_LAUNCH(CPT)                                                                            \
+  do {                                                                                                 \
+    static unsigned long long smem_set = 0;                                                            \
+    const int smem = ad_smem_floats<CPT>() * (int)sizeof(float);                                       \
+    const int rc_attr = ensure_dynamic_smem((const void*)attn_decode_kernel<CPT>, smem, &smem_set);    \
+    if (rc_attr != MSTR_OK) return rc_attr;                                                            \
+    attn_decode_kernel<CPT><<<ceil_div(B, 8 * CPT), 256, smem, st>>>(p);                               \
+  } while (0)
+  const int sms = sm_count();
+  if (ceil_div(B, 32) >= sms) MSTR_AD_LAUNCH(4);
+  else if (ceil_div(B, 16) >= sms) MSTR_AD_LAUNCH(2);
+  else MSTR_AD_LAUNCH(1);
+#undef MSTR_AD_LAUNCH
   MSTR_LAUNCH_CHECK("attn_decode_kernel");
   return MSTR_OK;
 }

@@ -5,8 +5,11 @@
 // t = T-1..0 with the *_reverse parameters).  The input projection is a separate GEMM
 // (mstr_conv_gemm_*), its result gates_x already contains b_ih + b_hh.
 //
-// grid = (ceil(B / 56), 2 directions): 74 x 2 = 148 CTAs at B = 4096, one per SM, one wave.
-// Per CTA: h_t and c_t of its 56 crops stay in shared memory for the whole sequence; W_hh
+// grid = (ceil(B / (8 CPT)), 2 directions) with CPT = 7, 4, 2 or 1 crops per thread, the largest that still gives every
+// SM a CTA: 74 x 2 = 148 CTAs of 56 crops at B = 4096; at B = 256 CPT = 1 gives 64 CTAs of 8 crops instead of 10 of 56
+// (every CTA streams all of W_hh per step whatever its tile, so small tiles cost L2 traffic, not time, while the
+// recurrence is latency bound).  A crop's arithmetic does not depend on CPT.
+// Per CTA: h_t and c_t of its 8 CPT crops stay in shared memory for the whole sequence; W_hh
 // (1024 x 256 fp32 = 1 MB per direction, L2 resident) is streamed through a 3-deep cp.async ring
 // (stream_gemm.cuh).  A thread owns the four gate rows of one hidden unit for 7 crops, so the
 // sigmoid/tanh cell update is thread-local.  fp32 FMA throughout (parity mode and, in round 1,
@@ -16,17 +19,17 @@
 namespace mstr {
 
 constexpr int LS_H = 256;             // hidden size (model.py:30)
-constexpr int LS_CPT = 7;             // crops per thread
-constexpr int LS_BT = 8 * LS_CPT;     // crops per CTA = 56
 constexpr int LS_HLD = LS_H + 4;      // padded h row
-constexpr int LS_SMEM_FLOATS = 2 * LS_BT * LS_HLD + LS_BT * LS_H + SG_NBUF * SG_WBUF_FLOATS;
+template <int CPT> constexpr int ls_smem_floats() { return 2 * 8 * CPT * LS_HLD + 8 * CPT * LS_H + SG_NBUF * SG_WBUF_FLOATS; }
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
 
+template <int LS_CPT>                 // crops per thread; 8 LS_CPT crops per CTA
 __global__ void __launch_bounds__(256, 1)
 bilstm_recurrent_kernel(const float* __restrict__ gates_x, const float* __restrict__ w_hh,
                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int B, int T) {
+  constexpr int LS_BT = 8 * LS_CPT;
   extern __shared__ __align__(16) float smem_f[];
   float* h_cur = smem_f;
   float* h_nxt = h_cur + LS_BT * LS_HLD;
@@ -128,15 +131,23 @@ extern "C" __attribute__((visibility("default"))) int mstr_bilstm_recurrent(cons
   MSTR_REQUIRE(B > 0 && T > 0, MSTR_ERR_BAD_ARG, "mstr_bilstm_recurrent: bad size");
   MSTR_REQUIRE(Hd == LS_H, MSTR_ERR_UNSUPPORTED, "mstr_bilstm_recurrent: hidden size %d != %d", Hd, LS_H);
   MSTR_REQUIRE(aligned16(w_hh), MSTR_ERR_BAD_ARG, "mstr_bilstm_recurrent: w_hh must be 16-byte aligned");
-  static unsigned long long smem_set = 0;
-  const int smem = LS_SMEM_FLOATS * (int)sizeof(float);
-  {
-    const int rc_attr = ensure_dynamic_smem((const void*)bilstm_recurrent_kernel, smem, &smem_set);
-    if (rc_attr != MSTR_OK) return rc_attr;
-  }
-  dim3 grid(ceil_div(B, LS_BT), 2);
-  bilstm_recurrent_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(gates_x, w_hh, out_f32,
-                                                                   (__nv_bfloat16*)out_bf16, B, T);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* ob = (__nv_bfloat16*)out_bf16;
+#define MSTR_LS_LAUNCH(CPT)                                                                                         \
+  do {                                                                                                              \
+    static unsigned long long smem_set = 0;                                                                         \
+    const int smem = ls_smem_floats<CPT>() * (int)sizeof(float);                                                    \
+    const int rc_attr = ensure_dynamic_smem((const void*)bilstm_recurrent_kernel<CPT>, smem, &smem_set);            \
+    if (rc_attr != MSTR_OK) return rc_attr;                                                                         \
+    bilstm_recurrent_kernel<CPT><<<dim3(ceil_div(B, 8 * CPT), 2), 256, smem, st>>>(gates_x, w_hh, out_f32, ob, B, T); \
+  } while (0)
+  // the largest tile that still gives every SM a CTA (2 directions)
+  const int sms = sm_count();
+  if (2 * ceil_div(B, 56) >= sms) MSTR_LS_LAUNCH(7);
+  else if (2 * ceil_div(B, 32) >= sms) MSTR_LS_LAUNCH(4);
+  else if (2 * ceil_div(B, 16) >= sms) MSTR_LS_LAUNCH(2);
+  else MSTR_LS_LAUNCH(1);
+#undef MSTR_LS_LAUNCH
   MSTR_LAUNCH_CHECK("bilstm_recurrent_kernel");
   return MSTR_OK;
 }

@@ -5,8 +5,8 @@ The modules read these attributes at call time exactly where the reference does
 Linear_Embedding.forward, semantic_vectors.py:35-47; ``ENCODER`` in Model.forward, model.py:99).
 The LSTM/LSTM recognition path is the hot path (SURVEY.md 8 a-e); 'Transformer' (or 'Oscar') encoder with the 'Transformer' or
 'Linear' decoder (the reference's own defaults) is the widening row f4.  The attributes of the fusion experiments
-are kept so that code reading them does not break; PRE_ENCODER_MLP and PRE_DECODER_MLP are implemented, turning one
-of the others on raises NotImplementedError.
+are kept so that code reading them does not break; PRE_ENCODER_MLP, PRE_DECODER_MLP, CLS_DECODER_INIT and POST_DECODER_MLP are
+implemented; OSCAR_ENCODER and MULTIHEAD_* raise NotImplementedError (they fail in the reference's own forward).
 """
 import string
 

@@ -25,8 +25,8 @@ Two things differ from the reference's code, neither in the numbers it defines:
 
 Of the semantic-fusion switches (config.py:40-53) ``PRE_ENCODER_MLP`` and ``PRE_DECODER_MLP`` are built - they are what
 makes the object-tag vectors of ``Linear_Embedding`` reach the prediction (``relevant_semantic`` / ``combine_with_semantic``
-below) -; ``OSCAR_ENCODER``, ``CLS_DECODER_INIT``, ``MULTIHEAD_*`` and ``POST_DECODER_MLP`` raise NotImplementedError at
-construction.  Eval mode only (dropout is the identity).
+below) -; ``CLS_DECODER_INIT`` and ``POST_DECODER_MLP`` too.  ``OSCAR_ENCODER`` and the ``MULTIHEAD_*`` switches raise
+NotImplementedError at construction: they raise in the reference itself (tensor-shape errors in its forward).  Eval mode only (dropout is the identity).
 """
 from __future__ import annotations
 
@@ -116,32 +116,54 @@ class MLP(nn.Module):
         return h
 
 
-def _relevance_pack(mlp: MLP, feat_dim: int, precision: str):
+def _pad_w(w: torch.Tensor, pad: int) -> torch.Tensor:
+    """Weight [N, K] zero-padded to multiples of ``pad`` in both dimensions (pad = 1: unchanged)."""
+    n, k = w.shape
+    N, K = -(-n // pad) * pad, -(-k // pad) * pad
+    if (N, K) == (n, k):
+        return w.contiguous()
+    out = torch.zeros((N, K), device=w.device, dtype=w.dtype)
+    out[:n, :k] = w
+    return out
+
+
+def _pad_v(v: torch.Tensor, pad: int) -> torch.Tensor:
+    n = v.shape[0]
+    N = -(-n // pad) * pad
+    if N == n:
+        return v.contiguous()
+    out = torch.zeros((N,), device=v.device, dtype=v.dtype)
+    out[:n] = v
+    return out
+
+
+def _relevance_pack(mlp: MLP, feat_dim: int, precision: str, pad: int = 1):
     """The 3-layer relevance MLP on cat(column feature [feat_dim], object vector): first layer split into its column
-    and its object half, last layer (-> 1 score) as a vector."""
+    and its object half, last layer (-> 1 score) as a vector.  ``pad``: every dimension zero-padded to a multiple of it
+    (the 97-wide layers of POST_DECODER_MLP on GEMM tiles of 128; padded channels stay exactly zero through the ReLUs)."""
     fc0, fc1, fc2 = mlp.linears()
     if fc2.out_features != 1:
         raise NotImplementedError("the relevance MLP must end in one score")
 
     def build():
         w0 = _f(fc0.weight)
-        return {"w0_feat": wrap_weight(w0[:, :feat_dim].contiguous(), precision), "b0": _f(fc0.bias),
-                "w0_sem": wrap_weight(w0[:, feat_dim:].contiguous(), precision),
-                "w1": wrap_weight(_f(fc1.weight), precision), "b1": _f(fc1.bias),
-                "w2": _f(fc2.weight).view(-1).contiguous(), "b2": float(fc2.bias.detach().float().item())}
-    return cached(mlp, ("relevance", precision, feat_dim), [p for fc in (fc0, fc1, fc2) for p in (fc.weight, fc.bias)], build)
+        return {"w0_feat": wrap_weight(_pad_w(w0[:, :feat_dim], pad), precision), "b0": _pad_v(_f(fc0.bias), pad),
+                "w0_sem": wrap_weight(_pad_w(w0[:, feat_dim:], pad), precision),
+                "w1": wrap_weight(_pad_w(_f(fc1.weight), pad), precision), "b1": _pad_v(_f(fc1.bias), pad),
+                "w2": _pad_v(_f(fc2.weight).view(-1), pad), "b2": float(fc2.bias.detach().float().item())}
+    return cached(mlp, ("relevance", precision, feat_dim, pad), [p for fc in (fc0, fc1, fc2) for p in (fc.weight, fc.bias)], build)
 
 
-def relevant_semantic(feats: torch.Tensor, sem_vec: torch.Tensor, mlp: MLP) -> torch.Tensor:
+def relevant_semantic(feats: torch.Tensor, sem_vec: torch.Tensor, mlp: MLP, feat_dim: int = 0, pad: int = 1) -> torch.Tensor:
     """get_relevant_semantic (encoders.py:89-111, decoders.py:147-170): feats [B, T, F] (activation dtype), sem_vec
     [B, O, E] f32 -> [B, T, E]: for every (column, object) pair ``mlp(cat(column, object))`` is a score, soft-maxed over
     the objects, weighting the sum of the object vectors.  The reference materialises cat(...) for all T x O pairs; the
     first layer is linear, so its column half runs once per column and its object half once per object (two GEMMs) and
     ``pair_add_relu`` forms the T x O hidden rows; the middle layer is one GEMM over them, the last layer + softmax +
-    weighted sum one kernel."""
+    weighted sum one kernel.  ``feat_dim`` / ``pad``: the un-padded feature width when feats / sem_vec arrive zero-padded."""
     precision = config.PRECISION
     dt = act_dtype(precision)
-    pk = _relevance_pack(mlp, feats.shape[-1], precision)
+    pk = _relevance_pack(mlp, feat_dim or feats.shape[-1], precision, pad)
     sem32 = sem_vec.contiguous().float()
     a = ops.linear(feats, pk["w0_feat"], pk["b0"])                                  # [B, T, Hd]
     s_ = ops.linear(ops.cast(sem32, dt), pk["w0_sem"], None)                        # [B, O, Hd]
@@ -150,27 +172,31 @@ def relevant_semantic(feats: torch.Tensor, sem_vec: torch.Tensor, mlp: MLP) -> t
     return ops.relevance_reduce(h, pk["w2"], pk["b2"], sem32)                       # [B, T, E]
 
 
-def _combine_pack(mlp: MLP, feat_dim: int, precision: str):
+def _combine_pack(mlp: MLP, feat_dim: int, precision: str, pad: int = 1):
     lins = mlp.linears()
 
     def build():
         w0 = _f(lins[0].weight)
-        rest = [(wrap_weight(_f(fc.weight), precision), _f(fc.bias)) for fc in lins[1:]]
-        return {"w0_feat": wrap_weight(w0[:, :feat_dim].contiguous(), precision), "b0": _f(lins[0].bias),
-                "w0_sem": wrap_weight(w0[:, feat_dim:].contiguous(), precision), "rest": rest}
-    return cached(mlp, ("combine", precision, feat_dim), [p for fc in lins for p in (fc.weight, fc.bias)], build)
+        rest = [(wrap_weight(_pad_w(_f(fc.weight), pad), precision), _pad_v(_f(fc.bias), pad)) for fc in lins[1:]]
+        return {"w0_feat": wrap_weight(_pad_w(w0[:, :feat_dim], pad), precision), "b0": _pad_v(_f(lins[0].bias), pad),
+                "w0_sem": wrap_weight(_pad_w(w0[:, feat_dim:], pad), precision), "rest": rest}
+    return cached(mlp, ("combine", precision, feat_dim, pad), [p for fc in lins for p in (fc.weight, fc.bias)], build)
 
 
-def combine_with_semantic(feats: torch.Tensor, rel: torch.Tensor, mlp: MLP) -> torch.Tensor:
-    """feats + combine_mlp(cat(feats, rel)) (encoders.py:131-134, decoders.py:220-222) without materialising the
-    concatenation: the first layer as two GEMMs (the second adds the first in its epilogue), the residual ``feats`` in
-    the epilogue of the last."""
-    pk = _combine_pack(mlp, feats.shape[-1], config.PRECISION)
+def combine_with_semantic(feats: torch.Tensor, rel: torch.Tensor, mlp: MLP, feat_dim: int = 0, pad: int = 1,
+                          want_f32: bool = False) -> torch.Tensor:
+    """feats + combine_mlp(cat(feats, rel)) (encoders.py:131-134, decoders.py:220-222, :289-295) without materialising
+    the concatenation: the first layer as two GEMMs (the second adds the first in its epilogue), the residual ``feats`` in
+    the epilogue of the last (``want_f32``: that last result in f32 whatever the activation dtype)."""
+    pk = _combine_pack(mlp, feat_dim or feats.shape[-1], config.PRECISION, pad)
     h = ops.linear(feats, pk["w0_feat"], pk["b0"])
     h = ops.linear(rel, pk["w0_sem"], None, residual=h, relu=True)
     for i, (w, b) in enumerate(pk["rest"]):
         last = i == len(pk["rest"]) - 1
-        h = ops.linear(h, w, b, relu=not last, residual=feats if last else None)
+        if last and want_f32 and config.PRECISION == 'bf16':
+            h = ops.linear(h, w, b, residual=feats, want_f32=True, want_bf16=False)
+        else:
+            h = ops.linear(h, w, b, relu=not last, residual=feats if last else None)
     return h
 
 
@@ -400,8 +426,18 @@ class TF_Decoder(nn.Module):
             self.relevant_mlp = MLP(input_size=(config.EMBED_DIM * 2), hidden_size=config.EMBED_DIM, num_classes=1, num_layers=3)
             self.combine_mlp = MLP(input_size=(config.EMBED_DIM * 2), hidden_size=config.EMBED_DIM, num_classes=config.EMBED_DIM,
                                    num_layers=2)
-        _no_fusion('CLS_DECODER_INIT', 'POST_DECODER_MLP')
-        self.sem_cls = False
+        # decoders.py:126-130.  get_semantic_cls (:196-201) soft-maxes the relevant semantics over the columns and then SUMS
+        # over the same axis: every entry is 1 whatever sem_cls_mlp computes, so the first target position's embedding is
+        # replaced by a vector of ones (the MLP is created for the state dict and never evaluated).
+        self.sem_cls = bool(config.CLS_DECODER_INIT)
+        if self.sem_cls:
+            self.sem_cls_mlp = MLP(input_size=(config.EMBED_DIM * 2), hidden_size=config.EMBED_DIM, num_classes=1, num_layers=3)
+        self.post_decoder = bool(config.POST_DECODER_MLP)
+        if self.post_decoder:         # decoders.py:132-135 (attribute names as in the reference, typo included)
+            self.post_decoder_mlp = MLP(input_size=(num_classes * 2), hidden_size=num_classes, num_classes=1, num_layers=3)
+            self.post_deocer_combine_mlp = MLP(input_size=(num_classes * 2), hidden_size=num_classes, num_classes=num_classes,
+                                               num_layers=3)
+            self.sem_to_classes = nn.Linear(config.EMBED_DIM, num_classes)
 
     def _generate_square_subsequent_mask(self, sz):
         mask = (torch.triu(torch.ones(sz, sz)) == 1).transpose(0, 1)
@@ -462,13 +498,15 @@ class TF_Decoder(nn.Module):
             if tokens.shape[1] != L:
                 raise ValueError("text must hold MAX_TEXT_LENGTH + 1 = %d target positions" % L)
             x = ops.embed_tokens(tokens, pk["emb"], pe, 0, dt)
+            if self.sem_cls:
+                x[:, 0, :] = self._cls_embedding(B, pe, dt, dev)[:, 0, :]
             for layer, kv in zip(layers, mem_kv):
                 x = layer.forward_sequence(x, kv)
             cls = self._classes(ops.layer_norm(x, *final), pk)                        # [B, L, Cpad] f32
             logits = torch.empty((B, L, C), device=dev, dtype=torch.float32)
             ids = torch.empty((B, L), device=dev, dtype=torch.int32)
             ops.argmax_tokens(cls.view(B * L, -1), C, logits.view(B * L, C), ids.view(B * L), None)
-            return {"logits": logits, "ids": ids, "lengths": _lengths(ids)}
+            return self._post(logits, ids, semantics)
         # greedy (decoders.py:250-279): position t reads targets[t] (targets[0] = 0 = [GO]) and yields targets[t+1]
         steps = config.MAX_TEXT_LENGTH
         logits = torch.empty((B, steps, C), device=dev, dtype=torch.float32)
@@ -477,12 +515,46 @@ class TF_Decoder(nn.Module):
         k_cache = [torch.empty((B, steps, E), device=dev, dtype=dt) for _ in layers]
         v_cache = [torch.empty((B, steps, E), device=dev, dtype=dt) for _ in layers]
         for t in range(steps):
-            x = ops.embed_tokens(tok, pk["emb"], pe, t, dt).view(B, E)
+            x = (self._cls_embedding(B, pe, dt, dev) if (t == 0 and self.sem_cls)
+                 else ops.embed_tokens(tok, pk["emb"], pe, t, dt)).view(B, E)
             for i, layer in enumerate(layers):
                 x = layer.forward_step(x, t, k_cache[i], v_cache[i], mem_kv[i])
             cls = self._classes(ops.layer_norm(x, *final), pk)                        # [B, Cpad] f32
             ops.argmax_tokens(cls, C, logits[:, t], ids[:, t], tok.view(B))
-        return {"logits": logits, "ids": ids, "lengths": _lengths(ids)}
+        return self._post(logits, ids, semantics)
+
+    def _cls_embedding(self, B, pe, dt, dev):
+        """CLS_DECODER_INIT: ones (see __init__) + pe[0], [B, 1, E] in the activation dtype."""
+        return ops.add_pos_encoding(torch.ones((B, 1, pe.shape[1]), device=dev, dtype=torch.float32), pe, dt)
+
+    def _post(self, logits, ids, semantics):
+        """POST_DECODER_MLP (decoders.py:284-295): output = output + post_deocer_combine_mlp(cat(output, relevant semantics))
+        with the semantics mapped to class space by sem_to_classes.  The greedy feedback inside the loop used the logits
+        BEFORE this step (decoders.py:276-279), as here; the returned ids are the argmax of the final logits.  The
+        97-wide layers run on GEMM tiles of 128 with zero padding."""
+        if not self.post_decoder:
+            return {"logits": logits, "ids": ids, "lengths": _lengths(ids)}
+        if semantics is None:
+            raise ValueError("config.POST_DECODER_MLP needs the semantic vectors")
+        precision = config.PRECISION
+        dt = act_dtype(precision)
+        B, S, C = logits.shape
+        pad = 128
+        Cp = -(-C // pad) * pad
+        stc = self.sem_to_classes
+        w_s, b_s = cached(stc, ("sem_to_classes", precision), [stc.weight, stc.bias],
+                          lambda: (wrap_weight(_pad_w(_f(stc.weight), pad), precision), _pad_v(_f(stc.bias), pad)))
+        sem = ops.cast(semantics.contiguous().float(), dt)
+        sem_c = ops.linear(sem, w_s, b_s, want_f32=True, want_bf16=False) if precision == 'bf16' else ops.linear(sem, w_s, b_s)
+        feats32 = torch.zeros((B, S, Cp), device=logits.device, dtype=torch.float32)
+        feats32[..., :C] = logits
+        feats = ops.cast(feats32, dt)
+        rel = relevant_semantic(feats, sem_c, self.post_decoder_mlp, feat_dim=C, pad=pad)       # [B, S, Cp]
+        out = combine_with_semantic(feats, rel, self.post_deocer_combine_mlp, feat_dim=C, pad=pad, want_f32=True)
+        final = torch.empty((B, S, C), device=logits.device, dtype=torch.float32)
+        ids2 = torch.empty((B, S), device=logits.device, dtype=torch.int32)
+        ops.argmax_tokens(ops.cast(out, torch.float32).view(B * S, Cp), C, final.view(B * S, C), ids2.view(B * S), None)
+        return {"logits": final, "ids": ids2, "lengths": _lengths(ids2)}
 
     def forward(self, encoder_output, text, semantics, is_train):
         return self.decode(encoder_output, text, is_train, semantics=semantics)["logits"]

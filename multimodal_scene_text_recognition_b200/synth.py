@@ -349,7 +349,8 @@ def positional_table(d_model: int, max_len: int = 26) -> np.ndarray:
 
 def transformer_spec(decoder: str = "Transformer", hidden_dim: int = 512, embed_dim: int = 256, ff: int = 2048,
                      num_classes: int = 97, layers: int = 6, pre_encoder_mlp: bool = False,
-                     pre_decoder_mlp: bool = False) -> List[Tuple[str, Tuple[int, ...], str]]:
+                     pre_decoder_mlp: bool = False, cls_decoder_init: bool = False,
+                     post_decoder_mlp: bool = False) -> List[Tuple[str, Tuple[int, ...], str]]:
     """(name, shape, kind) of the encoder / decoder tensors of the Transformer configurations (TF_Encoder with
     TF_Decoder: 462 tensors with the rest of the model, with Linear_Decoder: 314)."""
     spec: List[Tuple[str, Tuple[int, ...], str]] = []
@@ -408,6 +409,13 @@ def transformer_spec(decoder: str = "Transformer", hidden_dim: int = 512, embed_
     if pre_decoder_mlp:                 # decoders.py:122-124
         mlp("decoder.relevant_mlp.", (2 * embed_dim, embed_dim, embed_dim, 1))
         mlp("decoder.combine_mlp.", (2 * embed_dim, embed_dim, embed_dim))
+    if cls_decoder_init:                # decoders.py:126-128
+        mlp("decoder.sem_cls_mlp.", (2 * embed_dim, embed_dim, embed_dim, 1))
+    if post_decoder_mlp:                # decoders.py:132-135
+        mlp("decoder.post_decoder_mlp.", (2 * num_classes, num_classes, num_classes, 1))
+        mlp("decoder.post_deocer_combine_mlp.", (2 * num_classes, num_classes, num_classes, num_classes))
+        spec.extend([("decoder.sem_to_classes.weight", (num_classes, embed_dim), "lin"),
+                     ("decoder.sem_to_classes.bias", (num_classes,), "bias")])
     return spec
 
 
@@ -419,7 +427,8 @@ TRANSFORMER_GAINS = {"classes": 4.0, "embedding": 0.5, "qk": 4.0, "enc_linear2":
 
 
 def make_state_dict_transformer(seed: int = 999, decoder: str = "Transformer", geom: Geometry = CFG_A,
-                                pre_encoder_mlp: bool = False, pre_decoder_mlp: bool = False) -> Dict[str, np.ndarray]:
+                                pre_encoder_mlp: bool = False, pre_decoder_mlp: bool = False, cls_decoder_init: bool = False,
+                                post_decoder_mlp: bool = False) -> Dict[str, np.ndarray]:
     """Seeded synthetic weights of the Transformer / Transformer (or Transformer / Linear) configuration: the rectifier,
     ResNet and embedding table of ``make_state_dict`` plus independent random weights for every encoder / decoder layer
     (the reference's default init makes the six layers equal copies, encoders.py:80, and decodes every crop to one
@@ -428,7 +437,8 @@ def make_state_dict_transformer(seed: int = 999, decoder: str = "Transformer", g
     out = {k: v for k, v in base.items() if not (k.startswith("encoder.") or k.startswith("decoder."))}
     rng = np.random.Generator(np.random.PCG64(seed + 7))
     for name, shape, kind in transformer_spec(decoder, num_classes=geom.num_classes, pre_encoder_mlp=pre_encoder_mlp,
-                                              pre_decoder_mlp=pre_decoder_mlp):
+                                              pre_decoder_mlp=pre_decoder_mlp, cls_decoder_init=cls_decoder_init,
+                                              post_decoder_mlp=post_decoder_mlp):
         if kind == "pe":
             v = positional_table(shape[2], shape[0])
         elif kind == "xavier":

@@ -123,7 +123,7 @@ def _decoder_stack(x, memory, sd, prefix, layers):
 
 
 def tf_decoder(enc, sd, max_len=25, text: Optional[np.ndarray] = None, dt=np.float32, layers=6, prefix="decoder.",
-               semantics=None):
+               semantics=None, cls_init=False, post_semantics=None):
     """TF_Decoder.forward (decoders.py:213-296 of the class body, :228-279 the two branches).
     text None: greedy, logits [B, max_len, C]; text [B, >= max_len + 1]: teacher forcing, logits [B, max_len + 1, C]."""
     enc = enc.astype(dt)
@@ -134,18 +134,33 @@ def tf_decoder(enc, sd, max_len=25, text: Optional[np.ndarray] = None, dt=np.flo
     pe = sd[prefix + "pos_encoder.pe"].astype(dt)[:, 0, :]
     w_c, b_c = sd[prefix + "emb_to_classes.weight"].astype(dt), sd[prefix + "emb_to_classes.bias"].astype(dt)
     B = enc.shape[0]
+    def embed(tokens):
+        e = emb[tokens].copy()
+        if cls_init:
+            # CLS_DECODER_INIT (decoders.py:196-201,236-238,260-262): softmax over the columns of the relevant semantics,
+            # then the SUM over the same axis - a vector of ones whatever sem_cls_mlp computes - replaces position 0
+            rel = get_relevant_semantic(memory, post_or_sem.astype(dt), sd, prefix + "sem_cls_mlp.")
+            e[:, 0] = softmax(rel, axis=1).sum(axis=1)
+        return e + pe[None, :tokens.shape[1]]
+
+    def post(out):
+        if post_semantics is None:
+            return out
+        # POST_DECODER_MLP (decoders.py:284-295)
+        sem_c = linear(post_semantics.astype(dt), sd[prefix + "sem_to_classes.weight"].astype(dt), sd[prefix + "sem_to_classes.bias"].astype(dt))
+        return pre_mlp_fusion(out, sem_c, sd, prefix + "post_decoder_mlp.", prefix + "post_deocer_combine_mlp.")
+    post_or_sem = post_semantics if post_semantics is not None else semantics
     if text is not None:
         L = max_len + 1
-        x = emb[text[:, :L]] + pe[None, :L]
-        return linear(_decoder_stack(x, memory, sd, prefix, layers), w_c, b_c)
+        return post(linear(_decoder_stack(embed(text[:, :L]), memory, sd, prefix, layers), w_c, b_c))
     targets = np.zeros((B, max_len + 1), np.int64)
     out = np.zeros((B, max_len, w_c.shape[0]), dt)
     for t in range(max_len):
-        x = emb[targets[:, :t + 1]] + pe[None, :t + 1]        # the reference embeds all positions and slices [:t+1]
+        x = embed(targets[:, :t + 1])                         # the reference embeds all positions and slices [:t+1]
         y = linear(_decoder_stack(x, memory, sd, prefix, layers), w_c, b_c)
         targets[:, t + 1] = y[:, -1].argmax(axis=1)
         out[:, t] = y[:, t]
-    return out
+    return post(out)
 
 
 def linear_decoder(enc, sd, dt=np.float32, prefix="decoder."):

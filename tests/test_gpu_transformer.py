@@ -339,3 +339,28 @@ def test_semantic_fusion_matches_reference_golden(tf_config, golden_dir):
         assert_close(host(encb), g["enc"], 8e-2, "encoder output with fusion (bf16)")
     finally:
         config.PRE_ENCODER_MLP = config.PRE_DECODER_MLP = False
+
+
+def test_cls_and_post_decoder_switches_match_reference_golden(tf_config, golden_dir, g_tf):
+    """CLS_DECODER_INIT (the first target embedding replaced by the reference's "semantic cls" vector, which is ones) and
+    POST_DECODER_MLP (the logits refined with the semantic vectors mapped to class space; 97-wide layers on 128-wide
+    GEMM tiles) against the reference's unmodified TF_Decoder.forward, greedy and teacher forced."""
+    g = np.load(os.path.join(golden_dir, "cfg_tf_fusion2.npz"))
+    sd = synth.make_state_dict_transformer(999, cls_decoder_init=True, post_decoder_mlp=True)
+    try:
+        config.CLS_DECODER_INIT = config.POST_DECODER_MLP = True
+        for precision, tol in (("fp32", 3e-4), ("tf32", 3e-4)):
+            m = _model(sd, precision)
+            sem = dev(g["semantics"])
+            with torch.no_grad():
+                out = m.decoder.decode(dev(g_tf["enc"]), None, False, semantics=sem)
+                tf = m.decoder(dev(g_tf["enc"]), dev(g_tf["text"]), sem, True)
+            assert np.array_equal(host(out["ids"]), g["ids"]), precision
+            assert_close(host(out["logits"]), g["logits"], tol, "logits with CLS + POST (%s)" % precision)
+            assert_close(host(tf), g["logits_tf"], tol, "teacher-forced logits with CLS + POST (%s)" % precision)
+        mb = _model(sd, "bf16")
+        with torch.no_grad():
+            tfb = mb.decoder(dev(g_tf["enc"]), dev(g_tf["text"]), dev(g["semantics"]), True)
+        assert_close(host(tfb), g["logits_tf"], 3e-2, "teacher-forced logits with CLS + POST (bf16)")
+    finally:
+        config.CLS_DECODER_INIT = config.POST_DECODER_MLP = False

@@ -136,3 +136,14 @@ def test_fusion_mirror_state_dict():
     finally:
         config.PRE_ENCODER_MLP = config.PRE_DECODER_MLP = config.POST_DECODER_MLP = False
         config.ENCODER, config.DECODER = saved
+
+
+def test_cls_and_post_decoder_switches_oracle(golden_dir, g_tf):
+    """CLS_DECODER_INIT + POST_DECODER_MLP: oracle against the reference's unmodified TF_Decoder.forward."""
+    g = np.load(os.path.join(golden_dir, "cfg_tf_fusion2.npz"))
+    assert abs(float(g["cls_min"]) - 1) < 1e-6 and abs(float(g["cls_max"]) - 1) < 1e-6   # the reference's "semantic cls" is ones
+    sd = synth.make_state_dict_transformer(999, cls_decoder_init=True, post_decoder_mlp=True)
+    lg = tfo.tf_decoder(g_tf["enc"], sd, cls_init=True, post_semantics=g["semantics"])
+    assert np.array_equal(lg.argmax(2), g["ids"]) and _rel(lg, g["logits"]) < 1e-4
+    tf = tfo.tf_decoder(g_tf["enc"], sd, text=g_tf["text"], cls_init=True, post_semantics=g["semantics"])
+    assert _rel(tf, g["logits_tf"]) < 1e-4

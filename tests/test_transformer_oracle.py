@@ -130,11 +130,14 @@ def test_fusion_mirror_state_dict():
         sd = synth.make_state_dict_transformer(999, pre_encoder_mlp=True, pre_decoder_mlp=True)
         assert len(m.state_dict()) == len(sd) == 485          # the reference's count with both switches on
         M.load_numpy_state_dict(m, sd)
-        with pytest.raises(NotImplementedError):
-            config.POST_DECODER_MLP = True
-            M.Model()
+        config.PRE_ENCODER_MLP = config.PRE_DECODER_MLP = False
+        config.CLS_DECODER_INIT = config.POST_DECODER_MLP = True
+        m2 = M.Model()
+        sd2 = synth.make_state_dict_transformer(999, cls_decoder_init=True, post_decoder_mlp=True)
+        assert len(m2.state_dict()) == len(sd2) == 482
+        M.load_numpy_state_dict(m2, sd2)
     finally:
-        config.PRE_ENCODER_MLP = config.PRE_DECODER_MLP = config.POST_DECODER_MLP = False
+        config.PRE_ENCODER_MLP = config.PRE_DECODER_MLP = config.POST_DECODER_MLP = config.CLS_DECODER_INIT = False
         config.ENCODER, config.DECODER = saved
 
 

@@ -114,6 +114,10 @@ int mstr_conv_gemm_bf16_dual(const void* x, const void* x2, const void* w_cat, c
                              const void* residual, void* out_bf16, float* out_f32, int B, int H, int W, int C_in,
                              int C_in2, int C_out, int R, int S, int stride_h, int stride_w, int pad_h, int pad_w,
                              int relu, mstr_stream_t stream);
+/* Test hook: which kernel mstr_conv_gemm_bf16 uses where both apply (C_in % 64 == 0, C_out % 256 == 0).  0 (default): the
+ * CTA-pair kernel, except for problems of at most one wave of 128 x 128 tiles, which take the single-CTA kernel;
+ * 1: the single-CTA kernel always; 2: CTA pairs always.  The two give bit-identical results. */
+int mstr_debug_gemm_route(int route);
 
 /* TF32 parity mode on the tensor cores (error-compensated 3xTF32, see csrc/conv_tf32.cu): fp32 NHWC
  * activations and fp32 results like mstr_conv_gemm_f32, ~fp32 accuracy, tcgen05.mma.kind::tf32.

@@ -29,6 +29,7 @@ SIGNATURES = {
     "mstr_conv_gemm_f32": (c_int, [_P, _P, _P, _P, _P, _P] + [_I] * 12 + [_P]),
     "mstr_conv_gemm_bf16": (c_int, [_P, _P, _P, _P, _P, _P, _P] + [_I] * 12 + [_P]),
     "mstr_conv_gemm_bf16_dual": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 13 + [_P]),
+    "mstr_debug_gemm_route": (c_int, [_I]),
     "mstr_conv_gemm_tf32": (c_int, [_P, _P, _P, _P, _P, _P, _P] + [_I] * 12 + [_P]),
     "mstr_maxpool_nhwc": (c_int, [_P, _P] + [_I] * 11 + [_P]),
     "mstr_maxpool2x2_ring_bf16": (c_int, [_P, _P, _I, _I, _I, _I, _P]),

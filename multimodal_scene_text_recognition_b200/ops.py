@@ -120,6 +120,16 @@ class _on:
         return False
 
 
+_SM_COUNT = {}
+
+
+def _sm_count(device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return MSTR_F32
@@ -290,7 +300,8 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
     out_b = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     out_f = torch.empty((B, P, Q, Cout), device=x.device, dtype=torch.float32) if want_f32 else None
     # which kernel mstr_conv_gemm_bf16 dispatches to (conv_tc.cu): the CTA-pair kernel for C_out % 256 == 0
-    variant = "conv_gemm_bf16_2cta" if (Cin % 64 == 0 and Cout % 256 == 0) else "conv_gemm_bf16_1cta"
+    one_wave = Cout % 128 == 0 and -(-(B * P * Q) // 128) * (Cout // 128) <= _sm_count(x.device)
+    variant = "conv_gemm_bf16_2cta" if (Cin % 64 == 0 and Cout % 256 == 0 and not one_wave) else "conv_gemm_bf16_1cta"
     with _timed(variant, flops, "flop", desc), _on(x, w, scale, shift, residual) as st:
         check(lib().mstr_conv_gemm_bf16(ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(out_b), ptr(out_f),
                                         B, H, W, Cin, Cout, R, S, stride[0], stride[1], pad[0], pad[1], int(relu),
@@ -298,6 +309,11 @@ def conv_gemm(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], s
     if want_f32 and want_bf16:
         return out_b, out_f
     return out_f if want_f32 else out_b
+
+
+def gemm_route(route: int) -> None:
+    """Test hook (mstr_debug_gemm_route): 0 = default dispatch, 1 = single-CTA GEMM kernel always, 2 = CTA pairs always."""
+    check(lib().mstr_debug_gemm_route(int(route)), "mstr_debug_gemm_route")
 
 
 def conv_gemm_dual(x: torch.Tensor, x2: torch.Tensor, w_cat: torch.Tensor, shift: torch.Tensor, *, kernel: Tuple[int, int],

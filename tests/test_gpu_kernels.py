@@ -155,8 +155,17 @@ def test_linear_f32_small_n():
     assert_close(host(out), np.maximum(x.astype(np.float64) @ w.T + b, 0), 2e-6, "linear f32 N=40")
 
 
+@pytest.fixture(params=[0, 2], ids=["default-dispatch", "cta-pairs-forced"])
+def gemm_route(request):
+    """Small test shapes are one-wave problems, which the default dispatch gives to the single-CTA kernel: run the GEMM
+    tests a second time with CTA pairs forced wherever they apply, so that both kernels keep their coverage."""
+    ops.gemm_route(request.param)
+    yield request.param
+    ops.gemm_route(0)
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv_gemm_bf16_tcgen05(case):
+def test_conv_gemm_bf16_tcgen05(case, gemm_route):
     stride, pad, relu = case[7], case[8], case[10]
     x, w, scale, shift, res = _conv_inputs(case, 5, True)
     ref = _conv_ref(x, w, scale, shift, res, stride, pad, relu)      # fp64 on the bf16-rounded operands
@@ -193,7 +202,7 @@ def test_conv_gemm_bf16_two_accumulators_per_cta():
 
 @pytest.mark.parametrize("B,H,W,planes,inplanes", [(3, 8, 25, 256, 128), (5, 4, 26, 512, 256), (3, 16, 50, 128, 64),
                                                    (193, 16, 50, 128, 64)])
-def test_conv_gemm_bf16_fused_downsample(B, H, W, planes, inplanes):
+def test_conv_gemm_bf16_fused_downsample(B, H, W, planes, inplanes, gemm_route):
     """mstr_conv_gemm_bf16_dual: 3x3 conv + fused 1x1 branch + ReLU in one accumulator (CTA-pair kernel for
     C_out % 256 == 0, single-CTA kernel with one or two accumulators per CTA for C_out = 128)."""
     r = rng(31)
@@ -232,7 +241,7 @@ def test_conv_gemm_bf16_many_tiles():
     assert_close(host(out_f), ref, 2e-5, "conv_gemm_bf16 400 tiles")
 
 
-def test_small_im2col_tensor_map():
+def test_small_im2col_tensor_map(gemm_route):
     """im2col tensor maps over tensors smaller than 128 KiB need the descriptor fix of tc_common.cuh
     (fix_small_im2col_map; drivers <= CUDA 13.1).  3x3 convolutions over 20 KiB .. 100 KiB activations on every
     tensor-core kernel that builds such a map - single-CTA bf16, CTA-pair bf16, 3xTF32 - against the oracle: if a
@@ -696,3 +705,30 @@ def test_resize_to_tensor_flags_oversized_crop():
     out = ops.resize_to_tensor_u8(px, off, sz, (4, 4))      # crop larger than the declared bound: NaN, no overrun
     torch.cuda.synchronize()
     assert torch.isnan(out).all()
+
+
+def test_gemm_kernels_bit_identical_and_one_wave_rule():
+    """mstr_conv_gemm_bf16 picks the single-CTA kernel for problems of at most one wave of 128 x 128 tiles and the CTA-pair
+    kernel beyond; the choice depends on the batch, so the two kernels must give bit-identical results (bias, ReLU,
+    residual, 1x1 and 3x3, bf16 and f32 outputs) - otherwise a crop's result would depend on its batch."""
+    r = rng(61)
+    bf = torch.bfloat16
+    cases = [((512, 1, 1, 256), (768, 1, 1, 256)), ((4096, 1, 1, 2048), (256, 1, 1, 2048)), ((300, 1, 1, 512), (2048, 1, 1, 512)),
+             ((6, 4, 26, 256), (512, 3, 3, 256)), ((40, 8, 25, 128), (256, 3, 3, 128))]
+    try:
+        for xs, ws in cases:
+            x = dev(orc.round_bf16(r.standard_normal(xs).astype(np.float32)), bf)
+            w = dev(orc.round_bf16((r.standard_normal(ws) / np.sqrt(ws[1] * ws[2] * ws[3])).astype(np.float32)), bf)
+            sc, sh = dev(r.uniform(0.5, 1.5, ws[0]).astype(np.float32)), dev(r.normal(0, 0.2, ws[0]).astype(np.float32))
+            pad = (ws[1] // 2, ws[2] // 2)
+            res = dev(orc.round_bf16(r.standard_normal((xs[0], xs[1], xs[2], ws[0])).astype(np.float32)), bf)
+            outs = []
+            for route in (1, 2, 0):
+                ops.gemm_route(route)
+                ob, of = ops.conv_gemm(x, w, sc, sh, res, pad=pad, relu=True, want_f32=True, want_bf16=True)
+                outs.append((ob.clone(), of.clone()))
+            torch.cuda.synchronize()
+            for ob, of in outs[1:]:
+                assert torch.equal(ob, outs[0][0]) and torch.equal(of, outs[0][1]), (xs, ws)
+    finally:
+        ops.gemm_route(0)

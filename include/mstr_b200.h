@@ -133,6 +133,10 @@ int mstr_conv_gemm_tf32(const float* x, const float* w_hi, const float* w_lo, co
  * mstr_maxpool_nhwc : nn.MaxPool2d with -inf padding (feature_extraction.py:66,72,78).
  * mstr_mean_hw      : AdaptiveAvgPool2d(1) of the localisation net (transformation.py:57):
  *                     NHWC [B][H][W][C] -> [B][C] f32.
+ * mstr_locnet_head  : the head of the localisation net in one launch (transformation.py:57,60-61,76-81):
+ *                     AdaptiveAvgPool2d(1) -> Linear(C = 512, H1 = 256) + ReLU -> Linear(256, O = 2F), every product an
+ *                     fp32 FMA.  feat NHWC [B][HW][C] (bf16 or f32); w1t = localization_fc1 weight TRANSPOSED to
+ *                     [C][H1], w2t = localization_fc2 weight transposed to [H1][O]; out [B][O] f32.
  * mstr_mean_h       : model.py:92-93 permute+AdaptiveAvgPool2d((None,1))+squeeze:
  *                     NHWC [B][H][W][C] -> [B][W][C] (mean over H) in out_dtype (+ optional f32).
  * mstr_cast         : f32 <-> bf16 element cast.
@@ -165,6 +169,8 @@ int mstr_conv3x3_flat_pool_bf16(const void* x, const void* w, const float* scale
 int mstr_debug_flat_desc_mode(int mode);
 int mstr_mean_hw(const void* x, float* out, int dtype, int B, int H, int W, int C,
                  mstr_stream_t stream);
+int mstr_locnet_head(const void* feat, int dtype, const float* w1t, const float* b1, const float* w2t, const float* b2,
+                     float* out, int B, int HW, int C, int H1, int O, mstr_stream_t stream);
 int mstr_mean_h(const void* x, void* out, float* out_f32, int dtype, int B, int H, int W, int C,
                 mstr_stream_t stream);
 int mstr_cast(const void* x, void* out, int src_dtype, int dst_dtype, int64_t n,

@@ -37,6 +37,7 @@ SIGNATURES = {
     "mstr_conv3x3_flat_pool_bf16": (c_int, [_P, _P, _P, _P, _P] + [_I] * 6 + [_P]),
     "mstr_debug_flat_desc_mode": (c_int, [_I]),
     "mstr_mean_hw": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "mstr_locnet_head": (c_int, [_P, _I, _P, _P, _P, _P, _P] + [_I] * 5 + [_P]),
     "mstr_mean_h": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mstr_cast": (c_int, [_P, _P, _I, _I, c_int64, _P]),
     "mstr_embed_semantics": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -84,16 +84,13 @@ class LocalizationNetwork(nn.Module):
             h = ops.conv_gemm(h, w, scale, shift, pad=(1, 1), relu=True)
             if i != 12:
                 h = ops.maxpool_nhwc(h, (2, 2), (2, 2), (0, 0))
-        feat = ops.mean_hw(h)                                       # AdaptiveAvgPool2d(1) + view
-        fc1 = self.localization_fc1[0]
-        w1 = fc1.weight.detach().float().contiguous()
-        if precision != 'fp32':
-            # fp32-accurate on the tensor cores (3xTF32 split, ~5e-6): the fp32 FMA kernel needs ~95 us for this
-            # M = B, N = 256, K = 512 GEMM (one under-filled wave), the fiducial points must stay fp32-accurate
-            w1 = cached(self, "fc1_tf32x3", [fc1.weight], lambda: ops.SplitWeight(fc1.weight.detach().float().contiguous()))
-        hid = ops.linear(feat, w1, fc1.bias.detach().float().contiguous(), relu=True)
-        fc2 = self.localization_fc2
-        c = ops.linear(hid, fc2.weight.detach().float().contiguous(), fc2.bias.detach().float().contiguous())
+        # AdaptiveAvgPool2d(1) + view, fc1 + ReLU, fc2 as one fp32 launch: the fiducial points stay fp32-accurate in every
+        # precision mode (transformation.py:76-81)
+        fc1, fc2 = self.localization_fc1[0], self.localization_fc2
+        w1t, b1, w2t, b2 = cached(self, "head_f32", [fc1.weight, fc1.bias, fc2.weight, fc2.bias], lambda: (
+            fc1.weight.detach().float().t().contiguous(), fc1.bias.detach().float().contiguous(),
+            fc2.weight.detach().float().t().contiguous(), fc2.bias.detach().float().contiguous()))
+        c = ops.locnet_head(h, w1t, b1, w2t, b2)
         return c.view(B, self.F, 2)
 
 

@@ -381,6 +381,28 @@ def mean_hw(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def locnet_head(feat: torch.Tensor, w1t: torch.Tensor, b1: torch.Tensor, w2t: torch.Tensor,
+                b2: torch.Tensor) -> torch.Tensor:
+    """Localisation head in one launch: NHWC feat [B,H,W,512] -> mean over HW -> fc1 + ReLU -> fc2, [B, O] f32.
+
+    w1t [512, 256] and w2t [256, O] are the TRANSPOSED nn.Linear weights (transformation.py:60-61), f32."""
+    _req(feat, "feat")
+    for name, t in (("w1t", w1t), ("b1", b1), ("w2t", w2t), ("b2", b2)):
+        _req(t, name)
+        if t.dtype != torch.float32:
+            raise TypeError(f"locnet_head: {name} must be float32")
+    B, H, W, C = feat.shape
+    H1, O = w2t.shape
+    if tuple(w1t.shape) != (C, H1) or b1.numel() != H1 or b2.numel() != O:
+        raise ValueError("locnet_head: weight shapes do not chain")
+    out = torch.empty((B, O), device=feat.device, dtype=torch.float32)
+    work = feat.numel() * feat.element_size() + 4 * (w1t.numel() + w2t.numel() + out.numel())
+    with _on(feat, w1t, b1, w2t, b2) as st, _timed("locnet_head", work, "byte", "GAP + fc1 + fc2 of the localisation net"):
+        check(lib().mstr_locnet_head(ptr(feat), _dt(feat), ptr(w1t), ptr(b1), ptr(w2t), ptr(b2), ptr(out), B, H * W, C, H1, O,
+                                     st), "mstr_locnet_head")
+    return out
+
+
 def mean_h(x: torch.Tensor, want_f32: bool = False):
     """NHWC [B,H,W,C] -> [B,W,C] mean over H, in x.dtype (and optionally an f32 copy)."""
     _req(x, "x")

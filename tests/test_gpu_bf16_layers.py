@@ -250,10 +250,19 @@ def test_sequence_model_from_gpu_features_matches_matched_oracle(bf16_run, sd_cf
         tf = m.decoder(st["enc1"].contiguous(), dev(text), None, True)
     ref_tf = orc.attention_decode(enc1, sd_cfg_a, 26, 97, text=text, dt=f32, quant="bf16")
     r_tf = err(host(tf), ref_tf)[1]
-    print("\nsequence model from the GPU's own features vs matched oracle: enc1 %.2e, teacher-forced logits %.2e, "
-          "greedy ids equal on %.3f of the steps" % (r_enc, r_tf, steps_equal))
+    # 26 recurrent steps whose bf16 hidden state the oracle re-rounds at the same points, but from exact tanh / exp where
+    # the kernel uses tanh.approx / ex2.approx: the cell state carries ~1e-3 per step, which is ~1e-2 of the largest logit
+    # for every crop (the rms), and a flipped bf16 rounding of h early in ONE crop moves that crop's later logits by a few
+    # 1e-2 (the worst logit: 1.2e-2 ... 5.8e-2 over the feature sets measured, ids unchanged) - so bulk and tail are gated
+    # separately, both far below what a wrong weight, gate order or step index produces (O(1), and the ids gate)
+    d_tf = np.abs(host(tf).astype(np.float64) - ref_tf) / np.abs(ref_tf).max()
+    rms_tf = float(np.sqrt((d_tf ** 2).mean()))
+    print("\nsequence model from the GPU's own features vs matched oracle: enc1 %.2e, teacher-forced logits rms %.2e, "
+          "worst %.2e (99.9th percentile %.2e), greedy ids equal on %.3f of the steps"
+          % (r_enc, rms_tf, r_tf, float(np.quantile(d_tf, 0.999)), steps_equal))
     assert r_enc <= 2e-2, "encoder output vs matched oracle: %.3e" % r_enc
-    assert r_tf <= 3e-2, "teacher-forced logits vs matched oracle: %.3e" % r_tf
+    assert rms_tf <= 1.5e-2, "teacher-forced logits vs matched oracle, rms: %.3e" % rms_tf
+    assert r_tf <= 1e-1, "teacher-forced logits vs matched oracle, worst logit: %.3e" % r_tf
     assert steps_equal >= 0.95, "greedy ids equal the matched oracle on %.3f of the steps" % steps_equal
 
 

@@ -367,6 +367,30 @@ def test_maxpool_nhwc(dtype, H, W, k, s, p):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B", [1, 13, 2371])
+def test_locnet_head_is_fp32_accurate_and_batch_invariant(dtype, B):
+    """GAP + fc1 + ReLU + fc2 of the localisation net in one launch (transformation.py:57,60-61,76-81) against float64;
+    a crop's fiducials must not depend on which batch (CTA tile, 8- or 16-crop kernel) it is in."""
+    r = rng(81)
+    x = orc.round_bf16(np.maximum(r.standard_normal((B, 4, 12, 512)), 0).astype(np.float32))
+    w1 = (r.standard_normal((256, 512)) * 0.06).astype(np.float32)
+    b1 = (r.standard_normal(256) * 0.1).astype(np.float32)
+    w2 = (r.standard_normal((40, 256)) * 0.08).astype(np.float32)
+    b2 = r.standard_normal(40).astype(np.float32)
+    ref = np.maximum(x.astype(np.float64).mean(axis=(1, 2)) @ w1.T.astype(np.float64) + b1, 0) @ w2.T.astype(np.float64) + b2
+    args = [dev(np.ascontiguousarray(w1.T)), dev(b1), dev(np.ascontiguousarray(w2.T)), dev(b2)]
+    xd = dev(x, dtype)
+    out = ops.locnet_head(xd, *args)
+    torch.cuda.synchronize()
+    assert_close(host(out), ref, 3e-6, "locnet_head")
+    # same crops as a 5-crop batch starting at crop 3 (other tile position, 8-crop kernel): identical bits
+    if B > 8:
+        sub = ops.locnet_head(xd[3:8].contiguous(), *args)
+        torch.cuda.synchronize()
+        assert np.array_equal(host(sub), host(out)[3:8])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_mean_reductions_and_cast(dtype):
     x = orc.round_bf16(rng(8).standard_normal((5, 3, 65, 512)).astype(np.float32))
     xd = dev(x, dtype)

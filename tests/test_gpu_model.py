@@ -59,6 +59,28 @@ def test_fp32_matches_reference_golden(sd_cfg_a, golden_dir):
     assert_close(host(tf), g["logits_tf"], 3e-4, "teacher-forced logits vs reference")
 
 
+@pytest.mark.parametrize("precision,tol,tol_grid", [("fp32", 1e-6, 2e-5), ("tf32", 2e-6, 2e-5), ("bf16", 2e-3, 2e-3)])
+def test_fiducial_points_match_reference_golden(sd_cfg_a, golden_dir, precision, tol, tol_grid):
+    """Direct gate on LocalizationNetwork (transformation.py:74-82): the fiducial points C' [B, F, 2] the reference
+    produced for these crops (non-zero fc2 weight in the recipe, so C' depends on the image), and the sampling grid
+    built from them.  The head (pool + fc1 + fc2) is fp32 in every mode; bf16 enters through the three convolutions.
+    Measured: C' 5.7e-8 (fp32), 2.0e-7 (3xTF32 convolutions), 2.7e-4 (bf16); the fp32 grid carries ~1e-5 of cancellation
+    error in both implementations (tests/test_oracle_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "cfg_a.npz"))
+    wseed, dseed, B = [int(v) for v in g["meta"]]
+    x, _, _, _ = _inputs(B, seed=dseed)
+    m = load_model(sd_cfg_a, precision=precision, TPS_GRID="reference")
+    tps = m.Transformation
+    with torch.no_grad():
+        c = tps.LocalizationNetwork(dev(x))
+        grid = tps.GridGenerator.build_P_prime(c)
+    torch.cuda.synchronize()
+    assert c.dtype == torch.float32 and tuple(c.shape) == tuple(g["c_prime"].shape)
+    r = assert_close(host(c), g["c_prime"], tol, "fiducial points vs reference (%s)" % precision)
+    rg = assert_close(host(grid).reshape(B, -1, 2)[:, ::7], g["grid"], tol_grid, "sampling grid vs reference (%s)" % precision)
+    print("\nC' vs reference golden (%s): %.2e, grid %.2e" % (precision, r, rg))
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tf32", 1e-4), ("bf16", 2e-2)])
 def test_reference_default_init_golden(golden_dir, precision, tol):
     """The reference's own random init (torch.manual_seed(config.RANDOM_SEED); Model()) rebuilt from the seed

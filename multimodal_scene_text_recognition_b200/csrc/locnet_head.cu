@@ -1,15 +1,19 @@
 // Head of the localisation network in ONE launch: AdaptiveAvgPool2d(1) -> Linear(512, 256) + ReLU -> Linear(256, 2F)
 // (modules/transformation.py:57,60-61,76-81).  It produces the 2F fiducial coordinates the TPS grid is built from, so
 // every product is an fp32 FMA in all precision modes (the three launches it replaces - mean_hw, a 3xTF32 GEMM with one
-// under-filled wave, an fp32 GEMM with N = 40 - took ~130 us at 4096 crops and ~90 us at 512, almost all of it latency).
+// under-filled wave, an fp32 GEMM with N = 40 - took ~130 us at 4096 crops and ~90 us at 512, almost all of it latency;
+// this kernel: 125 us and 28 us).
 //
-// One CTA of 1024 threads per tile of CT = 8 or 16 crops:
+// One CTA of 1024 threads per tile of CT = 8 crops (16 crops per CTA halve the L2 reads of the fc1 weight and measured the
+// same 125 us at 4096 crops, 39 instead of 28 us at 512):
 //   1. pooling: 128 threads per crop, four consecutive channels each: a position row of a crop is one
 //      coalesced 1 KB (bf16) / 2 KB (f32) request; the pooled vectors [CT][512] go to shared memory;
 //   2. fc1: thread = (K quarter q, output j): partial dot products over k in [128 q, 128 q + 128) for all crops of the
 //      tile, weights read as w1t[k][j] (K-major copy: coalesced over j, L2 resident), pooled values broadcast from shared
 //      memory; the four partials are summed in shared memory in the fixed order q = 0..3, + bias, ReLU;
-//   3. fc2: thread = (crop, output o): dot over 256 with w2t[:][o] (K-major copy, 40 KB, L1/L2).
+//   3. fc2: thread = (crop, output o): dot over 256 with w2t[:][o] (K-major copy, 40 KB, brought into shared memory
+//      by cp.async while the tile is pooled: read from L2 by a cold CTA it was 32 dependent round trips, 2/3 of the CTA's
+//      35 us).
 // Every crop's arithmetic has a fixed order that does not depend on the tile or the batch it is in.
 #include "common.cuh"
 
@@ -38,8 +42,13 @@ locnet_head_kernel(const T* __restrict__ feat, const float* __restrict__ w1t, co
   float (*s_pool)[LH_C] = reinterpret_cast<float (*)[LH_C]>(lh_smem);                            // [CT][512]
   float (*s_part)[CT][LH_H1] = reinterpret_cast<float (*)[CT][LH_H1]>(lh_smem + CT * LH_C);      // [4][CT][256]
   float (*s_hid)[LH_H1] = reinterpret_cast<float (*)[LH_H1]>(lh_smem);   // reuses the pooled tile after fc1
+  float* s_w2 = lh_smem + CT * LH_C + 4 * CT * LH_H1;                   // [256][O], lands while the tile is pooled
   const int tid = threadIdx.x;
   const int crop0 = blockIdx.x * CT;
+  for (int i = tid; i < LH_H1 * O / 4; i += LH_THREADS)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(s_w2 + 4 * i)),
+                 "l"(w2t + 4 * i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
   // ---- 1. pooling: 128 threads per crop, 4 channels each, 8 crops per pass
   for (int c = tid >> 7; c < CT; c += LH_THREADS / 128) {
     const int ch = (tid & 127) * 4;
@@ -47,7 +56,7 @@ locnet_head_kernel(const T* __restrict__ feat, const float* __restrict__ w1t, co
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     if (crop < B) {
       const T* p = feat + ((size_t)crop * HW) * LH_C + ch;
-#pragma unroll 8
+#pragma unroll 16
       for (int i = 0; i < HW; ++i, p += LH_C) lh_add4(p, a0, a1, a2, a3);
     }
     const float inv = 1.f / (float)HW;
@@ -61,7 +70,7 @@ locnet_head_kernel(const T* __restrict__ feat, const float* __restrict__ w1t, co
 #pragma unroll
     for (int c = 0; c < CT; ++c) acc[c] = 0.f;
     const float* w = w1t + (size_t)(q * 128) * LH_H1 + j;
-#pragma unroll 1
+#pragma unroll 4   // 16 weight loads in flight per thread
     for (int k = 0; k < 128; k += 4) {
       const float w0 = __ldg(w + (size_t)k * LH_H1), w1 = __ldg(w + (size_t)(k + 1) * LH_H1);
       const float w2 = __ldg(w + (size_t)(k + 2) * LH_H1), w3 = __ldg(w + (size_t)(k + 3) * LH_H1);
@@ -81,15 +90,16 @@ locnet_head_kernel(const T* __restrict__ feat, const float* __restrict__ w1t, co
     const float v = ((s_part[0][c][j] + s_part[1][c][j]) + s_part[2][c][j]) + s_part[3][c][j] + __ldg(b1 + j);
     s_hid[c][j] = fmaxf(v, 0.f);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  // ---- 3. fc2: thread = (crop, output o), weights K-major so a warp reads consecutive o
+  // ---- 3. fc2: thread = (crop, output o), weights K-major in shared memory so a warp reads consecutive o
   for (int i = tid; i < CT * O; i += LH_THREADS) {
     const int c = i / O, o = i % O;
     const int crop = crop0 + c;
     if (crop >= B) continue;
     float a = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < LH_H1; ++k) a = fmaf(s_hid[c][k], __ldg(w2t + (size_t)k * O + o), a);
+    for (int k = 0; k < LH_H1; ++k) a = fmaf(s_hid[c][k], s_w2[k * O + o], a);
     out[(size_t)crop * O + o] = a + __ldg(b2 + o);
   }
 }
@@ -97,14 +107,11 @@ locnet_head_kernel(const T* __restrict__ feat, const float* __restrict__ w1t, co
 template <typename T, int CT>
 static int lh_launch(const T* feat, const float* w1t, const float* b1, const float* w2t, const float* b2, float* out,
                      int B, int HW, int O, cudaStream_t st) {
-  constexpr int smem = (CT * LH_C + 4 * CT * LH_H1) * (int)sizeof(float);
-  static bool configured[64] = {};
-  int dev = 0;
-  MSTR_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && !configured[dev]) {
-    MSTR_CUDA(cudaFuncSetAttribute(locnet_head_kernel<T, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[dev] = true;
-  }
+  const int smem = (CT * LH_C + 4 * CT * LH_H1 + LH_H1 * O) * (int)sizeof(float);
+  constexpr int smem_max = (CT * LH_C + 4 * CT * LH_H1 + LH_H1 * 128) * (int)sizeof(float);   // O <= 128
+  static unsigned long long smem_set = 0;
+  const int rc = ensure_dynamic_smem((const void*)locnet_head_kernel<T, CT>, smem_max, &smem_set);
+  if (rc != MSTR_OK) return rc;
   locnet_head_kernel<T, CT><<<ceil_div(B, CT), LH_THREADS, smem, st>>>(feat, w1t, b1, w2t, b2, out, B, HW, O);
   MSTR_LAUNCH_CHECK("locnet_head_kernel");
   return MSTR_OK;
@@ -119,18 +126,11 @@ extern "C" __attribute__((visibility("default"))) int mstr_locnet_head(const voi
   using namespace mstr;
   MSTR_REQUIRE(feat && w1t && b1 && w2t && b2 && out, MSTR_ERR_BAD_ARG, "mstr_locnet_head: null pointer");
   MSTR_REQUIRE(B > 0 && HW > 0 && O > 0, MSTR_ERR_BAD_ARG, "mstr_locnet_head: bad size");
-  MSTR_REQUIRE(C == LH_C && H1 == LH_H1 && O <= 128, MSTR_ERR_UNSUPPORTED,
-               "mstr_locnet_head: written for %d channels, %d hidden units, <= 128 outputs (got %d, %d, %d)", LH_C, LH_H1, C, H1, O);
+  MSTR_REQUIRE(C == LH_C && H1 == LH_H1 && O <= 128 && O % 4 == 0, MSTR_ERR_UNSUPPORTED,
+               "mstr_locnet_head: written for %d channels, %d hidden units, <= 128 outputs in multiples of 4 (got %d, %d, %d)", LH_C, LH_H1, C, H1, O);
   cudaStream_t st = (cudaStream_t)stream;
-  // 16 crops per CTA once that still fills the SMs (halves the L2 reads of the 512 KB fc1 weight), else 8
-  const bool wide = ceil_div(B, 16) >= 148;
-  if (dtype == MSTR_BF16) {
-    auto f = static_cast<const __nv_bfloat16*>(feat);
-    return wide ? lh_launch<__nv_bfloat16, 16>(f, w1t, b1, w2t, b2, out, B, HW, O, st)
-                : lh_launch<__nv_bfloat16, 8>(f, w1t, b1, w2t, b2, out, B, HW, O, st);
-  }
+  if (dtype == MSTR_BF16)
+    return lh_launch<__nv_bfloat16, 8>(static_cast<const __nv_bfloat16*>(feat), w1t, b1, w2t, b2, out, B, HW, O, st);
   MSTR_REQUIRE(dtype == MSTR_F32, MSTR_ERR_BAD_ARG, "mstr_locnet_head: unknown dtype %d", dtype);
-  auto f = static_cast<const float*>(feat);
-  return wide ? lh_launch<float, 16>(f, w1t, b1, w2t, b2, out, B, HW, O, st)
-              : lh_launch<float, 8>(f, w1t, b1, w2t, b2, out, B, HW, O, st);
+  return lh_launch<float, 8>(static_cast<const float*>(feat), w1t, b1, w2t, b2, out, B, HW, O, st);
 }

@@ -3,6 +3,6 @@ set -u
 mkdir -p gpurun_out
 L=gpurun_out/r02q.log
 : > $L
-timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -m gpu -p no:cacheprovider -k "locnet or fiducial" 2>&1 | tail -3 >> $L
-for b in 512 4096; do timeout 300 python tools/stage_breakdown.py a $b bf16 2>&1 | grep -E "locnet|sum" >> $L; done
+timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -p no:cacheprovider -k "attn or decode" 2>&1 | tail -3 >> $L
+timeout 600 python tools/tune_seq.py 256 512 4096 2>&1 | grep -E "attn_decode|phase trace|fine (hp|cell) tile 0" >> $L
 grep -v "^$" $L | tail -70

@@ -816,7 +816,12 @@ attn_decode_persistent_kernel(const __grid_constant__ PdMaps maps, const __nv_bf
       // counter, fetched while the current crop is being worked on, so the phase ends within one crop time (~12 us at
       // 4096 crops) of the first idle warp whatever B is.  Logical index l <-> crop l (even steps) / B-1-l (odd steps):
       // the zig-zag described above.  Tried on top of this and measured slower at 4096 crops (25.3 us per step): L2
-      // evict-first / no-L1-allocate loads (25.9), one bulk L2 prefetch of the crop's proj + enc block per crop (29.2).
+      // evict-first / no-L1-allocate loads (25.9), one bulk L2 prefetch of the crop's proj + enc block per crop (29.2),
+      // an evict_last / evict_first split of the crops so that 65 % of proj + enc stays in L2 (25.9), and the crop's two
+      // blocks bulk-copied into shared memory (five 26 KB buffers per SM, one warp each) and scored from there (45.3; 5.4
+      // instead of 4.4 us at 512 crops).  None of the memory-side changes helps because the phase is not waiting for memory:
+      // a crop is ~1500 dependent-ish warp instructions (208 tanh on the MUFU pipe, 130 shuffle steps, the online
+      // softmax), 28 crops per SM per step, and 16 warps per SM is all the latency hiding there is at 128 registers.
       int* counter = s.live + 2 + i;
       float* part = part_base + (size_t)warp * AT_VSUB * AT_PART;
       int l = gg;

@@ -290,3 +290,24 @@ def test_bf16_properties_at_benchmark_batch(sd_cfg_a):
         k = min(int(L[b]) + 1, 26)
         assert np.array_equal(ei[b, :k], fi[b, :k]) and not ei[b, k:].any()
     assert (L < 26).mean() > 0.02, "the synthetic weights should make some crops emit [s]"
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_ragged_batch_sizes_give_the_same_rows(sd_cfg_a, precision):
+    """Batch sizes on both sides of every tile / wave boundary of the kernels (1 crop; 127 / 129 crops: the 128-row MMA
+    tiles of the recurrences; 593: first size past the one-crop-per-four-warps attention; 801: past the BiLSTM cluster
+    kernel's capacity; 2369: more crops than decoder warps): every crop's ids and logits are the ones it gets inside
+    one 2369-crop batch, whatever batch it arrives in."""
+    sizes = [1, 3, 127, 129, 593, 801]
+    B = 2369
+    x, ov, sc, io = _inputs(B, seed=77)
+    m = load_model(sd_cfg_a, precision=precision, DECODER_EARLY_EXIT=False)
+    full = _run(m, x, ov, sc, io)
+    assert np.isfinite(host(full["logits"])).all()
+    lo = 0
+    for n in sizes:
+        part = _run(m, x[lo:lo + n], ov[lo:lo + n], sc[lo:lo + n], io[lo:lo + n])
+        assert torch.equal(part["ids"], full["ids"][lo:lo + n]), "ids of a %d-crop batch (%s)" % (n, precision)
+        assert torch.equal(part["logits"], full["logits"][lo:lo + n]), "logits of a %d-crop batch (%s)" % (n, precision)
+        assert torch.equal(part["lengths"], full["lengths"][lo:lo + n])
+        lo += n

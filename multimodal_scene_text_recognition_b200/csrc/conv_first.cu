@@ -10,6 +10,12 @@
 // pipe.  The input strip (3 or 4 rows x 6 columns per channel) is read once into registers with
 // coalesced loads.  Lanes of a warp cover consecutive channel groups first, so the 16-byte bf16
 // stores of 4 (8) neighbouring lanes form one contiguous 64-byte (128-byte) run of the NHWC output.
+// Round 2, measured and not kept (0.85 ms for the two launches at 4096 crops either way): requesting image b + 1's
+// window before image b is computed (load latency is not what the warps wait for), and a [half][group][4] weight
+// order in shared memory that removes the 2-way bank conflicts ncu counts on the weight loads at Cout = 64 (38 M of
+// 74 M wavefronts; the LSU pipe is busy, but not the limiter).  The 1 -> 64 launch runs at 47 % of the fp32 FMA rate
+// (7.55 GFMA in 0.45 ms; 288 of a thread's ~630 instructions are packed FMAs), the 1 -> 32 launch at 2.5 TB/s of
+// output writes.
 #include "common.cuh"
 
 namespace mstr {

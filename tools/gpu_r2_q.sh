@@ -3,14 +3,6 @@ set -u
 mkdir -p gpurun_out
 L=gpurun_out/r02q.log
 : > $L
-timeout 600 python bench.py --no-extras --no-cpu-baseline > gpurun_out/r02q_n1.json 2>> $L
-echo "n1 exit $?" >> $L
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --no-extras --no-cpu-baseline > gpurun_out/r02q_n2.json 2>> $L
-echo "n2 exit $?" >> $L
-python - <<PY >> $L
-import json
-for f in ('n1','n2'):
-    d=json.loads(open('gpurun_out/r02q_%s.json'%f).read().strip().splitlines()[-1])
-    print(f, d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], d['ranks'])
-PY
-grep -v "^$" $L | tail -30
+timeout 900 python -m pytest tests/test_gpu_kernels.py -q -m gpu -p no:cacheprovider -k "tps" 2>&1 | tail -3 >> $L
+for b in 512 4096; do timeout 300 python tools/stage_breakdown.py a $b bf16 2>&1 | grep -E "first|sum|maxpool|flat|tps" >> $L; done
+grep -v "^$" $L | tail -70

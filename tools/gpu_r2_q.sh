@@ -3,15 +3,8 @@ set -u
 mkdir -p gpurun_out
 L=gpurun_out/r02q.log
 : > $L
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r02q_n2.json 2>> $L
-echo "n2 exit $?" >> $L
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/r02q_ref2.json 2>> $L
-echo "ref2 exit $?" >> $L
-python - <<PY >> $L
-import json
-d=json.loads(open('gpurun_out/r02q_n2.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['ranks'], list(d.keys()))
-print(d.get('weak_scaling'))
-print(open('gpurun_out/r02q_ref2.json').read()[:400])
-PY
-grep -v "^$" $L | grep -v "OMP_NUM\|\*\*\*" | tail -20
+timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -p no:cacheprovider -k "attn or decode" 2>&1 | tail -3 >> $L
+timeout 600 python tools/tune_seq.py 256 512 2048 4096 2>&1 | grep -E "attn_decode|phase trace|arrival spread" >> $L
+timeout 600 python tools/soak_decoder.py >> $L 2>&1
+echo "soak exit $?" >> $L
+grep -v "^$" $L | tail -70

@@ -245,8 +245,9 @@ int mstr_attn_decode(const float* enc, const float* proj, const float* w_h2h, co
  * bf16 operands (enc, proj, h, ctx, weights), f32 accumulation, cell state, logits.
  *   enc_bf16, proj_bf16 [B][T][Hd] bf16
  *   w_head [384][Hd] bf16: rows 0..255 = h2h.weight, rows 256..256+C-1 = generator.weight, rest zero
- *   w_cat  [4*Hd][2*Hd] bf16: [rnn.weight_ih[:, :Hd] | rnn.weight_hh] with rows re-ordered like
- *          mstr_bilstm_recurrent_bf16's w_hh_packed (chunk*128 + g*32 + j <- g*Hd + chunk*32 + j)
+ *   w_cat  [4*Hd][2*Hd] bf16: [rnn.weight_ih[:, :Hd] | rnn.weight_hh] with rows re-ordered so that every 64 rows hold
+ *          the four gates of 16 hidden units (chunk*64 + g*16 + j <- g*Hd + chunk*16 + j): the cell GEMM then runs on
+ *          64- or 128-column tiles
  *   w_tok  [C][4*Hd] f32 = rnn.weight_ih[:, Hd:]^T (original gate-major columns); bias [4*Hd] f32, or NULL when
  *          the caller has already added it to every row of w_tok (one load less per gate and unit)
  *   workspace: mstr_attn_decode_bf16_workspace_bytes(B, Hd) bytes of device memory (16-byte aligned)

@@ -215,27 +215,32 @@ __device__ __forceinline__ void at_head_logits_epilogue(const DecodeState& s, fl
   }
 }
 
-// ---- cell epilogue: this tile = 32 hidden units x 4 gates of 128 crops; this warp: 16 of the units -------
+// ---- cell epilogue: this tile = 32 (N64: 16) hidden units x 4 gates of 128 crops; this warp: 16 (8) of the units ----
+// Weight rows (= accumulator columns) are ordered [chunk of 16 units][gate][unit] (ops.pack_gate_rows_bf16): a 128-column
+// tile is two such chunks, one per warp half; a 64-column tile (N64, small batches: half the MMA and half the epilogue
+// per CTA, twice the CTAs) is one chunk whose 16 units the two warp halves share.
 // Everything the LSTM cell needs besides the accumulator - the token's row of W_tok (+ bias) and the previous cell
 // state - does not depend on this phase's GEMM, and the per-lane (row = crop, rows 4 KB apart) gathers cost 32 L1
 // wavefronts per instruction: ALL of them are issued before the accumulator is awaited (`wait_acc` blocks on the TMA
 // loads and the MMAs, which do not use the load/store path), so that what follows the wait is only TMEM loads, the
 // gate math and the stores.  (Loading one group of 4 units ahead left ~3 of the 5 us of this epilogue exposed.)
-template <typename WaitAcc, typename Release>
+template <bool N64, typename WaitAcc, typename Release>
 __device__ __forceinline__ void at_cell_epilogue(const DecodeState& s, const uint32_t taddr, const EpiWho& w, const int m0,
                                                  const int n_tile, const int step, WaitAcc wait_acc, Release release) {
+  constexpr int UNITS = N64 ? 8 : 16;                    // units of this warp
+  constexpr int NSUB = UNITS / 4;
   const int crop = m0 + w.row();
   const bool valid = crop < s.B;
-  const int ubase = w.half * 16;                         // first of this warp's 16 units within the tile's 32
-  const int unit0 = n_tile * 32 + ubase;
+  const int unit0 = N64 ? n_tile * 16 + w.half * 8 : n_tile * 32 + w.half * 16;
+  const uint32_t col0 = N64 ? (uint32_t)(w.half * 8) : (uint32_t)(w.half * 64);   // + gate * 16 + unit within the chunk
   const int tok = valid ? __ldcg(s.tok + crop) : 0;
   const float* wt = s.w_tok + (size_t)tok * (4 * AT_H);
   float* ccol = s.cst + (size_t)unit0 * s.B + (valid ? crop : 0);   // cell state is kept [H][B]: lane = crop is coalesced
   __nv_bfloat16* hrow = s.xh[(step + 1) & 1] + (size_t)(valid ? crop : 0) * (2 * AT_H) + AT_H + unit0;
-  float4 add4[4][4];                                     // [group of 4 units][gate]
-  float cprev[16];
+  float4 add4[NSUB][4];                                  // [group of 4 units][gate]
+  float cprev[UNITS];
 #pragma unroll
-  for (int sub = 0; sub < 4; ++sub) {
+  for (int sub = 0; sub < NSUB; ++sub) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int col = g * AT_H + unit0 + sub * 4;
@@ -248,16 +253,16 @@ __device__ __forceinline__ void at_cell_epilogue(const DecodeState& s, const uin
     }
   }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) cprev[j] = valid ? __ldcg(ccol + (size_t)j * s.B) : 0.f;
+  for (int j = 0; j < UNITS; ++j) cprev[j] = valid ? __ldcg(ccol + (size_t)j * s.B) : 0.f;
   wait_acc();
   uint32_t hpk[4];
 #pragma unroll
-  for (int sub = 0; sub < 4; ++sub) {
+  for (int sub = 0; sub < NSUB; ++sub) {
     uint32_t a[4][4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) tmem_ld4(taddr + (uint32_t)(g * 32 + ubase + sub * 4), a[g]);
+    for (int g = 0; g < 4; ++g) tmem_ld4(taddr + col0 + (uint32_t)(g * 16 + sub * 4), a[g]);
     tmem_ld_wait();
-    if (sub == 3) {                                    // the accumulator is in registers: hand it back
+    if (sub == NSUB - 1) {                                    // the accumulator is in registers: hand it back
       tc_fence_before();
       release();
     }
@@ -512,7 +517,7 @@ rnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         at_head_logits_epilogue(s, reinterpret_cast<float*>(smem), taddr, w, m0, step, wait_first, nothing);
       }
     } else {
-      at_cell_epilogue(s, taddr, w, m0, n_tile, step, [&] { mbar_wait(tfull_bar, 0); tc_fence_after(); }, nothing);
+      at_cell_epilogue<false>(s, taddr, w, m0, n_tile, step, [&] { mbar_wait(tfull_bar, 0); tc_fence_after(); }, nothing);
     }
   }
 
@@ -651,12 +656,12 @@ struct PdPipe {            // running ring / accumulator state of one role, carr
 };
 
 struct PdMaps {
-  CUtensorMap h[2], xh[2], head, cat, hp;
+  CUtensorMap h[2], xh[2], head, cat, cat64, hp;   // cat64: the cell weights with a 64-row box (128 x 64 tiles)
 };
 
 // One GEMM phase over this CTA's tiles: first, first + gridDim.x, ... of the n_count x m_tiles tiles (column tile
 // fastest).  EPI 0: head, n_count column tiles starting at n_first; EPI 1: cell.
-template <int EPI>
+template <int EPI, int BN = AT_BLOCK>
 __device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmHp,
                                               const DecodeState& s, const int step, const int num_k, const int first,
                                               const int n_first,
@@ -673,9 +678,9 @@ __device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUte
         const int n_tile = n_first + tile % n_count, m0 = (tile / n_count) * AT_BLOCK;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[pipe.stage], pipe.phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[pipe.stage], 2 * AT_TILE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[pipe.stage], AT_TILE_BYTES + BN * 128);
           tma_load_2d(sA + pipe.stage * AT_TILE_BYTES, tmA, &full_bar[pipe.stage], kb * 64, m0);
-          tma_load_2d(sB + pipe.stage * AT_TILE_BYTES, tmB, &full_bar[pipe.stage], kb * 64, n_tile * AT_BLOCK);
+          tma_load_2d(sB + pipe.stage * AT_TILE_BYTES, tmB, &full_bar[pipe.stage], kb * 64, n_tile * BN);
           if (kb == 0) PD_FINE(FINE_ID, 1);
           if (++pipe.stage == AT_STAGES) { pipe.stage = 0; pipe.phase ^= 1; }
         }
@@ -683,7 +688,7 @@ __device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUte
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(AT_BLOCK, AT_BLOCK);
+      constexpr uint32_t idesc = make_idesc_bf16(AT_BLOCK, BN);
       for (int tile = first; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar, pipe.acc_phase ^ 1);       // the epilogue of the previous tile has drained the accumulator
         tc_fence_after();
@@ -730,7 +735,7 @@ __device__ __forceinline__ void pd_gemm_phase(const CUtensorMap* tmA, const CUte
           at_head_logits_epilogue(s, reinterpret_cast<float*>(stg), taddr, w, m0, step, wait_acc, release);
         }
       } else {
-        at_cell_epilogue(s, taddr, w, m0, n_tile, step, wait_acc, release);
+        at_cell_epilogue<BN == 64>(s, taddr, w, m0, n_tile, step, wait_acc, release);
       }
       if (tr) PD_FINE(FINE_ID, 7);
       pipe.acc_phase ^= 1;
@@ -758,7 +763,7 @@ attn_decode_persistent_kernel(const __grid_constant__ PdMaps maps, const __nv_bf
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&maps.h[0]); prefetch_tensormap(&maps.h[1]);
     prefetch_tensormap(&maps.xh[0]); prefetch_tensormap(&maps.xh[1]);
-    prefetch_tensormap(&maps.head); prefetch_tensormap(&maps.cat); prefetch_tensormap(&maps.hp);
+    prefetch_tensormap(&maps.head); prefetch_tensormap(&maps.cat); prefetch_tensormap(&maps.cat64); prefetch_tensormap(&maps.hp);
     for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, AT_EPI_WARPS);                   // one arrival per epilogue warp
@@ -841,8 +846,15 @@ attn_decode_persistent_kernel(const __grid_constant__ PdMaps maps, const __nv_bf
     pd_grid_barrier(gbar, target, trace_n);
     if (split && s.early_exit && __ldcg(s.live) == 0) break;
     // ---- cell_i
-    pd_gemm_phase<1>(&maps.xh[i & 1], &maps.cat, &maps.hp, s, step, 2 * AT_H / 64, (int)blockIdx.x, 0, 4 * AT_H / AT_BLOCK, m_tiles,
-                     sA, sB, stg, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
+    // 128 x 64 tiles while they all fit the grid at once (<= 1152 crops on 148 SMs): the 128 x 128 x 16 MMA of one CTA
+    // runs at about half rate (8 KB of shared-memory operands per 64 cycles = the whole port), so a tile's 32 MMAs and
+    // its epilogue are the phase; halving the tile halves both and uses twice the SMs.  Same K order: same bits.
+    if (16 * m_tiles <= G)
+      pd_gemm_phase<1, 64>(&maps.xh[i & 1], &maps.cat64, &maps.hp, s, step, 2 * AT_H / 64, (int)blockIdx.x, 0, 4 * AT_H / 64, m_tiles,
+                           sA, sB, stg, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
+    else
+      pd_gemm_phase<1>(&maps.xh[i & 1], &maps.cat, &maps.hp, s, step, 2 * AT_H / 64, (int)blockIdx.x, 0, 4 * AT_H / AT_BLOCK, m_tiles,
+                       sA, sB, stg, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, pipe);
     pd_grid_barrier(gbar, target, trace_n);
   }
   tc_fence_before();
@@ -939,6 +951,9 @@ static int decode_run(const DecodeArgs& a, uint8_t* ws, int B, cudaStream_t st, 
   if (rc != MSTR_OK) return rc;
   rc = encode_tiled_2d_bf16(g_attn_enc, &tmCat, a.w_cat, 2 * AT_H, 4 * AT_H, 64, AT_BLOCK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != MSTR_OK) return rc;
+  alignas(64) CUtensorMap tmCat64;
+  rc = encode_tiled_2d_bf16(g_attn_enc, &tmCat64, a.w_cat, 2 * AT_H, 4 * AT_H, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != MSTR_OK) return rc;
   rc = encode_output_2d(g_attn_enc, &tmHp, s.hp, true, (uint64_t)AT_H, (uint64_t)B);
   if (rc != MSTR_OK) return rc;
 
@@ -946,7 +961,7 @@ static int decode_run(const DecodeArgs& a, uint8_t* ws, int B, cudaStream_t st, 
   const int W = attention_warps_per_crop(B, sm_count());
   if (persistent) {
     PdMaps maps;
-    maps.h[0] = tmH[0]; maps.h[1] = tmH[1]; maps.xh[0] = tmXH[0]; maps.xh[1] = tmXH[1]; maps.head = tmHead; maps.cat = tmCat;
+    maps.h[0] = tmH[0]; maps.h[1] = tmH[1]; maps.xh[0] = tmXH[0]; maps.xh[1] = tmXH[1]; maps.head = tmHead; maps.cat = tmCat; maps.cat64 = tmCat64;
     maps.hp = tmHp;
     if (W == 4) return launch_persistent<4>(maps, a.enc, a.proj, s, st);
     if (W == 2) return launch_persistent<2>(maps, a.enc, a.proj, s, st);

@@ -629,11 +629,12 @@ def attn_decode(enc: torch.Tensor, proj: torch.Tensor, packed: dict, steps: int,
 
 
 def pack_gate_rows_bf16(w: torch.Tensor) -> torch.Tensor:
-    """[4H, K] f32 (gate-major rows i,f,g,o) -> bf16 with rows ordered (chunk of 32 units, gate, unit)."""
+    """[4H, K] f32 (gate-major rows i,f,g,o) -> bf16 with rows ordered (chunk of 16 units, gate, unit): every 64 rows
+    hold all four gates of 16 hidden units, so the decoder's cell GEMM can use 64- or 128-column tiles (attn_tc.cu)."""
     four_h, k = w.shape
     hd = four_h // 4
     assert four_h == 4 * hd and hd % 32 == 0
-    return w.reshape(4, hd // 32, 32, k).permute(1, 0, 2, 3).reshape(four_h, k).to(torch.bfloat16).contiguous()
+    return w.reshape(4, hd // 16, 16, k).permute(1, 0, 2, 3).reshape(four_h, k).to(torch.bfloat16).contiguous()
 
 
 def resize_to_tensor_u8(pixels: torch.Tensor, offsets: torch.Tensor, sizes_hw: torch.Tensor, max_in_hw,

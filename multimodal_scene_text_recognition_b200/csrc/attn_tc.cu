@@ -13,7 +13,7 @@
 //            result, bit for bit - does not depend on how many warps a batch size gets; writes ctx (bf16) into the left
 //            half of the [ctx | h] operand buffer
 //   cell_i   gates = [ctx_i | h_i] [W_ctx | W_hh]^T + W_tok[token_i] + bias -> (h_{i+1}, c_{i+1})
-//            tcgen05 GEMM, N = 1024 with rows packed (chunk of 32 units, gate, unit) so that one 128-column tile
+//            tcgen05 GEMM, N = 1024 with rows packed (chunk of 16 units, gate, unit) so that a 64- or 128-column tile
 //            carries i,f,g,o of the same units and the LSTM cell is thread-local in the epilogue; c stays f32 in global
 //            memory (L2 resident, transposed [H][B]), h_{i+1} is written as bf16 into the right half of the other
 //            [ctx | h] buffer

@@ -165,3 +165,19 @@ def test_default_init_matches_reference_constructor():
     sums = np.array([float(sd[k].double().sum()) for k in names])
     abss = np.array([float(sd[k].double().abs().sum()) for k in names])
     assert np.array_equal(sums, g["param_sums"]) and np.array_equal(abss, g["param_abs_sums"])
+
+
+def test_decoder_weight_packing_order_matches_the_header():
+    """include/mstr_b200.h documents w_cat's row order as chunk*64 + g*16 + j <- g*Hd + chunk*16 + j (every 64 rows hold
+    the four gates of 16 hidden units, so the cell GEMM can run on 64- or 128-column tiles)."""
+    import torch
+    from multimodal_scene_text_recognition_b200 import ops
+    hd, k = 256, 8
+    # row r holds r % 251 in every column: exactly representable in bf16, and distinct for the rows compared below
+    w = (torch.arange(4 * hd, dtype=torch.float32) % 251).view(-1, 1).repeat(1, k)
+    packed = ops.pack_gate_rows_bf16(w).float()
+    assert packed.shape == (4 * hd, k)
+    for chunk in (0, 1, 7, 15):
+        for g in range(4):
+            for j in (0, 5, 15):
+                assert torch.equal(packed[chunk * 64 + g * 16 + j], w[g * hd + chunk * 16 + j])
